@@ -1,0 +1,164 @@
+/*
+ * include/parth_b200.h -- C ABI of the B200-native dynamic-reuse ordering path.
+ *
+ * The reference has no C ABI: its boundary is the C++ class PARTH::ParthAPI
+ * (reference include/parth/parth.h:25 -> src/Parth/include/ParthAPI.h:16-145).  The drop-in class
+ * in include/parth/ParthAPI.h keeps that surface and forwards every call to the entry points
+ * below; each entry point cites the reference member it replaces.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns an int status: 0 = PARTH_B200_OK, negative = PARTH_B200_ERR_*,
+ *     positive = a cudaError_t passed through.  parth_b200_last_error() gives the text.
+ *   - pointers are HOST pointers unless the function name ends in _dev.
+ *   - one handle owns one CUDA stream and all device state; like the reference class it is not
+ *     thread-safe and not re-entrant.
+ *   - there is NO CPU fallback: if no CUDA device is usable, parth_b200_create fails.
+ *
+ * Separator-tree fixture layout (flat int32; the reference keeps per-node std::vectors,
+ * HMD.h:18-104):
+ *   meta[node*7 + k], k = 0..6 : left, right, node_id, parent, offset, level, org_size
+ *                                heap order, children of i are 2i+1 / 2i+2, empty node <=> node_id -1
+ *   node_ptr[nodes+1]          : start of each node's slice in dofs[] / labels[]
+ *   dofs[M_n]                  : HMDNode::DOFs concatenated in heap order
+ *   labels[M_n]                : HMDNode::permuted_new_label, same indexing
+ */
+#ifndef PARTH_B200_H
+#define PARTH_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct parth_b200 parth_b200;
+
+enum {
+  PARTH_B200_OK = 0,
+  PARTH_B200_ERR_ARG = -1,        /* null pointer / inconsistent sizes */
+  PARTH_B200_ERR_NO_DEVICE = -2,  /* no usable CUDA device: the library has no CPU path */
+  PARTH_B200_ERR_NO_TREE = -3,    /* cold start requested but no tree imported and no decomposer set */
+  PARTH_B200_ERR_INPUT = -4,      /* matrix indices out of range */
+  PARTH_B200_ERR_INTERNAL = -5,
+  PARTH_B200_ERR_UNSUPPORTED = -6 /* e.g. METIS leaf ordering requested on the device */
+};
+
+/* ReorderingType, reference ParthTypes.h:11 */
+enum { PARTH_B200_METIS = 0, PARTH_B200_AMD = 1, PARTH_B200_MORTON_CODE = 2 };
+
+/* what to do with dirty COARSE nodes (the reference re-dissects them with METIS,
+ * Integrator.cpp:812-849, which is outside the device path -- see DESIGN.md) */
+enum {
+  PARTH_B200_COARSE_REPAIR = 0,   /* device: relocate one endpoint of every broken edge into the
+                                     common separator, re-order the touched nodes (default) */
+  PARTH_B200_COARSE_CALLBACK = 1, /* host callback re-dissects the extracted sub-mesh */
+  PARTH_B200_COARSE_REPORT = 2    /* leave the permutation, report PARTH_B200_NEEDS_REDISSECT */
+};
+#define PARTH_B200_NEEDS_REDISSECT 100 /* positive, non-error status of compute_permutation */
+
+const char *parth_b200_version(void);
+const char *parth_b200_last_error(const parth_b200 *h);
+
+/* ParthAPI::ParthAPI / ~ParthAPI, ParthAPI.cpp:47-60.  device < 0: current device. */
+int parth_b200_create(parth_b200 **out, int device);
+int parth_b200_destroy(parth_b200 *h);
+/* ParthAPI::clearParth, ParthAPI.cpp:62-74 */
+int parth_b200_clear(parth_b200 *h);
+
+/* setReorderingType/NDLevels/Verbose + public fields lagging, activate_aggressive_reuse,
+ * integrator.relocate_lvl / lag_lvl; ParthAPI.cpp:13-45, ParthAPI.h:19-25, Integrator.h:24-28 */
+int parth_b200_set_options(parth_b200 *h, int reorder_type, int nd_levels, int lagging,
+                           int aggressive_reuse, int relocate_lvl, int lag_lvl, int verbose);
+int parth_b200_set_coarse_policy(parth_b200 *h, int policy);
+/* optional hint: the caller guarantees a structurally symmetric matrix with sorted columns, so
+ * the build skips its symmetry proof (default 0 = prove it on the device, fall back to the
+ * general sort/dedupe kernels when the proof fails) */
+int parth_b200_set_assume_symmetric(parth_b200 *h, int on);
+
+/* ParthAPI::setMatrix -> computeMeshFromMatrix, ParthAPI.cpp:100-124,366-418 */
+int parth_b200_set_matrix(parth_b200 *h, int N, const int *Ap, const int *Ai, int dim);
+int parth_b200_set_matrix_dev(parth_b200 *h, int N, const int *dAp, const int *dAi, int nnz, int dim);
+/* ParthAPI::setMesh, ParthAPI.cpp:76-98 (host arrays are copied to the device) */
+int parth_b200_set_mesh(parth_b200 *h, int n, const int *Mp, const int *Mi);
+int parth_b200_set_mesh_dev(parth_b200 *h, int n, const int *dMp, const int *dMi, int nnz);
+/* ParthAPI::setNewToOldDOFMap -> computeOldToNewDOFMap, ParthAPI.cpp:126-189; len 0 clears */
+int parth_b200_set_new_to_old_map(parth_b200 *h, const int *map, int len);
+
+/* current mesh graph (ParthAPI::Mp / Mi / M_n, ParthAPI.h:66-71) */
+int parth_b200_mesh_dims(parth_b200 *h, int *M_n, int *nnz);
+int parth_b200_get_mesh(parth_b200 *h, int *Mp, int *Mi);
+int parth_b200_mesh_dev(parth_b200 *h, const int **dMp, const int **dMi);
+
+/* tree fixture in / out (ParthAPI::hmd public members, HMD.h:94-104) */
+int parth_b200_import_tree(parth_b200 *h, int M_n, int levels, int nodes, const int *meta,
+                           const int *node_ptr, const int *dofs, const int *labels,
+                           const int *Mp_prev, const int *Mi_prev);
+int parth_b200_tree_dims(parth_b200 *h, int *M_n, int *levels, int *nodes);
+int parth_b200_export_tree(parth_b200 *h, int *meta, int *node_ptr, int *dofs, int *labels,
+                           int *dof2node, int *mesh_perm);
+
+/* cold decomposition hook (HMD::initHMD, HMD.cpp:89-120): called with the host mesh when
+ * computePermutation needs a tree and none exists; must fill the fixture arrays. */
+typedef int (*parth_b200_decomposer)(void *user, int M_n, const int *Mp, const int *Mi, int levels,
+                                     int nodes, int *meta, int *node_ptr, int *dofs, int *labels);
+int parth_b200_set_decomposer(parth_b200 *h, parth_b200_decomposer fn, void *user);
+
+/* ParthAPI::computePermutation, ParthAPI.cpp:191-279.  perm must hold M_n*dim ints. */
+int parth_b200_compute_permutation(parth_b200 *h, int *perm, int dim);
+int parth_b200_compute_permutation_dev(parth_b200 *h, int *dperm, int dim);
+/* ParthAPI::mapMeshPermToMatrixPerm, ParthAPI.cpp:285-337 (dim == -1: sim_dim) */
+int parth_b200_map_mesh_perm_to_matrix_perm(parth_b200 *h, const int *mesh_perm, int n, int *out,
+                                            int dim);
+int parth_b200_map_mesh_perm_to_matrix_perm_dev(parth_b200 *h, const int *dmesh_perm, int n,
+                                                int *dout, int dim);
+
+/* ParthAPI::getReuse / getNumChanges, ParthAPI.cpp:339-341; changed_dof_edges, ParthAPI.h:77;
+ * integrator.dirty_*_HMD_nodes_saved, Integrator.h:20-21; timers ParthAPI.h:87-91 in the order
+ * init, dof_change_integrator, change_computation, compute_permutation, map_mesh_to_matrix */
+double parth_b200_get_reuse(parth_b200 *h);
+int parth_b200_get_num_changes(parth_b200 *h);
+int parth_b200_get_changed_edges(parth_b200 *h, int *pairs, int cap_pairs);
+int parth_b200_get_dirty_nodes(parth_b200 *h, int *fine, int *nfine, int *coarse, int *ncoarse);
+int parth_b200_get_timers(parth_b200 *h, double t[5]);
+int parth_b200_get_mesh_perm(parth_b200 *h, int *mesh_perm, int cap);
+int parth_b200_mesh_perm_dev(parth_b200 *h, const int **dmesh_perm);
+
+/* stage-wise entry points (parity tests drive the same public Integrator/HMD members in the
+ * reference: Integrator.h:40-144, HMD.h:112-252) */
+int parth_b200_stage_integrate(parth_b200 *h);             /* Integrator::integrateDOFChanges */
+int parth_b200_stage_detect(parth_b200 *h, int *nchanged); /* Integrator::computeChangedEdges */
+int parth_b200_stage_permute_fine(parth_b200 *h, const int *nodes, int n); /* permuteFineHMDNodes */
+int parth_b200_stage_submesh(parth_b200 *h, int node, int coarse, int *n, int *nnz, int *Mp,
+                             int *Mi, int *local_to_global); /* createMultiSubMesh / getCoarseMesh */
+/* approximate-minimum-degree ordering of one graph on the device (HMD::AMDNodeNDPermutation,
+ * HMD.cpp:58-75); batch of `count` graphs concatenated CSR-of-CSR style */
+int parth_b200_amd_batch(parth_b200 *h, int count, const int *graph_ptr /*count+1, in vertices*/,
+                         const int *Mp /*per graph n+1, concatenated*/, const int *Mi, int *perm);
+
+/* stage (d): elimination tree, column counts and nnz(L) of P*A*P' for the current mesh graph and
+ * permutation perm[new]=old (NULL: current mesh_perm).  Replaces cholmod_analyze_p as used in
+ * reference src/utils/ParthTestUtils.cpp:15-59; etree as src/utils/etree.cpp:39-115. */
+int parth_b200_symbolic(parth_b200 *h, const int *perm, int *parent, int *colcount, int64_t *lnz);
+
+/* instrumentation: device time of the last call's stages (CUDA events on the handle's stream)
+ * and the number of kernels launched by the library since creation */
+typedef struct {
+  double build_ms, detect_ms, integrate_ms, dirty_ms, reorder_ms, assemble_ms, expand_ms, symbolic_ms;
+  double build_kernel_ms;       /* dominant build kernel only */
+  long long kernels_launched;
+  int build_path;               /* 1 = proven-symmetric filter path, 2 = general sort/dedupe path */
+  long long h2d_bytes, d2h_bytes; /* bytes moved by the last set_* / compute_* call */
+} parth_b200_stats;
+int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out);
+int parth_b200_synchronize(parth_b200 *h);
+/* the stream all work of this handle runs on (cudaStream_t) */
+void *parth_b200_stream(parth_b200 *h);
+
+/* multi-GPU: shard the row-block stages; rank/world as in torch.distributed.  The data-path
+ * exchange (gather of dirty permutation slices) is driven by the caller over NCCL, see
+ * INTEGRATION.md; row-block stages need no collective. */
+int parth_b200_set_shard(parth_b200 *h, int rank, int world);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,38 @@
+// parth_b200/csrc/build.cuh -- interface of graph_build.cu (stage a).
+#pragma once
+#include "common.cuh"
+
+namespace pb {
+
+enum : unsigned { BUILD_UNSORTED = 1u, BUILD_ASYM = 2u, BUILD_RANGE = 4u };
+
+struct BuildStatus {
+  unsigned flags;       // BUILD_* bits raised by the filter path
+  unsigned diff_mod;    // (kept upper - kept lower) modulo 2^31; 0 <=> counts match
+  int nnz_out;          // entries written to Mi
+  int pad;
+  unsigned long long tile_counter;
+};
+
+struct BuildArgs {
+  const int *Ap, *Ai;
+  const int *V;   // dim > 1: exclusive prefix of samples per block-column (M+1); dim == 1: unused
+  int dim, M, Q;  // Q = number of samples (nnzA for dim == 1)
+  int *tile_c;    // num_tiles + 1
+  int *Mp, *Mi;
+  BuildStatus *status;
+  unsigned long long *desc;
+  int check_mirror;
+};
+
+int build_filter_tiles(int M, int Q);
+int build_filter_launch(const BuildArgs &a, cudaStream_t s);
+int build_sample_prefix_launch(const int *Ap, int M, int dim, int *ns_tmp, int *V,
+                               unsigned long long *scan_ws, cudaStream_t s);
+int build_general_count_launch(const BuildArgs &a, int *cnt, int *ptr, unsigned long long *scan_ws,
+                               cudaStream_t s);
+int build_general_finish_launch(const BuildArgs &a, int *cnt, const int *ptr, int *tmp, int *uniq,
+                                unsigned long long *scan_ws, cudaStream_t s);
+int build_general_gather_launch(const BuildArgs &a, const int *ptr, const int *tmp, cudaStream_t s);
+
+}  // namespace pb

@@ -1,0 +1,71 @@
+// parth_b200/csrc/handle.cuh -- the opaque handle behind include/parth_b200.h.
+//
+// Device state is flat SoA int32 (no per-node std::vectors as in reference HMD.h:18-104):
+//   graph     Mp/Mi (current), Mp_prev/Mi_prev (snapshot, swapped not copied when owned)
+//   tree      meta on host AND device (<= 8191 nodes), node_ptr, dofs, labels, dof2node, mesh_perm
+//   scratch   grow-only buffers, so a steady-state update performs no allocation
+#pragma once
+#include <string>
+#include <vector>
+
+#include "../../include/parth_b200.h"
+#include "build.cuh"
+#include "common.cuh"
+
+struct parth_b200 {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  std::string err;
+
+  // ---- options (reference ParthAPI.h:19-25, Integrator.h:24-28)
+  int reorder_type = PARTH_B200_METIS, nd_levels = 8, lagging = 1, aggressive = 0;
+  int relocate_lvl = 2, lag_lvl = 5, verbose = 1, sim_dim = 1;
+  int coarse_policy = PARTH_B200_COARSE_REPAIR, assume_symmetric = 0;
+  int rank = 0, world = 1;
+  parth_b200_decomposer decomposer = nullptr;
+  void *decomposer_user = nullptr;
+
+  // ---- matrix staging for the host-pointer API
+  pb::DevBuf<int> dAp, dAi;
+
+  // ---- mesh graph
+  int M_n = 0, nnzM = 0;
+  const int *Mp = nullptr, *Mi = nullptr;  // device pointers of the current graph
+  bool mesh_owned = false;                 // Mp/Mi live in Mp_own/Mi_own (or were swapped into *_prev)
+  pb::DevBuf<int> Mp_own, Mi_own;
+  int M_n_prev = 0, nnz_prev = 0;
+  pb::DevBuf<int> Mp_prev, Mi_prev;
+
+  // ---- DOF maps (reference ParthAPI.h:79-84)
+  int map_len = 0;  // 0: no map
+  pb::DevBuf<int> new_to_old, old_to_new;
+  int n_added = 0, n_removed = 0;
+  pb::DevBuf<int> added, removed;
+
+  // ---- separator tree
+  bool tree_init = false;
+  int num_levels = 0, num_nodes = 0, tree_M = 0;
+  std::vector<int> meta;      // host mirror, nodes*7
+  std::vector<int> node_ptr;  // host mirror, nodes+1
+  pb::DevBuf<int> d_meta, d_node_ptr, d_dofs, d_labels, d_dof2node, d_mesh_perm;
+  pb::DevBuf<int> d_dofs2, d_labels2;  // double buffers for integration / relocation
+
+  // ---- results of the last computePermutation
+  double reuse = 0.0;
+  int n_changed = 0;
+  pb::DevBuf<int> d_changed;  // pairs
+  std::vector<int> dirty_fine, dirty_coarse, dirty_fine_saved, dirty_coarse_saved;
+  double timers[5] = {0, 0, 0, 0, 0};
+
+  // ---- scratch
+  pb::DevBuf<int> V, ns_tmp, tile_c, cnt, ptr, tmp, uniq;
+  pb::DevBuf<unsigned long long> desc, scan_ws;
+  pb::DevBuf<pb::BuildStatus> bstatus;
+  pb::DevBuf<int> w0, w1, w2, w3, w4, w5;  // general-purpose int scratch
+  pb::DevBuf<int> d_out;                   // staging for host-pointer outputs
+  pb::PinBuf<int> pin;                     // small pinned read-backs
+  pb::PinBuf<int> pin_big;                 // pinned staging for big host transfers
+
+  parth_b200_stats stats = {};
+};

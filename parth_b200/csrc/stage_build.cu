@@ -1,0 +1,93 @@
+// parth_b200/csrc/stage_build.cu -- host driver of stage (a): picks the filter path, checks its
+// proof flags, falls back to the general kernels (graph_build.cu).
+#include "build.cuh"
+#include "scan.cuh"
+#include "stages.cuh"
+
+namespace pb {
+
+void read_ints(parth_b200 &h, const int *dsrc, int *dst, size_t n) {
+  h.pin.reserve(n);
+  PB_CUDA(cudaMemcpyAsync(h.pin.p, dsrc, sizeof(int) * n, cudaMemcpyDeviceToHost, h.stream));
+  PB_CUDA(cudaStreamSynchronize(h.stream));
+  for (size_t i = 0; i < n; i++) dst[i] = h.pin.p[i];
+  h.stats.d2h_bytes += (long long)(sizeof(int) * n);
+}
+
+void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, int dim) {
+  cudaStream_t s = h.stream;
+  const int M = N / dim;
+  StageTimer total(h, h.ev0, h.ev1);
+
+  h.scan_ws.reserve(scan_ws_words((size_t)M + 1), s);
+  int Q = nnz;
+  if (dim != 1) {
+    h.V.reserve((size_t)M + 2, s);
+    h.ns_tmp.reserve((size_t)M + 1, s);
+    h.stats.kernels_launched += build_sample_prefix_launch(dAp, M, dim, h.ns_tmp.p, h.V.p, h.scan_ws.p, s);
+    read_ints(h, h.V.p + M, &Q, 1);
+  }
+
+  BuildArgs a{};
+  a.Ap = dAp; a.Ai = dAi; a.V = h.V.p; a.dim = dim; a.M = M; a.Q = Q;
+  a.check_mirror = h.assume_symmetric ? 0 : 1;
+  const int tiles = build_filter_tiles(M, Q);
+  h.tile_c.reserve((size_t)tiles + 2, s);
+  h.desc.reserve((size_t)tiles + 1, s);
+  // after a snapshot-by-swap the "own" buffers hold stale data and are free to be overwritten
+  h.Mp_own.reserve((size_t)M + 1, s);
+  h.Mi_own.reserve((size_t)(Q > 0 ? Q : 1), s);
+  a.tile_c = h.tile_c.p; a.desc = h.desc.p; a.status = h.bstatus.p;
+  a.Mp = h.Mp_own.p; a.Mi = h.Mi_own.p;
+
+  BuildStatus st{};
+  cudaEventRecord(h.ev2, s);
+  h.stats.kernels_launched += build_filter_launch(a, s);
+  cudaEventRecord(h.ev3, s);
+  static_assert(sizeof(BuildStatus) % sizeof(int) == 0, "BuildStatus is read back as ints");
+  read_ints(h, reinterpret_cast<const int *>(h.bstatus.p), reinterpret_cast<int *>(&st),
+            sizeof(BuildStatus) / sizeof(int));
+  {
+    float t = 0;
+    cudaEventElapsedTime(&t, h.ev2, h.ev3);
+    h.stats.build_kernel_ms = t;
+  }
+  if (st.flags & BUILD_RANGE)
+    throw StatusError(PARTH_B200_ERR_INPUT, "set_matrix: row index out of range");
+  const bool proven = st.flags == 0 && (h.assume_symmetric || st.diff_mod == 0);
+  if (proven) {
+    h.nnzM = st.nnz_out;
+    h.stats.build_path = 1;
+  } else {
+    // general path: any triangle, unsorted columns, duplicates
+    h.cnt.reserve((size_t)M + 1, s);
+    h.ptr.reserve((size_t)M + 2, s);
+    h.uniq.reserve((size_t)M + 1, s);
+    h.stats.kernels_launched += build_general_count_launch(a, h.cnt.p, h.ptr.p, h.scan_ws.p, s);
+    int total_pairs = 0;
+    read_ints(h, h.ptr.p + M, &total_pairs, 1);
+    read_ints(h, reinterpret_cast<const int *>(h.bstatus.p), reinterpret_cast<int *>(&st),
+              sizeof(BuildStatus) / sizeof(int));
+    if (st.flags & BUILD_RANGE)
+      throw StatusError(PARTH_B200_ERR_INPUT, "set_matrix: row index out of range");
+    h.tmp.reserve((size_t)(total_pairs > 0 ? total_pairs : 1), s);
+    h.Mi_own.reserve((size_t)(total_pairs > 0 ? total_pairs : 1), s);
+    a.Mi = h.Mi_own.p;
+    h.stats.kernels_launched +=
+        build_general_finish_launch(a, h.cnt.p, h.ptr.p, h.tmp.p, h.uniq.p, h.scan_ws.p, s);
+    int nnzM = 0;
+    read_ints(h, h.Mp_own.p + M, &nnzM, 1);
+    h.stats.kernels_launched += build_general_gather_launch(a, h.ptr.p, h.tmp.p, s);
+    h.nnzM = nnzM;
+    h.stats.build_path = 2;
+  }
+  total.stop();
+  h.Mp = h.Mp_own.p;
+  h.Mi = h.Mi_own.p;
+  h.M_n = M;
+  h.mesh_owned = true;
+  h.map_len = 0;
+  h.stats.build_ms = total.ms();
+}
+
+}  // namespace pb

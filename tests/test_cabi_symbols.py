@@ -1,0 +1,55 @@
+"""CPU: the C-ABI shared library loads and exports every symbol include/parth_b200.h declares
+(no compute without a GPU), and the product path fails loudly instead of falling back."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from parth_b200 import build
+    build.build()
+    return ctypes.CDLL(build.LIB)
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "parth_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(parth_b200_[a-z0-9_]+)\s*\(", text)) - {"parth_b200_decomposer"})
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_symbols()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_python_binding_lists_the_same_symbols():
+    from parth_b200 import api
+    assert sorted(api.SYMBOLS) == declared_symbols()
+
+
+def test_no_cpu_fallback_without_a_device():
+    import torch
+    from parth_b200 import api
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(api.ParthError) as e:
+        api.ParthAPI()
+    assert e.value.code == -2
+
+
+def test_product_never_imports_the_oracle():
+    bad = []
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "parth_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                s = open(os.path.join(dirpath, f)).read()
+                if re.search(r"^\s*(from|import)\s+oracle\b|cpu_parth|liboracle|libparth_ref", s, flags=re.M):
+                    bad.append(f)
+    assert not bad, bad

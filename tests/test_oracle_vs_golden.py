@@ -1,0 +1,83 @@
+"""CPU: the plain-C restatement (oracle/, kind "port") against the committed golden fixtures that
+tests/golden/make_golden.py produced by running the UNMODIFIED reference (oracle/_ref)."""
+import numpy as np
+import pytest
+
+from parth_b200 import synth
+from tests import scenario_defs as sd
+from tests.golden import fixtures
+
+NEEDS_REDISSECT = -10
+
+
+@pytest.mark.parametrize("name", ["original", "0", "1", "2", "3", "4"])
+def test_build_reference_matrices(port, name):
+    N, Ap, Ai = fixtures.matrix(name)
+    o = port.CpuParth("port")
+    o.setMatrix(N, Ap, Ai, 1)
+    Mp, Mi = o.mesh()
+    g = fixtures.build_golden(name)
+    assert (len(Mp) - 1, len(Mi)) == (g["M_n"], g["nnz"])
+    assert synth.hexhash(Mp) == g["hash_Mp"] and synth.hexhash(Mi) == g["hash_Mi"]
+
+
+def test_build_known_sizes_of_survey_appendix_b1():
+    # mesh nnz = nnzA - N for the structurally symmetric fixtures
+    want = {"original": 64704, "0": 64706, "1": 64712, "2": 64706, "3": 64706, "4": 64706}
+    for k, v in want.items():
+        assert fixtures.build_golden(k)["nnz"] == v and fixtures.build_golden(k)["M_n"] == 10786
+
+
+@pytest.mark.parametrize("name", sorted(sd.build_cases()))
+def test_build_synthetic(port, name):
+    N, Ap, Ai, dim = sd.build_cases()[name]
+    o = port.CpuParth("port")
+    o.setMatrix(N, Ap, Ai, dim)
+    Mp, Mi = o.mesh()
+    g = fixtures.build_golden(name)
+    assert synth.hexhash(Mp) == g["hash_Mp"] and synth.hexhash(Mi) == g["hash_Mi"]
+    # full, lower-only and kron-3 inputs give the same graph
+    assert g["hash_Mi"] == fixtures.build_golden("grid20_full")["hash_Mi"] and g["nnz"] == 45600
+
+
+def test_expansion_known_answer(port):
+    # SURVEY.md Appendix B.2
+    mp = (7919 * np.arange(8000) + 13) % 8000
+    out = port.CpuParth("port").mapMeshPermToMatrixPerm(mp, 3)
+    assert out[:6].tolist() == [39, 40, 41, 23796, 23797, 23798]
+    assert np.array_equal(out, (mp[:, None] * 3 + np.arange(3)).reshape(-1))
+
+
+SCEN = sd.scenario_list()
+GOLD = fixtures.scenarios()
+
+
+@pytest.mark.parametrize("name", sorted(SCEN))
+def test_scenario(port, name):
+    exp = GOLD[name]
+    sc = SCEN[name]
+    # the port cannot run METIS: leaf re-ordering with METIS and coarse re-dissection are out
+    res = sd.run_scenario(port, "port", sc)
+    assert int(res["num_changes"]) == int(exp["num_changes"])
+    assert str(res["edges_hash"]) == str(exp["edges_hash"])
+    assert res["dirty_fine"].tolist() == exp["dirty_fine"].tolist()
+    assert res["dirty_coarse"].tolist() == exp["dirty_coarse"].tolist()
+    assert float(res["reuse"]) == float(exp["reuse"])
+    if int(exp["deterministic"]):
+        assert int(res["status"]) == 0
+        for k in exp:
+            if k.endswith("_hash"):
+                assert str(res[k]) == str(exp[k]), k
+    else:
+        assert int(res["status"]) == NEEDS_REDISSECT
+
+
+def test_kat_values_of_survey_appendix_b4():
+    g = GOLD
+    assert float(g["kat48_123_124_lag1"]["reuse"]) == pytest.approx(0.974835, abs=1e-6)
+    assert g["kat48_123_124_lag1"]["dirty_coarse"].tolist() == [61]
+    assert g["kat48_125_126_lag1"]["dirty_coarse"].tolist() == [] and float(g["kat48_125_126_lag1"]["reuse"]) == 1.0
+    assert int(g["kat48_125_126_lag1"]["num_changes"]) == 1
+    assert g["kat48_125_126_lag0"]["dirty_coarse"].tolist() == [62]
+    assert float(g["kat48_255_256_lag0"]["reuse"]) == pytest.approx(0.992188, abs=1e-6)
+    assert int(g["kat48_1_3_lag1"]["num_changes"]) == 0 and int(g["kat48_3_3_lag0"]["num_changes"]) == 0
