@@ -237,3 +237,199 @@ int parth_b200_mesh_dev(parth_b200 *h, const int **dMp, const int **dMi) {
 }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------ tree, permutation, results
+extern "C" {
+
+int parth_b200_set_new_to_old_map(parth_b200 *h, const int *map, int len) {
+  PB_API_BEGIN
+  if (len < 0 || (len > 0 && !map)) throw StatusError(PARTH_B200_ERR_ARG, "set_new_to_old_map: bad argument");
+  stage_set_map(*h, map, len);
+  PB_API_END
+}
+
+int parth_b200_import_tree(parth_b200 *h, int M_n, int levels, int nodes, const int *meta,
+                           const int *node_ptr, const int *dofs, const int *labels,
+                           const int *Mp_prev, const int *Mi_prev) {
+  PB_API_BEGIN
+  if (!meta || !node_ptr || !dofs || !labels) throw StatusError(PARTH_B200_ERR_ARG, "import_tree: null array");
+  stage_import_tree(*h, M_n, levels, nodes, meta, node_ptr, dofs, labels, Mp_prev, Mi_prev);
+  PB_API_END
+}
+
+int parth_b200_tree_dims(parth_b200 *h, int *M_n, int *levels, int *nodes) {
+  if (!h || !M_n || !levels || !nodes) return PARTH_B200_ERR_ARG;
+  *M_n = h->tree_M;
+  *levels = h->num_levels;
+  *nodes = h->num_nodes;
+  return h->tree_init ? PARTH_B200_OK : PARTH_B200_ERR_NO_TREE;
+}
+
+int parth_b200_export_tree(parth_b200 *h, int *meta, int *node_ptr, int *dofs, int *labels,
+                           int *dof2node, int *mesh_perm) {
+  PB_API_BEGIN
+  if (!meta || !node_ptr) throw StatusError(PARTH_B200_ERR_ARG, "export_tree: null array");
+  stage_export_tree(*h, meta, node_ptr, dofs, labels, dof2node, mesh_perm);
+  PB_API_END
+}
+
+int parth_b200_compute_permutation_dev(parth_b200 *h, int *dperm, int dim) {
+  int rc = PARTH_B200_OK;
+  PB_API_BEGIN
+  if (!dperm || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "computePermutation: bad argument");
+  h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
+  rc = stage_compute_permutation(*h, dperm, dim);
+  PB_CUDA(cudaStreamSynchronize(h->stream));
+  if (rc != PARTH_B200_OK) return rc;
+  PB_API_END
+}
+
+int parth_b200_compute_permutation(parth_b200 *h, int *perm, int dim) {
+  int rc = PARTH_B200_OK;
+  PB_API_BEGIN
+  if (!perm || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "computePermutation: bad argument");
+  h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
+  const size_t n_out = (size_t)h->M_n * dim;
+  h->d_out.reserve(n_out > 0 ? n_out : 1, h->stream);
+  rc = stage_compute_permutation(*h, h->d_out.p, dim);
+  if (rc == PARTH_B200_OK) {
+    PB_CUDA(cudaMemcpyAsync(perm, h->d_out.p, sizeof(int) * n_out, cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (long long)(sizeof(int) * n_out);
+  }
+  PB_CUDA(cudaStreamSynchronize(h->stream));
+  if (rc != PARTH_B200_OK) return rc;
+  PB_API_END
+}
+
+int parth_b200_map_mesh_perm_to_matrix_perm_dev(parth_b200 *h, const int *dmesh_perm, int n,
+                                                int *dout, int dim) {
+  PB_API_BEGIN
+  if (!dmesh_perm || !dout || n <= 0) throw StatusError(PARTH_B200_ERR_ARG, "mapMeshPermToMatrixPerm: bad argument");
+  if (dim == -1) dim = h->sim_dim;
+  stage_expand(*h, dmesh_perm, n, dim, dout);
+  PB_CUDA(cudaStreamSynchronize(h->stream));
+  PB_API_END
+}
+
+int parth_b200_map_mesh_perm_to_matrix_perm(parth_b200 *h, const int *mesh_perm, int n, int *out,
+                                            int dim) {
+  PB_API_BEGIN
+  if (!mesh_perm || !out || n <= 0) throw StatusError(PARTH_B200_ERR_ARG, "mapMeshPermToMatrixPerm: bad argument");
+  if (dim == -1) dim = h->sim_dim;
+  h->w0.reserve((size_t)n, h->stream);
+  h->d_out.reserve((size_t)n * dim, h->stream);
+  PB_CUDA(cudaMemcpyAsync(h->w0.p, mesh_perm, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+  stage_expand(*h, h->w0.p, n, dim, h->d_out.p);
+  PB_CUDA(cudaMemcpyAsync(out, h->d_out.p, sizeof(int) * (size_t)n * dim, cudaMemcpyDeviceToHost, h->stream));
+  PB_CUDA(cudaStreamSynchronize(h->stream));
+  h->stats.h2d_bytes = (long long)sizeof(int) * n;
+  h->stats.d2h_bytes = (long long)sizeof(int) * n * dim;
+  PB_API_END
+}
+
+double parth_b200_get_reuse(parth_b200 *h) { return h ? h->reuse : 0.0; }
+int parth_b200_get_num_changes(parth_b200 *h) { return h ? h->n_changed : 0; }
+
+int parth_b200_get_changed_edges(parth_b200 *h, int *pairs, int cap_pairs) {
+  if (!h) return PARTH_B200_ERR_ARG;
+  try {
+    PB_CUDA(cudaSetDevice(h->device));
+    const int n = h->n_changed < cap_pairs ? h->n_changed : cap_pairs;
+    if (n > 0 && pairs) {
+      PB_CUDA(cudaMemcpyAsync(pairs, h->d_changed.p, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+      PB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+  } catch (const std::exception &e) {
+    h->err = e.what();
+    return PARTH_B200_ERR_INTERNAL;
+  }
+  return h->n_changed;
+}
+
+int parth_b200_get_dirty_nodes(parth_b200 *h, int *fine, int *nfine, int *coarse, int *ncoarse) {
+  if (!h || !nfine || !ncoarse) return PARTH_B200_ERR_ARG;
+  *nfine = (int)h->dirty_fine_saved.size();
+  *ncoarse = (int)h->dirty_coarse_saved.size();
+  if (fine) std::memcpy(fine, h->dirty_fine_saved.data(), sizeof(int) * h->dirty_fine_saved.size());
+  if (coarse) std::memcpy(coarse, h->dirty_coarse_saved.data(), sizeof(int) * h->dirty_coarse_saved.size());
+  return PARTH_B200_OK;
+}
+
+int parth_b200_get_timers(parth_b200 *h, double t[5]) {
+  if (!h || !t) return PARTH_B200_ERR_ARG;
+  for (int i = 0; i < 5; i++) t[i] = h->timers[i];
+  return PARTH_B200_OK;
+}
+
+int parth_b200_get_mesh_perm(parth_b200 *h, int *mesh_perm, int cap) {
+  if (!h || !mesh_perm) return PARTH_B200_ERR_ARG;
+  if (!h->tree_init) return 0;
+  if (h->tree_M > cap) return PARTH_B200_ERR_ARG;
+  try {
+    PB_CUDA(cudaSetDevice(h->device));
+    PB_CUDA(cudaMemcpyAsync(mesh_perm, h->d_mesh_perm.p, sizeof(int) * (size_t)h->tree_M, cudaMemcpyDeviceToHost, h->stream));
+    PB_CUDA(cudaStreamSynchronize(h->stream));
+  } catch (const std::exception &e) {
+    h->err = e.what();
+    return PARTH_B200_ERR_INTERNAL;
+  }
+  return h->tree_M;
+}
+
+int parth_b200_mesh_perm_dev(parth_b200 *h, const int **dmesh_perm) {
+  if (!h || !dmesh_perm) return PARTH_B200_ERR_ARG;
+  *dmesh_perm = h->tree_init ? h->d_mesh_perm.p : nullptr;
+  return PARTH_B200_OK;
+}
+
+int parth_b200_stage_integrate(parth_b200 *h) {
+  PB_API_BEGIN
+  if (!h->tree_init || h->map_len == 0) throw StatusError(PARTH_B200_ERR_ARG, "stage_integrate: needs a tree and a map");
+  stage_integrate(*h);
+  PB_CUDA(cudaStreamSynchronize(h->stream));
+  PB_API_END
+}
+
+int parth_b200_stage_detect(parth_b200 *h, int *nchanged) {
+  PB_API_BEGIN
+  if (!h->tree_init || !h->Mp) throw StatusError(PARTH_B200_ERR_ARG, "stage_detect: needs a tree and a mesh");
+  stage_detect(*h);
+  if (nchanged) *nchanged = h->n_changed;
+  PB_API_END
+}
+
+int parth_b200_stage_permute_fine(parth_b200 *h, const int *nodes, int n) {
+  PB_API_BEGIN
+  if (!h->tree_init || !h->Mp || (n > 0 && !nodes)) throw StatusError(PARTH_B200_ERR_ARG, "stage_permute_fine: bad argument");
+  stage_permute_fine(*h, std::vector<int>(nodes, nodes + n));
+  PB_CUDA(cudaStreamSynchronize(h->stream));
+  PB_API_END
+}
+
+int parth_b200_stage_submesh(parth_b200 *h, int node, int coarse, int *n, int *nnz, int *Mp, int *Mi,
+                             int *local_to_global) {
+  PB_API_BEGIN
+  if (!h->tree_init || !h->Mp || !n || !nnz || node < 0 || node >= h->num_nodes)
+    throw StatusError(PARTH_B200_ERR_ARG, "stage_submesh: bad argument");
+  stage_submesh(*h, node, coarse, n, nnz, Mp, Mi, local_to_global);
+  PB_API_END
+}
+
+int parth_b200_amd_batch(parth_b200 *h, int count, const int *graph_ptr, const int *Mp, const int *Mi,
+                         int *perm) {
+  PB_API_BEGIN
+  if (count < 0 || !graph_ptr || !Mp || !Mi || !perm) throw StatusError(PARTH_B200_ERR_ARG, "amd_batch: bad argument");
+  stage_amd_batch(*h, count, graph_ptr, Mp, Mi, perm);
+  PB_API_END
+}
+
+int parth_b200_symbolic(parth_b200 *h, const int *perm, int *parent, int *colcount, int64_t *lnz) {
+  PB_API_BEGIN
+  if (!h->Mp || !lnz) throw StatusError(PARTH_B200_ERR_ARG, "symbolic: needs a mesh");
+  long long v = 0;
+  stage_symbolic(*h, perm, parent, colcount, &v);
+  *lnz = v;
+  PB_API_END
+}
+
+}  // extern "C"

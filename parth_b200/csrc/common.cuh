@@ -158,20 +158,36 @@ __device__ __forceinline__ long long tile_lookback(unsigned long long *desc, int
   if (lane == 0) st_relaxed_u64(desc + tile, kTileAgg | (unsigned long long)aggregate);
   long long excl = 0;
   int look = tile - 1;
-  while (true) {
-    int idx = look - lane;
-    unsigned long long d = kTilePre;  // lanes past the front behave like a zero inclusive prefix
-    if (idx >= 0) {
-      do { d = ld_relaxed_u64(desc + idx); } while ((d >> 62) == 0);
-    }
-    unsigned full = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-    int first = full ? __ffs(full) - 1 : 32;  // nearest predecessor holding an inclusive prefix
-    long long v = (lane <= first) ? (long long)(d & kTileVal) : 0;
+  // A walker retires kLookWide*32 predecessors per L2 round trip.  The chained scan sustains at
+  // most that many tiles per round trip chip-wide, so the window (and the tile size) must be
+  // large enough that this bound sits below the HBM time of the kernel.
+  constexpr int kLookWide = 4;
+  bool done = false;
+  while (!done) {
+    unsigned long long d[kLookWide];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    excl = (excl + v) & (long long)kTileVal;
-    if (full) break;
-    look -= 32;
+    for (int u = 0; u < kLookWide; u++) {
+      const int idx = look - lane - 32 * u;
+      // lanes past the front behave like a zero inclusive prefix
+      d[u] = idx >= 0 ? ld_relaxed_u64(desc + idx) : kTilePre;
+    }
+#pragma unroll
+    for (int u = 0; u < kLookWide; u++) {
+      if (done) break;
+      const int idx = look - lane - 32 * u;
+      while ((d[u] >> 62) == 0) {  // predecessor has not published yet: back off, then re-read
+        __nanosleep(32);
+        d[u] = ld_relaxed_u64(desc + idx);
+      }
+      const unsigned full = __ballot_sync(0xffffffffu, (d[u] >> 62) == 2);
+      const int first = full ? __ffs(full) - 1 : 32;  // nearest predecessor with an inclusive prefix
+      long long v = (lane <= first) ? (long long)(d[u] & kTileVal) : 0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      excl = (excl + v) & (long long)kTileVal;
+      if (full) done = true;
+    }
+    look -= 32 * kLookWide;
   }
   if (lane == 0)
     st_relaxed_u64(desc + tile, kTilePre | ((unsigned long long)(excl + aggregate) & kTileVal));

@@ -1,0 +1,229 @@
+// parth_b200/csrc/detect.cu -- stage (b): change detection against the snapshot graph.
+//
+// Replaces Integrator::computeChangedEdges + computeTheAddedRemovedEdgesForDOF + 
+// problematicEdgeCondition (reference src/Parth/Integrator.cpp:23-42,259-338,895-921):
+//   row i is "changed" if its degree or any entry differs from the snapshot; a changed row reports
+//   every (i, nbr > i) whose separator-tree nodes are neither equal nor ancestor-related, in
+//   (row, stored position) order.
+//
+// Device formulation:
+//   diff_rows         streaming comparison.  A CTA owns a block of rows; if the row-pointer shift
+//                     Mp[i]-Mp_prev[i] is constant over the block and the two entry ranges are
+//                     byte-identical, no row of the block changed (exact, not a heuristic) and the
+//                     kernel is a shifted memcmp running at HBM speed: algorithmic bytes
+//                     2*4*[(M+1)+nnzM].  Only blocks that fail do the per-row comparison.
+//   list_changed_rows ordered compaction of the changed-row bitmap (popc scan outside)
+//   count/emit        per changed row (few): problematic-edge count, exclusive scan, ordered emit
+#include "tree.cuh"
+
+namespace pb {
+
+constexpr int K2_THREADS = 256;
+constexpr int K2_ROWS = 2048;  // rows per CTA (multiple of 32: one bitmap word per warp-row-group)
+
+__device__ __forceinline__ bool is_separator_d(int sep, int node) {
+  int a = (node - 1) / 2;
+  while (a > sep && a > 0) a = (a - 1) / 2;
+  return a == sep;
+}
+
+// Integrator::problematicEdgeCondition
+__device__ __forceinline__ bool problematic_d(const int *__restrict__ dof2node, int a, int b) {
+  int na = __ldg(dof2node + a), nb = __ldg(dof2node + b);
+  int big = na, small = nb;
+  if (small > big) { int t = big; big = small; small = t; }
+  return !(small == big || is_separator_d(small, big));
+}
+
+__global__ void __launch_bounds__(K2_THREADS)
+diff_rows_kernel(const int *__restrict__ Mp, const int *__restrict__ Mi,
+                 const int *__restrict__ Mp_prev, const int *__restrict__ Mi_prev, int M,
+                 unsigned *__restrict__ row_bits, DetectCounters *__restrict__ cnt) {
+  __shared__ int s_bad;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int r0 = blockIdx.x * K2_ROWS;
+  const int r1 = r0 + K2_ROWS < M ? r0 + K2_ROWS : M;
+  if (tid == 0) s_bad = 0;
+  __syncthreads();
+  const int p0 = Mp[r0], pp0 = Mp_prev[r0];
+  const int delta = p0 - pp0;
+  int bad = 0;
+  // (1) constant shift of the row pointers over [r0, r1]
+  for (int i = r0 + tid; i <= r1; i += K2_THREADS) bad |= (ld_stream(Mp + i) - ld_stream(Mp_prev + i)) != delta;
+  // (2) identical entries (lengths match whenever (1) holds; guard with the new length otherwise)
+  const int len = Mp[r1] - p0, lenp = Mp_prev[r1] - pp0;
+  const int n = len < lenp ? len : lenp;
+  const int *a = Mi + p0;
+  const int *b = Mi_prev + pp0;
+  int j = tid;
+  for (; j + 3 * K2_THREADS < n; j += 4 * K2_THREADS) {
+    int x0 = ld_stream(a + j), x1 = ld_stream(a + j + K2_THREADS), x2 = ld_stream(a + j + 2 * K2_THREADS),
+        x3 = ld_stream(a + j + 3 * K2_THREADS);
+    int y0 = ld_stream(b + j), y1 = ld_stream(b + j + K2_THREADS), y2 = ld_stream(b + j + 2 * K2_THREADS),
+        y3 = ld_stream(b + j + 3 * K2_THREADS);
+    bad |= (x0 != y0) | (x1 != y1) | (x2 != y2) | (x3 != y3);
+  }
+  for (; j < n; j += K2_THREADS) bad |= ld_stream(a + j) != ld_stream(b + j);
+  if (bad) s_bad = 1;
+  __syncthreads();
+  const int word0 = r0 >> 5;
+  const int n_words = (r1 - r0 + 31) >> 5;
+  if (!s_bad) {
+    for (int w = tid; w < n_words; w += K2_THREADS) row_bits[word0 + w] = 0u;
+    return;
+  }
+  // per-row comparison (Integrator.cpp:269-288), one thread per row, one bitmap word per warp pass
+  int changed_here = 0;
+  for (int base = r0 + (tid & ~31); base < r1; base += K2_THREADS) {
+    const int i = base + lane;
+    bool ch = false;
+    if (i < r1) {
+      const int s = Mp[i], e = Mp[i + 1], sp = Mp_prev[i], ep = Mp_prev[i + 1];
+      ch = (e - s) != (ep - sp);
+      for (int k = 0; !ch && k < e - s; k++) ch = Mi[s + k] != Mi_prev[sp + k];
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, ch);
+    if (lane == 0) { row_bits[base >> 5] = m; changed_here += __popc(m); }
+  }
+  if (lane == 0 && changed_here) atomicAdd(&cnt->changed_rows, changed_here);
+  if (tid == 0) atomicAdd(&cnt->dirty_tiles, 1);
+}
+
+// DOF-map variant (Integrator.cpp:290-337): row cur is compared with the surviving, re-labelled
+// neighbours of its old row; added DOFs are always changed.  One thread per row.
+__global__ void diff_rows_mapped_kernel(const int *__restrict__ Mp, const int *__restrict__ Mi,
+                                        const int *__restrict__ Mp_prev, const int *__restrict__ Mi_prev,
+                                        const int *__restrict__ new_to_old,
+                                        const int *__restrict__ old_to_new, int M,
+                                        unsigned *__restrict__ row_bits, DetectCounters *__restrict__ cnt) {
+  const int cur = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool ch = false;
+  if (cur < M) {
+    const int old = new_to_old[cur];
+    if (old == -1) ch = true;
+    else {
+      const int s = Mp[cur], len = Mp[cur + 1] - s;
+      int j = 0;
+      for (int p = Mp_prev[old]; p < Mp_prev[old + 1]; p++) {
+        const int m = __ldg(old_to_new + Mi_prev[p]);
+        if (m == -1) continue;
+        if (j < len && Mi[s + j] != m) ch = true;
+        j++;
+      }
+      if (j != len) ch = true;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, ch);
+  if (lane == 0 && (cur >> 5) < ((M + 31) >> 5)) {
+    row_bits[cur >> 5] = m;
+    if (m) atomicAdd(&cnt->changed_rows, __popc(m));
+  }
+}
+
+__global__ void list_changed_rows_kernel(const unsigned *__restrict__ row_bits,
+                                         const int *__restrict__ word_prefix, int n_words, int M,
+                                         int *__restrict__ rows) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= n_words) return;
+  unsigned m = row_bits[w];
+  int o = word_prefix[w];
+  while (m) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    rows[o++] = (w << 5) + b;
+  }
+}
+
+// computeTheAddedRemovedEdgesForDOF (Integrator.cpp:23-42): one warp per changed row
+__global__ void count_row_edges_kernel(const int *__restrict__ rows, int n_rows,
+                                       const int *__restrict__ Mp, const int *__restrict__ Mi,
+                                       const int *__restrict__ dof2node, int *__restrict__ counts) {
+  const int lane = threadIdx.x & 31;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k >= n_rows) return;
+  const int i = rows[k];
+  int c = 0;
+  for (int p = Mp[i] + lane; p < Mp[i + 1]; p += 32) {
+    const int nb = Mi[p];
+    c += (i < nb) && problematic_d(dof2node, i, nb);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0) counts[k] = c;
+}
+
+__global__ void emit_row_edges_kernel(const int *__restrict__ rows, int n_rows,
+                                      const int *__restrict__ Mp, const int *__restrict__ Mi,
+                                      const int *__restrict__ dof2node,
+                                      const int *__restrict__ offsets, int *__restrict__ edges) {
+  const int lane = threadIdx.x & 31;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k >= n_rows) return;
+  const int i = rows[k];
+  int o = offsets[k];
+  const int s = Mp[i], e = Mp[i + 1];
+  for (int b = s; b < e; b += 32) {
+    const int p = b + lane;
+    bool hit = false;
+    int nb = 0;
+    if (p < e) {
+      nb = Mi[p];
+      hit = (i < nb) && problematic_d(dof2node, i, nb);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int at = o + __popc(m & ((1u << lane) - 1u));
+      edges[2 * at] = i;
+      edges[2 * at + 1] = nb;
+    }
+    o += __popc(m);
+  }
+}
+
+// ------------------------------------------------------------------ host launchers
+int launch_diff_rows(const int *Mp, const int *Mi, const int *Mp_prev, const int *Mi_prev, int M,
+                     unsigned *row_bits, DetectCounters *cnt, cudaStream_t s) {
+  PB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(DetectCounters), s));
+  const int blocks = (M + K2_ROWS - 1) / K2_ROWS;
+  diff_rows_kernel<<<blocks, K2_THREADS, 0, s>>>(Mp, Mi, Mp_prev, Mi_prev, M, row_bits, cnt);
+  PB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int launch_diff_rows_mapped(const int *Mp, const int *Mi, const int *Mp_prev, const int *Mi_prev,
+                            const int *new_to_old, const int *old_to_new, int M, unsigned *row_bits,
+                            DetectCounters *cnt, cudaStream_t s) {
+  PB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(DetectCounters), s));
+  const int threads = ((M + 31) / 32) * 32;
+  diff_rows_mapped_kernel<<<(threads + 255) / 256, 256, 0, s>>>(Mp, Mi, Mp_prev, Mi_prev, new_to_old,
+                                                                old_to_new, M, row_bits, cnt);
+  PB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int launch_list_changed_rows(const unsigned *row_bits, const int *word_prefix, int n_words, int M,
+                             int *rows, cudaStream_t s) {
+  list_changed_rows_kernel<<<(n_words + 255) / 256, 256, 0, s>>>(row_bits, word_prefix, n_words, M, rows);
+  PB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int launch_count_row_edges(const int *rows, int n_rows, const int *Mp, const int *Mi,
+                           const int *dof2node, int *counts, cudaStream_t s) {
+  const long long threads = (long long)n_rows * 32;
+  count_row_edges_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rows, n_rows, Mp, Mi, dof2node, counts);
+  PB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int launch_emit_row_edges(const int *rows, int n_rows, const int *Mp, const int *Mi,
+                          const int *dof2node, const int *offsets, int *edges, cudaStream_t s) {
+  const long long threads = (long long)n_rows * 32;
+  emit_row_edges_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rows, n_rows, Mp, Mi, dof2node,
+                                                                         offsets, edges);
+  PB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+}  // namespace pb

@@ -5,16 +5,16 @@
 // (c,r) and (r,c) for r != c; sort; unique; CSR with strictly ascending rows.
 //
 // The reference materialises every pair and sorts 2*nnz tuples.  Here:
-//   * "filter" path (build_sym_kernel): ONE streaming pass.  If every sampled column is
+//   * "filter" path (build_filter_kernel): ONE streaming pass.  If every sampled column is
 //     non-decreasing and the sampled pattern is structurally symmetric, the sorted-unique pair
 //     list restricted to row r IS column r's off-diagonal samples, so the output is a stream
 //     compaction of the input.  The kernel proves both properties while it compacts (ordering
 //     against the previous sample; symmetry by finding the mirror (r,c) of every kept (c,r),
 //     r > c, plus an upper/lower count match, which turns the injection into a bijection) and
-//     raises a flag if the proof fails.  Work is split by merge-path over (columns, samples) so
-//     every thread owns the same number of path items whatever the degree distribution; output
-//     offsets come from a decoupled look-back chained scan, so input is read once and output
-//     written once: algorithmic bytes = 4*[(N+1) + nnzA/dim + (M+1) + nnzM].
+//     raises a flag if the proof fails.  Work is tiled by samples (2048 per CTA), so every thread
+//     owns the same number of samples whatever the degree distribution; output offsets come from
+//     a decoupled look-back chained scan, so input is read once and output written once:
+//     algorithmic bytes = 4*[(N+1) + nnzA/dim + (M+1) + nnzM].
 //   * general path (gen_* kernels): count -> scan -> scatter -> per-row bitonic sort + unique ->
 //     scan -> gather.  Any triangle, unsorted columns, duplicates.  Same result as the filter
 //     path wherever both apply (tests/test_gpu_build.py).
@@ -26,29 +26,24 @@
 namespace pb {
 
 constexpr int K1_THREADS = 256;
-constexpr int K1_ITEMS = 9;  // odd: the per-thread walk over shared memory is bank-conflict free
-constexpr int K1_TILE = K1_THREADS * K1_ITEMS;
+constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_ITEMS = 16;
+constexpr int K1_TILE = K1_THREADS * K1_ITEMS;  // samples per tile
+constexpr int K1_WTILE = K1_TILE / K1_WARPS;    // samples per warp (warp-contiguous layout)
+constexpr int K1_SHORT = 32;                    // columns up to this length are filled by one thread
 
-// number of row-ends (V[c+1]) consumed before path diagonal `diag`
-__device__ __forceinline__ int merge_path(long long diag, const int *row_end, int M, long long Q,
-                                          long long q_base) {
-  long long lo = diag > Q ? diag - Q : 0;
-  long long hi = diag < M ? diag : M;
-  while (lo < hi) {
-    long long mid = (lo + hi) >> 1;
-    if ((long long)row_end[mid] <= q_base + diag - 1 - mid) lo = mid + 1; else hi = mid;
-  }
-  return (int)lo;
-}
-
-__global__ void build_partition_kernel(const int *__restrict__ V, int M, int Q, int num_tiles,
+// tile_c[t] = column that holds sample t*K1_TILE (last c < M with V[c] <= q)
+__global__ void build_partition_kernel(const int *__restrict__ V, int M, int num_tiles,
                                        int *__restrict__ tile_c) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t > num_tiles) return;
-  long long path = (long long)M + Q;
-  long long d = (long long)t * K1_TILE;
-  if (d > path) d = path;
-  tile_c[t] = merge_path(d, V + 1, M, Q, 0);
+  if (t >= num_tiles) return;
+  const long long q = (long long)t * K1_TILE;
+  int lo = 0, hi = M;  // first c with V[c] > q
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if ((long long)V[mid] <= q) lo = mid + 1; else hi = mid;
+  }
+  tile_c[t] = lo - 1;
 }
 
 // samples per block-column for dim > 1 (ParthAPI.cpp:373: r_ptr += dim)
@@ -61,194 +56,238 @@ __global__ void build_sample_count_kernel(const int *__restrict__ Ap, int M, int
   ns[mc] = len > 0 ? (len + dim - 1) / dim : 0;
 }
 
-// is `target` among the sampled mesh rows of block-column `col`?
+// Is `target` among the sampled mesh rows of block-column `col`?  [vs, ve) is the column's
+// sample range.  Looks in the tile's staged samples when the whole column is staged (staged
+// slots hold the mesh row, or ~row once the owning column has classified the slot as dropped).
 template <bool DIM1>
-__device__ __forceinline__ bool mirror_in_global(const int *__restrict__ Ap,
-                                                 const int *__restrict__ Ai,
-                                                 const int *__restrict__ V, int dim, int col,
-                                                 int target) {
-  int lo = 0, hi, base;
-  if (DIM1) {
-    base = __ldg(Ap + col);
-    hi = __ldg(Ap + col + 1) - base;
-  } else {
-    base = __ldg(Ap + (long long)col * dim);
-    hi = __ldg(V + col + 1) - __ldg(V + col);
-  }
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    int v = DIM1 ? __ldg(Ai + base + mid) : __ldg(Ai + base + (long long)mid * dim) / dim;
-    if (v < target) lo = mid + 1; else hi = mid;
-  }
-  if (lo >= (DIM1 ? __ldg(Ap + col + 1) - base : __ldg(V + col + 1) - __ldg(V + col))) return false;
-  int v = DIM1 ? __ldg(Ai + base + lo) : __ldg(Ai + base + (long long)lo * dim) / dim;
-  return v == target;
-}
-
-template <bool DIM1>
-__global__ void __launch_bounds__(K1_THREADS)
-build_sym_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, const int *__restrict__ V,
-                 int dim, int M, int Q, const int *__restrict__ tile_c, int num_tiles,
-                 int *__restrict__ Mp, int *__restrict__ Mi, BuildStatus *__restrict__ st,
-                 unsigned long long *__restrict__ desc, int check_mirror) {
-  __shared__ int s_vs[K1_TILE + 2];
-  __shared__ int s_val[K1_TILE];
-  __shared__ int s_out[K1_TILE];
-  __shared__ int s_rank[K1_TILE + 1];
-  __shared__ int s_scan[33];
-  __shared__ int s_diff[K1_THREADS / 32];
-  __shared__ int s_tile;
-  __shared__ long long s_base;
-
-  const int tid = threadIdx.x;
-  if (tid == 0) s_tile = (int)atomicAdd(&st->tile_counter, 1ull);
-  __syncthreads();
-  const int tile = s_tile;
-  const long long path = (long long)M + Q;
-  const long long d0 = (long long)tile * K1_TILE;
-  const long long d1 = d0 + K1_TILE < path ? d0 + K1_TILE : path;
-  const int c0 = tile_c[tile], c1 = tile_c[tile + 1];
-  const int q0 = (int)(d0 - c0), q1 = (int)(d1 - c1);
-  const int nc = c1 - c0;  // columns that end inside this tile
-  const int nq = q1 - q0;  // samples inside this tile
-  const int total_items = (int)(d1 - d0);
-
-  for (int i = tid; i <= nc + 1; i += K1_THREADS) {
-    int c = c0 + i;
-    s_vs[i] = c <= M ? V[c] : INT_MAX;
-  }
-  if (DIM1) {
-    for (int j = tid; j < nq; j += K1_THREADS) s_val[j] = ld_stream(Ai + q0 + j);
-  }
-  __syncthreads();
-
-  // thread-level merge-path split inside the tile
-  const int diag = tid * K1_ITEMS < total_items ? tid * K1_ITEMS : total_items;
-  int ci;
-  {
-    int lo = diag > nq ? diag - nq : 0;
-    int hi = diag < nc ? diag : nc;
+__device__ __forceinline__ bool mirror_present(const int *__restrict__ Ap,
+                                               const int *__restrict__ Ai, int dim, int col,
+                                               int target, int vs, int ve, int q0, int q1,
+                                               const volatile int *s_val) {
+  int lo = 0, hi = ve - vs;
+  const int n = hi;
+  if (vs >= q0 && ve <= q1) {
+    const volatile int *a = s_val + (vs - q0);
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
-      if (s_vs[mid + 1] <= q0 + diag - 1 - mid) lo = mid + 1; else hi = mid;
+      int x = a[mid];
+      x = x < 0 ? ~x : x;
+      if (x < target) lo = mid + 1; else hi = mid;
     }
-    ci = lo;
+    if (lo >= n) return false;
+    int x = a[lo];
+    return (x < 0 ? ~x : x) == target;
   }
-  const int qi = diag - ci;
+  if (DIM1) {
+    const int *a = Ai + vs;
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (__ldg(a + mid) < target) lo = mid + 1; else hi = mid;
+    }
+    return lo < n && __ldg(a + lo) == target;
+  }
+  const int *a = Ai + __ldg(Ap + (long long)col * dim);
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(a + (long long)mid * dim) / dim < target) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && __ldg(a + (long long)lo * dim) / dim == target;
+}
 
-  // ---- pass 1: classify samples, prove ordering and symmetry
-  unsigned keepmask = 0;
-  int kept = 0, diff = 0;
-  unsigned flags = 0;
-  {
-    int c = ci, q = qi;
-#pragma unroll
-    for (int it = 0; it < K1_ITEMS; it++) {
-      if (diag + it >= total_items) break;
-      const int rend = s_vs[c + 1];
-      const int aq = q0 + q;
-      if (aq < rend) {
-        const int mc = c0 + c;
-        const int rstart = s_vs[c];
-        int mr, prev = -1;
-        const bool has_prev = aq > rstart;
-        if (DIM1) {
-          mr = s_val[q];
-          if (has_prev) prev = q > 0 ? s_val[q - 1] : __ldg(Ai + aq - 1);
-        } else {
-          const long long p = (long long)__ldg(Ap + (long long)mc * dim) + (long long)(aq - rstart) * dim;
-          mr = __ldg(Ai + p) / dim;
-          s_val[q] = mr;
-          if (has_prev) prev = __ldg(Ai + p - dim) / dim;
-        }
-        bool keep = mr != mc;
-        if (has_prev) {
-          if (mr < prev) flags |= BUILD_UNSORTED;
-          else if (mr == prev) keep = false;
-        }
-        if ((unsigned)mr >= (unsigned)M) { flags |= BUILD_RANGE; keep = false; }
-        if (keep) {
-          keepmask |= 1u << it;
-          kept++;
-          if (mr > mc) {
-            diff++;
-            if (check_mirror) {
-              bool ok;
-              const int rel = mr - c0;
-              if (DIM1 && rel >= 1 && rel < nc) {
-                // mirror column lies wholly inside this tile's staged samples
-                int lo = s_vs[rel] - q0, hi = s_vs[rel + 1] - q0;
-                const int end = hi;
-                while (lo < hi) {
-                  int mid = (lo + hi) >> 1;
-                  if (s_val[mid] < mc) lo = mid + 1; else hi = mid;
-                }
-                ok = lo < end && s_val[lo] == mc;
-              } else {
-                ok = mirror_in_global<DIM1>(Ap, Ai, V, dim, mr, mc);
-              }
-              if (!ok) flags |= BUILD_ASYM;
-            }
-          } else {
-            diff--;
-          }
-        }
-        q++;
-      } else {
-        c++;
+// classification of one sample of column c (Integrator-independent; ParthAPI.cpp:374-381 plus the
+// sort/unique that follows): returns true if the sample survives into the mesh row
+template <bool DIM1>
+__device__ __forceinline__ bool classify(int c, int v, bool has_prev, int prev, int M,
+                                         const int *__restrict__ Ap, const int *__restrict__ Ai,
+                                         const int *__restrict__ V, int dim, int q0, int q1,
+                                         const volatile int *s_val, int check_mirror,
+                                         unsigned &flags, int &diff) {
+  bool keep = v != c;
+  if (has_prev) {
+    if (v < prev) flags |= BUILD_UNSORTED;
+    else if (v == prev) keep = false;
+  }
+  if ((unsigned)v >= (unsigned)M) { flags |= BUILD_RANGE; return false; }
+  if (keep) {
+    if (v > c) {
+      diff++;
+      if (check_mirror) {
+        const int vs = __ldg(V + v), ve = __ldg(V + v + 1);
+        if (!mirror_present<DIM1>(Ap, Ai, dim, v, c, vs, ve, q0, q1, s_val)) flags |= BUILD_ASYM;
       }
+    } else {
+      diff--;
     }
   }
+  return keep;
+}
 
-  int total_kept;
-  const int excl = block_excl_scan<K1_THREADS>(kept, s_scan, &total_kept);
-  // block sum of (upper - lower)
-  {
-    int d = diff;
+// One tile = K1_TILE consecutive samples.  Phases:
+//   A  stage the samples in shared memory (DIM1: straight 128-bit copy of Ai)
+//   B  one thread per column of the tile's column window walks that column's staged samples:
+//      diagonal / duplicate / order / mirror checks with the previous sample in a register; a
+//      dropped sample is overwritten by its complement (~v < 0).  Columns longer than K1_SHORT
+//      samples are walked by a whole warp.
+//   C  warp-contiguous pass over the samples: ballot ranks -> compaction into shared memory, and
+//      the exclusive rank of every slot (needed for Mp at column starts).  Warp 0 resolves the
+//      tile's global output offset by decoupled look-back meanwhile.
+//   D  coalesced stores of Mi, and of Mp for the column starts this tile owns
+template <bool DIM1>
+__global__ void __launch_bounds__(K1_THREADS)
+build_filter_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai,
+                    const int *__restrict__ V, int dim, int M, int Q,
+                    const int *__restrict__ tile_c, int num_tiles, int *__restrict__ Mp,
+                    int *__restrict__ Mi, BuildStatus *__restrict__ st,
+                    unsigned long long *__restrict__ desc, int check_mirror) {
+  __shared__ __align__(16) int s_val[K1_TILE];  // staged samples; exclusive ranks after phase C
+  __shared__ __align__(16) int s_out[K1_TILE];  // compacted output
+  __shared__ int s_wsum[K1_WARPS], s_wdiff[K1_WARPS];
+  __shared__ int s_long[K1_TILE / K1_SHORT + 1];
+  __shared__ int s_nlong;
+  __shared__ long long s_base;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // tiles are taken in blockIdx order: the hardware dispatches CTAs of a 1-D grid in that order,
+  // so every predecessor of a resident tile is resident or finished (the look-back cannot starve)
+  const int tile = blockIdx.x;
+  const bool last = tile == num_tiles - 1;
+  const int q0 = tile * K1_TILE;
+  const int nq = Q - q0 < K1_TILE ? Q - q0 : K1_TILE;
+  const int q1 = q0 + nq;
+  const int cA = tile_c[tile];
+  const int cEnd = last ? M : tile_c[tile + 1];
+  if (tid == 0) s_nlong = 0;
+
+  // ---- A
+  if (DIM1) {
+    if (nq == K1_TILE && ((reinterpret_cast<uintptr_t>(Ai) & 15) == 0)) {
+      const int4 *src = reinterpret_cast<const int4 *>(Ai + q0);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
-    if ((tid & 31) == 0) s_diff[tid >> 5] = d;
+      for (int k = 0; k < K1_ITEMS / 4; k++)
+        reinterpret_cast<int4 *>(s_val)[tid + k * K1_THREADS] = ld_stream4(src + tid + k * K1_THREADS);
+    } else {
+      for (int j = tid; j < nq; j += K1_THREADS) s_val[j] = ld_stream(Ai + q0 + j);
+    }
+  } else {
+    // dim > 1: each column's thread gathers its own strided samples
+    for (int c = cA + tid; c <= cEnd && c < M; c += K1_THREADS) {
+      const int vs = __ldg(V + c), ve = __ldg(V + c + 1);
+      const int a = vs > q0 ? vs : q0, b = ve < q1 ? ve : q1;
+      const int *col = Ai + __ldg(Ap + (long long)c * dim);
+      for (int p = a; p < b; p++) s_val[p - q0] = __ldg(col + (long long)(p - vs) * dim) / dim;
+    }
+  }
+  __syncthreads();
+
+  // ---- B
+  int diff = 0;
+  unsigned flags = 0;
+  const volatile int *vval = s_val;
+  for (int c = cA + tid; c <= cEnd && c < M; c += K1_THREADS) {
+    const int vs = __ldg(V + c), ve = __ldg(V + c + 1);
+    const int a = vs > q0 ? vs : q0, b = ve < q1 ? ve : q1;
+    if (b <= a) continue;
+    if (b - a > K1_SHORT) { s_long[atomicAdd(&s_nlong, 1)] = c; continue; }
+    bool has_prev = a > vs;  // only when the tile starts in the middle of this column
+    int prev = 0;
+    if (has_prev)
+      prev = DIM1 ? __ldg(Ai + a - 1)
+                  : __ldg(Ai + (long long)__ldg(Ap + (long long)c * dim) + (long long)(a - 1 - vs) * dim) / dim;
+    for (int p = a; p < b; p++) {
+      const int v = vval[p - q0];
+      if (!classify<DIM1>(c, v, has_prev, prev, M, Ap, Ai, V, dim, q0, q1, vval, check_mirror, flags, diff))
+        s_val[p - q0] = ~v;
+      prev = v;
+      has_prev = true;
+    }
+  }
+  __syncthreads();
+  for (int li = warp; li < s_nlong; li += K1_WARPS) {
+    const int c = s_long[li];
+    const int vs = __ldg(V + c), ve = __ldg(V + c + 1);
+    const int a = vs > q0 ? vs : q0, b = ve < q1 ? ve : q1;
+    int carry = 0;
+    bool carry_ok = a > vs;
+    if (carry_ok)
+      carry = DIM1 ? __ldg(Ai + a - 1)
+                   : __ldg(Ai + (long long)__ldg(Ap + (long long)c * dim) + (long long)(a - 1 - vs) * dim) / dim;
+    for (int p0 = a; p0 < b; p0 += 32) {
+      const int p = p0 + lane;
+      const int v = p < b ? vval[p - q0] : 0;
+      int prev = __shfl_up_sync(0xffffffffu, v, 1);
+      bool has_prev = true;
+      if (lane == 0) { prev = carry; has_prev = carry_ok; }
+      if (p < b &&
+          !classify<DIM1>(c, v, has_prev, prev, M, Ap, Ai, V, dim, q0, q1, vval, check_mirror, flags, diff))
+        s_val[p - q0] = ~v;
+      carry = __shfl_sync(0xffffffffu, v, 31);
+      carry_ok = true;
+    }
   }
   if (flags) atomicOr(&st->flags, flags);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
   __syncthreads();
-  if (tid < 32) {
-    int d = tid < K1_THREADS / 32 ? s_diff[tid] : 0;
+
+  // ---- C: per-warp kept counts, then ranks
+  unsigned keepbits = 0;
+  int wcount = 0;
+#pragma unroll
+  for (int k = 0; k < K1_ITEMS; k++) {
+    const int j = warp * K1_WTILE + k * 32 + lane;
+    const bool keep = j < nq && s_val[j] >= 0;
+    keepbits |= (keep ? 1u : 0u) << k;
+    wcount += __popc(__ballot_sync(0xffffffffu, keep));
+  }
+  if (lane == 0) { s_wsum[warp] = wcount; s_wdiff[warp] = diff; }
+  __syncthreads();
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < K1_WARPS; w++) {
+    const int x = s_wsum[w];
+    if (w < warp) woff += x;
+    total += x;
+  }
+  if (warp == 0) {
+    int d = lane < K1_WARPS ? s_wdiff[lane] : 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
     // pack: low 31 bits kept count, next 31 bits (upper - lower) modulo 2^31
-    long long agg = (long long)total_kept | ((long long)((unsigned)d & 0x7fffffffu) << 31);
-    long long b = tile_lookback(desc, tile, agg);
-    if (tid == 0) {
+    const long long agg = (long long)total | ((long long)((unsigned)d & 0x7fffffffu) << 31);
+    const long long b = tile_lookback(desc, tile, agg);
+    if (lane == 0) {
       s_base = b;
-      if (tile == num_tiles - 1) {
-        long long incl = (b + agg) & (long long)kTileVal;
+      if (last) {
+        const long long incl = (b + agg) & (long long)kTileVal;
         st->nnz_out = (int)(incl & 0x7fffffff);
         st->diff_mod = (unsigned)((incl >> 31) & 0x7fffffff);
       }
     }
   }
-  __syncthreads();
-  const int base = (int)(s_base & 0x7fffffff);
-
-  // ---- pass 2: compact into shared memory, then coalesced stores
   {
-    int c = ci, q = qi, r = excl;
+    int run = woff;
 #pragma unroll
-    for (int it = 0; it < K1_ITEMS; it++) {
-      if (diag + it >= total_items) break;
-      if (q0 + q < s_vs[c + 1]) {
-        if ((keepmask >> it) & 1u) s_out[r++] = s_val[q];
-        q++;
-      } else {
-        s_rank[c] = r;
-        c++;
-      }
+    for (int k = 0; k < K1_ITEMS; k++) {
+      const int j = warp * K1_WTILE + k * 32 + lane;
+      const bool keep = (keepbits >> k) & 1u;
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      const int pre = run + __popc(m & ((1u << lane) - 1u));
+      if (keep) s_out[pre] = s_val[j];
+      s_val[j] = pre;  // the slot now holds its exclusive rank (its value has been consumed)
+      run += __popc(m);
     }
   }
   __syncthreads();
-  for (int j = tid; j < total_kept; j += K1_THREADS) st_stream(Mi + base + j, s_out[j]);
-  for (int i = tid; i < nc; i += K1_THREADS) Mp[c0 + 1 + i] = base + s_rank[i];
-  if (tile == 0 && tid == 0) Mp[0] = 0;
+
+  // ---- D
+  const int base = (int)(s_base & 0x7fffffff);
+  for (int i = tid; i < total; i += K1_THREADS) st_stream(Mi + base + i, s_out[i]);
+  // column starts owned by this tile: q0 < V[c] <= q1 (tile 0 also owns V[c] == 0), so runs of
+  // empty columns on a tile boundary and the closing Mp[M] are written exactly once
+  for (int c = (tile == 0 ? 0 : cA) + tid; c <= cEnd; c += K1_THREADS) {
+    const int vs = __ldg(V + c);
+    if ((vs > q0 && vs <= q1) || (tile == 0 && vs == 0)) Mp[c] = base + (vs < q1 ? s_val[vs - q0] : total);
+  }
 }
 
 // ------------------------------------------------------------------ general path
@@ -341,32 +380,31 @@ __global__ void gen_gather_kernel(const int *__restrict__ ptr, const int *__rest
 }
 
 // ------------------------------------------------------------------ host drivers
+int build_filter_tiles(int M, int Q) { (void)M; return (Q + K1_TILE - 1) / K1_TILE; }
+
 int build_filter_launch(const BuildArgs &a, cudaStream_t s) {
   int launches = 0;
-  const int *V = a.Ap;
-  if (a.dim != 1) V = a.V;
-  const long long path = (long long)a.M + a.Q;
-  const int num_tiles = (int)((path + K1_TILE - 1) / K1_TILE);
-  if (num_tiles == 0) return 0;
+  const int *V = a.dim == 1 ? a.Ap : a.V;
+  const int num_tiles = build_filter_tiles(a.M, a.Q);
   PB_CUDA(cudaMemsetAsync(a.status, 0, sizeof(BuildStatus), s));
+  if (num_tiles == 0) {  // no samples at all: empty graph
+    PB_CUDA(cudaMemsetAsync(a.Mp, 0, sizeof(int) * ((size_t)a.M + 1), s));
+    return 0;
+  }
   PB_CUDA(cudaMemsetAsync(a.desc, 0, sizeof(unsigned long long) * (size_t)num_tiles, s));
-  build_partition_kernel<<<(num_tiles + 1 + 255) / 256, 256, 0, s>>>(V, a.M, a.Q, num_tiles, a.tile_c);
+  build_partition_kernel<<<(num_tiles + 255) / 256, 256, 0, s>>>(V, a.M, num_tiles, a.tile_c);
   launches++;
   if (a.dim == 1)
-    build_sym_kernel<true><<<num_tiles, K1_THREADS, 0, s>>>(a.Ap, a.Ai, V, 1, a.M, a.Q, a.tile_c,
-                                                            num_tiles, a.Mp, a.Mi, a.status, a.desc,
-                                                            a.check_mirror);
+    build_filter_kernel<true><<<num_tiles, K1_THREADS, 0, s>>>(a.Ap, a.Ai, V, 1, a.M, a.Q, a.tile_c,
+                                                               num_tiles, a.Mp, a.Mi, a.status,
+                                                               a.desc, a.check_mirror);
   else
-    build_sym_kernel<false><<<num_tiles, K1_THREADS, 0, s>>>(a.Ap, a.Ai, V, a.dim, a.M, a.Q, a.tile_c,
-                                                             num_tiles, a.Mp, a.Mi, a.status, a.desc,
-                                                             a.check_mirror);
+    build_filter_kernel<false><<<num_tiles, K1_THREADS, 0, s>>>(a.Ap, a.Ai, V, a.dim, a.M, a.Q,
+                                                                a.tile_c, num_tiles, a.Mp, a.Mi,
+                                                                a.status, a.desc, a.check_mirror);
   launches++;
   PB_CUDA(cudaGetLastError());
   return launches;
-}
-
-int build_filter_tiles(int M, int Q) {
-  return (int)(((long long)M + Q + K1_TILE - 1) / K1_TILE);
 }
 
 int build_sample_prefix_launch(const int *Ap, int M, int dim, int *ns_tmp, int *V,

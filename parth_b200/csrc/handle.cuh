@@ -11,6 +11,7 @@
 #include "../../include/parth_b200.h"
 #include "build.cuh"
 #include "common.cuh"
+#include "tree.cuh"
 
 struct parth_b200 {
   int device = 0;
@@ -48,7 +49,7 @@ struct parth_b200 {
   int num_levels = 0, num_nodes = 0, tree_M = 0;
   std::vector<int> meta;      // host mirror, nodes*7
   std::vector<int> node_ptr;  // host mirror, nodes+1
-  pb::DevBuf<int> d_meta, d_node_ptr, d_dofs, d_labels, d_dof2node, d_mesh_perm;
+  pb::DevBuf<int> d_meta, d_node_ptr, d_visit, d_dofs, d_labels, d_dof2node, d_mesh_perm;
   pb::DevBuf<int> d_dofs2, d_labels2;  // double buffers for integration / relocation
 
   // ---- results of the last computePermutation
@@ -62,6 +63,7 @@ struct parth_b200 {
   pb::DevBuf<int> V, ns_tmp, tile_c, cnt, ptr, tmp, uniq;
   pb::DevBuf<unsigned long long> desc, scan_ws;
   pb::DevBuf<pb::BuildStatus> bstatus;
+  pb::DevBuf<pb::DetectCounters> dcnt;
   pb::DevBuf<int> w0, w1, w2, w3, w4, w5;  // general-purpose int scratch
   pb::DevBuf<int> d_out;                   // staging for host-pointer outputs
   pb::PinBuf<int> pin;                     // small pinned read-backs

@@ -1,0 +1,350 @@
+// parth_b200/csrc/stage_perm.cu -- host drivers: tree import/export, change detection, dirty
+// sets, permutation assembly / expansion, and the computePermutation control flow
+// (reference src/Parth/ParthAPI.cpp:191-279, src/Parth/Integrator.cpp:546-683).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "scan.cuh"
+#include "stages.cuh"
+#include "tree.cuh"
+
+namespace pb {
+
+// ------------------------------------------------------------------ tree fixture in / out
+static void compute_visit(parth_b200 &h, std::vector<int> &visit) {
+  // nodes reached by the recursion from the root through stored left/right links
+  // (HMD::assignCoarseLocalPermToGlobal, HMD.cpp:348-363)
+  visit.assign(h.num_nodes, 0);
+  if (h.num_nodes == 0 || h.meta[2] == -1) return;
+  std::vector<int> stack{0};
+  while (!stack.empty()) {
+    int x = stack.back();
+    stack.pop_back();
+    visit[x] = 1;
+    int l = h.meta[x * 7 + 0], r = h.meta[x * 7 + 1];
+    if (l != -1) stack.push_back(l);
+    if (r != -1) stack.push_back(r);
+  }
+}
+
+void upload_tree_meta(parth_b200 &h) {
+  cudaStream_t s = h.stream;
+  const int nodes = h.num_nodes;
+  h.d_meta.reserve((size_t)nodes * 7, s);
+  h.d_node_ptr.reserve((size_t)nodes + 1, s);
+  h.d_visit.reserve((size_t)nodes, s);
+  std::vector<int> visit;
+  compute_visit(h, visit);
+  // pageable sources: cudaMemcpyAsync returns after staging them, so the vectors may change later
+  PB_CUDA(cudaMemcpyAsync(h.d_meta.p, h.meta.data(), sizeof(int) * (size_t)nodes * 7, cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(h.d_node_ptr.p, h.node_ptr.data(), sizeof(int) * ((size_t)nodes + 1), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(h.d_visit.p, visit.data(), sizeof(int) * (size_t)nodes, cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+}
+
+void assemble_all(parth_b200 &h) {
+  h.d_mesh_perm.reserve((size_t)std::max(h.tree_M, 1), h.stream);
+  h.stats.kernels_launched += launch_assemble_all(h.d_node_ptr.p, h.d_meta.p, h.d_visit.p, h.num_nodes,
+                                                  h.d_dofs.p, h.d_labels.p, h.node_ptr[h.num_nodes],
+                                                  h.d_mesh_perm.p, h.stream);
+}
+
+void stage_import_tree(parth_b200 &h, int M_n, int levels, int nodes, const int *meta,
+                       const int *node_ptr, const int *dofs, const int *labels, const int *Mp_prev,
+                       const int *Mi_prev) {
+  cudaStream_t s = h.stream;
+  if (nodes <= 0 || M_n <= 0 || node_ptr[nodes] > M_n)
+    throw StatusError(PARTH_B200_ERR_ARG, "import_tree: inconsistent sizes");
+  h.num_levels = levels;
+  h.nd_levels = levels;
+  h.num_nodes = nodes;
+  h.tree_M = M_n;
+  h.meta.assign(meta, meta + (size_t)nodes * 7);
+  h.node_ptr.assign(node_ptr, node_ptr + nodes + 1);
+  const int total = node_ptr[nodes];
+  h.d_dofs.reserve((size_t)M_n, s);
+  h.d_labels.reserve((size_t)M_n, s);
+  h.d_dof2node.reserve((size_t)M_n, s);
+  PB_CUDA(cudaMemcpyAsync(h.d_dofs.p, dofs, sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(h.d_labels.p, labels, sizeof(int) * (size_t)total, cudaMemcpyHostToDevice, s));
+  upload_tree_meta(h);
+  PB_CUDA(cudaMemsetAsync(h.d_dof2node.p, 0, sizeof(int) * (size_t)M_n, s));
+  h.stats.kernels_launched += launch_dof2node(h.d_node_ptr.p, nodes, h.d_dofs.p, total, h.d_dof2node.p, s);
+  h.d_mesh_perm.reserve((size_t)M_n, s);
+  PB_CUDA(cudaMemsetAsync(h.d_mesh_perm.p, 0, sizeof(int) * (size_t)M_n, s));
+  assemble_all(h);
+  h.tree_init = true;
+  if (Mp_prev && Mi_prev) {
+    const int nnz = Mp_prev[M_n];
+    h.Mp_prev.reserve((size_t)M_n + 1, s);
+    h.Mi_prev.reserve((size_t)std::max(nnz, 1), s);
+    PB_CUDA(cudaMemcpyAsync(h.Mp_prev.p, Mp_prev, sizeof(int) * ((size_t)M_n + 1), cudaMemcpyHostToDevice, s));
+    if (nnz > 0)
+      PB_CUDA(cudaMemcpyAsync(h.Mi_prev.p, Mi_prev, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, s));
+    h.M_n_prev = M_n;
+    h.nnz_prev = nnz;
+  }
+  PB_CUDA(cudaStreamSynchronize(s));
+}
+
+void stage_export_tree(parth_b200 &h, int *meta, int *node_ptr, int *dofs, int *labels, int *dof2node,
+                       int *mesh_perm) {
+  cudaStream_t s = h.stream;
+  if (!h.tree_init) throw StatusError(PARTH_B200_ERR_NO_TREE, "export_tree: no tree");
+  const int total = h.node_ptr[h.num_nodes];
+  std::memcpy(meta, h.meta.data(), sizeof(int) * h.meta.size());
+  std::memcpy(node_ptr, h.node_ptr.data(), sizeof(int) * h.node_ptr.size());
+  if (dofs) PB_CUDA(cudaMemcpyAsync(dofs, h.d_dofs.p, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost, s));
+  if (labels) PB_CUDA(cudaMemcpyAsync(labels, h.d_labels.p, sizeof(int) * (size_t)total, cudaMemcpyDeviceToHost, s));
+  if (dof2node)
+    PB_CUDA(cudaMemcpyAsync(dof2node, h.d_dof2node.p, sizeof(int) * (size_t)h.tree_M, cudaMemcpyDeviceToHost, s));
+  if (mesh_perm)
+    PB_CUDA(cudaMemcpyAsync(mesh_perm, h.d_mesh_perm.p, sizeof(int) * (size_t)h.tree_M, cudaMemcpyDeviceToHost, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+}
+
+// ------------------------------------------------------------------ (b) change detection
+// Integrator::computeChangedEdges (Integrator.cpp:259-338).  Result: h.d_changed / h.n_changed.
+void stage_detect(parth_b200 &h) {
+  cudaStream_t s = h.stream;
+  const int M = h.M_n;
+  StageTimer tm(h, h.ev0, h.ev1);
+  h.n_changed = 0;
+  const int n_words = (M + 31) / 32;
+  h.w0.reserve((size_t)n_words + 1, s);  // row bitmap
+  h.w1.reserve((size_t)n_words + 2, s);  // popc prefix
+  h.dcnt.reserve(1, s);
+  h.scan_ws.reserve(scan_ws_words((size_t)std::max(n_words, M) + 1), s);
+  unsigned *bits = reinterpret_cast<unsigned *>(h.w0.p);
+  if (h.map_len > 0)
+    h.stats.kernels_launched += launch_diff_rows_mapped(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, h.new_to_old.p,
+                                                        h.old_to_new.p, M, bits, h.dcnt.p, s);
+  else
+    h.stats.kernels_launched += launch_diff_rows(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt.p, s);
+  int cnt[4];
+  read_ints(h, reinterpret_cast<const int *>(h.dcnt.p), cnt, 4);
+  const int n_rows = cnt[0];
+  if (n_rows > 0) {
+    h.stats.kernels_launched += exclusive_scan<1>(h.w0.p, h.w1.p, n_words, h.scan_ws.p, s);
+    h.w2.reserve((size_t)n_rows + 1, s);  // changed rows, ascending
+    h.w3.reserve((size_t)n_rows + 2, s);  // per-row edge counts -> offsets
+    h.stats.kernels_launched += launch_list_changed_rows(bits, h.w1.p, n_words, M, h.w2.p, s);
+    h.stats.kernels_launched += launch_count_row_edges(h.w2.p, n_rows, h.Mp, h.Mi, h.d_dof2node.p, h.w3.p, s);
+    h.w4.reserve((size_t)n_rows + 2, s);
+    h.stats.kernels_launched += exclusive_scan<0>(h.w3.p, h.w4.p, n_rows, h.scan_ws.p, s);
+    int n_edges = 0;
+    read_ints(h, h.w4.p + n_rows, &n_edges, 1);
+    if (n_edges > 0) {
+      h.d_changed.reserve((size_t)n_edges * 2, s);
+      h.stats.kernels_launched += launch_emit_row_edges(h.w2.p, n_rows, h.Mp, h.Mi, h.d_dof2node.p, h.w4.p,
+                                                        h.d_changed.p, s);
+    }
+    h.n_changed = n_edges;
+  }
+  tm.stop();
+  h.stats.detect_ms = tm.ms();
+}
+
+// ------------------------------------------------------------------ (b) dirty sets on 2^(L+1)-1 nodes
+static bool node_is_leaf(const parth_b200 &h, int x) { return h.meta[x * 7] == -1 && h.meta[x * 7 + 1] == -1; }
+
+static void unmark_children(const parth_b200 &h, int x, std::vector<int> &marker) {
+  // HMD::unMarkLeftRightSubMeshes (HMD.cpp:421-432)
+  std::vector<int> stack{x};
+  while (!stack.empty()) {
+    int y = stack.back();
+    stack.pop_back();
+    int l = h.meta[y * 7], r = h.meta[y * 7 + 1];
+    if (l != -1) { marker[l] = 0; stack.push_back(l); }
+    if (r != -1) { marker[r] = 0; stack.push_back(r); }
+  }
+}
+
+static long long subtree_size(const parth_b200 &h, int x) {
+  // |HMD::getAssignedDOFsOfCoarseHMD| (HMD.cpp:434-447)
+  long long tot = 0;
+  std::vector<int> stack{x};
+  while (!stack.empty()) {
+    int y = stack.back();
+    stack.pop_back();
+    tot += h.node_ptr[y + 1] - h.node_ptr[y];
+    int l = h.meta[y * 7], r = h.meta[y * 7 + 1];
+    if (l != -1) stack.push_back(l);
+    if (r != -1) stack.push_back(r);
+  }
+  return tot;
+}
+
+// findRegionConnections + filterChanges + lag filter + getReuseRatio
+// (Integrator.cpp:685-810, 616-647).  `pre_fine` = nodes already queued by the relocation step.
+void stage_dirty_sets(parth_b200 &h, const std::vector<int> &pre_fine) {
+  cudaStream_t s = h.stream;
+  const int nn = h.num_nodes;
+  StageTimer tm(h, h.ev0, h.ev1);
+  h.w5.reserve((size_t)nn * 2, s);
+  PB_CUDA(cudaMemsetAsync(h.w5.p, 0, sizeof(int) * (size_t)nn * 2, s));
+  h.stats.kernels_launched += launch_mark_dirty_nodes(h.d_changed.p, h.n_changed, h.d_dof2node.p, h.d_meta.p,
+                                                      h.w5.p, h.w5.p + nn, s);
+  std::vector<int> flags((size_t)nn * 2);
+  read_ints(h, h.w5.p, flags.data(), (size_t)nn * 2);
+  const int *within = flags.data(), *lca = flags.data() + nn;
+
+  h.dirty_fine = pre_fine;
+  for (int x = 0; x < nn; x++) if (within[x]) h.dirty_fine.push_back(x);
+  if (h.aggressive) {
+    std::sort(h.dirty_fine.begin(), h.dirty_fine.end());
+    h.dirty_fine.erase(std::unique(h.dirty_fine.begin(), h.dirty_fine.end()), h.dirty_fine.end());
+  }
+  std::vector<int> coarse;
+  for (int x = 0; x < nn; x++) if (lca[x]) coarse.push_back(x);
+  std::vector<int> cflag(nn, 0), fflag(nn, 0);
+  for (int x : coarse) { cflag[x] = 1; fflag[x] = 1; }
+  for (int x : h.dirty_fine) fflag[x] = 1;
+  for (int x : coarse) {
+    if (cflag[x] == 1) { unmark_children(h, x, cflag); unmark_children(h, x, fflag); }
+    fflag[x] = 0;
+  }
+  h.dirty_coarse.clear();
+  for (int x = 0; x < nn; x++) if (cflag[x] == 1) h.dirty_coarse.push_back(x);
+  {
+    std::vector<int> keep;
+    for (int x : h.dirty_fine) if (fflag[x] == 1) keep.push_back(x);
+    h.dirty_fine.swap(keep);
+  }
+  if (h.lagging) {
+    std::vector<int> keep;
+    for (int x : h.dirty_fine) if (!node_is_leaf(h, x)) keep.push_back(x);
+    h.dirty_fine.swap(keep);
+    const int lvl = ((int)std::pow(2, h.lag_lvl + 1) - 1) - 1;  // getLastHMDNodeInLevel(lag_lvl) - 1
+    keep.clear();
+    for (int x : h.dirty_coarse) if (x < lvl) keep.push_back(x);
+    h.dirty_coarse.swap(keep);
+  }
+  h.dirty_coarse_saved = h.dirty_coarse;
+  h.dirty_fine_saved = h.dirty_fine;
+  double nodes = 0;
+  for (int x : h.dirty_coarse) nodes += (double)subtree_size(h, x);
+  for (int x : h.dirty_fine) nodes += h.node_ptr[x + 1] - h.node_ptr[x];
+  h.reuse = h.tree_M != 0 ? 1 - (nodes * 1.0 / h.tree_M) : 0.0;
+  tm.stop();
+  h.stats.dirty_ms = tm.ms();
+}
+
+// ------------------------------------------------------------------ (e) expansion
+void stage_expand(parth_b200 &h, const int *dmesh_perm, int n, int dim, int *dout) {
+  StageTimer tm(h, h.ev0, h.ev1);
+  h.stats.kernels_launched += launch_expand(dmesh_perm, n, dim, dout, h.stream);
+  tm.stop();
+  h.stats.expand_ms = tm.ms();
+}
+
+// (a19) snapshot, ParthAPI.cpp:270-278: a buffer swap when the graph is ours, a copy when borrowed
+void stage_snapshot(parth_b200 &h) {
+  cudaStream_t s = h.stream;
+  if (h.mesh_owned && h.Mp == h.Mp_own.p) {
+    h.Mp_own.swap(h.Mp_prev);
+    h.Mi_own.swap(h.Mi_prev);
+  } else if (h.Mp != h.Mp_prev.p) {
+    h.Mp_prev.reserve((size_t)h.M_n + 1, s);
+    h.Mi_prev.reserve((size_t)std::max(h.nnzM, 1), s);
+    PB_CUDA(cudaMemcpyAsync(h.Mp_prev.p, h.Mp, sizeof(int) * ((size_t)h.M_n + 1), cudaMemcpyDeviceToDevice, s));
+    if (h.nnzM > 0)
+      PB_CUDA(cudaMemcpyAsync(h.Mi_prev.p, h.Mi, sizeof(int) * (size_t)h.nnzM, cudaMemcpyDeviceToDevice, s));
+  }
+  h.Mp = h.Mp_prev.p;  // the current graph and the snapshot are now the same arrays
+  h.Mi = h.Mi_prev.p;
+  h.mesh_owned = true;
+  h.M_n_prev = h.M_n;
+  h.nnz_prev = h.nnzM;
+  h.map_len = 0;
+  h.n_added = h.n_removed = 0;
+}
+
+// cold start (HMD::initHMD, HMD.cpp:89-120): the separator tree comes from the host decomposer
+static void cold_start(parth_b200 &h) {
+  if (!h.decomposer)
+    throw StatusError(PARTH_B200_ERR_NO_TREE,
+                      "computePermutation: no separator tree (import one or set a decomposer)");
+  cudaStream_t s = h.stream;
+  int levels = h.nd_levels;
+  if (levels > 12) levels = 10;  // HMD.cpp:98-100
+  const int nodes = (int)std::pow(2, levels + 1) - 1;
+  std::vector<int> Mp((size_t)h.M_n + 1), Mi((size_t)std::max(h.nnzM, 1));
+  PB_CUDA(cudaMemcpyAsync(Mp.data(), h.Mp, sizeof(int) * Mp.size(), cudaMemcpyDeviceToHost, s));
+  if (h.nnzM > 0)
+    PB_CUDA(cudaMemcpyAsync(Mi.data(), h.Mi, sizeof(int) * (size_t)h.nnzM, cudaMemcpyDeviceToHost, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+  std::vector<int> meta((size_t)nodes * 7, -1), node_ptr((size_t)nodes + 1, 0), dofs((size_t)h.M_n), labels((size_t)h.M_n);
+  int rc = h.decomposer(h.decomposer_user, h.M_n, Mp.data(), Mi.data(), levels, nodes, meta.data(),
+                        node_ptr.data(), dofs.data(), labels.data());
+  if (rc != 0) throw StatusError(PARTH_B200_ERR_NO_TREE, "decomposer callback failed");
+  stage_import_tree(h, h.M_n, levels, nodes, meta.data(), node_ptr.data(), dofs.data(), labels.data(), nullptr, nullptr);
+}
+
+// Integrator::getGlobalPerm (Integrator.cpp:546-683) after detection found changes
+static int global_perm(parth_b200 &h) {
+  std::vector<int> pre_fine;
+  if (h.aggressive) {
+    const int thr = (int)std::pow(2, h.relocate_lvl + 1) - 1;  // getLastHMDNodeInLevel(relocate_lvl)
+    stage_relocate(h, thr, pre_fine);
+  }
+  stage_dirty_sets(h, pre_fine);
+  const bool full = h.reuse < 0.2;
+  if (full) {
+    h.dirty_fine.clear();
+    h.dirty_coarse.assign(1, 0);
+    h.reuse = 0;
+  }
+  if (!h.dirty_coarse.empty()) {
+    if (h.coarse_policy == PARTH_B200_COARSE_REPORT) return PARTH_B200_NEEDS_REDISSECT;
+    // fine nodes first, as the reference does (Integrator.cpp:659)
+    if (!full) stage_permute_fine(h, h.dirty_fine);
+    return stage_coarse(h);
+  }
+  stage_permute_fine(h, h.dirty_fine);
+  return PARTH_B200_OK;
+}
+
+// ParthAPI::computePermutation (ParthAPI.cpp:191-279); dperm: device buffer of M_n*dim ints
+int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
+  for (double &t : h.timers) t = 0;
+  h.reuse = 0;
+  h.n_changed = 0;
+  h.sim_dim = dim;
+  h.stats.detect_ms = h.stats.integrate_ms = h.stats.dirty_ms = h.stats.reorder_ms = 0;
+  h.stats.assemble_ms = h.stats.expand_ms = 0;
+  if (!h.Mp || h.M_n <= 0) throw StatusError(PARTH_B200_ERR_ARG, "computePermutation: no mesh set");
+  if (h.M_n != h.M_n_prev && h.map_len == 0) h.tree_init = false;
+  int rc = PARTH_B200_OK;
+  if (!h.tree_init) {
+    cold_start(h);
+    h.timers[0] = 0;  // host callback: not device time
+    stage_expand(h, h.d_mesh_perm.p, h.M_n, dim, dperm);
+    h.timers[4] = h.stats.expand_ms * 1e-3;
+    h.reuse = 0;
+  } else {
+    if (h.map_len > 0) {
+      stage_integrate(h);
+      h.timers[1] = h.stats.integrate_ms * 1e-3;
+    }
+    stage_detect(h);
+    h.timers[2] = h.stats.detect_ms * 1e-3;
+    cudaEventRecord(h.ev2, h.stream);
+    if (h.n_changed == 0) {
+      h.reuse = 1;
+    } else {
+      rc = global_perm(h);
+    }
+    if (rc == PARTH_B200_OK) stage_expand(h, h.d_mesh_perm.p, h.M_n, dim, dperm);
+    cudaEventRecord(h.ev3, h.stream);
+    cudaEventSynchronize(h.ev3);
+    float t = 0;
+    cudaEventElapsedTime(&t, h.ev2, h.ev3);
+    h.timers[3] = t * 1e-3;
+  }
+  stage_snapshot(h);
+  return rc;
+}
+
+}  // namespace pb

@@ -2,6 +2,7 @@
 #pragma once
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "handle.cuh"
 
@@ -33,5 +34,33 @@ void read_ints(parth_b200 &h, const int *dsrc, int *dst, size_t n);
 
 // (a1) ParthAPI::computeMeshFromMatrix
 void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, int dim);
+
+// stage_perm.cu
+void upload_tree_meta(parth_b200 &h);
+void assemble_all(parth_b200 &h);
+void stage_import_tree(parth_b200 &h, int M_n, int levels, int nodes, const int *meta,
+                       const int *node_ptr, const int *dofs, const int *labels, const int *Mp_prev,
+                       const int *Mi_prev);
+void stage_export_tree(parth_b200 &h, int *meta, int *node_ptr, int *dofs, int *labels, int *dof2node,
+                       int *mesh_perm);
+void stage_detect(parth_b200 &h);
+void stage_dirty_sets(parth_b200 &h, const std::vector<int> &pre_fine);
+void stage_expand(parth_b200 &h, const int *dmesh_perm, int n, int dim, int *dout);
+void stage_snapshot(parth_b200 &h);
+int stage_compute_permutation(parth_b200 &h, int *dperm, int dim);
+
+// stage_maps.cu: (a3) DOF-map inversion, (a6) integration, (f2) relocation
+void stage_set_map(parth_b200 &h, const int *map, int len);
+void stage_integrate(parth_b200 &h);
+void stage_relocate(parth_b200 &h, int threshold_node, std::vector<int> &dirty_fine_out);
+
+// stage_reorder.cu: (a12-a14) extraction + ordering of dirty fine nodes, coarse-node policy
+void stage_permute_fine(parth_b200 &h, const std::vector<int> &nodes);
+int stage_coarse(parth_b200 &h);
+void stage_submesh(parth_b200 &h, int node, int coarse, int *n, int *nnz, int *Mp, int *Mi, int *l2g);
+void stage_amd_batch(parth_b200 &h, int count, const int *graph_ptr, const int *Mp, const int *Mi, int *perm);
+
+// stage_symbolic.cu: (d) etree + column counts
+void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent, int *colcount, long long *lnz);
 
 }  // namespace pb
