@@ -4,7 +4,7 @@
 
 namespace pb {
 
-enum : unsigned { BUILD_UNSORTED = 1u, BUILD_ASYM = 2u, BUILD_RANGE = 4u };
+enum : unsigned { BUILD_UNSORTED = 1u, BUILD_ASYM = 2u, BUILD_RANGE = 4u, BUILD_WIDE = 8u, BUILD_DUP = 16u };
 
 struct BuildStatus {
   unsigned flags;       // BUILD_* bits raised by the filter path

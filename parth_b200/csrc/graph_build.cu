@@ -25,12 +25,14 @@
 
 namespace pb {
 
-constexpr int K1_THREADS = 256;
-constexpr int K1_WARPS = K1_THREADS / 32;
+constexpr int K1_WORKERS = 256;                 // threads that process columns / samples
+constexpr int K1_THREADS = K1_WORKERS + 32;     // + one warp that only resolves the look-back
 constexpr int K1_ITEMS = 16;
-constexpr int K1_TILE = K1_THREADS * K1_ITEMS;  // samples per tile
-constexpr int K1_WTILE = K1_TILE / K1_WARPS;    // samples per warp (warp-contiguous layout)
-constexpr int K1_SHORT = 32;                    // columns up to this length are filled by one thread
+constexpr int K1_TILE = K1_WORKERS * K1_ITEMS;  // samples per tile
+constexpr int K1_WORDS = K1_TILE / 32;          // bitmap words per tile
+constexpr int K1_WTILE = K1_TILE / (K1_WORKERS / 32);  // samples per worker warp
+constexpr int K1_SHORT = 32;                    // up to this many mirror probes are done by one thread
+constexpr int K1_CCAP = K1_TILE + 2;            // column-window capacity
 
 // tile_c[t] = column that holds sample t*K1_TILE (last c < M with V[c] <= q)
 __global__ void build_partition_kernel(const int *__restrict__ V, int M, int num_tiles,
@@ -56,82 +58,58 @@ __global__ void build_sample_count_kernel(const int *__restrict__ Ap, int M, int
   ns[mc] = len > 0 ? (len + dim - 1) / dim : 0;
 }
 
-// Is `target` among the sampled mesh rows of block-column `col`?  [vs, ve) is the column's
-// sample range.  Looks in the tile's staged samples when the whole column is staged (staged
-// slots hold the mesh row, or ~row once the owning column has classified the slot as dropped).
+__device__ __forceinline__ int slot_row(int x) { return x; }
+
+// first position in [lo, hi) of column c's samples whose mesh row is >= target; the column is
+// read from the staged tile when it lies wholly inside it, else from global memory
 template <bool DIM1>
-__device__ __forceinline__ bool mirror_present(const int *__restrict__ Ap,
-                                               const int *__restrict__ Ai, int dim, int col,
-                                               int target, int vs, int ve, int q0, int q1,
-                                               const volatile int *s_val) {
+__device__ __forceinline__ int column_lower_bound(const int *__restrict__ Ap,
+                                                  const int *__restrict__ Ai, int dim, int c, int vs,
+                                                  int ve, int target, int q0, int q1,
+                                                  const volatile int *s_val, int *found_row) {
   int lo = 0, hi = ve - vs;
   const int n = hi;
+  int row = -1;
   if (vs >= q0 && ve <= q1) {
     const volatile int *a = s_val + (vs - q0);
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
-      int x = a[mid];
-      x = x < 0 ? ~x : x;
-      if (x < target) lo = mid + 1; else hi = mid;
+      if (slot_row(a[mid]) < target) lo = mid + 1; else hi = mid;
     }
-    if (lo >= n) return false;
-    int x = a[lo];
-    return (x < 0 ? ~x : x) == target;
-  }
-  if (DIM1) {
+    if (lo < n) row = slot_row(a[lo]);
+  } else if (DIM1) {
     const int *a = Ai + vs;
     while (lo < hi) {
       int mid = (lo + hi) >> 1;
       if (__ldg(a + mid) < target) lo = mid + 1; else hi = mid;
     }
-    return lo < n && __ldg(a + lo) == target;
-  }
-  const int *a = Ai + __ldg(Ap + (long long)col * dim);
-  while (lo < hi) {
-    int mid = (lo + hi) >> 1;
-    if (__ldg(a + (long long)mid * dim) / dim < target) lo = mid + 1; else hi = mid;
-  }
-  return lo < n && __ldg(a + (long long)lo * dim) / dim == target;
-}
-
-// classification of one sample of column c (Integrator-independent; ParthAPI.cpp:374-381 plus the
-// sort/unique that follows): returns true if the sample survives into the mesh row
-template <bool DIM1>
-__device__ __forceinline__ bool classify(int c, int v, bool has_prev, int prev, int M,
-                                         const int *__restrict__ Ap, const int *__restrict__ Ai,
-                                         const int *__restrict__ V, int dim, int q0, int q1,
-                                         const volatile int *s_val, int check_mirror,
-                                         unsigned &flags, int &diff) {
-  bool keep = v != c;
-  if (has_prev) {
-    if (v < prev) flags |= BUILD_UNSORTED;
-    else if (v == prev) keep = false;
-  }
-  if ((unsigned)v >= (unsigned)M) { flags |= BUILD_RANGE; return false; }
-  if (keep) {
-    if (v > c) {
-      diff++;
-      if (check_mirror) {
-        const int vs = __ldg(V + v), ve = __ldg(V + v + 1);
-        if (!mirror_present<DIM1>(Ap, Ai, dim, v, c, vs, ve, q0, q1, s_val)) flags |= BUILD_ASYM;
-      }
-    } else {
-      diff--;
+    if (lo < n) row = __ldg(a + lo);
+  } else {
+    const int *a = Ai + __ldg(Ap + (long long)c * dim);
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (__ldg(a + (long long)mid * dim) / dim < target) lo = mid + 1; else hi = mid;
     }
+    if (lo < n) row = __ldg(a + (long long)lo * dim) / dim;
   }
-  return keep;
+  *found_row = row;
+  return vs + lo;
 }
 
-// One tile = K1_TILE consecutive samples.  Phases:
-//   A  stage the samples in shared memory (DIM1: straight 128-bit copy of Ai)
-//   B  one thread per column of the tile's column window walks that column's staged samples:
-//      diagonal / duplicate / order / mirror checks with the previous sample in a register; a
-//      dropped sample is overwritten by its complement (~v < 0).  Columns longer than K1_SHORT
-//      samples are walked by a whole warp.
-//   C  warp-contiguous pass over the samples: ballot ranks -> compaction into shared memory, and
-//      the exclusive rank of every slot (needed for Mp at column starts).  Warp 0 resolves the
-//      tile's global output offset by decoupled look-back meanwhile.
-//   D  coalesced stores of Mi, and of Mp for the column starts this tile owns
+// One tile = K1_TILE consecutive samples.
+//   A   stage the samples in shared memory (DIM1: straight 128-bit copy of Ai)
+//   B   column side, one worker thread per column of the tile's column window: binary search for
+//       the diagonal (columns are proven non-decreasing in C1, else the result is discarded),
+//       mark its slot dropped, set the column's head bit, add (upper - lower) of the in-tile part
+//       to the symmetry count, and probe the mirror (r,c) of every in-tile (c,r), r > c
+//   C1  sample side, warp-contiguous: order / duplicate / range proof against the previous sample
+//       (shuffle + head bit), dropped bitmap by ballot
+//   C2  prefix of dropped counts per bitmap word (one warp); the extra warp then resolves the
+//       tile's global offset by decoupled look-back while the workers compact:
+//       rank(j) = j - dropped_before(j)
+//   E   coalesced stores of Mi; Mp[c] = base + rank(V[c]) for the column starts this tile owns
+// Duplicates inside a column, disorder, asymmetry, or a column window wider than K1_CCAP raise a
+// flag: the host then runs the general path instead.
 template <bool DIM1>
 __global__ void __launch_bounds__(K1_THREADS)
 build_filter_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai,
@@ -139,14 +117,17 @@ build_filter_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai,
                     const int *__restrict__ tile_c, int num_tiles, int *__restrict__ Mp,
                     int *__restrict__ Mi, BuildStatus *__restrict__ st,
                     unsigned long long *__restrict__ desc, int check_mirror) {
-  __shared__ __align__(16) int s_val[K1_TILE];  // staged samples; exclusive ranks after phase C
-  __shared__ __align__(16) int s_out[K1_TILE];  // compacted output
-  __shared__ int s_wsum[K1_WARPS], s_wdiff[K1_WARPS];
-  __shared__ int s_long[K1_TILE / K1_SHORT + 1];
-  __shared__ int s_nlong;
+  __shared__ __align__(16) int s_val[K1_TILE];  // staged samples
+  __shared__ __align__(16) int s_out[K1_TILE];  // compacted tile
+  __shared__ unsigned s_head[K1_WORDS];         // bit j: sample j is the first of its column
+  __shared__ unsigned s_drop[K1_WORDS];         // bit j: sample j does not survive
+  __shared__ int s_dpre[K1_WORDS + 1];          // dropped samples before word w
+  __shared__ int s_long[2 * (K1_TILE / K1_SHORT + 2)];
+  __shared__ int s_nlong, s_diff, s_prev0;
   __shared__ long long s_base;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool worker = tid < K1_WORKERS;
   // tiles are taken in blockIdx order: the hardware dispatches CTAs of a 1-D grid in that order,
   // so every predecessor of a resident tile is resident or finished (the look-back cannot starve)
   const int tile = blockIdx.x;
@@ -156,15 +137,21 @@ build_filter_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai,
   const int q1 = q0 + nq;
   const int cA = tile_c[tile];
   const int cEnd = last ? M : tile_c[tile + 1];
-  if (tid == 0) s_nlong = 0;
+  const int w0 = tile == 0 ? 0 : cA;  // tile 0 also owns the empty columns in front of sample 0
+  int wn = cEnd - w0 + 1;             // columns in the window
+  if (tid == 0) { s_nlong = 0; s_diff = 0; }
+  for (int w = tid; w < K1_WORDS; w += K1_THREADS) {
+    s_head[w] = 0u;
+    // slots past the end of the last tile count as dropped
+    const int rem = nq - w * 32;
+    s_drop[w] = rem >= 32 ? 0u : (rem <= 0 ? 0xffffffffu : ~((1u << rem) - 1u));
+  }
 
   // ---- A
   if (DIM1) {
     if (nq == K1_TILE && ((reinterpret_cast<uintptr_t>(Ai) & 15) == 0)) {
       const int4 *src = reinterpret_cast<const int4 *>(Ai + q0);
-#pragma unroll
-      for (int k = 0; k < K1_ITEMS / 4; k++)
-        reinterpret_cast<int4 *>(s_val)[tid + k * K1_THREADS] = ld_stream4(src + tid + k * K1_THREADS);
+      for (int k = tid; k < K1_TILE / 4; k += K1_THREADS) reinterpret_cast<int4 *>(s_val)[k] = ld_stream4(src + k);
     } else {
       for (int j = tid; j < nq; j += K1_THREADS) s_val[j] = ld_stream(Ai + q0 + j);
     }
@@ -177,81 +164,122 @@ build_filter_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai,
       for (int p = a; p < b; p++) s_val[p - q0] = __ldg(col + (long long)(p - vs) * dim) / dim;
     }
   }
+  if (tid == 0) {
+    // sample just before the tile, if the tile starts in the middle of column cA
+    const int vsA = __ldg(V + cA);
+    int pv = -1;
+    if (vsA < q0)
+      pv = DIM1 ? __ldg(Ai + q0 - 1)
+                : __ldg(Ai + (long long)__ldg(Ap + (long long)cA * dim) + (long long)(q0 - 1 - vsA) * dim) / dim;
+    s_prev0 = pv;
+  }
   __syncthreads();
+  if (wn > K1_CCAP) {
+    // a run of > K1_TILE empty columns inside one tile: leave it to the general path, but keep
+    // the scan chain alive
+    if (tid == 0) atomicOr(&st->flags, BUILD_WIDE);
+    wn = 0;
+  }
 
-  // ---- B
+  const volatile int *vval = s_val;
   int diff = 0;
   unsigned flags = 0;
-  const volatile int *vval = s_val;
-  for (int c = cA + tid; c <= cEnd && c < M; c += K1_THREADS) {
-    const int vs = __ldg(V + c), ve = __ldg(V + c + 1);
-    const int a = vs > q0 ? vs : q0, b = ve < q1 ? ve : q1;
-    if (b <= a) continue;
-    if (b - a > K1_SHORT) { s_long[atomicAdd(&s_nlong, 1)] = c; continue; }
-    bool has_prev = a > vs;  // only when the tile starts in the middle of this column
-    int prev = 0;
-    if (has_prev)
-      prev = DIM1 ? __ldg(Ai + a - 1)
-                  : __ldg(Ai + (long long)__ldg(Ap + (long long)c * dim) + (long long)(a - 1 - vs) * dim) / dim;
-    for (int p = a; p < b; p++) {
-      const int v = vval[p - q0];
-      if (!classify<DIM1>(c, v, has_prev, prev, M, Ap, Ai, V, dim, q0, q1, vval, check_mirror, flags, diff))
-        s_val[p - q0] = ~v;
-      prev = v;
-      has_prev = true;
+  // ---- B
+  if (worker) {
+    for (int lc = tid; lc < wn; lc += K1_WORKERS) {
+      const int c = w0 + lc;
+      if (c >= M) continue;
+      const int vs = __ldg(V + c), ve = __ldg(V + c + 1);
+      const int a = vs > q0 ? vs : q0, b = ve < q1 ? ve : q1;
+      if (b <= a) continue;
+      if (vs >= q0) atomicOr(&s_head[(vs - q0) >> 5], 1u << ((vs - q0) & 31));
+      int row;
+      const int dpos = column_lower_bound<DIM1>(Ap, Ai, dim, c, vs, ve, c, q0, q1, vval, &row);
+      const int has_diag = row == c;
+      if (has_diag && dpos >= a && dpos < b) atomicOr(&s_drop[(dpos - q0) >> 5], 1u << ((dpos - q0) & 31));
+      int lo_end = dpos < a ? a : (dpos > b ? b : dpos);          // in-tile samples below the diagonal
+      int up_beg = dpos + has_diag;
+      up_beg = up_beg < a ? a : (up_beg > b ? b : up_beg);        // in-tile samples above it
+      diff += (b - up_beg) - (lo_end - a);
+      if (check_mirror && b > up_beg) {
+        if (b - up_beg > K1_SHORT) {
+          const int k = atomicAdd(&s_nlong, 1);
+          s_long[2 * k] = c;
+          s_long[2 * k + 1] = up_beg;
+        } else {
+          for (int p = up_beg; p < b; p++) {
+            const int r = slot_row(vval[p - q0]);
+            if ((unsigned)r < (unsigned)M) {
+              int rr;
+              const int rs = __ldg(V + r), re = __ldg(V + r + 1);
+              column_lower_bound<DIM1>(Ap, Ai, dim, r, rs, re, c, q0, q1, vval, &rr);
+              if (rr != c) flags |= BUILD_ASYM;
+            }
+          }
+        }
+      }
     }
   }
   __syncthreads();
-  for (int li = warp; li < s_nlong; li += K1_WARPS) {
-    const int c = s_long[li];
-    const int vs = __ldg(V + c), ve = __ldg(V + c + 1);
-    const int a = vs > q0 ? vs : q0, b = ve < q1 ? ve : q1;
-    int carry = 0;
-    bool carry_ok = a > vs;
-    if (carry_ok)
-      carry = DIM1 ? __ldg(Ai + a - 1)
-                   : __ldg(Ai + (long long)__ldg(Ap + (long long)c * dim) + (long long)(a - 1 - vs) * dim) / dim;
-    for (int p0 = a; p0 < b; p0 += 32) {
-      const int p = p0 + lane;
-      const int v = p < b ? vval[p - q0] : 0;
-      int prev = __shfl_up_sync(0xffffffffu, v, 1);
-      bool has_prev = true;
-      if (lane == 0) { prev = carry; has_prev = carry_ok; }
-      if (p < b &&
-          !classify<DIM1>(c, v, has_prev, prev, M, Ap, Ai, V, dim, q0, q1, vval, check_mirror, flags, diff))
-        s_val[p - q0] = ~v;
-      carry = __shfl_sync(0xffffffffu, v, 31);
-      carry_ok = true;
+  const int nlong = s_nlong;
+  if (worker) {
+    // columns with many in-tile upper entries: one warp probes them
+    for (int li = warp; li < nlong; li += K1_WORKERS / 32) {
+      const int c = s_long[2 * li], up_beg = s_long[2 * li + 1];
+      const int ve = __ldg(V + c + 1);
+      const int b = ve < q1 ? ve : q1;
+      for (int p = up_beg + lane; p < b; p += 32) {
+        const int r = slot_row(vval[p - q0]);
+        if ((unsigned)r < (unsigned)M) {
+          int rr;
+          const int rs = __ldg(V + r), re = __ldg(V + r + 1);
+          column_lower_bound<DIM1>(Ap, Ai, dim, r, rs, re, c, q0, q1, vval, &rr);
+          if (rr != c) flags |= BUILD_ASYM;
+        }
+      }
+    }
+    // ---- C1
+    int carry = s_prev0;  // row of the sample before this warp's first sample
+    if (warp > 0) carry = vval[warp * K1_WTILE - 1];
+#pragma unroll 4
+    for (int k = 0; k < K1_WTILE / 32; k++) {
+      const int j = warp * K1_WTILE + k * 32 + lane;
+      const int row = j < nq ? vval[j] : 0;
+      int prev = __shfl_up_sync(0xffffffffu, row, 1);
+      if (lane == 0) prev = carry;
+      carry = __shfl_sync(0xffffffffu, row, 31);
+      const unsigned hw = s_head[(warp * K1_WTILE >> 5) + k];
+      const bool head = (hw >> lane) & 1u;
+      if (j < nq) {
+        if (!head && row <= prev) flags |= (row < prev) ? BUILD_UNSORTED : BUILD_DUP;
+        if ((unsigned)row >= (unsigned)M) flags |= BUILD_RANGE;
+      }
     }
   }
-  if (flags) atomicOr(&st->flags, flags);
+  // block sum of (upper - lower), flags
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
+  if (lane == 0 && diff) atomicAdd(&s_diff, diff);
+  if (flags) atomicOr(&st->flags, flags);
   __syncthreads();
-
-  // ---- C: per-warp kept counts, then ranks
-  unsigned keepbits = 0;
-  int wcount = 0;
-#pragma unroll
-  for (int k = 0; k < K1_ITEMS; k++) {
-    const int j = warp * K1_WTILE + k * 32 + lane;
-    const bool keep = j < nq && s_val[j] >= 0;
-    keepbits |= (keep ? 1u : 0u) << k;
-    wcount += __popc(__ballot_sync(0xffffffffu, keep));
-  }
-  if (lane == 0) { s_wsum[warp] = wcount; s_wdiff[warp] = diff; }
-  __syncthreads();
-  int woff = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < K1_WARPS; w++) {
-    const int x = s_wsum[w];
-    if (w < warp) woff += x;
-    total += x;
-  }
+  // ---- C2: prefix of dropped counts per word (warp 0: K1_WORDS/32 words per lane)
   if (warp == 0) {
-    int d = lane < K1_WARPS ? s_wdiff[lane] : 0;
+    constexpr int PER = K1_WORDS / 32;
+    int cnt[PER], sum = 0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+    for (int u = 0; u < PER; u++) { cnt[u] = __popc(s_drop[lane * PER + u]); sum += cnt[u]; }
+    int run = warp_incl_scan(sum, lane) - sum;
+#pragma unroll
+    for (int u = 0; u < PER; u++) { s_dpre[lane * PER + u] = run; run += cnt[u]; }
+    if (lane == 31) s_dpre[K1_WORDS] = run;
+  }
+  __syncthreads();
+  // slots past nq were pre-marked dropped, so kept = K1_TILE - dropped
+  const int total = K1_TILE - s_dpre[K1_WORDS];
+
+  if (!worker) {
+    // ---- look-back warp: global offset of the tile, overlapped with the compaction
+    const int d = s_diff;
     // pack: low 31 bits kept count, next 31 bits (upper - lower) modulo 2^31
     const long long agg = (long long)total | ((long long)((unsigned)d & 0x7fffffffu) << 31);
     const long long b = tile_lookback(desc, tile, agg);
@@ -263,30 +291,31 @@ build_filter_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai,
         st->diff_mod = (unsigned)((incl >> 31) & 0x7fffffff);
       }
     }
-  }
-  {
-    int run = woff;
-#pragma unroll
-    for (int k = 0; k < K1_ITEMS; k++) {
-      const int j = warp * K1_WTILE + k * 32 + lane;
-      const bool keep = (keepbits >> k) & 1u;
-      const unsigned m = __ballot_sync(0xffffffffu, keep);
-      const int pre = run + __popc(m & ((1u << lane) - 1u));
-      if (keep) s_out[pre] = s_val[j];
-      s_val[j] = pre;  // the slot now holds its exclusive rank (its value has been consumed)
-      run += __popc(m);
+  } else {
+#pragma unroll 4
+    for (int k = 0; k < K1_WTILE / 32; k++) {
+      const int w = (warp * K1_WTILE >> 5) + k;
+      const int j = w * 32 + lane;
+      const unsigned dm = s_drop[w];
+      if (!((dm >> lane) & 1u)) s_out[j - s_dpre[w] - __popc(dm & ((1u << lane) - 1u))] = s_val[j];
     }
   }
   __syncthreads();
 
-  // ---- D
+  // ---- E
   const int base = (int)(s_base & 0x7fffffff);
   for (int i = tid; i < total; i += K1_THREADS) st_stream(Mi + base + i, s_out[i]);
   // column starts owned by this tile: q0 < V[c] <= q1 (tile 0 also owns V[c] == 0), so runs of
   // empty columns on a tile boundary and the closing Mp[M] are written exactly once
-  for (int c = (tile == 0 ? 0 : cA) + tid; c <= cEnd; c += K1_THREADS) {
+  for (int lc = tid; lc < wn; lc += K1_THREADS) {
+    const int c = w0 + lc;
     const int vs = __ldg(V + c);
-    if ((vs > q0 && vs <= q1) || (tile == 0 && vs == 0)) Mp[c] = base + (vs < q1 ? s_val[vs - q0] : total);
+    if ((vs > q0 && vs <= q1) || (tile == 0 && vs == 0)) {
+      const int pos = vs - q0;
+      int rank = total;
+      if (pos < K1_TILE && vs < q1) rank = pos - s_dpre[pos >> 5] - __popc(s_drop[pos >> 5] & ((1u << (pos & 31)) - 1u));
+      Mp[c] = base + rank;
+    }
   }
 }
 

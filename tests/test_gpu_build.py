@@ -65,12 +65,11 @@ def test_unsorted_columns_and_duplicates(gpu_api, port):
     for c in range(N):  # shuffle every column: the ordering proof must fail -> general path
         rng.shuffle(Ai[Ap[c]:Ap[c + 1]])
     check(gpu_api, port, N, Ap, Ai, 1, expect_path=2)
-    # duplicates inside columns (adjacent after sorting) stay on the filter path
+    # duplicates inside columns are removed like the reference's sort+unique does
     N, Ap, Ai = synth.poisson3d(6)
-    deg = np.diff(Ap)
     Ai2 = np.repeat(Ai, 2)
     Ap2 = (Ap * 2).astype(np.int32)
-    check(gpu_api, port, N, Ap2, Ai2, 1, expect_path=1)
+    check(gpu_api, port, N, Ap2, Ai2, 1, expect_path=2)
 
 
 def test_one_missing_mirror_entry_is_detected(gpu_api, port):
@@ -102,6 +101,23 @@ def test_random_sparse_with_empty_columns(gpu_api, port):
         # symmetrised version takes the filter path
         _, Ap, Ai = synth.coo_to_csc(N, np.concatenate([r, c]), np.concatenate([c, r]))
         check(gpu_api, port, N, Ap, Ai, 1, expect_path=1)
+
+
+def test_long_runs_of_empty_columns(gpu_api, port):
+    # more empty columns than one tile's column window holds, in front, in the middle, at the end
+    N = 30000
+    blk = np.arange(40)
+    r0, c0 = np.meshgrid(blk, blk)
+    r = np.concatenate([r0.ravel() + 12000, r0.ravel() + 21000])
+    c = np.concatenate([c0.ravel() + 12000, c0.ravel() + 21000])
+    _, Ap, Ai = synth.coo_to_csc(N, r, c)
+    check(gpu_api, port, N, Ap, Ai, 1)
+    # moderate runs stay on the filter path
+    N = 3000
+    r = np.concatenate([r0.ravel() + 500, r0.ravel() + 2900])
+    c = np.concatenate([c0.ravel() + 500, c0.ravel() + 2900])
+    _, Ap, Ai = synth.coo_to_csc(N, r, c)
+    check(gpu_api, port, N, Ap, Ai, 1, expect_path=1)
 
 
 def test_dense_column_and_skewed_degrees(gpu_api, port):
