@@ -285,11 +285,17 @@ class ParthAPI:
         self._check(self.lib.parth_b200_set_decomposer(self.h, self._decomposer_ref, None))
 
     # ---- the path
-    def computePermutation(self, dim=3):
-        """returns (status, perm): status 0, or NEEDS_REDISSECT under COARSE_REPORT"""
+    def computePermutation(self, dim=3, out=None):
+        """returns (status, perm): status 0, or NEEDS_REDISSECT under COARSE_REPORT.
+        `out`: optional caller-owned int32 buffer of at least M_n*dim entries (e.g. pinned memory)"""
         self._push_options()
         n, _ = self.mesh_dims()
-        perm = np.empty(max(n * dim, 1), np.int32)
+        if out is not None:
+            if out.dtype != np.int32 or not out.flags.c_contiguous or out.size < n * dim:
+                raise ValueError("out must be a contiguous int32 array of at least M_n*dim entries")
+            perm = out
+        else:
+            perm = np.empty(max(n * dim, 1), np.int32)
         rc = self._check(self.lib.parth_b200_compute_permutation(self.h, _p(perm), int(dim)), allow=(NEEDS_REDISSECT,))
         return rc, perm[:n * dim]
 

@@ -13,11 +13,13 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libparth_b200.so")
 
-NVCC_FLAGS = [
+OBJ = os.path.join(CSRC, "_obj")
+NVCC_COMPILE = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
+NVCC_LINK = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -36,20 +38,45 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not needs_build():
-        return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I" + os.path.join(ROOT, "include")] + sources() + ["-o", LIB]
+def _compile_one(args):
+    src, obj, verbose = args
+    cmd = [_nvcc()] + NVCC_COMPILE + ["-I" + os.path.join(ROOT, "include"), "-c", src, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     env = dict(os.environ)
     env.pop("CC", None)
     env.pop("CXX", None)
     r = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    return r.returncode, " ".join(cmd), r.stdout + r.stderr
+
+
+def build(force=False, verbose=False):
+    """one object per .cu (compiled in parallel, only when stale), then one link"""
+    if not force and not needs_build():
+        return LIB
+    os.makedirs(OBJ, exist_ok=True)
+    headers = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
+    newest_header = max(os.path.getmtime(h) for h in headers)
+    jobs, objs = [], []
+    for src in sources():
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), newest_header):
+            jobs.append((src, obj, verbose))
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
+        for rc, cmd, out in ex.map(_compile_one, jobs):
+            if rc != 0:
+                raise RuntimeError("nvcc failed:\n" + cmd + "\n" + out)
+            if verbose:
+                print(out)
+    env = dict(os.environ)
+    env.pop("CC", None)
+    env.pop("CXX", None)
+    cmd = [_nvcc()] + NVCC_LINK + objs + ["-o", LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+        raise RuntimeError("link failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
     return LIB
 
 

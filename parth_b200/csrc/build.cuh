@@ -23,6 +23,7 @@ struct BuildArgs {
   BuildStatus *status;
   unsigned long long *desc;
   int check_mirror;
+  cudaEvent_t ev_a, ev_b;  // optional: bracket the filter kernel alone (roofline timing)
 };
 
 int build_filter_tiles(int M, int Q);

@@ -5,9 +5,6 @@ namespace pb {
 void stage_set_map(parth_b200 &h, const int *, int len) { if (len == 0) { h.map_len = 0; return; } TODO_STAGE("set_new_to_old_map"); }
 void stage_integrate(parth_b200 &) { TODO_STAGE("integrate"); }
 void stage_relocate(parth_b200 &, int, std::vector<int> &) { TODO_STAGE("relocate"); }
-void stage_permute_fine(parth_b200 &, const std::vector<int> &nodes) { if (nodes.empty()) return; TODO_STAGE("permute_fine"); }
 int stage_coarse(parth_b200 &) { TODO_STAGE("coarse"); }
-void stage_submesh(parth_b200 &, int, int, int *, int *, int *, int *, int *) { TODO_STAGE("submesh"); }
-void stage_amd_batch(parth_b200 &, int, const int *, const int *, const int *, int *) { TODO_STAGE("amd_batch"); }
 void stage_symbolic(parth_b200 &, const int *, int *, int *, long long *) { TODO_STAGE("symbolic"); }
 }

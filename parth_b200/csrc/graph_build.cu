@@ -423,6 +423,7 @@ int build_filter_launch(const BuildArgs &a, cudaStream_t s) {
   PB_CUDA(cudaMemsetAsync(a.desc, 0, sizeof(unsigned long long) * (size_t)num_tiles, s));
   build_partition_kernel<<<(num_tiles + 255) / 256, 256, 0, s>>>(V, a.M, num_tiles, a.tile_c);
   launches++;
+  if (a.ev_a) cudaEventRecord(a.ev_a, s);
   if (a.dim == 1)
     build_filter_kernel<true><<<num_tiles, K1_THREADS, 0, s>>>(a.Ap, a.Ai, V, 1, a.M, a.Q, a.tile_c,
                                                                num_tiles, a.Mp, a.Mi, a.status,
@@ -431,6 +432,7 @@ int build_filter_launch(const BuildArgs &a, cudaStream_t s) {
     build_filter_kernel<false><<<num_tiles, K1_THREADS, 0, s>>>(a.Ap, a.Ai, V, a.dim, a.M, a.Q,
                                                                 a.tile_c, num_tiles, a.Mp, a.Mi,
                                                                 a.status, a.desc, a.check_mirror);
+  if (a.ev_b) cudaEventRecord(a.ev_b, s);
   launches++;
   PB_CUDA(cudaGetLastError());
   return launches;

@@ -65,6 +65,9 @@ struct parth_b200 {
   pb::DevBuf<pb::BuildStatus> bstatus;
   pb::DevBuf<pb::DetectCounters> dcnt;
   pb::DevBuf<int> w0, w1, w2, w3, w4, w5;  // general-purpose int scratch
+  // stage (c): node list, vertex offsets, per-vertex counts, sub-mesh CSR, pivots, AMD slabs
+  pb::DevBuf<int> r_list, r_vtx, r_cnt, r_G, r_sub, r_perm, r_ws, r_chosen, r_g2l, r_l2g;
+  pb::DevBuf<long long> r_wsptr;
   pb::DevBuf<int> d_out;                   // staging for host-pointer outputs
   pb::PinBuf<int> pin;                     // small pinned read-backs
   pb::PinBuf<int> pin_big;                 // pinned staging for big host transfers

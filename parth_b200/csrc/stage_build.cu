@@ -41,13 +41,13 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   a.Mp = h.Mp_own.p; a.Mi = h.Mi_own.p;
 
   BuildStatus st{};
-  cudaEventRecord(h.ev2, s);
+  a.ev_a = h.ev2; a.ev_b = h.ev3;
   h.stats.kernels_launched += build_filter_launch(a, s);
-  cudaEventRecord(h.ev3, s);
   static_assert(sizeof(BuildStatus) % sizeof(int) == 0, "BuildStatus is read back as ints");
   read_ints(h, reinterpret_cast<const int *>(h.bstatus.p), reinterpret_cast<int *>(&st),
             sizeof(BuildStatus) / sizeof(int));
-  {
+  h.stats.build_kernel_ms = 0;
+  if (tiles > 0) {
     float t = 0;
     cudaEventElapsedTime(&t, h.ev2, h.ev3);
     h.stats.build_kernel_ms = t;

@@ -1,0 +1,213 @@
+// parth_b200/csrc/stage_reorder.cu -- host drivers of stage (c): extraction of dirty fine nodes
+// (extract.cu), batched ordering (amd.cu), label / permutation update.
+// Reference: Integrator::permuteFineHMDNodes (src/Parth/Integrator.cpp:851-893),
+// HMD::createMultiSubMesh (HMD.cpp:538-612), HMD::getCoarseMesh (HMD.cpp:465-481),
+// HMD::AMDNodeNDPermutation (HMD.cpp:58-75).
+#include <algorithm>
+
+#include "reorder.cuh"
+#include "scan.cuh"
+#include "stages.cuh"
+
+namespace pb {
+
+namespace {
+
+struct Batch {
+  int count = 0, total = 0, nnz = 0;
+  std::vector<int> vtx;  // count + 1
+};
+
+// uploads the node list / vertex offsets and builds the concatenated sub-mesh CSR (r_G, r_sub)
+Batch extract_fine(parth_b200 &h, const std::vector<int> &nodes) {
+  cudaStream_t s = h.stream;
+  Batch b;
+  b.count = (int)nodes.size();
+  b.vtx.assign(b.count + 1, 0);
+  for (int g = 0; g < b.count; g++) {
+    const int nd = nodes[g];
+    if (nd < 0 || nd >= h.num_nodes) throw StatusError(PARTH_B200_ERR_ARG, "permute_fine: node id out of range");
+    b.vtx[g + 1] = b.vtx[g] + (h.node_ptr[nd + 1] - h.node_ptr[nd]);
+  }
+  b.total = b.vtx[b.count];
+  h.r_list.reserve((size_t)b.count + 1, s);
+  h.r_vtx.reserve((size_t)b.count + 2, s);
+  h.r_cnt.reserve((size_t)b.total + 1, s);
+  h.r_G.reserve((size_t)b.total + 2, s);
+  h.scan_ws.reserve(scan_ws_words((size_t)b.total + 1), s);
+  PB_CUDA(cudaMemcpyAsync(h.r_list.p, nodes.data(), sizeof(int) * (size_t)b.count, cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(h.r_vtx.p, b.vtx.data(), sizeof(int) * ((size_t)b.count + 1), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaStreamSynchronize(s));  // pageable sources
+  h.stats.kernels_launched += launch_extract_count(h.r_list.p, h.r_vtx.p, b.count, b.total, h.d_node_ptr.p,
+                                                   h.d_dofs.p, h.Mp, h.Mi, h.d_dof2node.p, h.r_cnt.p, s);
+  h.stats.kernels_launched += exclusive_scan<0>(h.r_cnt.p, h.r_G.p, b.total, h.scan_ws.p, s);
+  read_ints(h, h.r_G.p + b.total, &b.nnz, 1);
+  h.r_sub.reserve((size_t)std::max(b.nnz, 1), s);
+  h.stats.kernels_launched += launch_extract_fill(h.r_list.p, h.r_vtx.p, b.count, b.total, h.d_node_ptr.p,
+                                                  h.d_dofs.p, h.Mp, h.Mi, h.d_dof2node.p, h.r_G.p, h.r_sub.p, s);
+  return b;
+}
+
+// orders every graph of the batch held in r_vtx / r_G / r_sub into r_perm
+void order_batch(parth_b200 &h, const Batch &b, const std::vector<int> &graph_nnz) {
+  cudaStream_t s = h.stream;
+  std::vector<long long> wsptr((size_t)b.count + 1, 0);
+  for (int g = 0; g < b.count; g++)
+    wsptr[g + 1] = wsptr[g] + (graph_nnz[g] > 0 ? amd_slab_ints(b.vtx[g + 1] - b.vtx[g], graph_nnz[g]) : 0);
+  h.r_wsptr.reserve((size_t)b.count + 1, s);
+  h.r_ws.reserve((size_t)std::max<long long>(wsptr[b.count], 1), s);
+  h.r_perm.reserve((size_t)std::max(b.total, 1), s);
+  PB_CUDA(cudaMemcpyAsync(h.r_wsptr.p, wsptr.data(), sizeof(long long) * ((size_t)b.count + 1), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+  h.stats.kernels_launched += launch_amd_batch(b.count, h.r_vtx.p, h.r_G.p, h.r_sub.p, h.r_wsptr.p, h.r_ws.p,
+                                               h.r_perm.p, s);
+}
+
+std::vector<int> batch_graph_nnz(parth_b200 &h, const Batch &b) {
+  // G at the graph boundaries -> entries per graph
+  std::vector<int> at((size_t)b.count + 1), out((size_t)b.count);
+  h.w5.reserve((size_t)b.count + 1, h.stream);
+  // small strided read: gather on the host side from individual copies would cost count syncs,
+  // so copy the whole prefix array when it is small, else gather with cudaMemcpy2D-free loop
+  std::vector<int> G((size_t)b.total + 1);
+  if (b.total + 1 > 0) {
+    PB_CUDA(cudaMemcpyAsync(G.data(), h.r_G.p, sizeof(int) * ((size_t)b.total + 1), cudaMemcpyDeviceToHost, h.stream));
+    PB_CUDA(cudaStreamSynchronize(h.stream));
+    h.stats.d2h_bytes += (long long)sizeof(int) * (b.total + 1);
+  }
+  for (int g = 0; g < b.count; g++) out[g] = G[b.vtx[g + 1]] - G[b.vtx[g]];
+  return out;
+}
+
+bool device_orders_with_amd(const parth_b200 &h) {
+  // the device has one ordering kernel (AMD).  METIS_NodeND leaf ordering (ReorderingType METIS,
+  // HMD.cpp:34-56) is third-party and not reproduced; under the REPAIR policy AMD stands in for
+  // it, otherwise the request is refused so that parity runs never silently diverge.
+  return h.reorder_type == PARTH_B200_AMD || h.coarse_policy == PARTH_B200_COARSE_REPAIR;
+}
+
+}  // namespace
+
+// Integrator::permuteFineHMDNodes
+void stage_permute_fine(parth_b200 &h, const std::vector<int> &nodes) {
+  if (nodes.empty()) return;
+  cudaStream_t s = h.stream;
+  cudaEvent_t e0, e1;
+  PB_CUDA(cudaEventCreate(&e0));
+  PB_CUDA(cudaEventCreate(&e1));
+  cudaEventRecord(e0, s);
+  Batch b = extract_fine(h, nodes);
+  std::vector<int> gnnz = batch_graph_nnz(h, b);
+  if (!device_orders_with_amd(h))
+    for (int g = 0; g < b.count; g++)
+      if (gnnz[g] > 0) {
+        cudaEventDestroy(e0); cudaEventDestroy(e1);
+        throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
+                          "permute_fine: METIS_NodeND leaf ordering is not available on the device "
+                          "(use ReorderingType AMD or the REPAIR coarse policy)");
+      }
+  if (h.reorder_type == PARTH_B200_MORTON_CODE) {
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    // the reference prints "Morton code is not implemented yet" and leaves perm unset (HMD.cpp:82-83)
+    throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "permute_fine: MORTON_CODE is not implemented in the reference");
+  }
+  order_batch(h, b, gnnz);
+  h.stats.kernels_launched += launch_apply_order(h.r_list.p, h.r_vtx.p, b.count, b.total, h.d_node_ptr.p,
+                                                 h.d_meta.p, h.d_dofs.p, h.r_perm.p, h.d_labels.p,
+                                                 h.d_mesh_perm.p, s);
+  cudaEventRecord(e1, s);
+  cudaEventSynchronize(e1);
+  float t = 0;
+  cudaEventElapsedTime(&t, e0, e1);
+  h.stats.reorder_ms += t;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+}
+
+// HMD::createMultiSubMesh for one node (coarse == 0) / HMD::getCoarseMesh (coarse == 1)
+void stage_submesh(parth_b200 &h, int node, int coarse, int *n_out, int *nnz_out, int *Mp, int *Mi, int *l2g) {
+  cudaStream_t s = h.stream;
+  if (!coarse) {
+    Batch b = extract_fine(h, std::vector<int>{node});
+    *n_out = b.total;
+    *nnz_out = b.nnz;
+    if (Mp) read_ints(h, h.r_G.p, Mp, (size_t)b.total + 1);
+    if (Mi && b.nnz > 0) read_ints(h, h.r_sub.p, Mi, (size_t)b.nnz);
+    if (l2g && b.total > 0) read_ints(h, h.d_dofs.p + h.node_ptr[node], l2g, (size_t)b.total);
+    return;
+  }
+  // pre-order list of the sub-tree's nodes (HMD::getAssignedDOFsOfCoarseHMD, HMD.cpp:434-447)
+  std::vector<int> list, stack{node};
+  while (!stack.empty()) {
+    int x = stack.back();
+    stack.pop_back();
+    if (h.meta[x * 7 + 2] == -1) continue;
+    list.push_back(x);
+    if (h.meta[x * 7 + 1] != -1) stack.push_back(h.meta[x * 7 + 1]);
+    if (h.meta[x * 7] != -1) stack.push_back(h.meta[x * 7]);
+  }
+  const int M = h.M_n;
+  h.r_list.reserve(list.size() + 1, s);
+  h.r_chosen.reserve((size_t)M + 1, s);
+  h.r_g2l.reserve((size_t)M + 2, s);
+  h.scan_ws.reserve(scan_ws_words((size_t)M + 1), s);
+  PB_CUDA(cudaMemcpyAsync(h.r_list.p, list.data(), sizeof(int) * list.size(), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+  PB_CUDA(cudaMemsetAsync(h.r_chosen.p, 0, sizeof(int) * (size_t)M, s));
+  h.stats.kernels_launched += launch_mark_nodes(h.r_list.p, (int)list.size(), h.d_node_ptr.p, h.d_dofs.p, h.r_chosen.p, s);
+  h.stats.kernels_launched += exclusive_scan<0>(h.r_chosen.p, h.r_g2l.p, M, h.scan_ws.p, s);
+  int n = 0;
+  read_ints(h, h.r_g2l.p + M, &n, 1);
+  h.r_l2g.reserve((size_t)std::max(n, 1), s);
+  h.r_cnt.reserve((size_t)n + 1, s);
+  h.r_G.reserve((size_t)n + 2, s);
+  h.stats.kernels_launched += launch_compact_chosen(h.r_chosen.p, h.r_g2l.p, M, h.r_l2g.p, s);
+  h.stats.kernels_launched += launch_marker_count(h.r_l2g.p, n, h.Mp, h.Mi, h.r_chosen.p, h.r_cnt.p, s);
+  h.stats.kernels_launched += exclusive_scan<0>(h.r_cnt.p, h.r_G.p, n, h.scan_ws.p, s);
+  int nnz = 0;
+  read_ints(h, h.r_G.p + n, &nnz, 1);
+  h.r_sub.reserve((size_t)std::max(nnz, 1), s);
+  h.stats.kernels_launched += launch_marker_fill(h.r_l2g.p, n, h.Mp, h.Mi, h.r_chosen.p, h.r_g2l.p, h.r_G.p, h.r_sub.p, s);
+  *n_out = n;
+  *nnz_out = nnz;
+  if (Mp) read_ints(h, h.r_G.p, Mp, (size_t)n + 1);
+  if (Mi && nnz > 0) read_ints(h, h.r_sub.p, Mi, (size_t)nnz);
+  if (l2g && n > 0) read_ints(h, h.r_l2g.p, l2g, (size_t)n);
+}
+
+// HMD::AMDNodeNDPermutation on a batch of host graphs (sorted, duplicate-free rows)
+void stage_amd_batch(parth_b200 &h, int count, const int *graph_ptr, const int *Mp, const int *Mi, int *perm) {
+  cudaStream_t s = h.stream;
+  if (count == 0) return;
+  Batch b;
+  b.count = count;
+  b.vtx.assign(graph_ptr, graph_ptr + count + 1);
+  b.total = b.vtx[count];
+  std::vector<int> G((size_t)b.total + 1), gnnz((size_t)count);
+  long long base = 0;
+  const int *mp = Mp;
+  for (int g = 0; g < count; g++) {
+    const int n = b.vtx[g + 1] - b.vtx[g];
+    for (int k = 0; k < n; k++) G[b.vtx[g] + k] = (int)(base + mp[k]);
+    gnnz[g] = mp[n];
+    base += mp[n];
+    mp += n + 1;
+  }
+  G[b.total] = (int)base;
+  b.nnz = (int)base;
+  h.r_vtx.reserve((size_t)count + 2, s);
+  h.r_G.reserve((size_t)b.total + 2, s);
+  h.r_sub.reserve((size_t)std::max(b.nnz, 1), s);
+  PB_CUDA(cudaMemcpyAsync(h.r_vtx.p, b.vtx.data(), sizeof(int) * ((size_t)count + 1), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(h.r_G.p, G.data(), sizeof(int) * ((size_t)b.total + 1), cudaMemcpyHostToDevice, s));
+  if (b.nnz > 0)
+    PB_CUDA(cudaMemcpyAsync(h.r_sub.p, Mi, sizeof(int) * (size_t)b.nnz, cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+  order_batch(h, b, gnnz);
+  if (b.total > 0) {
+    PB_CUDA(cudaMemcpyAsync(perm, h.r_perm.p, sizeof(int) * (size_t)b.total, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+  }
+}
+
+}  // namespace pb
