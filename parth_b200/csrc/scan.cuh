@@ -10,7 +10,7 @@ constexpr int kScanTile = kScanThreads * kScanItems;
 
 // ws: [0] = dynamic tile counter (as u64), [1..] tile descriptors; must be zeroed before launch.
 // out[i] = sum_{j<i} f(in[j]) for i in [0, n]; out has n+1 entries (out[n] = total).
-// MODE 0: f(x) = x;  MODE 1: f(x) = popc(x);  MODE 2: f(x) = (x != 0)
+// MODE 0: f(x) = x;  MODE 1: f(x) = popc(x);  MODE 2: f(x) = (x != 0);  MODE 3: f(x) = (x == -1)
 template <int MODE>
 __global__ void __launch_bounds__(kScanThreads)
 scan_excl_kernel(const int *in, int *out, int n, unsigned long long *ws) {
@@ -29,6 +29,7 @@ scan_excl_kernel(const int *in, int *out, int n, unsigned long long *ws) {
     int x = i < n ? in[i] : 0;
     if (MODE == 1) x = __popc((unsigned)x);
     if (MODE == 2) x = x != 0;
+    if (MODE == 3) x = (i < n) && x == -1;
     v[k] = x;
     sum += x;
   }

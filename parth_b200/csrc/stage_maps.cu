@@ -1,0 +1,625 @@
+// parth_b200/csrc/stage_maps.cu -- DOF-map stages on the flat separator tree:
+//   (a3) ParthAPI::setNewToOldDOFMap / computeOldToNewDOFMap   (reference ParthAPI.cpp:126-189)
+//   (a6) Integrator::integrateDOFChanges                         (Integrator.cpp:44-257)
+//   (f2) Integrator::relocateDOFsForAggressiveReuse              (Integrator.cpp:377-544)
+//
+// Both tree edits are "some entries leave their node, some DOFs join a node" and share one
+// device formulation ("regroup"):
+//   * label compaction inside a node (the reference's O(deleted x node) loop, Integrator.cpp:86-91)
+//     = exclusive scan of "deleted" flags laid out in LABEL space: new = old - #deleted labels below
+//   * surviving entries keep their relative order -> stream compaction by an exclusive scan
+//   * joining DOFs are appended in ascending id with labels size, size+1, ..., then the
+//     reference sorts DOFs but not the labels (Integrator.cpp:241-244, 536-539) -> dofs[] is the
+//     sorted MERGE of survivors and joiners while labels[] stays positional
+//   * offsets: one post-order walk over <= 8191 nodes on the host (HMD.cpp:681-697)
+// Added-DOF placement (Integrator.cpp:118-202) is an order-dependent FIFO; it is reproduced
+// exactly by a wavefront schedule: within one pass a DOF waits for its still-unplaced added
+// neighbours with a smaller id (they precede it in the queue), sees the placements of earlier
+// passes, and ignores later-queue neighbours even if they were placed in the same pass.
+#include <algorithm>
+#include <cmath>
+
+#include "scan.cuh"
+#include "stages.cuh"
+#include "tree.cuh"
+
+namespace pb {
+
+namespace {
+
+constexpr int kNoInit = 1 << 30;  // "no relocation target" (reference: num_HMD_nodes + 1)
+
+__device__ __forceinline__ int node_of_entry_d(const int *__restrict__ node_ptr, int nodes, int k) {
+  int lo = 0, hi = nodes;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(node_ptr + mid) <= k) lo = mid + 1; else hi = mid;
+  }
+  return lo - 1;
+}
+
+__device__ __forceinline__ bool is_sep_d(int sep, int node) {
+  if (sep > node) return false;
+  int a = (node - 1) / 2;
+  while (a > sep && a > 0) a = (a - 1) / 2;
+  return a == sep;
+}
+
+__device__ __forceinline__ int lca_d(const int *__restrict__ meta, int first, int second) {
+  int hi = first, lo = second;
+  if (__ldg(meta + hi * 7 + 5) < __ldg(meta + lo * 7 + 5)) { hi = second; lo = first; }
+  while (__ldg(meta + hi * 7 + 5) != __ldg(meta + lo * 7 + 5)) hi = __ldg(meta + hi * 7 + 3);
+  while (hi != lo) { hi = __ldg(meta + hi * 7 + 3); lo = __ldg(meta + lo * 7 + 3); }
+  return hi;
+}
+
+// ---------------------------------------------------------------- (a3) map inversion
+__global__ void fill_kernel(int *__restrict__ a, int n, int v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+__global__ void invert_map_kernel(const int *__restrict__ n2o, int M, int M_prev, int *__restrict__ o2n,
+                                  int *__restrict__ bad) {
+  int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= M) return;
+  int o = n2o[n];
+  if (o == -1) return;
+  if ((unsigned)o >= (unsigned)M_prev) { *bad = 1; return; }
+  o2n[o] = n;
+}
+
+// ascending list of the positions i with a[i] == -1, given the exclusive scan of that predicate
+__global__ void list_minus_one_kernel(const int *__restrict__ a, const int *__restrict__ pre, int n,
+                                      int *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && a[i] == -1) out[pre[i]] = i;
+}
+
+// ---------------------------------------------------------------- regroup, step 1
+// MODE 0 (integrate): v = old_to_new[dof], stays iff v != -1;   MODE 1 (relocate): v = dof, stays
+// iff target[dof] == kNoInit.  keep[k] in entry space, del[] in label space; integrate also
+// seeds nd2n[v] = node for the entries that stay.
+template <int MODE>
+__global__ void regroup_flags_kernel(const int *__restrict__ node_ptr, int nodes, const int *__restrict__ dofs,
+                                     const int *__restrict__ labels, int total, const int *__restrict__ key,
+                                     int *__restrict__ keep, int *__restrict__ del, int *__restrict__ nd2n) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= total) return;
+  const int nd = node_of_entry_d(node_ptr, nodes, k);
+  const int d = dofs[k];
+  int stays;
+  if (MODE == 0) {
+    const int v = __ldg(key + d);
+    stays = v != -1;
+    if (stays) nd2n[v] = nd;
+  } else {
+    stays = __ldg(key + d) == kNoInit;
+  }
+  keep[k] = stays;
+  del[__ldg(node_ptr + nd) + labels[k]] = !stays;
+}
+
+__global__ void gather_kernel(const int *__restrict__ src, const int *__restrict__ idx, int n, int *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = src[idx[i]];
+}
+
+// step 2: compacted survivors (ids and compacted labels) in entry order
+template <int MODE>
+__global__ void regroup_compact_kernel(const int *__restrict__ node_ptr, int nodes, const int *__restrict__ dofs,
+                                       const int *__restrict__ labels, int total, const int *__restrict__ key,
+                                       const int *__restrict__ S_keep, const int *__restrict__ S_del,
+                                       int *__restrict__ survC, int *__restrict__ labC) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= total) return;
+  if (S_keep[k + 1] == S_keep[k]) return;
+  const int nd = node_of_entry_d(node_ptr, nodes, k);
+  const int a = __ldg(node_ptr + nd);
+  const int lab = labels[k];
+  const int t = S_keep[k];
+  survC[t] = MODE == 0 ? __ldg(key + dofs[k]) : dofs[k];
+  labC[t] = lab - (S_del[a + lab] - S_del[a]);
+}
+
+// ---------------------------------------------------------------- joiners: per-node rank
+// one CTA per touched node walks the (ascending) joiner list: rank = position among the joiners of
+// the same node; joinS[aptr[node] + rank] = dof
+__global__ void __launch_bounds__(256)
+rank_joiners_kernel(const int *__restrict__ touched, const int *__restrict__ join, const int *__restrict__ join_node,
+                    int n_join, const int *__restrict__ aptr, int *__restrict__ joinS) {
+  __shared__ int s_scan[33];
+  const int node = touched[blockIdx.x];
+  const int base = aptr[node];
+  int running = 0;
+  for (int i0 = 0; i0 < n_join; i0 += 256) {
+    const int i = i0 + threadIdx.x;
+    const int f = i < n_join && __ldg(join_node + i) == node;
+    int total;
+    const int ex = block_excl_scan<256>(f, s_scan, &total);
+    if (f) joinS[base + running + ex] = join[i];
+    running += total;
+  }
+}
+
+__global__ void count_joiners_kernel(const int *__restrict__ join_node, int n_join, int *__restrict__ cnt) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_join) atomicAdd(cnt + join_node[i], 1);
+}
+
+__device__ __forceinline__ int lower_bound_d(const int *__restrict__ a, int n, int v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(a + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// step 3a: survivors into the merged node slices
+__global__ void regroup_place_surv_kernel(const int *__restrict__ sptr, const int *__restrict__ aptr,
+                                          const int *__restrict__ nptr, int nodes, int total_surv,
+                                          const int *__restrict__ survC, const int *__restrict__ labC,
+                                          const int *__restrict__ joinS, int *__restrict__ dofs2,
+                                          int *__restrict__ labels2, int *__restrict__ unsorted) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total_surv) return;
+  const int nd = node_of_entry_d(sptr, nodes, t);
+  const int j = t - __ldg(sptr + nd);
+  const int v = survC[t];
+  const int na = __ldg(aptr + nd + 1) - __ldg(aptr + nd);
+  int shift = 0;
+  if (na > 0) {
+    shift = lower_bound_d(joinS + __ldg(aptr + nd), na, v);
+    if (j > 0 && survC[t - 1] > v) *unsorted = 1;  // the merge needs ascending survivors
+  }
+  const int base = __ldg(nptr + nd);
+  dofs2[base + j + shift] = v;
+  labels2[base + j] = labC[t];
+}
+
+// step 3b: joiners
+__global__ void regroup_place_join_kernel(const int *__restrict__ sptr, const int *__restrict__ aptr,
+                                          const int *__restrict__ nptr, int nodes, int n_join,
+                                          const int *__restrict__ survC, const int *__restrict__ joinS,
+                                          int *__restrict__ dofs2, int *__restrict__ labels2) {
+  int u = blockIdx.x * blockDim.x + threadIdx.x;
+  if (u >= n_join) return;
+  const int nd = node_of_entry_d(aptr, nodes, u);
+  const int r = u - __ldg(aptr + nd);
+  const int v = joinS[u];
+  const int s0 = __ldg(sptr + nd), ns = __ldg(sptr + nd + 1) - s0;
+  const int shift = lower_bound_d(survC + s0, ns, v);
+  const int base = __ldg(nptr + nd);
+  dofs2[base + r + shift] = v;
+  labels2[base + ns + r] = ns + r;
+}
+
+// ---------------------------------------------------------------- (a6) added-DOF placement
+// state[d] for an added DOF d: placed_pass (0 = not placed) and dec (sweep in which its decision
+// for the current pass was taken).  A decision taken in sweep s is visible from sweep s+1 on.
+struct PlaceCounters { int undecided; int placed_in_pass; int pad0, pad1; };
+
+__global__ void place_sweep_kernel(const int *__restrict__ added, int n_added, const int *__restrict__ Mp,
+                                   const int *__restrict__ Mi, const int *__restrict__ n2o,
+                                   const int *__restrict__ meta, int *nd2n, int *placed_pass, int *dec,
+                                   int pass, int pass_start, int sweep, PlaceCounters *cnt) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_added) return;
+  const int d = added[q];
+  if (placed_pass[d] != 0) return;   // placed in an earlier pass or earlier in this one
+  if (dec[d] >= pass_start) return;  // deferred in this pass already
+  const int s = Mp[d], e = Mp[d + 1];
+  // ready <=> every still-unplaced-at-pass-start added neighbour with a smaller id has decided
+  for (int p = s; p < e; p++) {
+    const int nb = Mi[p];
+    if (nb >= d || __ldg(n2o + nb) != -1) continue;
+    const int pp = placed_pass[nb];
+    if (pp != 0 && pp < pass) continue;
+    const int dn = dec[nb];
+    if (!(dn >= pass_start && dn < sweep)) return;  // not decided yet (or decided in this very sweep)
+  }
+  // visible node of a neighbour, -1 if none
+  auto visible = [&](int nb) -> int {
+    if (__ldg(n2o + nb) != -1) return nd2n[nb];
+    const int pp = placed_pass[nb];
+    if (pp != 0 && (pp < pass || nb < d)) return nd2n[nb];
+    return -1;
+  };
+  int first = -1, result = -1;
+  bool many = false;
+  for (int p = s; p < e; p++) {
+    const int r = visible(Mi[p]);
+    if (r == -1) continue;
+    if (first == -1) first = r;
+    else if (r != first) many = true;
+  }
+  if (first == -1) {  // no placed neighbour: next ring
+    dec[d] = sweep;
+    atomicSub(&cnt->undecided, 1);
+    return;
+  }
+  if (!many) result = first;
+  else {
+    // minimum over all pairs of distinct neighbour nodes of {descendant if ancestor-related, else LCA}
+    int mn = 1 << 30;
+    for (int p = s; p < e; p++) {
+      const int ra = visible(Mi[p]);
+      if (ra == -1) continue;
+      for (int p2 = p + 1; p2 < e; p2++) {
+        const int rb = visible(Mi[p2]);
+        if (rb == -1 || rb == ra) continue;
+        const int big = ra > rb ? ra : rb, small = ra > rb ? rb : ra;
+        const int c = is_sep_d(small, big) ? big : lca_d(meta, small, big);
+        mn = c < mn ? c : mn;
+      }
+    }
+    result = mn;
+  }
+  nd2n[d] = result;
+  __threadfence();
+  placed_pass[d] = pass;
+  dec[d] = sweep;
+  atomicSub(&cnt->undecided, 1);
+  atomicAdd(&cnt->placed_in_pass, 1);
+}
+
+__global__ void count_unplaced_kernel(const int *__restrict__ added, int n_added, const int *__restrict__ placed_pass,
+                                      PlaceCounters *cnt) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n_added && placed_pass[added[q]] == 0) atomicAdd(&cnt->undecided, 1);
+}
+
+__global__ void finish_added_kernel(const int *__restrict__ added, int n_added, int spare, int *__restrict__ nd2n,
+                                    int *__restrict__ join_node) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_added) return;
+  const int d = added[q];
+  int nd = nd2n[d];
+  if (nd == -1) { nd = spare; nd2n[d] = spare; }
+  join_node[q] = nd;
+}
+
+// ---------------------------------------------------------------- (f2) relocation targets
+__global__ void occ_kernel(const int *__restrict__ edges, int n_edges, int *__restrict__ occ) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  atomicAdd(occ + edges[2 * e], 1);
+  atomicAdd(occ + edges[2 * e + 1], 1);
+}
+
+__global__ void relocate_targets_kernel(const int *__restrict__ edges, int n_edges, const int *__restrict__ dof2node,
+                                        const int *__restrict__ meta, const int *__restrict__ occ, int threshold,
+                                        int *__restrict__ target, int *__restrict__ keep_edge) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int a = edges[2 * e], b = edges[2 * e + 1];
+  const int na = __ldg(dof2node + a), nb = __ldg(dof2node + b);
+  const int big = na > nb ? na : nb, small = na > nb ? nb : na;
+  int keep = 0;
+  if (small == big) keep = 1;
+  else if (!is_sep_d(small, big)) {
+    const int cs = lca_d(meta, na, nb);
+    if (cs < threshold) atomicMin(target + (occ[a] > occ[b] ? a : b), cs);
+    else keep = 1;
+  }
+  keep_edge[e] = keep;
+}
+
+__global__ void compact_edges_kernel(const int *__restrict__ edges, int n_edges, const int *__restrict__ keep_edge,
+                                     const int *__restrict__ pre, int *__restrict__ out) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges || !keep_edge[e]) return;
+  out[2 * pre[e]] = edges[2 * e];
+  out[2 * pre[e] + 1] = edges[2 * e + 1];
+}
+
+__global__ void moved_flags_kernel(const int *__restrict__ target, int M, int *__restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < M) flag[i] = target[i] != kNoInit;
+}
+
+__global__ void list_moved_kernel(const int *__restrict__ flag, const int *__restrict__ pre, const int *__restrict__ target,
+                                  int M, int *__restrict__ moved, int *__restrict__ moved_node, int *__restrict__ dof2node) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M || !flag[i]) return;
+  moved[pre[i]] = i;
+  moved_node[pre[i]] = target[i];
+  dof2node[i] = target[i];
+}
+
+inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
+
+// HMD::getCoarseHMDNodeOffset (HMD.cpp:525-536) on the host mirror
+int coarse_offset(const parth_b200 &h, int node) {
+  int cur = h.meta[node * 7 + 2];
+  while (h.meta[cur * 7] != -1) cur = h.meta[cur * 7];
+  if (h.meta[cur * 7 + 1] != -1) return coarse_offset(h, h.meta[cur * 7 + 1]);
+  return h.meta[cur * 7 + 4];
+}
+
+// HMD::updateCoarseHMDNodeOffset(0) (HMD.cpp:681-697): post-order prefix of the node sizes
+void update_offsets(parth_b200 &h) {
+  if (h.meta[2] == -1) return;
+  double acc = coarse_offset(h, 0);
+  // iterative post-order through the stored links
+  std::vector<std::pair<int, int>> stack{{0, 0}};
+  while (!stack.empty()) {
+    auto &top = stack.back();
+    const int x = top.first;
+    if (top.second == 0) {
+      top.second = 1;
+      if (h.meta[x * 7] != -1) { stack.push_back({h.meta[x * 7], 0}); continue; }
+    }
+    if (top.second == 1) {
+      top.second = 2;
+      if (h.meta[x * 7 + 1] != -1) { stack.push_back({h.meta[x * 7 + 1], 0}); continue; }
+    }
+    h.meta[x * 7 + 4] = (int)acc;
+    acc += h.node_ptr[x + 1] - h.node_ptr[x];
+    stack.pop_back();
+  }
+}
+
+// Shared tail of integrate / relocate.  On entry: keep[] (w0) and del[] (w1) are filled for the
+// `total` old entries; join (ascending ids) / join_node hold the n_join DOFs that enter nodes.
+// Rebuilds dofs/labels (double buffered), node_ptr, offsets.  Returns the touched-node list.
+template <int MODE>
+std::vector<int> regroup_finish(parth_b200 &h, int total, const int *key, const int *d_join, const int *d_join_node,
+                                int n_join, int new_total) {
+  cudaStream_t s = h.stream;
+  const int nn = h.num_nodes;
+  h.scan_ws.reserve(scan_ws_words((size_t)std::max(total, n_join) + 1), s);
+  h.w2.reserve((size_t)total + 2, s);  // S_keep
+  h.w3.reserve((size_t)total + 2, s);  // S_del
+  h.stats.kernels_launched += exclusive_scan<0>(h.w0.p, h.w2.p, total, h.scan_ws.p, s);
+  h.stats.kernels_launched += exclusive_scan<0>(h.w1.p, h.w3.p, total, h.scan_ws.p, s);
+  // survivors per node
+  h.w4.reserve((size_t)nn * 3 + 8, s);
+  gather_kernel<<<nblk(nn + 1), 256, 0, s>>>(h.w2.p, h.d_node_ptr.p, nn + 1, h.w4.p);
+  h.stats.kernels_launched++;
+  std::vector<int> sptr((size_t)nn + 1), aptr((size_t)nn + 1, 0), nptr((size_t)nn + 1, 0), cnt((size_t)nn, 0);
+  read_ints(h, h.w4.p, sptr.data(), (size_t)nn + 1);
+  const int total_surv = sptr[nn];
+  // joiners per node
+  if (n_join > 0) {
+    PB_CUDA(cudaMemsetAsync(h.w4.p, 0, sizeof(int) * (size_t)nn, s));
+    count_joiners_kernel<<<nblk(n_join), 256, 0, s>>>(d_join_node, n_join, h.w4.p);
+    h.stats.kernels_launched++;
+    read_ints(h, h.w4.p, cnt.data(), (size_t)nn);
+  }
+  std::vector<int> touched;
+  for (int x = 0; x < nn; x++) {
+    aptr[x + 1] = aptr[x] + cnt[x];
+    nptr[x + 1] = nptr[x] + (sptr[x + 1] - sptr[x]) + cnt[x];
+    if (cnt[x]) touched.push_back(x);
+  }
+  if (nptr[nn] != new_total) throw StatusError(PARTH_B200_ERR_INTERNAL, "regroup: entry count mismatch");
+  // device copies of the three pointer arrays + touched list
+  h.w5.reserve((size_t)3 * (nn + 1) + touched.size() + 8, s);
+  int *d_sptr = h.w5.p, *d_aptr = h.w5.p + (nn + 1), *d_nptr = h.w5.p + 2 * (nn + 1), *d_touched = h.w5.p + 3 * (nn + 1);
+  PB_CUDA(cudaMemcpyAsync(d_sptr, sptr.data(), sizeof(int) * ((size_t)nn + 1), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(d_aptr, aptr.data(), sizeof(int) * ((size_t)nn + 1), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(d_nptr, nptr.data(), sizeof(int) * ((size_t)nn + 1), cudaMemcpyHostToDevice, s));
+  if (!touched.empty())
+    PB_CUDA(cudaMemcpyAsync(d_touched, touched.data(), sizeof(int) * touched.size(), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+  // compacted survivors
+  h.r_cnt.reserve((size_t)std::max(total_surv, 1), s);  // survC
+  h.r_G.reserve((size_t)std::max(total_surv, 1), s);    // labC
+  h.r_sub.reserve((size_t)std::max(n_join, 1), s);      // joinS
+  if (total > 0) {
+    regroup_compact_kernel<MODE><<<nblk(total), 256, 0, s>>>(h.d_node_ptr.p, nn, h.d_dofs.p, h.d_labels.p, total, key,
+                                                            h.w2.p, h.w3.p, h.r_cnt.p, h.r_G.p);
+    h.stats.kernels_launched++;
+  }
+  if (!touched.empty()) {
+    rank_joiners_kernel<<<(unsigned)touched.size(), 256, 0, s>>>(d_touched, d_join, d_join_node, n_join, d_aptr, h.r_sub.p);
+    h.stats.kernels_launched++;
+  }
+  h.d_dofs2.reserve((size_t)std::max(new_total, 1), s);
+  h.d_labels2.reserve((size_t)std::max(new_total, 1), s);
+  h.dcnt.reserve(1, s);
+  int *d_flag = reinterpret_cast<int *>(h.dcnt.p);
+  PB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
+  if (total_surv > 0) {
+    regroup_place_surv_kernel<<<nblk(total_surv), 256, 0, s>>>(d_sptr, d_aptr, d_nptr, nn, total_surv, h.r_cnt.p, h.r_G.p,
+                                                              h.r_sub.p, h.d_dofs2.p, h.d_labels2.p, d_flag);
+    h.stats.kernels_launched++;
+  }
+  if (n_join > 0) {
+    regroup_place_join_kernel<<<nblk(n_join), 256, 0, s>>>(d_sptr, d_aptr, d_nptr, nn, n_join, h.r_cnt.p, h.r_sub.p,
+                                                          h.d_dofs2.p, h.d_labels2.p);
+    h.stats.kernels_launched++;
+  }
+  int unsorted = 0;
+  read_ints(h, d_flag, &unsorted, 1);
+  if (unsorted)
+    throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
+                      "DOF map: surviving DOFs of a node that receives DOFs are not in ascending order "
+                      "(the reference expects survivors to keep their order, remeshPatch.cpp:160-176)");
+  h.d_dofs.swap(h.d_dofs2);
+  h.d_labels.swap(h.d_labels2);
+  h.node_ptr = nptr;
+  update_offsets(h);
+  upload_tree_meta(h);
+  return touched;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ (a3)
+void stage_set_map(parth_b200 &h, const int *map, int len) {
+  cudaStream_t s = h.stream;
+  h.map_len = 0;
+  h.n_added = h.n_removed = 0;
+  if (len == 0 || h.M_n_prev == 0) return;  // ParthAPI.cpp:138-142: no previous mesh -> the map is dropped
+  if (len != h.M_n) throw StatusError(PARTH_B200_ERR_ARG, "setNewToOldDOFMap: map length must equal M_n");
+  const int M = h.M_n, Mp = h.M_n_prev;
+  h.new_to_old.reserve((size_t)M, s);
+  h.old_to_new.reserve((size_t)Mp, s);
+  PB_CUDA(cudaMemcpyAsync(h.new_to_old.p, map, sizeof(int) * (size_t)M, cudaMemcpyHostToDevice, s));
+  h.stats.h2d_bytes += (long long)sizeof(int) * M;
+  h.dcnt.reserve(1, s);
+  int *d_bad = reinterpret_cast<int *>(h.dcnt.p);
+  PB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
+  fill_kernel<<<nblk(Mp), 256, 0, s>>>(h.old_to_new.p, Mp, -1);
+  invert_map_kernel<<<nblk(M), 256, 0, s>>>(h.new_to_old.p, M, Mp, h.old_to_new.p, d_bad);
+  h.stats.kernels_launched += 2;
+  h.scan_ws.reserve(scan_ws_words((size_t)std::max(M, Mp) + 1), s);
+  h.w0.reserve((size_t)std::max(M, Mp) + 2, s);
+  h.stats.kernels_launched += exclusive_scan<3>(h.new_to_old.p, h.w0.p, M, h.scan_ws.p, s);
+  int n_added = 0, bad = 0;
+  read_ints(h, h.w0.p + M, &n_added, 1);
+  read_ints(h, d_bad, &bad, 1);
+  if (bad) throw StatusError(PARTH_B200_ERR_INPUT, "setNewToOldDOFMap: old DOF id out of range");
+  h.added.reserve((size_t)std::max(n_added, 1), s);
+  list_minus_one_kernel<<<nblk(M), 256, 0, s>>>(h.new_to_old.p, h.w0.p, M, h.added.p);
+  h.stats.kernels_launched += 1 + exclusive_scan<3>(h.old_to_new.p, h.w0.p, Mp, h.scan_ws.p, s);
+  int n_removed = 0;
+  read_ints(h, h.w0.p + Mp, &n_removed, 1);
+  h.removed.reserve((size_t)std::max(n_removed, 1), s);
+  list_minus_one_kernel<<<nblk(Mp), 256, 0, s>>>(h.old_to_new.p, h.w0.p, Mp, h.removed.p);
+  h.stats.kernels_launched++;
+  if ((double)n_added > 0.4 * M) {  // ParthAPI.cpp:181-188: too many new DOFs -> forget everything, cold start
+    h.tree_init = false;
+    return;
+  }
+  h.map_len = len;
+  h.n_added = n_added;
+  h.n_removed = n_removed;
+}
+
+// ------------------------------------------------------------------ (a6)
+void stage_integrate(parth_b200 &h) {
+  cudaStream_t s = h.stream;
+  StageTimer tm(h, h.ev0, h.ev1);
+  const int nn = h.num_nodes, M = h.M_n;
+  const int total = h.node_ptr[nn];
+  h.w0.reserve((size_t)std::max(total, M) + 2, s);  // keep
+  h.w1.reserve((size_t)std::max(total, M) + 2, s);  // del (label space)
+  h.r_chosen.reserve((size_t)M + 1, s);             // nd2n -> becomes dof2node
+  fill_kernel<<<nblk(M), 256, 0, s>>>(h.r_chosen.p, M, -1);
+  h.stats.kernels_launched++;
+  if (total > 0) {
+    regroup_flags_kernel<0><<<nblk(total), 256, 0, s>>>(h.d_node_ptr.p, nn, h.d_dofs.p, h.d_labels.p, total,
+                                                       h.old_to_new.p, h.w0.p, h.w1.p, h.r_chosen.p);
+    h.stats.kernels_launched++;
+  }
+  int *nd2n = h.r_chosen.p;
+  const int n_added = h.n_added;
+  h.r_perm.reserve((size_t)std::max(n_added, 1), s);  // node of each added DOF
+  if (n_added > 0) {
+    // ---- ring placement (Integrator.cpp:118-202)
+    h.r_g2l.reserve((size_t)M + 1, s);  // placed_pass
+    h.r_l2g.reserve((size_t)M + 1, s);  // dec
+    PB_CUDA(cudaMemsetAsync(h.r_g2l.p, 0, sizeof(int) * (size_t)M, s));
+    fill_kernel<<<nblk(M), 256, 0, s>>>(h.r_l2g.p, M, -1);
+    h.stats.kernels_launched++;
+    pb::DevBuf<int> cbuf;
+    cbuf.reserve(8, s);
+    PlaceCounters *d_cnt = reinterpret_cast<PlaceCounters *>(cbuf.p);
+    int sweep = 0;
+    for (int pass = 1;; pass++) {
+      PB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(PlaceCounters), s));
+      count_unplaced_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.r_g2l.p, d_cnt);
+      h.stats.kernels_launched++;
+      const int pass_start = sweep;
+      int c[4] = {0, 0, 0, 0};
+      read_ints(h, reinterpret_cast<const int *>(d_cnt), c, 4);
+      if (c[0] == 0) break;
+      while (c[0] > 0) {
+        // a few sweeps per read-back: a sweep with nothing ready is a cheap no-op
+        for (int rep = 0; rep < 4; rep++) {
+          place_sweep_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.Mp, h.Mi, h.new_to_old.p, h.d_meta.p,
+                                                          nd2n, h.r_g2l.p, h.r_l2g.p, pass, pass_start, sweep, d_cnt);
+          h.stats.kernels_launched++;
+          sweep++;
+        }
+        read_ints(h, reinterpret_cast<const int *>(d_cnt), c, 4);
+      }
+      if (c[1] == 0) break;  // a pass that placed nothing ends the loop
+    }
+    // ---- leftovers: last empty leaf, else the last node (Integrator.cpp:204-217)
+    h.w2.reserve((size_t)total + 2, s);
+    h.scan_ws.reserve(scan_ws_words((size_t)total + 1), s);
+    h.stats.kernels_launched += exclusive_scan<0>(h.w0.p, h.w2.p, total, h.scan_ws.p, s);
+    h.w4.reserve((size_t)nn * 3 + 8, s);
+    gather_kernel<<<nblk(nn + 1), 256, 0, s>>>(h.w2.p, h.d_node_ptr.p, nn + 1, h.w4.p);
+    h.stats.kernels_launched++;
+    std::vector<int> sp((size_t)nn + 1);
+    read_ints(h, h.w4.p, sp.data(), (size_t)nn + 1);
+    int spare = -1;
+    for (int x = nn - 1; x >= 0; x--)
+      if (h.meta[x * 7] == -1 && h.meta[x * 7 + 1] == -1 && sp[x + 1] == sp[x]) { spare = x; break; }
+    if (spare == -1) spare = nn - 1;
+    finish_added_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, spare, nd2n, h.r_perm.p);
+    h.stats.kernels_launched++;
+  }
+  regroup_finish<0>(h, total, h.old_to_new.p, h.added.p, h.r_perm.p, n_added, M);
+  // DOF_to_HMD_node = new_DOF_to_HMD_node; mesh_perm.clear(); resize(M_n); assign from the root
+  h.d_dof2node.swap(h.r_chosen);
+  h.tree_M = M;
+  h.d_mesh_perm.reserve((size_t)std::max(M, 1), s);
+  PB_CUDA(cudaMemsetAsync(h.d_mesh_perm.p, 0, sizeof(int) * (size_t)M, s));
+  assemble_all(h);
+  tm.stop();
+  h.stats.integrate_ms = tm.ms();
+}
+
+// ------------------------------------------------------------------ (f2)
+// Moves one endpoint of every changed edge whose common separator lies above `threshold_node`
+// into that separator; the edge list keeps only the edges that still need a repair.
+void stage_relocate(parth_b200 &h, int threshold_node, std::vector<int> &dirty_fine_out, bool filter_edges) {
+  cudaStream_t s = h.stream;
+  const int nn = h.num_nodes, M = h.tree_M, ne = h.n_changed;
+  if (ne <= 0) return;
+  const int total = h.node_ptr[nn];
+  h.r_chosen.reserve((size_t)M + 1, s);  // occ
+  h.r_g2l.reserve((size_t)M + 2, s);     // target
+  h.r_l2g.reserve((size_t)std::max(M, ne) + 2, s);  // moved flag / its prefix lives in w1
+  h.w0.reserve((size_t)std::max(std::max(total, M), ne) + 2, s);
+  h.w1.reserve((size_t)std::max(std::max(total, M), ne) + 2, s);
+  h.scan_ws.reserve(scan_ws_words((size_t)std::max(std::max(total, M), ne) + 1), s);
+  PB_CUDA(cudaMemsetAsync(h.r_chosen.p, 0, sizeof(int) * (size_t)M, s));
+  fill_kernel<<<nblk(M), 256, 0, s>>>(h.r_g2l.p, M, kNoInit);
+  occ_kernel<<<nblk(ne), 256, 0, s>>>(h.d_changed.p, ne, h.r_chosen.p);
+  relocate_targets_kernel<<<nblk(ne), 256, 0, s>>>(h.d_changed.p, ne, h.d_dof2node.p, h.d_meta.p, h.r_chosen.p,
+                                                  threshold_node, h.r_g2l.p, h.w0.p);
+  h.stats.kernels_launched += 3;
+  // filtered edge list, order preserved
+  h.stats.kernels_launched += exclusive_scan<0>(h.w0.p, h.w1.p, ne, h.scan_ws.p, s);
+  int kept = 0;
+  read_ints(h, h.w1.p + ne, &kept, 1);
+  h.w2.reserve((size_t)std::max(kept, 1) * 2, s);
+  compact_edges_kernel<<<nblk(ne), 256, 0, s>>>(h.d_changed.p, ne, h.w0.p, h.w1.p, h.w2.p);
+  h.stats.kernels_launched++;
+  if (filter_edges) {
+    if (kept > 0)
+      PB_CUDA(cudaMemcpyAsync(h.d_changed.p, h.w2.p, sizeof(int) * 2 * (size_t)kept, cudaMemcpyDeviceToDevice, s));
+    h.n_changed = kept;
+  }
+  // moved DOFs, ascending
+  moved_flags_kernel<<<nblk(M), 256, 0, s>>>(h.r_g2l.p, M, h.r_l2g.p);
+  h.stats.kernels_launched += 1 + exclusive_scan<0>(h.r_l2g.p, h.w1.p, M, h.scan_ws.p, s);
+  int n_moved = 0;
+  read_ints(h, h.w1.p + M, &n_moved, 1);
+  if (n_moved == 0) return;
+  h.r_perm.reserve((size_t)n_moved, s);  // moved ids
+  h.r_ws.reserve((size_t)n_moved, s);    // their target nodes
+  if (total > 0) {
+    // flags are computed BEFORE dof2node is redirected (the nodes that lose DOFs are the old ones)
+    regroup_flags_kernel<1><<<nblk(total), 256, 0, s>>>(h.d_node_ptr.p, nn, h.d_dofs.p, h.d_labels.p, total,
+                                                       h.r_g2l.p, h.w0.p, h.r_chosen.p /*del, reuses occ*/, nullptr);
+    h.stats.kernels_launched++;
+  }
+  list_moved_kernel<<<nblk(M), 256, 0, s>>>(h.r_l2g.p, h.w1.p, h.r_g2l.p, M, h.r_perm.p, h.r_ws.p, h.d_dof2node.p);
+  h.stats.kernels_launched++;
+  // regroup_finish expects del[] in w1
+  PB_CUDA(cudaMemcpyAsync(h.w1.p, h.r_chosen.p, sizeof(int) * (size_t)total, cudaMemcpyDeviceToDevice, s));
+  std::vector<int> touched = regroup_finish<1>(h, total, h.r_g2l.p, h.r_perm.p, h.r_ws.p, n_moved, total);
+  dirty_fine_out.insert(dirty_fine_out.end(), touched.begin(), touched.end());
+  assemble_all(h);
+}
+
+}  // namespace pb

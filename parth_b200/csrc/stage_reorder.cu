@@ -175,6 +175,25 @@ void stage_submesh(parth_b200 &h, int node, int coarse, int *n_out, int *nnz_out
   if (l2g && n > 0) read_ints(h, h.r_l2g.p, l2g, (size_t)n);
 }
 
+// Dirty COARSE nodes.  The reference re-dissects the sub-tree with METIS_ComputeVertexSeparator
+// (Integrator::rePartitionCoarseHMDNode, Integrator.cpp:812-849), which is third-party and not
+// reproduced on the device.  REPAIR restores the separator property instead: one endpoint of every
+// broken edge moves into the common separator of its two nodes (the reference's own relocation
+// rule, Integrator.cpp:377-544, applied without a level limit) and the nodes that received DOFs
+// are re-ordered.  The reported dirty sets / reuse / changed-edge list stay the reference's.
+int stage_coarse(parth_b200 &h) {
+  if (h.coarse_policy == PARTH_B200_COARSE_CALLBACK)
+    throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "coarse policy CALLBACK: no re-dissection callback registered");
+  std::vector<int> touched;
+  stage_relocate(h, 1 << 29, touched, /*filter_edges=*/false);
+  std::vector<int> nodes = h.dirty_fine;
+  nodes.insert(nodes.end(), touched.begin(), touched.end());
+  std::sort(nodes.begin(), nodes.end());
+  nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+  stage_permute_fine(h, nodes);
+  return PARTH_B200_OK;
+}
+
 // HMD::AMDNodeNDPermutation on a batch of host graphs (sorted, duplicate-free rows)
 void stage_amd_batch(parth_b200 &h, int count, const int *graph_ptr, const int *Mp, const int *Mi, int *perm) {
   cudaStream_t s = h.stream;

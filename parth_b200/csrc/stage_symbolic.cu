@@ -1,0 +1,444 @@
+// parth_b200/csrc/stage_symbolic.cu -- stage (d): elimination tree, column counts and nnz(L) of
+// P*A*P' for the current mesh graph (full symmetric pattern, no diagonal) and perm[new] = old.
+//
+// Where the reference gets them: src/Parth never computes them; its ecosystem calls CHOLMOD
+// (cholmod_analyze_p with a given permutation, L_NNZ = cm.lnz*2 - N; reference
+// src/utils/ParthTestUtils.cpp:15-59, src/LinSysSolver/CHOLMODSolver.cpp:108-151) and carries an
+// in-tree Liu etree (sym_lib::compute_etree, src/utils/etree.cpp:39-115).  Both results are
+// mathematical functions of (pattern, permutation), so any exact algorithm is bit-identical.
+//
+// Device formulation
+//   etree     Liu's algorithm with path compression is sequential along a root path, but the
+//             separator tree makes sub-trees independent: in the post-order layout a column of node
+//             X only sees smaller columns inside X's own sub-tree.  One warp per separator-tree node
+//             (lanes walk the neighbours of one column concurrently; concurrent walks only ever
+//             write the same value), nodes of one wave in one launch, waves bottom-up.  Edges that
+//             break the separator property (the reference keeps them when lagging drops a dirty
+//             node) become extra wave dependencies, so the result stays exact.
+//   colcount  Gilbert-Ng-Peyton skeleton counting without the sequential union-find: an Euler tour
+//             of the etree ranked by pointer jumping gives pre-order intervals; a neighbour k < i
+//             of row i is a leaf of the row sub-tree iff no other neighbour lies in its interval;
+//             consecutive leaves meet at an LCA found by binary lifting on the interval test;
+//             column counts are interval sums of the per-vertex deltas.
+#include <algorithm>
+#include <cstring>
+
+#include "scan.cuh"
+#include "stages.cuh"
+
+namespace pb {
+
+namespace {
+
+inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
+
+__global__ void invert_perm_kernel(const int *__restrict__ perm, int n, int *__restrict__ inv, int *__restrict__ bad) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int o = perm[k];
+  if ((unsigned)o >= (unsigned)n) { *bad = 1; return; }
+  inv[o] = k;
+}
+
+__global__ void fill_i32(int *__restrict__ a, long long n, int v) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = v;
+}
+
+__device__ __forceinline__ bool heap_is_ancestor_or_self(int anc, int node) {
+  while (node > anc) node = (node - 1) >> 1;
+  return node == anc;
+}
+
+// columns whose smaller neighbours leave the sub-tree of their node: (node of neighbour, node of column)
+__global__ void find_violations_kernel(const int *__restrict__ perm, const int *__restrict__ inv,
+                                       const int *__restrict__ Mp, const int *__restrict__ Mi,
+                                       const int *__restrict__ dof2node, int n, int *__restrict__ pairs, int cap,
+                                       int *__restrict__ count) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int old = perm[j];
+  const int X = __ldg(dof2node + old);
+  for (int p = Mp[old]; p < Mp[old + 1]; p++) {
+    const int nb = Mi[p];
+    if (__ldg(inv + nb) >= j) continue;
+    const int A = __ldg(dof2node + nb);
+    if (A == X || heap_is_ancestor_or_self(X, A)) continue;
+    const int at = atomicAdd(count, 1);
+    if (at < cap) { pairs[2 * at] = A; pairs[2 * at + 1] = X; }
+  }
+}
+
+// Liu's etree over the column ranges of one wave; one warp per range
+__global__ void etree_wave_kernel(const int *__restrict__ ranges, int n_ranges, const int *__restrict__ perm,
+                                  const int *__restrict__ inv, const int *__restrict__ Mp, const int *__restrict__ Mi,
+                                  volatile int *anc, int *parent) {
+  const int lane = threadIdx.x & 31;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= n_ranges) return;
+  const int b = ranges[2 * w], e = ranges[2 * w + 1];
+  for (int j = b; j < e; j++) {
+    const int old = __ldg(perm + j);
+    const int s = __ldg(Mp + old), t = __ldg(Mp + old + 1);
+    for (int p = s + lane; p < t; p += 32) {
+      int k = __ldg(inv + __ldg(Mi + p));
+      if (k >= j) continue;
+      for (;;) {
+        const int a = anc[k];
+        if (a == j) break;
+        anc[k] = j;
+        if (a == -1) { parent[k] = j; break; }
+        k = a;
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------- Euler tour of the etree
+// children CSR by parent; roots hang under the virtual vertex n
+__global__ void child_count_kernel(const int *__restrict__ parent, int n, int *__restrict__ cnt) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int p = parent[j];
+  atomicAdd(cnt + (p == -1 ? n : p), 1);
+}
+__global__ void child_fill_kernel(const int *__restrict__ parent, int n, const int *__restrict__ cptr,
+                                  int *__restrict__ fill, int *__restrict__ child, int *__restrict__ slot) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int p = parent[j];
+  if (p == -1) p = n;
+  const int at = atomicAdd(fill + p, 1);
+  child[cptr[p] + at] = j;
+  slot[j] = at;  // position among the siblings
+}
+// tour elements: 2j = "enter j", 2j+1 = "leave j"; succ links them in DFS order; element weights
+// count the "enter" events, so rank-before(enter j) = pre-order number
+__global__ void tour_succ_kernel(const int *__restrict__ parent, int n, const int *__restrict__ cptr,
+                                 const int *__restrict__ child, const int *__restrict__ slot,
+                                 unsigned long long *__restrict__ link) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int nc = cptr[j + 1] - cptr[j];
+  // enter j -> enter first child, or leave j
+  const unsigned succ_enter = nc > 0 ? 2u * (unsigned)child[cptr[j]] : 2u * (unsigned)j + 1u;
+  // leave j -> enter next sibling, or leave parent (virtual root: end of list)
+  int p = parent[j];
+  if (p == -1) p = n;
+  const int sl = slot[j];
+  unsigned succ_leave;
+  if (sl + 1 < cptr[p + 1] - cptr[p]) succ_leave = 2u * (unsigned)child[cptr[p] + sl + 1];
+  else succ_leave = p == n ? 0xffffffffu : 2u * (unsigned)p + 1u;
+  // link = (successor << 32) | number of "enter" events from this element to the end of its hop
+  link[2 * (size_t)j] = ((unsigned long long)succ_enter << 32) | 1ull;
+  link[2 * (size_t)j + 1] = ((unsigned long long)succ_leave << 32) | 0ull;
+}
+// Wyllie pointer jumping: after ceil(log2(2n)) rounds the low word holds the number of "enter"
+// events from the element (inclusive) to the end of the tour
+__global__ void tour_jump_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
+                                 long long m, int *__restrict__ active) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const unsigned long long a = in[i];
+  const unsigned s = (unsigned)(a >> 32);
+  if (s == 0xffffffffu) { out[i] = a; return; }
+  const unsigned long long b = in[s];
+  out[i] = (b & 0xffffffff00000000ull) | (unsigned long long)((unsigned)a + (unsigned)b);
+  *active = 1;
+}
+__global__ void tour_extract_kernel(const unsigned long long *__restrict__ link, int n, int *__restrict__ tin,
+                                    int *__restrict__ size) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int after_enter = (int)(unsigned)link[2 * (size_t)j];      // enters from "enter j" on, inclusive
+  const int after_leave = (int)(unsigned)link[2 * (size_t)j + 1];  // enters after "leave j"
+  tin[j] = n - after_enter;
+  size[j] = after_enter - after_leave;
+}
+
+// ---------------------------------------------------------------- binary lifting
+__global__ void lift_init_kernel(const int *__restrict__ parent, int n, int *__restrict__ up0) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) up0[j] = parent[j];
+}
+__global__ void lift_step_kernel(const int *__restrict__ prev, int n, int *__restrict__ next, int *__restrict__ any) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int a = prev[j];
+  const int b = a == -1 ? -1 : prev[a];
+  next[j] = b;
+  if (b != -1) *any = 1;
+}
+
+// ---------------------------------------------------------------- skeleton deltas
+// delta[j] = [j is an etree leaf] - #children(j) + sum over rows of the leaf / LCA corrections
+__global__ void delta_base_kernel(const int *__restrict__ cptr, int n, int *__restrict__ delta) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int nc = cptr[j + 1] - cptr[j];
+  delta[j] = (nc == 0 ? 1 : 0) - nc;
+}
+
+__global__ void delta_rows_kernel(const int *__restrict__ perm, const int *__restrict__ inv,
+                                  const int *__restrict__ Mp, const int *__restrict__ Mi, int n,
+                                  const int *__restrict__ tin, const int *__restrict__ size,
+                                  const int *__restrict__ up, int levels, int *__restrict__ delta) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int old = perm[i];
+  const int s = Mp[old], e = Mp[old + 1];
+  for (int p = s; p < e; p++) {
+    const int k = __ldg(inv + Mi[p]);
+    if (k >= i) continue;
+    const int tk = __ldg(tin + k), ek = tk + __ldg(size + k);
+    // leaf of the row sub-tree <=> no other lower neighbour inside k's interval; previous leaf =
+    // the lower neighbour with the largest interval that ends at or before tin[k]
+    bool leaf = true;
+    int best = -1, best_t = -1;
+    for (int q = s; q < e; q++) {
+      if (q == p) continue;
+      const int k2 = __ldg(inv + Mi[q]);
+      if (k2 >= i) continue;
+      const int t2 = __ldg(tin + k2);
+      if (t2 > tk && t2 < ek) { leaf = false; break; }
+      if (t2 + __ldg(size + k2) <= tk && t2 > best_t) { best_t = t2; best = k2; }
+    }
+    if (!leaf) continue;
+    atomicAdd(delta + k, 1);
+    if (best == -1) continue;
+    // LCA(best, k): lowest ancestor of `best` whose interval contains tin[k]
+    int x = best;
+    for (int b = levels - 1; b >= 0; b--) {
+      const int a = __ldg(up + (size_t)b * n + x);
+      if (a == -1) continue;
+      const int ta = __ldg(tin + a);
+      if (!(ta <= tk && tk < ta + __ldg(size + a))) x = a;
+    }
+    atomicSub(delta + __ldg(up + x), 1);  // parent of x
+  }
+}
+
+__global__ void scatter_by_tin_kernel(const int *__restrict__ delta, const int *__restrict__ tin, int n,
+                                      int *__restrict__ out) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) out[tin[j]] = delta[j];
+}
+__global__ void colcount_kernel(const int *__restrict__ pre, const int *__restrict__ tin, const int *__restrict__ size,
+                                int n, int *__restrict__ colcount, unsigned long long *__restrict__ lnz) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  long long c = 0;
+  if (j < n) {
+    const int t = tin[j];
+    c = pre[t + size[j]] - pre[t];
+    colcount[j] = (int)c;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(lnz, (unsigned long long)c);
+}
+
+}  // namespace
+
+void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *colcount_out, long long *lnz_out) {
+  cudaStream_t s = h.stream;
+  const int n = h.M_n;
+  StageTimer tm(h, h.ev0, h.ev1);
+  const bool tree_aware = perm_host == nullptr && h.tree_init && h.tree_M == n;
+  if (perm_host == nullptr && !tree_aware)
+    throw StatusError(PARTH_B200_ERR_ARG, "symbolic: no permutation given and no current mesh_perm");
+
+  // scratch: all grow-only on the handle would pin ~1 GB at 8 M DOF; this stage owns its buffers
+  DevBuf<int> perm, inv, anc, parent, flag;
+  perm.reserve((size_t)n, s); inv.reserve((size_t)n, s); anc.reserve((size_t)n, s); parent.reserve((size_t)n, s);
+  flag.reserve(8, s);
+  PB_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int) * 8, s));
+  if (perm_host) {
+    PB_CUDA(cudaMemcpyAsync(perm.p, perm_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s));
+    h.stats.h2d_bytes += (long long)sizeof(int) * n;
+  } else {
+    PB_CUDA(cudaMemcpyAsync(perm.p, h.d_mesh_perm.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, s));
+  }
+  fill_i32<<<nblk(n), 256, 0, s>>>(inv.p, n, -1);
+  invert_perm_kernel<<<nblk(n), 256, 0, s>>>(perm.p, n, inv.p, flag.p);
+  fill_i32<<<nblk(n), 256, 0, s>>>(anc.p, n, -1);
+  fill_i32<<<nblk(n), 256, 0, s>>>(parent.p, n, -1);
+  h.stats.kernels_launched += 4;
+  {
+    int bad = 0;
+    read_ints(h, flag.p, &bad, 1);
+    if (bad) throw StatusError(PARTH_B200_ERR_INPUT, "symbolic: perm is not a permutation of 0..M_n-1");
+  }
+
+  // ---- waves of column ranges
+  std::vector<std::vector<int>> waves;  // flattened (begin, end) pairs per wave
+  if (!tree_aware) {
+    waves.push_back({0, n});
+  } else {
+    const int nn = h.num_nodes;
+    const int cap = 1 << 16;
+    DevBuf<int> pairs;
+    pairs.reserve((size_t)cap * 2, s);
+    find_violations_kernel<<<nblk(n), 256, 0, s>>>(perm.p, inv.p, h.Mp, h.Mi, h.d_dof2node.p, n, pairs.p, cap, flag.p + 1);
+    h.stats.kernels_launched++;
+    int nv = 0;
+    read_ints(h, flag.p + 1, &nv, 1);
+    if (nv > cap) {
+      waves.push_back({0, n});  // too broken to schedule around: one sequential range
+    } else {
+      std::vector<int> pv((size_t)nv * 2);
+      if (nv > 0) {
+        PB_CUDA(cudaMemcpyAsync(pv.data(), pairs.p, sizeof(int) * 2 * (size_t)nv, cudaMemcpyDeviceToHost, s));
+        PB_CUDA(cudaStreamSynchronize(s));
+      }
+      // dependency X -> C: C = the child of LCA(A, X) on A's side (heap numbering)
+      std::vector<std::vector<int>> deps((size_t)nn);
+      for (int v = 0; v < nv; v++) {
+        int A = pv[2 * v], X = pv[2 * v + 1];
+        int a = A, x = X;
+        auto depth = [](int y) { int d = 0; while (y > 0) { y = (y - 1) >> 1; d++; } return d; };
+        int da = depth(a), dx = depth(x);
+        while (da > dx) { a = (a - 1) >> 1; da--; }
+        while (dx > da) { x = (x - 1) >> 1; dx--; }
+        if (a == x) continue;  // ancestor-related: cannot precede X in a consistent post-order layout
+        while (((a - 1) >> 1) != ((x - 1) >> 1)) { a = (a - 1) >> 1; x = (x - 1) >> 1; }
+        deps[X].push_back(a);
+      }
+      // post-order = ascending offset; wave(X) = 1 + max(children, dependencies)
+      std::vector<int> order;
+      for (int x = 0; x < nn; x++) if (h.meta[x * 7 + 2] != -1) order.push_back(x);
+      std::sort(order.begin(), order.end(), [&](int a, int b) {
+        const int oa = h.meta[a * 7 + 4], ob = h.meta[b * 7 + 4];
+        return oa != ob ? oa < ob : a > b;  // empty nodes share an offset: deeper (larger id) first
+      });
+      std::vector<int> wave((size_t)nn, 0), subw((size_t)nn, 0);  // subw: max wave inside the sub-tree
+      for (int x : order) {
+        int w = 0;
+        for (int c : {h.meta[x * 7], h.meta[x * 7 + 1]}) if (c != -1) w = std::max(w, subw[c] + 1);
+        for (int c : deps[x]) w = std::max(w, subw[c] + 1);
+        wave[x] = w;
+        subw[x] = w;
+        for (int c : {h.meta[x * 7], h.meta[x * 7 + 1]}) if (c != -1) subw[x] = std::max(subw[x], subw[c]);
+        const int sz = h.node_ptr[x + 1] - h.node_ptr[x];
+        if (sz == 0) continue;
+        if ((int)waves.size() <= w) waves.resize((size_t)w + 1);
+        waves[w].push_back(h.meta[x * 7 + 4]);
+        waves[w].push_back(h.meta[x * 7 + 4] + sz);
+      }
+    }
+  }
+  {
+    size_t total = 0;
+    for (auto &w : waves) total += w.size();
+    DevBuf<int> ranges;
+    ranges.reserve(std::max<size_t>(total, 2), s);
+    std::vector<int> flat;
+    flat.reserve(total);
+    for (auto &w : waves) flat.insert(flat.end(), w.begin(), w.end());
+    if (total) {
+      PB_CUDA(cudaMemcpyAsync(ranges.p, flat.data(), sizeof(int) * total, cudaMemcpyHostToDevice, s));
+      PB_CUDA(cudaStreamSynchronize(s));
+    }
+    size_t at = 0;
+    for (auto &w : waves) {
+      const int nr = (int)w.size() / 2;
+      if (nr > 0) {
+        etree_wave_kernel<<<nblk((long long)nr * 32), 256, 0, s>>>(ranges.p + at, nr, perm.p, inv.p, h.Mp, h.Mi, anc.p, parent.p);
+        h.stats.kernels_launched++;
+      }
+      at += w.size();
+    }
+    PB_CUDA(cudaStreamSynchronize(s));  // `ranges` is released on scope exit
+  }
+  if (parent_out) {
+    PB_CUDA(cudaMemcpyAsync(parent_out, parent.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    h.stats.d2h_bytes += (long long)sizeof(int) * n;
+  }
+
+  // ---- Euler tour -> pre-order intervals
+  DevBuf<int> cptr, ccnt, child, slot, tin, size;
+  cptr.reserve((size_t)n + 2, s); ccnt.reserve((size_t)n + 2, s); child.reserve((size_t)n + 1, s);
+  slot.reserve((size_t)n + 1, s); tin.reserve((size_t)n + 1, s); size.reserve((size_t)n + 1, s);
+  h.scan_ws.reserve(scan_ws_words((size_t)n + 2), s);
+  PB_CUDA(cudaMemsetAsync(ccnt.p, 0, sizeof(int) * ((size_t)n + 1), s));
+  child_count_kernel<<<nblk(n), 256, 0, s>>>(parent.p, n, ccnt.p);
+  h.stats.kernels_launched += 1 + exclusive_scan<0>(ccnt.p, cptr.p, n + 1, h.scan_ws.p, s);
+  PB_CUDA(cudaMemsetAsync(ccnt.p, 0, sizeof(int) * ((size_t)n + 1), s));
+  child_fill_kernel<<<nblk(n), 256, 0, s>>>(parent.p, n, cptr.p, ccnt.p, child.p, slot.p);
+  h.stats.kernels_launched++;
+  {
+    DevBuf<unsigned long long> la, lb;
+    const long long m = 2 * (long long)n;
+    la.reserve((size_t)m, s); lb.reserve((size_t)m, s);
+    tour_succ_kernel<<<nblk(n), 256, 0, s>>>(parent.p, n, cptr.p, child.p, slot.p, la.p);
+    h.stats.kernels_launched++;
+    unsigned long long *cur = la.p, *nxt = lb.p;
+    for (int round = 0; round < 40; round++) {
+      PB_CUDA(cudaMemsetAsync(flag.p + 2, 0, sizeof(int), s));
+      tour_jump_kernel<<<nblk(m), 256, 0, s>>>(cur, nxt, m, flag.p + 2);
+      h.stats.kernels_launched++;
+      std::swap(cur, nxt);
+      int active = 0;
+      read_ints(h, flag.p + 2, &active, 1);
+      if (!active) break;
+    }
+    tour_extract_kernel<<<nblk(n), 256, 0, s>>>(cur, n, tin.p, size.p);
+    h.stats.kernels_launched++;
+    PB_CUDA(cudaStreamSynchronize(s));
+  }
+
+  // ---- binary lifting table (levels x n)
+  int levels = 1;
+  DevBuf<int> up;
+  {
+    // grow level by level until no 2^b-th ancestor exists; capacity for the worst case is only
+    // reserved as needed (n ints per level)
+    std::vector<int *> lv;
+    size_t cap_levels = 24;
+    up.reserve((size_t)cap_levels * n, s);
+    lift_init_kernel<<<nblk(n), 256, 0, s>>>(parent.p, n, up.p);
+    h.stats.kernels_launched++;
+    for (;;) {
+      if ((size_t)levels == cap_levels) {
+        DevBuf<int> bigger;
+        bigger.reserve((size_t)(cap_levels + 8) * n, s);
+        PB_CUDA(cudaMemcpyAsync(bigger.p, up.p, sizeof(int) * (size_t)levels * n, cudaMemcpyDeviceToDevice, s));
+        PB_CUDA(cudaStreamSynchronize(s));
+        up.swap(bigger);
+        cap_levels += 8;
+      }
+      PB_CUDA(cudaMemsetAsync(flag.p + 3, 0, sizeof(int), s));
+      lift_step_kernel<<<nblk(n), 256, 0, s>>>(up.p + (size_t)(levels - 1) * n, n, up.p + (size_t)levels * n, flag.p + 3);
+      h.stats.kernels_launched++;
+      int any = 0;
+      read_ints(h, flag.p + 3, &any, 1);
+      if (!any) break;
+      levels++;
+    }
+  }
+
+  // ---- deltas, interval sums
+  DevBuf<int> delta, bytin, pre, cc;
+  DevBuf<unsigned long long> lnz;
+  delta.reserve((size_t)n + 1, s); bytin.reserve((size_t)n + 1, s); pre.reserve((size_t)n + 2, s); cc.reserve((size_t)n + 1, s);
+  lnz.reserve(1, s);
+  PB_CUDA(cudaMemsetAsync(lnz.p, 0, sizeof(unsigned long long), s));
+  delta_base_kernel<<<nblk(n), 256, 0, s>>>(cptr.p, n, delta.p);
+  delta_rows_kernel<<<nblk(n), 256, 0, s>>>(perm.p, inv.p, h.Mp, h.Mi, n, tin.p, size.p, up.p, levels, delta.p);
+  scatter_by_tin_kernel<<<nblk(n), 256, 0, s>>>(delta.p, tin.p, n, bytin.p);
+  h.stats.kernels_launched += 3 + exclusive_scan<0>(bytin.p, pre.p, n, h.scan_ws.p, s);
+  colcount_kernel<<<nblk(n), 256, 0, s>>>(pre.p, tin.p, size.p, n, cc.p, lnz.p);
+  h.stats.kernels_launched++;
+  unsigned long long total = 0;
+  PB_CUDA(cudaMemcpyAsync(&total, lnz.p, sizeof(total), cudaMemcpyDeviceToHost, s));
+  if (colcount_out) {
+    PB_CUDA(cudaMemcpyAsync(colcount_out, cc.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    h.stats.d2h_bytes += (long long)sizeof(int) * n;
+  }
+  PB_CUDA(cudaStreamSynchronize(s));
+  *lnz_out = (long long)total;
+  tm.stop();
+  h.stats.symbolic_ms = tm.ms();
+}
+
+}  // namespace pb

@@ -52,7 +52,7 @@ int stage_compute_permutation(parth_b200 &h, int *dperm, int dim);
 // stage_maps.cu: (a3) DOF-map inversion, (a6) integration, (f2) relocation
 void stage_set_map(parth_b200 &h, const int *map, int len);
 void stage_integrate(parth_b200 &h);
-void stage_relocate(parth_b200 &h, int threshold_node, std::vector<int> &dirty_fine_out);
+void stage_relocate(parth_b200 &h, int threshold_node, std::vector<int> &dirty_fine_out, bool filter_edges = true);
 
 // stage_reorder.cu: (a12-a14) extraction + ordering of dirty fine nodes, coarse-node policy
 void stage_permute_fine(parth_b200 &h, const std::vector<int> &nodes);

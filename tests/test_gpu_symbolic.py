@@ -1,0 +1,85 @@
+"""GPU parity of stage (d): elimination tree, column counts, nnz(L) through parth_b200_symbolic,
+against the known answers of SURVEY.md Appendix B.3 and the oracle restatement
+(oracle/symbolic_oracle.c: Liu etree as reference src/utils/etree.cpp:39-115, GNP column counts)."""
+import numpy as np
+import pytest
+
+from parth_b200 import synth
+from tests import scenario_defs as sd
+from tests.golden import fixtures
+
+pytestmark = pytest.mark.gpu
+
+KNOWN = [(4, "id", 883, "ae34fa4be431278a", "c0e867d071368ef2"), (4, "aff", 793, "40327beb9c7869df", "d0ae9c28000e4cf8"),
+         (10, "id", 91909, "893645aa74b640e2", "7c2e51f5e6747a22"), (10, "aff", 105344, "542865ea36be5dc9", "9a9f30513368fd45"),
+         (20, "id", 3055619, "22017dff8c180a8a", "67d730541666c882"), (20, "aff", 3782404, "cd291b33e8fe5d7d", "b99e69673626a4cd")]
+
+
+@pytest.mark.parametrize("n,kind,lnz,hp,hc", KNOWN)
+def test_known_answers(gpu_api, n, kind, lnz, hp, hc):
+    Mp, Mi = synth.grid_graph(n)
+    N = n ** 3
+    perm = np.arange(N) if kind == "id" else (7919 * np.arange(N) + 13) % N
+    g = gpu_api.ParthAPI()
+    g.setMesh(N, Mp, Mi)
+    parent, cc, got = g.symbolic(perm)
+    assert got == lnz and int(cc.sum()) == lnz
+    assert synth.hexhash(parent) == hp and synth.hexhash(cc) == hc
+
+
+def test_fish_identity(gpu_api):
+    N, Ap, Ai = fixtures.matrix("original")
+    g = gpu_api.ParthAPI()
+    g.setMatrix(N, Ap, Ai, 1)
+    parent, cc, lnz = g.symbolic(np.arange(N))
+    assert lnz == 1332839 and 2 * lnz - N == 2654892
+    assert synth.hexhash(parent) == "850524e425e24aad" and synth.hexhash(cc) == "f32816c21934ff66"
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_graphs_vs_oracle(gpu_api, port, seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(2, 400))
+    m = int(rng.integers(0, 5 * n))
+    r, c = rng.integers(0, n, m), rng.integers(0, n, m)
+    keep = r != c
+    _, Mp, Mi = synth.coo_to_csc(n, np.concatenate([r[keep], c[keep]]), np.concatenate([c[keep], r[keep]]))
+    perm = rng.permutation(n)
+    g = gpu_api.ParthAPI()
+    g.setMesh(n, Mp, Mi)
+    parent, cc, lnz = g.symbolic(perm)
+    op = port.etree(Mp, Mi, perm)
+    olnz, occ = port.colcount(Mp, Mi, perm, op)
+    assert np.array_equal(parent, op) and np.array_equal(cc, occ) and lnz == olnz
+
+
+@pytest.mark.parametrize("extra_edges", [0, 25])
+@pytest.mark.parametrize("key", [("geo", 16, 5), ("fish",), ("g12",)])
+def test_tree_aware_path_matches_oracle(gpu_api, port, key, extra_edges):
+    """perm = None: the current mesh_perm, scheduled by separator-tree node.  With extra edges the
+    separator property is broken (what lagging leaves behind) and the schedule must stay exact."""
+    tree, Mp, Mi = sd.tree_of(dict(tree=key))
+    M = len(Mp) - 1
+    if extra_edges:
+        rng = np.random.default_rng(9)
+        Mp, Mi = synth.add_edges(Mp, Mi, rng.integers(0, M, size=(extra_edges, 2)))
+    g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = tree.levels
+    g.import_tree(tree, Mp, Mi)
+    g.setMesh(M, Mp, Mi)
+    parent, cc, lnz = g.symbolic(None)
+    perm = g.mesh_perm()
+    op = port.etree(Mp, Mi, perm)
+    olnz, occ = port.colcount(Mp, Mi, perm, op)
+    assert np.array_equal(parent, op) and np.array_equal(cc, occ) and lnz == olnz
+    # the same permutation passed explicitly takes the schedule-free path: same result
+    p2, c2, l2 = g.symbolic(perm)
+    assert np.array_equal(p2, op) and np.array_equal(c2, occ) and l2 == olnz
+
+
+def test_bad_permutation_is_rejected(gpu_api):
+    Mp, Mi = synth.grid_graph(4)
+    g = gpu_api.ParthAPI()
+    g.setMesh(64, Mp, Mi)
+    bad = np.arange(64); bad[3] = 64
+    with pytest.raises(gpu_api.ParthError):
+        g.symbolic(bad)
