@@ -1,0 +1,289 @@
+/*
+ * include/parth/ParthAPI.h -- PARTH::ParthAPI, drop-in for the reference class
+ * (reference src/Parth/include/ParthAPI.h:16-145) on the dynamic-reuse ordering path.
+ *
+ * Same method names, argument meaning, defaults and public option / timer fields; every method is
+ * a thin forward to the C ABI in include/parth_b200.h (libparth_b200.so, CUDA sm_100a).  There is
+ * no CPU path: constructing the object without a usable GPU throws std::runtime_error, and any
+ * non-zero status of the library is thrown too (the reference itself reports errors only through
+ * assert / std::cerr, ParthAPI.cpp:191-279).
+ *
+ * Differences a maintainer should know (all documented in INTEGRATION.md):
+ *   - `hmd` and `integrator` are lazy HOST MIRRORS of device state (tools read hmd.HMD_tree[i].DOFs,
+ *     hmd.DOF_to_HMD_node, integrator.reuse_ratio, integrator.dirty_*_saved; reference
+ *     tests/example_creator.cpp:66-67, src/LinSysSolver/LinSysSolver.hpp:176,216-238): call
+ *     syncTreeMirror() before reading the tree vectors.
+ *   - cold start: the reference dissects with METIS inside HMD::Decompose (HMD.cpp:122-346).  Here a
+ *     host callback (setDecomposer) or the built-in BFS level-structure dissection builds the tree,
+ *     and every node is ordered by the device AMD kernel.
+ *   - dirty COARSE nodes are repaired on the device instead of re-dissected (setCoarsePolicy).
+ */
+#ifndef PARTH_B200_PARTHAPI_H
+#define PARTH_B200_PARTHAPI_H
+
+#include <cstdint>
+#include <iostream>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../parth_b200.h"
+
+namespace PARTH {
+
+/* reference ParthTypes.h:11 */
+enum ReorderingType { METIS = 0, AMD = 1, MORTON_CODE = 2 };
+
+class ParthAPI {
+public:
+  //============================ OPTIONS (ParthAPI.h:19-25) =================
+  ReorderingType reorder_type = ReorderingType::METIS;
+  int num_cores = 10;
+  bool verbose = true;
+  bool activate_aggressive_reuse = false;
+  bool lagging = true;
+  int ND_levels = 8;
+  int sim_dim = 1;
+
+  void setReorderingType(ReorderingType type) { reorder_type = type; }
+  ReorderingType getReorderingType() const { return reorder_type; }
+  void setVerbose(bool v) { verbose = v; }
+  bool getVerbose() const { return verbose; }
+  void setNDLevels(int num) { ND_levels = num; }
+  int getNDLevels() const { return ND_levels; }
+  void setRelocatedLevel(int lvl) { integrator.relocate_lvl = lvl; }
+  int getRelocatedLevel() const { return integrator.relocate_lvl; }
+  void setLagLevel(int lvl) { integrator.lag_lvl = lvl; }
+  int getLagLevel() const { return integrator.lag_lvl; }
+  /* stored and never used, like the reference (ParthAPI.cpp:34) */
+  void setNumberOfCores(int n) { num_cores = n; }
+  int getNumberOfCores() const { return num_cores; }
+
+  //============================ VARIABLES ================================
+  /* host mirrors of the pieces of HMD / Integrator that callers read */
+  struct HMDNodeMirror {
+    int left_node_idx = -1, right_node_idx = -1, node_id = -1, parent_idx = -1, offset = -1, level = -1,
+        org_size = -1;
+    std::vector<int> DOFs, permuted_new_label;
+    bool isLeaf() const { return left_node_idx == -1 && right_node_idx == -1; }
+  };
+  struct HMDMirror {
+    bool HMD_init = false;
+    int num_levels = 0, num_HMD_nodes = 0;
+    std::vector<HMDNodeMirror> HMD_tree;
+    std::vector<int> DOF_to_HMD_node;
+  } hmd;
+  struct IntegratorMirror {
+    int relocate_lvl = 2, lag_lvl = 5; /* Integrator.h:26-28 */
+    double reuse_ratio = 0.0;
+    std::vector<int> dirty_fine_HMD_nodes_saved, dirty_coarse_HMD_nodes_saved;
+  } integrator;
+
+  std::vector<int> Mp_vec, Mi_vec; /* filled on demand by syncMeshMirror() */
+  int *Mp = nullptr;
+  int *Mi = nullptr;
+  int M_n = 0;
+  int M_n_prev = 0;
+  std::vector<int> mesh_perm;
+  std::vector<std::pair<int, int>> changed_dof_edges;
+
+  double dof_change_integrator_time = 0.0;
+  double change_computation_time = 0.0;
+  double map_mesh_to_matrix_computation_time = 0.0;
+  double compute_permutation_time = 0.0;
+  double init_time = 0.0;
+
+  //============================ FUNCTIONS =================================
+  explicit ParthAPI(int device = -1) {
+    int rc = parth_b200_create(&h_, device);
+    if (rc != PARTH_B200_OK)
+      throw std::runtime_error(std::string("PARTH (B200): ") + parth_b200_last_error(nullptr));
+    parth_b200_use_builtin_decomposer(h_, 1);
+  }
+  ~ParthAPI() {
+    if (h_) parth_b200_destroy(h_);
+  }
+  ParthAPI(const ParthAPI &) = delete;
+  ParthAPI &operator=(const ParthAPI &) = delete;
+
+  /* ParthAPI.cpp:62-74 */
+  void clearParth() {
+    check(parth_b200_clear(h_));
+    mesh_perm.clear();
+    changed_dof_edges.clear();
+    hmd = HMDMirror();
+    M_n = M_n_prev = 0;
+    Mp = Mi = nullptr;
+  }
+
+  /* ParthAPI.cpp:76-98: the arrays are copied to the device during the call */
+  void setMesh(int n, int *Mp_in, int *Mi_in, std::vector<int> &map) {
+    setMesh(n, Mp_in, Mi_in);
+    setNewToOldDOFMap(map);
+  }
+  void setMesh(int n, int *Mp_in, int *Mi_in) {
+    pushOptions();
+    check(parth_b200_set_mesh(h_, n, Mp_in, Mi_in));
+    Mp = Mp_in;
+    Mi = Mi_in;
+    M_n = n;
+  }
+
+  /* ParthAPI.cpp:100-124, 366-418 */
+  void setMatrix(int N, int *Ap, int *Ai, int dim = 1) {
+    pushOptions();
+    check(parth_b200_set_matrix(h_, N, Ap, Ai, dim));
+    sim_dim = dim;
+    int nnz = 0;
+    parth_b200_mesh_dims(h_, &M_n, &nnz);
+    Mp = Mi = nullptr; /* the graph lives on the device; syncMeshMirror() copies it back */
+  }
+  void setMatrix(int N, int *Ap, int *Ai, std::vector<int> &map, int dim = 1) {
+    setMatrix(N, Ap, Ai, dim);
+    setNewToOldDOFMap(map);
+  }
+
+  /* ParthAPI.cpp:126-189 */
+  void setNewToOldDOFMap(std::vector<int> &map) {
+    check(parth_b200_set_new_to_old_map(h_, map.empty() ? nullptr : map.data(), (int)map.size()));
+    map_set_ = !map.empty();
+  }
+
+  /* ParthAPI.cpp:191-279; default dim is 3 as in the reference (ParthAPI.h:135) */
+  void computePermutation(std::vector<int> &perm, int dim = 3) {
+    pushOptions();
+    sim_dim = dim;
+    const bool warm = hmd.HMD_init && (M_n == M_n_prev || map_set_);
+    map_set_ = false;
+    perm.resize((size_t)M_n * dim);
+    int rc = parth_b200_compute_permutation(h_, perm.data(), dim);
+    if (rc != PARTH_B200_OK && rc != PARTH_B200_NEEDS_REDISSECT) check(rc);
+    needs_redissect = rc == PARTH_B200_NEEDS_REDISSECT;
+    double t[5];
+    parth_b200_get_timers(h_, t);
+    init_time = t[0];
+    dof_change_integrator_time = t[1];
+    change_computation_time = t[2];
+    compute_permutation_time = t[3];
+    map_mesh_to_matrix_computation_time = t[4];
+    integrator.reuse_ratio = parth_b200_get_reuse(h_);
+    const int nc = parth_b200_get_num_changes(h_);
+    std::vector<int> flat((size_t)(nc > 0 ? nc : 0) * 2);
+    if (nc > 0) parth_b200_get_changed_edges(h_, flat.data(), nc);
+    changed_dof_edges.resize((size_t)(nc > 0 ? nc : 0));
+    for (int e = 0; e < nc; e++) changed_dof_edges[e] = {flat[2 * e], flat[2 * e + 1]};
+    /* the reference prints this line on every warm update, even with verbose == false (ParthAPI.cpp:254) */
+    if (warm) std::cout << "+++ PARTH: number of bad edges are " << nc << std::endl;
+    int nf = 0, ncs = 0, tm = 0, lv = 0, nodes = 0;
+    parth_b200_tree_dims(h_, &tm, &lv, &nodes);
+    integrator.dirty_fine_HMD_nodes_saved.assign((size_t)(nodes > 0 ? nodes : 1), 0);
+    integrator.dirty_coarse_HMD_nodes_saved.assign((size_t)(nodes > 0 ? nodes : 1), 0);
+    parth_b200_get_dirty_nodes(h_, integrator.dirty_fine_HMD_nodes_saved.data(), &nf,
+                               integrator.dirty_coarse_HMD_nodes_saved.data(), &ncs);
+    integrator.dirty_fine_HMD_nodes_saved.resize((size_t)nf);
+    integrator.dirty_coarse_HMD_nodes_saved.resize((size_t)ncs);
+    mesh_perm.resize((size_t)M_n);
+    parth_b200_get_mesh_perm(h_, mesh_perm.data(), M_n);
+    M_n_prev = M_n;
+    hmd.HMD_init = true;
+    hmd.num_levels = lv;
+    hmd.num_HMD_nodes = nodes;
+  }
+
+  /* ParthAPI.cpp:285-337; dim == -1 means sim_dim */
+  void mapMeshPermToMatrixPerm(std::vector<int> &mesh_perm_in, std::vector<int> &matrix_perm, int dim = -1) {
+    if (dim == -1) dim = sim_dim;
+    matrix_perm.resize(mesh_perm_in.size() * (size_t)dim);
+    check(parth_b200_map_mesh_perm_to_matrix_perm(h_, mesh_perm_in.data(), (int)mesh_perm_in.size(),
+                                                  matrix_perm.data(), dim));
+  }
+
+  double getReuse() { return parth_b200_get_reuse(h_); }
+  int getNumChanges() { return parth_b200_get_num_changes(h_); }
+
+  /* ParthAPI.cpp:350-363 */
+  void printTiming() {
+    std::cout << "+++ PARTH: Timing START +++" << std::endl;
+    std::cout << "+++ PARTH: Init Time: " << init_time << " sec" << std::endl;
+    std::cout << "+++ PARTH: DOF Change Integration Time: " << dof_change_integrator_time << " sec" << std::endl;
+    std::cout << "+++ PARTH: Change Computation Time: " << change_computation_time << " sec" << std::endl;
+    std::cout << "+++ PARTH: Compute Permutation Time: " << compute_permutation_time << " sec" << std::endl;
+    std::cout << "+++ PARTH: Map Mesh to Matrix Computation Time: " << map_mesh_to_matrix_computation_time << " sec"
+              << std::endl;
+    std::cout << "+++ PARTH: Overall reuse: " << getReuse() << std::endl;
+    std::cout << "+++ PARTH: Timing END +++" << std::endl;
+  }
+  void resetTimers() {
+    init_time = map_mesh_to_matrix_computation_time = dof_change_integrator_time = 0.0;
+    change_computation_time = compute_permutation_time = 0.0;
+  }
+
+  //============================ B200 additions ============================
+  bool needs_redissect = false; /* last computePermutation ended with PARTH_B200_NEEDS_REDISSECT */
+  parth_b200 *handle() { return h_; }
+  void setCoarsePolicy(int policy) { check(parth_b200_set_coarse_policy(h_, policy)); }
+  void setAssumeSymmetric(bool on) { check(parth_b200_set_assume_symmetric(h_, on ? 1 : 0)); }
+  void setDecomposer(parth_b200_decomposer fn, void *user) { check(parth_b200_set_decomposer(h_, fn, user)); }
+
+  /* nnz(L) of P*A*P' for the current graph and permutation (NULL: current mesh_perm); what the
+   * reference ecosystem asks CHOLMOD for (src/utils/ParthTestUtils.cpp:15-59) */
+  int64_t symbolic(const std::vector<int> *perm, std::vector<int> &parent, std::vector<int> &colcount) {
+    parent.resize((size_t)M_n);
+    colcount.resize((size_t)M_n);
+    int64_t lnz = 0;
+    check(parth_b200_symbolic(h_, perm ? perm->data() : nullptr, parent.data(), colcount.data(), &lnz));
+    return lnz;
+  }
+
+  /* copy the separator tree back into `hmd` (HMD.h:94-104 layout) */
+  void syncTreeMirror() {
+    int tm = 0, lv = 0, nodes = 0;
+    if (parth_b200_tree_dims(h_, &tm, &lv, &nodes) != PARTH_B200_OK) return;
+    std::vector<int> meta((size_t)nodes * 7), node_ptr((size_t)nodes + 1), dofs((size_t)tm), labels((size_t)tm);
+    hmd.DOF_to_HMD_node.resize((size_t)tm);
+    mesh_perm.resize((size_t)tm);
+    check(parth_b200_export_tree(h_, meta.data(), node_ptr.data(), dofs.data(), labels.data(),
+                                 hmd.DOF_to_HMD_node.data(), mesh_perm.data()));
+    hmd.HMD_init = true;
+    hmd.num_levels = lv;
+    hmd.num_HMD_nodes = nodes;
+    hmd.HMD_tree.assign((size_t)nodes, HMDNodeMirror());
+    for (int x = 0; x < nodes; x++) {
+      HMDNodeMirror &t = hmd.HMD_tree[x];
+      const int *m = &meta[(size_t)x * 7];
+      t.left_node_idx = m[0]; t.right_node_idx = m[1]; t.node_id = m[2]; t.parent_idx = m[3];
+      t.offset = m[4]; t.level = m[5]; t.org_size = m[6];
+      t.DOFs.assign(dofs.begin() + node_ptr[x], dofs.begin() + node_ptr[x + 1]);
+      t.permuted_new_label.assign(labels.begin() + node_ptr[x], labels.begin() + node_ptr[x + 1]);
+    }
+  }
+  /* copy the mesh graph back (Mp_vec / Mi_vec, ParthAPI.h:63-67) and point Mp / Mi at it */
+  void syncMeshMirror() {
+    int nnz = 0;
+    parth_b200_mesh_dims(h_, &M_n, &nnz);
+    Mp_vec.resize((size_t)M_n + 1);
+    Mi_vec.resize((size_t)(nnz > 0 ? nnz : 1));
+    check(parth_b200_get_mesh(h_, Mp_vec.data(), Mi_vec.data()));
+    Mi_vec.resize((size_t)nnz);
+    Mp = Mp_vec.data();
+    Mi = Mi_vec.data();
+  }
+
+private:
+  parth_b200 *h_ = nullptr;
+  bool map_set_ = false;
+  void pushOptions() {
+    check(parth_b200_set_options(h_, (int)reorder_type, ND_levels, lagging ? 1 : 0, activate_aggressive_reuse ? 1 : 0,
+                                 integrator.relocate_lvl, integrator.lag_lvl, verbose ? 1 : 0));
+  }
+  void check(int rc) {
+    if (rc != PARTH_B200_OK)
+      throw std::runtime_error(std::string("PARTH (B200) status ") + std::to_string(rc) + ": " +
+                               parth_b200_last_error(h_));
+  }
+};
+
+}  // namespace PARTH
+
+#endif

@@ -101,6 +101,10 @@ int parth_b200_export_tree(parth_b200 *h, int *meta, int *node_ptr, int *dofs, i
 typedef int (*parth_b200_decomposer)(void *user, int M_n, const int *Mp, const int *Mi, int levels,
                                      int nodes, int *meta, int *node_ptr, int *dofs, int *labels);
 int parth_b200_set_decomposer(parth_b200 *h, parth_b200_decomposer fn, void *user);
+/* self-contained default for the cold start when no callback is set: host-side nested dissection
+ * by BFS level structures, every node then ordered by the device AMD kernel.  Off by default on
+ * the raw C ABI (a missing tree is an error); the C++ drop-in class switches it on. */
+int parth_b200_use_builtin_decomposer(parth_b200 *h, int on);
 
 /* ParthAPI::computePermutation, ParthAPI.cpp:191-279.  perm must hold M_n*dim ints. */
 int parth_b200_compute_permutation(parth_b200 *h, int *perm, int dim);

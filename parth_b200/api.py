@@ -55,6 +55,7 @@ SYMBOLS = {
     "parth_b200_tree_dims": (C.c_int, [_vp, _ip, _ip, _ip]),
     "parth_b200_export_tree": (C.c_int, [_vp] + [_ip] * 6),
     "parth_b200_set_decomposer": (C.c_int, [_vp, DECOMPOSER, _vp]),
+    "parth_b200_use_builtin_decomposer": (C.c_int, [_vp, C.c_int]),
     "parth_b200_compute_permutation": (C.c_int, [_vp, _ip, C.c_int]),
     "parth_b200_compute_permutation_dev": (C.c_int, [_vp, _vp, C.c_int]),
     "parth_b200_map_mesh_perm_to_matrix_perm": (C.c_int, [_vp, _ip, C.c_int, _ip, C.c_int]),
@@ -193,6 +194,9 @@ class ParthAPI:
 
     def setAssumeSymmetric(self, on):
         self._check(self.lib.parth_b200_set_assume_symmetric(self.h, int(on)))
+
+    def useBuiltinDecomposer(self, on=True):
+        self._check(self.lib.parth_b200_use_builtin_decomposer(self.h, int(on)))
 
     def setShard(self, rank, world):
         self._check(self.lib.parth_b200_set_shard(self.h, int(rank), int(world)))

@@ -139,6 +139,12 @@ int parth_b200_set_decomposer(parth_b200 *h, parth_b200_decomposer fn, void *use
   return PARTH_B200_OK;
 }
 
+int parth_b200_use_builtin_decomposer(parth_b200 *h, int on) {
+  if (!h) return PARTH_B200_ERR_ARG;
+  h->builtin_decomposer = on != 0;
+  return PARTH_B200_OK;
+}
+
 void *parth_b200_stream(parth_b200 *h) { return h ? (void *)h->stream : nullptr; }
 
 int parth_b200_synchronize(parth_b200 *h) {

@@ -24,6 +24,7 @@ struct parth_b200 {
   int relocate_lvl = 2, lag_lvl = 5, verbose = 1, sim_dim = 1;
   int coarse_policy = PARTH_B200_COARSE_REPAIR, assume_symmetric = 0;
   int rank = 0, world = 1;
+  bool builtin_decomposer = false, force_amd = false;
   parth_b200_decomposer decomposer = nullptr;
   void *decomposer_user = nullptr;
 

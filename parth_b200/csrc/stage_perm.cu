@@ -263,7 +263,7 @@ void stage_snapshot(parth_b200 &h) {
 
 // cold start (HMD::initHMD, HMD.cpp:89-120): the separator tree comes from the host decomposer
 static void cold_start(parth_b200 &h) {
-  if (!h.decomposer)
+  if (!h.decomposer && !h.builtin_decomposer)
     throw StatusError(PARTH_B200_ERR_NO_TREE,
                       "computePermutation: no separator tree (import one or set a decomposer)");
   cudaStream_t s = h.stream;
@@ -276,10 +276,22 @@ static void cold_start(parth_b200 &h) {
     PB_CUDA(cudaMemcpyAsync(Mi.data(), h.Mi, sizeof(int) * (size_t)h.nnzM, cudaMemcpyDeviceToHost, s));
   PB_CUDA(cudaStreamSynchronize(s));
   std::vector<int> meta((size_t)nodes * 7, -1), node_ptr((size_t)nodes + 1, 0), dofs((size_t)h.M_n), labels((size_t)h.M_n);
-  int rc = h.decomposer(h.decomposer_user, h.M_n, Mp.data(), Mi.data(), levels, nodes, meta.data(),
-                        node_ptr.data(), dofs.data(), labels.data());
+  const bool builtin = !h.decomposer;
+  int rc = builtin ? builtin_decomposer(nullptr, h.M_n, Mp.data(), Mi.data(), levels, nodes, meta.data(),
+                                        node_ptr.data(), dofs.data(), labels.data())
+                   : h.decomposer(h.decomposer_user, h.M_n, Mp.data(), Mi.data(), levels, nodes, meta.data(),
+                                  node_ptr.data(), dofs.data(), labels.data());
   if (rc != 0) throw StatusError(PARTH_B200_ERR_NO_TREE, "decomposer callback failed");
   stage_import_tree(h, h.M_n, levels, nodes, meta.data(), node_ptr.data(), dofs.data(), labels.data(), nullptr, nullptr);
+  if (builtin) {
+    // the built-in dissection hands back identity labels: order every node on the device
+    // (HMD::Decompose orders leaves and separators as it goes, HMD.cpp:248-250,297-301)
+    std::vector<int> all;
+    for (int x = 0; x < nodes; x++) if (node_ptr[x + 1] > node_ptr[x]) all.push_back(x);
+    h.force_amd = true;
+    try { stage_permute_fine(h, all); } catch (...) { h.force_amd = false; throw; }
+    h.force_amd = false;
+  }
 }
 
 // Integrator::getGlobalPerm (Integrator.cpp:546-683) after detection found changes

@@ -83,7 +83,7 @@ bool device_orders_with_amd(const parth_b200 &h) {
   // the device has one ordering kernel (AMD).  METIS_NodeND leaf ordering (ReorderingType METIS,
   // HMD.cpp:34-56) is third-party and not reproduced; under the REPAIR policy AMD stands in for
   // it, otherwise the request is refused so that parity runs never silently diverge.
-  return h.reorder_type == PARTH_B200_AMD || h.coarse_policy == PARTH_B200_COARSE_REPAIR;
+  return h.force_amd || h.reorder_type == PARTH_B200_AMD || h.coarse_policy == PARTH_B200_COARSE_REPAIR;
 }
 
 }  // namespace
@@ -106,7 +106,7 @@ void stage_permute_fine(parth_b200 &h, const std::vector<int> &nodes) {
                           "permute_fine: METIS_NodeND leaf ordering is not available on the device "
                           "(use ReorderingType AMD or the REPAIR coarse policy)");
       }
-  if (h.reorder_type == PARTH_B200_MORTON_CODE) {
+  if (h.reorder_type == PARTH_B200_MORTON_CODE && !h.force_amd) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     // the reference prints "Morton code is not implemented yet" and leaves perm unset (HMD.cpp:82-83)
     throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "permute_fine: MORTON_CODE is not implemented in the reference");

@@ -72,7 +72,7 @@ __global__ void find_violations_kernel(const int *__restrict__ perm, const int *
 // Liu's etree over the column ranges of one wave; one warp per range
 __global__ void etree_wave_kernel(const int *__restrict__ ranges, int n_ranges, const int *__restrict__ perm,
                                   const int *__restrict__ inv, const int *__restrict__ Mp, const int *__restrict__ Mi,
-                                  volatile int *anc, int *parent) {
+                                  volatile int *anc, int *parent, int n, int *__restrict__ err) {
   const int lane = threadIdx.x & 31;
   const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= n_ranges) return;
@@ -83,11 +83,13 @@ __global__ void etree_wave_kernel(const int *__restrict__ ranges, int n_ranges, 
     for (int p = s + lane; p < t; p += 32) {
       int k = __ldg(inv + __ldg(Mi + p));
       if (k >= j) continue;
-      for (;;) {
+      // a walk visits every vertex at most once; anything longer means the schedule was violated
+      for (int steps = 0;; steps++) {
         const int a = anc[k];
         if (a == j) break;
         anc[k] = j;
         if (a == -1) { parent[k] = j; break; }
+        if (steps > n) { *err = 1; break; }
         k = a;
       }
     }
@@ -311,12 +313,17 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
         const int oa = h.meta[a * 7 + 4], ob = h.meta[b * 7 + 4];
         return oa != ob ? oa < ob : a > b;  // empty nodes share an offset: deeper (larger id) first
       });
+      // A node whose columns reach outside its sub-tree links foreign components under its own
+      // columns, so any later walk may continue into it: it must run after EVERYTHING that
+      // precedes it in post-order (which also orders two such nodes with respect to each other).
       std::vector<int> wave((size_t)nn, 0), subw((size_t)nn, 0);  // subw: max wave inside the sub-tree
+      int max_before = -1;
       for (int x : order) {
         int w = 0;
         for (int c : {h.meta[x * 7], h.meta[x * 7 + 1]}) if (c != -1) w = std::max(w, subw[c] + 1);
-        for (int c : deps[x]) w = std::max(w, subw[c] + 1);
+        if (!deps[x].empty()) w = std::max(w, max_before + 1);
         wave[x] = w;
+        max_before = std::max(max_before, w);
         subw[x] = w;
         for (int c : {h.meta[x * 7], h.meta[x * 7 + 1]}) if (c != -1) subw[x] = std::max(subw[x], subw[c]);
         const int sz = h.node_ptr[x + 1] - h.node_ptr[x];
@@ -343,12 +350,15 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
     for (auto &w : waves) {
       const int nr = (int)w.size() / 2;
       if (nr > 0) {
-        etree_wave_kernel<<<nblk((long long)nr * 32), 256, 0, s>>>(ranges.p + at, nr, perm.p, inv.p, h.Mp, h.Mi, anc.p, parent.p);
+        etree_wave_kernel<<<nblk((long long)nr * 32), 256, 0, s>>>(ranges.p + at, nr, perm.p, inv.p, h.Mp, h.Mi, anc.p,
+                                                                   parent.p, n, flag.p + 4);
         h.stats.kernels_launched++;
       }
       at += w.size();
     }
-    PB_CUDA(cudaStreamSynchronize(s));  // `ranges` is released on scope exit
+    int err = 0;
+    read_ints(h, flag.p + 4, &err, 1);  // also keeps `ranges` alive until the waves are done
+    if (err) throw StatusError(PARTH_B200_ERR_INTERNAL, "symbolic: etree walk did not terminate");
   }
   if (parent_out) {
     PB_CUDA(cudaMemcpyAsync(parent_out, parent.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));

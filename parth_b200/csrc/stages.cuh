@@ -60,6 +60,10 @@ int stage_coarse(parth_b200 &h);
 void stage_submesh(parth_b200 &h, int node, int coarse, int *n, int *nnz, int *Mp, int *Mi, int *l2g);
 void stage_amd_batch(parth_b200 &h, int count, const int *graph_ptr, const int *Mp, const int *Mi, int *perm);
 
+// host_decompose.cu: BFS level-structure nested dissection (host), parth_b200_decomposer signature
+int builtin_decomposer(void *user, int M_n, const int *Mp, const int *Mi, int levels, int nodes, int *meta,
+                       int *node_ptr, int *dofs, int *labels);
+
 // stage_symbolic.cu: (d) etree + column counts
 void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent, int *colcount, long long *lnz);
 
