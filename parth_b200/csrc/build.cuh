@@ -4,14 +4,14 @@
 
 namespace pb {
 
-enum : unsigned { BUILD_UNSORTED = 1u, BUILD_ASYM = 2u, BUILD_RANGE = 4u, BUILD_WIDE = 8u, BUILD_DUP = 16u };
+enum : unsigned { BUILD_UNSORTED = 1u, BUILD_ASYM = 2u, BUILD_RANGE = 4u, BUILD_WIDE = 8u, BUILD_DUP = 16u, BUILD_NODIAG = 32u };
 
 struct BuildStatus {
   unsigned flags;       // BUILD_* bits raised by the filter path
   unsigned diff_mod;    // (kept upper - kept lower) modulo 2^31; 0 <=> counts match
   int nnz_out;          // entries written to Mi
   int pad;
-  unsigned long long tile_counter;
+  unsigned long long diff_sum;  // column-aligned kernel: sum of (upper - lower) over all columns, two's complement
 };
 
 struct BuildArgs {
@@ -27,6 +27,9 @@ struct BuildArgs {
 };
 
 int build_filter_tiles(int M, int Q);
+// graph_build_cols.cu (dim == 1): spec = closed-form offsets (every column holds its diagonal)
+int build_cols_tiles(int Q);
+int build_cols_launch(const BuildArgs &a, bool spec, cudaStream_t s);
 int build_filter_launch(const BuildArgs &a, cudaStream_t s);
 int build_sample_prefix_launch(const int *Ap, int M, int dim, int *ns_tmp, int *V,
                                unsigned long long *scan_ws, cudaStream_t s);

@@ -1,0 +1,339 @@
+// parth_b200/csrc/graph_build_cols.cu -- stage (a), dim == 1 fast path: column-aligned filter kernel.
+//
+// Same contract as build_filter_kernel (graph_build.cu): if every column is strictly ascending and
+// the pattern is structurally symmetric, the mesh graph of ParthAPI::computeMeshFromMatrix
+// (reference src/Parth/ParthAPI.cpp:366-418) is the input stream with the diagonal entries
+// removed; the kernel proves the preconditions while it compacts and raises flags otherwise.
+//
+// What is different: the work is tiled by WHOLE COLUMNS and done column-side.  A tile is the run
+// of columns whose samples start inside one window of K7_TILE samples, so tiles are balanced by
+// bytes, yet no column is split.  Per tile:
+//   A  stage the tile's samples in shared memory with aligned 128-bit loads
+//   B  one thread per column, 256 columns per round: walk the column once (strict order, range,
+//      diagonal position, lower/upper counts, optional mirror probes), block-scan the kept counts,
+//      copy the column without its diagonal into the output staging buffer
+//   E  coalesced stores of Mi; Mp[c] for the tile's columns
+// Per-sample bookkeeping (head bitmaps, dropped bitmaps, per-word prefixes) disappears: about 20
+// instructions per sample instead of ~100, which is what moves the kernel from issue-bound to
+// HBM-bound.
+//
+// Output offsets.  SPEC = true assumes every column holds its diagonal: then the number of
+// dropped samples before column c is exactly c, tile offsets are known in closed form
+// (Mp[c] = Ap[c] - c) and the tiles are fully independent -- no chained scan at all.  A column
+// without a diagonal raises BUILD_NODIAG and the host re-runs with SPEC = false, where the tile
+// offset comes from the decoupled look-back chain (resolved by an extra warp while the workers
+// compact).  Both give the reference's result bit for bit (tests/test_gpu_build.py).
+#include "build.cuh"
+
+namespace pb {
+
+constexpr int K7_WORKERS = 256;
+constexpr int K7_THREADS = K7_WORKERS + 32;  // + the look-back warp (idle when SPEC)
+constexpr int K7_TILE = 3584;                // samples per tile window (512 columns of a 7-point grid)
+constexpr int K7_CAP = 4608;                 // staged samples per tile: window + one column of <= 1024
+constexpr int K7_MAXROUNDS = 16;             // <= 4096 columns per tile (runs of empty columns)
+constexpr int K7_LONG = 64;                  // longer columns are walked by a whole warp
+
+// c_t = first column whose samples start at or after t*K7_TILE
+__global__ void build_cols_partition_kernel(const int *__restrict__ Ap, int M, int num_tiles,
+                                            int *__restrict__ tile_c) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t > num_tiles) return;
+  if (t == num_tiles) { tile_c[t] = M; return; }
+  const long long q = (long long)t * K7_TILE;
+  int lo = 0, hi = M;  // first c with Ap[c] >= q
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if ((long long)Ap[mid] < q) lo = mid + 1; else hi = mid;
+  }
+  tile_c[t] = lo;
+}
+
+// position of the first entry >= target in the ascending column [vs, ve); *found = that entry or -1
+__device__ __forceinline__ int col_lower_bound(const int *__restrict__ Ai, const int *s_val, int sbase,
+                                               int q0, int q1, int vs, int ve, int target, int *found) {
+  int lo = vs, hi = ve;
+  if (vs >= q0 && ve <= q1) {
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (s_val[mid - sbase] < target) lo = mid + 1; else hi = mid;
+    }
+    *found = lo < ve ? s_val[lo - sbase] : -1;
+  } else {
+    while (lo < hi) {
+      int mid = (lo + hi) >> 1;
+      if (__ldg(Ai + mid) < target) lo = mid + 1; else hi = mid;
+    }
+    *found = lo < ve ? __ldg(Ai + lo) : -1;
+  }
+  return lo;
+}
+
+template <bool SPEC>
+__global__ void __launch_bounds__(K7_THREADS)
+build_cols_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M, int Q,
+                  const int *__restrict__ tile_c, int num_tiles, int *__restrict__ Mp,
+                  int *__restrict__ Mi, BuildStatus *__restrict__ st,
+                  unsigned long long *__restrict__ desc, int check_mirror) {
+  __shared__ __align__(16) int s_val[K7_CAP + 4];
+  __shared__ __align__(16) int s_out[K7_CAP];
+  __shared__ int s_scan[33];
+  __shared__ int s_long[2 * (K7_CAP / K7_LONG + 2)];
+  __shared__ int s_nlong;
+  __shared__ long long s_base;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool worker = tid < K7_WORKERS;
+  const int tile = blockIdx.x;
+  const bool last = tile == num_tiles - 1;
+  const int c0 = tile_c[tile], c1 = tile_c[tile + 1];
+  int nc = c1 - c0;
+  const int q0 = __ldg(Ap + c0), q1 = __ldg(Ap + c1);
+  int nq = q1 - q0;
+  const int sbase = q0 & ~3;  // staged window starts at an aligned sample
+  unsigned flags = 0;
+  if (nq > K7_CAP || nc > K7_MAXROUNDS * K7_WORKERS) {
+    // a column longer than the slack or a long run of empty columns: another kernel handles it.
+    // Keep the scan chain alive with an empty aggregate.
+    if (tid == 0) atomicOr(&st->flags, BUILD_WIDE);
+    nc = 0;
+    nq = 0;
+  }
+  if (tid == 0) s_nlong = 0;
+
+  // ---- A: aligned 128-bit staging (the few samples in front of q0 are loaded but never used)
+  {
+    const int n4 = (q0 + nq - sbase + 3) >> 2;
+    const int4 *src = reinterpret_cast<const int4 *>(Ai + sbase);
+    const bool aligned = (reinterpret_cast<uintptr_t>(Ai) & 15) == 0;
+    if (aligned) {
+      // the last vector may reach past Q: guard it
+      const int safe4 = (Q - sbase) >> 2;
+      for (int k = tid; k < n4; k += K7_THREADS) {
+        if (k < safe4) reinterpret_cast<int4 *>(s_val)[k] = ld_stream4(src + k);
+        else
+          for (int u = 0; u < 4; u++) {
+            const int j = sbase + 4 * k + u;
+            s_val[4 * k + u] = j < Q ? ld_stream(Ai + j) : 0;
+          }
+      }
+    } else {
+      for (int j = tid; j < q0 + nq - sbase; j += K7_THREADS) s_val[j] = sbase + j < Q ? ld_stream(Ai + sbase + j) : 0;
+    }
+  }
+  __syncthreads();
+
+  long long diff = 0;  // (upper - lower) entries of this thread's columns
+  int running = 0;     // kept samples of the previous rounds
+  // ---- B: column rounds
+  const int rounds = (nc + K7_WORKERS - 1) / K7_WORKERS;
+  for (int rd = 0; rd < rounds; rd++) {
+    int kept = 0, vs = 0, ve = 0, dpos = -1, c = -1;
+    bool is_long = false;
+    if (worker) {
+      const int lc = rd * K7_WORKERS + tid;
+      if (lc < nc) {
+        c = c0 + lc;
+        vs = __ldg(Ap + c);
+        ve = __ldg(Ap + c + 1);
+        if (ve < vs) { flags |= BUILD_RANGE; ve = vs; }
+        is_long = ve - vs > K7_LONG;
+        if (!is_long) {
+          int prev = -1, low = 0;
+          for (int p = vs; p < ve; p++) {
+            const int r = s_val[p - sbase];
+            if (r <= prev) flags |= (r < 0) ? BUILD_RANGE : (r == prev ? BUILD_DUP : BUILD_UNSORTED);
+            if (r == c) dpos = p;
+            low += r < c;
+            prev = r;
+          }
+          if (prev >= M) flags |= BUILD_RANGE;
+          const int has = dpos >= 0;
+          kept = (ve - vs) - has;
+          diff += (ve - vs - has - low) - low;
+          if (SPEC && !has) flags |= BUILD_NODIAG;
+          if (check_mirror && !(flags & (BUILD_RANGE | BUILD_UNSORTED))) {
+            // every kept upper entry (c, r), r > c, must have its mirror (r, c)
+            for (int p = vs + low + has; p < ve; p++) {
+              const int r = s_val[p - sbase];
+              int found;
+              col_lower_bound(Ai, s_val, sbase, q0, q0 + nq, __ldg(Ap + r), __ldg(Ap + r + 1), c, &found);
+              if (found != c) flags |= BUILD_ASYM;
+            }
+          }
+        } else {
+          const int k = atomicAdd(&s_nlong, 1);
+          s_long[2 * k] = lc;
+          s_long[2 * k + 1] = 0;
+        }
+      }
+    }
+    __syncthreads();
+    // long columns of this round: one warp each; results come back through s_long
+    const int nlong = s_nlong;
+    if (nlong > 0) {
+      if (worker) {
+        for (int li = warp; li < nlong; li += K7_WORKERS / 32) {
+          const int lcc = s_long[2 * li];
+          const int cc = c0 + lcc;
+          const int a = __ldg(Ap + cc), b = __ldg(Ap + cc + 1);
+          int dp = -1, low = 0;
+          unsigned f = 0;
+          for (int p0 = a; p0 < b; p0 += 32) {
+            const int p = p0 + lane;
+            const int r = p < b ? s_val[p - sbase] : 0x7fffffff;
+            int prev = __shfl_up_sync(0xffffffffu, r, 1);
+            if (lane == 0) prev = p0 > a ? s_val[p0 - 1 - sbase] : -1;
+            if (p < b) {
+              if (r <= prev) f |= (r < 0) ? BUILD_RANGE : (r == prev ? BUILD_DUP : BUILD_UNSORTED);
+              if (r >= M) f |= BUILD_RANGE;
+              if (r == cc) dp = p;
+              low += r < cc;
+            }
+          }
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            low += __shfl_xor_sync(0xffffffffu, low, o);
+            dp = max(dp, __shfl_xor_sync(0xffffffffu, dp, o));
+            f |= __shfl_xor_sync(0xffffffffu, f, o);
+          }
+          const int has = dp >= 0;
+          if (check_mirror && !(f & (BUILD_RANGE | BUILD_UNSORTED))) {
+            for (int p = a + low + has + lane; p < b; p += 32) {
+              const int r = s_val[p - sbase];
+              int found;
+              col_lower_bound(Ai, s_val, sbase, q0, q0 + nq, __ldg(Ap + r), __ldg(Ap + r + 1), cc, &found);
+              if (found != cc) f |= BUILD_ASYM;
+            }
+          }
+          if (SPEC && !has) f |= BUILD_NODIAG;
+          flags |= f;
+          if (lane == 0) {
+            diff += (b - a - has - low) - low;
+            s_long[2 * li + 1] = dp;
+          }
+        }
+      }
+      __syncthreads();
+      if (worker && is_long) {
+        // fetch this column's diagonal position back
+        const int lc = rd * K7_WORKERS + tid;
+        for (int li = 0; li < nlong; li++)
+          if (s_long[2 * li] == lc) dpos = s_long[2 * li + 1];
+        kept = (ve - vs) - (dpos >= 0);
+      }
+      __syncthreads();
+      if (tid == 0) s_nlong = 0;
+    }
+    // offsets of this round's columns (the extra warp contributes zero)
+    int total;
+    int excl = 0;
+    {
+      // block_excl_scan over K7_THREADS threads: 9 warps
+      const int inc = warp_incl_scan(kept, lane);
+      if (lane == 31) s_scan[warp] = inc;
+      __syncthreads();
+      if (warp == 0) {
+        const int w = lane < K7_THREADS / 32 ? s_scan[lane] : 0;
+        const int wi = warp_incl_scan(w, lane);
+        if (lane < K7_THREADS / 32) s_scan[lane] = wi - w;
+        if (lane == K7_THREADS / 32 - 1) s_scan[32] = wi;
+      }
+      __syncthreads();
+      excl = s_scan[warp] + inc - kept;
+      total = s_scan[32];
+    }
+    if (worker && c >= 0) {
+      const int off = running + excl;
+      // Mp: final value when the offset is known in closed form, tile-relative otherwise (fixed in E)
+      if (SPEC) Mp[c] = vs - c; else Mp[c] = off;
+      if (!is_long) {
+        int o = off;
+        for (int p = vs; p < ve; p++)
+          if (p != dpos) s_out[o++] = s_val[p - sbase];
+      }
+    }
+    if (nlong > 0) {
+      // long columns are copied by their warp; offsets travel through s_long
+      if (worker && is_long) {
+        const int lc = rd * K7_WORKERS + tid;
+        for (int li = 0; li < nlong; li++)
+          if (s_long[2 * li] == lc) s_long[2 * li + 1] = running + excl;
+      }
+      __syncthreads();
+      if (worker) {
+        for (int li = warp; li < nlong; li += K7_WORKERS / 32) {
+          const int cc = c0 + s_long[2 * li];
+          const int off = s_long[2 * li + 1];
+          const int a = __ldg(Ap + cc), b = __ldg(Ap + cc + 1);
+          // diagonal position again (binary search in the staged, proven-ascending column)
+          int found;
+          const int dp = col_lower_bound(Ai, s_val, sbase, q0, q0 + nq, a, b, cc, &found);
+          const int dd = found == cc ? dp : -1;
+          for (int p = a + lane; p < b; p += 32)
+            if (p != dd) s_out[off + (p - a) - (dd >= 0 && p > dd)] = s_val[p - sbase];
+        }
+      }
+    }
+    running += total;
+    __syncthreads();  // s_scan / s_long are reused by the next round
+  }
+  if (flags) atomicOr(&st->flags, flags);
+  if (check_mirror) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
+    if (lane == 0 && diff) atomicAdd(&st->diff_sum, (unsigned long long)diff);
+  }
+
+  // ---- tile offset
+  const int total = running;
+  long long base;
+  if (SPEC) {
+    base = (long long)q0 - c0;
+    if (last && tid == 0) st->nnz_out = Q - M;
+  } else {
+    if (!worker) {
+      const long long b = tile_lookback(desc, tile, (long long)total);
+      if (lane == 0) {
+        s_base = b;
+        if (last) st->nnz_out = (int)(b + total);
+      }
+    }
+    __syncthreads();
+    base = s_base;
+  }
+  if (!SPEC) __syncthreads();
+
+  // ---- E
+  for (int i = tid; i < total; i += K7_THREADS) st_stream(Mi + base + i, s_out[i]);
+  if (!SPEC) {
+    // each worker fixes the tile-relative offsets it wrote itself
+    for (int lc = tid; worker && lc < nc; lc += K7_WORKERS) Mp[c0 + lc] += (int)base;
+  }
+  if (last && tid == 0) Mp[M] = (int)(base + total);
+}
+
+int build_cols_tiles(int Q) { return (Q + K7_TILE - 1) / K7_TILE; }
+
+int build_cols_launch(const BuildArgs &a, bool spec, cudaStream_t s) {
+  const int num_tiles = build_cols_tiles(a.Q);
+  PB_CUDA(cudaMemsetAsync(a.status, 0, sizeof(BuildStatus), s));
+  if (num_tiles == 0) {
+    PB_CUDA(cudaMemsetAsync(a.Mp, 0, sizeof(int) * ((size_t)a.M + 1), s));
+    return 0;
+  }
+  if (!spec) PB_CUDA(cudaMemsetAsync(a.desc, 0, sizeof(unsigned long long) * (size_t)num_tiles, s));
+  build_cols_partition_kernel<<<(num_tiles + 256) / 256, 256, 0, s>>>(a.Ap, a.M, num_tiles, a.tile_c);
+  if (a.ev_a) cudaEventRecord(a.ev_a, s);
+  if (spec)
+    build_cols_kernel<true><<<num_tiles, K7_THREADS, 0, s>>>(a.Ap, a.Ai, a.M, a.Q, a.tile_c, num_tiles, a.Mp, a.Mi,
+                                                           a.status, a.desc, a.check_mirror);
+  else
+    build_cols_kernel<false><<<num_tiles, K7_THREADS, 0, s>>>(a.Ap, a.Ai, a.M, a.Q, a.tile_c, num_tiles, a.Mp, a.Mi,
+                                                            a.status, a.desc, a.check_mirror);
+  if (a.ev_b) cudaEventRecord(a.ev_b, s);
+  PB_CUDA(cudaGetLastError());
+  return 2;
+}
+
+}  // namespace pb

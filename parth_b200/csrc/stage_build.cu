@@ -1,5 +1,7 @@
 // parth_b200/csrc/stage_build.cu -- host driver of stage (a): picks the filter path, checks its
 // proof flags, falls back to the general kernels (graph_build.cu).
+#include <algorithm>
+
 #include "build.cuh"
 #include "scan.cuh"
 #include "stages.cuh"
@@ -42,19 +44,41 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
 
   BuildStatus st{};
   a.ev_a = h.ev2; a.ev_b = h.ev3;
-  h.stats.kernels_launched += build_filter_launch(a, s);
   static_assert(sizeof(BuildStatus) % sizeof(int) == 0, "BuildStatus is read back as ints");
-  read_ints(h, reinterpret_cast<const int *>(h.bstatus.p), reinterpret_cast<int *>(&st),
-            sizeof(BuildStatus) / sizeof(int));
-  h.stats.build_kernel_ms = 0;
-  if (tiles > 0) {
-    float t = 0;
-    cudaEventElapsedTime(&t, h.ev2, h.ev3);
-    h.stats.build_kernel_ms = t;
+  auto read_status = [&]() {
+    read_ints(h, reinterpret_cast<const int *>(h.bstatus.p), reinterpret_cast<int *>(&st),
+              sizeof(BuildStatus) / sizeof(int));
+  };
+  bool diff_ok = true;
+  if (dim == 1) {
+    // column-aligned kernel; fall through its variants only when a flag asks for it, and remember
+    // the variant that worked so that steady-state updates launch it directly
+    const int tiles7 = build_cols_tiles(Q);
+    h.tile_c.reserve((size_t)std::max(tiles, tiles7) + 2, s);
+    h.desc.reserve((size_t)std::max(tiles, tiles7) + 1, s);
+    a.tile_c = h.tile_c.p; a.desc = h.desc.p;
+    for (;;) {
+      if (h.build_mode <= 1) {
+        h.stats.kernels_launched += build_cols_launch(a, h.build_mode == 0, s);
+        read_status();
+        if (h.build_mode == 0 && (st.flags & BUILD_NODIAG) && !(st.flags & ~(BUILD_NODIAG | BUILD_WIDE))) { h.build_mode = 1; continue; }
+        if ((st.flags & BUILD_WIDE) && !(st.flags & ~(BUILD_NODIAG | BUILD_WIDE))) { h.build_mode = 2; continue; }
+        diff_ok = st.diff_sum == 0;
+      } else {
+        h.stats.kernels_launched += build_filter_launch(a, s);
+        read_status();
+        diff_ok = st.diff_mod == 0;
+      }
+      break;
+    }
+  } else {
+    h.stats.kernels_launched += build_filter_launch(a, s);
+    read_status();
+    diff_ok = st.diff_mod == 0;
   }
   if (st.flags & BUILD_RANGE)
     throw StatusError(PARTH_B200_ERR_INPUT, "set_matrix: row index out of range");
-  const bool proven = st.flags == 0 && (h.assume_symmetric || st.diff_mod == 0);
+  const bool proven = st.flags == 0 && (h.assume_symmetric || diff_ok);
   if (proven) {
     h.nnzM = st.nnz_out;
     h.stats.build_path = 1;
