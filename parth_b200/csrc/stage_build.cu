@@ -76,6 +76,12 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
     read_status();
     diff_ok = st.diff_mod == 0;
   }
+  h.stats.build_kernel_ms = 0;
+  if (Q > 0) {  // the filter kernel of the last launch alone (events recorded around it)
+    float t = 0;
+    cudaEventElapsedTime(&t, h.ev2, h.ev3);
+    h.stats.build_kernel_ms = t;
+  }
   if (st.flags & BUILD_RANGE)
     throw StatusError(PARTH_B200_ERR_INPUT, "set_matrix: row index out of range");
   const bool proven = st.flags == 0 && (h.assume_symmetric || diff_ok);
