@@ -30,6 +30,9 @@ int build_filter_tiles(int M, int Q);
 // graph_build_cols.cu (dim == 1): spec = closed-form offsets (every column holds its diagonal)
 int build_cols_tiles(int Q);
 int build_cols_launch(const BuildArgs &a, bool spec, cudaStream_t s);
+// graph_build_pipe.cu (dim == 1, aligned arrays): persistent bulk-copy pipeline, closed-form offsets
+int build_pipe_supported(const BuildArgs &a);
+int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s);
 int build_filter_launch(const BuildArgs &a, cudaStream_t s);
 int build_sample_prefix_launch(const int *Ap, int M, int dim, int *ns_tmp, int *V,
                                unsigned long long *scan_ws, cudaStream_t s);

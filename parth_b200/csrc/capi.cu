@@ -53,6 +53,7 @@ int parth_b200_create(parth_b200 **out, int device) {
     if (device < 0) PB_CUDA(cudaGetDevice(&device));
     h->device = device;
     PB_CUDA(cudaSetDevice(device));
+    PB_CUDA(cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device));
     PB_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     PB_CUDA(cudaEventCreate(&h->ev0));
     PB_CUDA(cudaEventCreate(&h->ev1));

@@ -1,0 +1,355 @@
+// parth_b200/csrc/graph_build_pipe.cu -- stage (a), dim == 1: persistent bulk-copy pipeline.
+//
+// Same mathematics as build_cols_spec_kernel (graph_build_cols.cu): when every column of a
+// structurally symmetric, column-sorted matrix holds its diagonal, the mesh graph of
+// ParthAPI::computeMeshFromMatrix (reference src/Parth/ParthAPI.cpp:366-418) is the input with
+// one sample (the diagonal) removed per column, so Mp[c] = Ap[c] - c in closed form and tiles are
+// independent.  What changes is how the bytes move:
+//   * tiles are fixed runs of TC columns (TC chosen on the host from the average column length);
+//   * a persistent CTA (2 per SM) walks its tiles with a two-stage ring: a producer warp issues
+//     cp.async.bulk (TMA engine, SASS UBLKCP) copies of the NEXT tile's Ai window and Ap slice
+//     straight into shared memory and signals an mbarrier, while 512 consumer threads work on the
+//     current tile -- DRAM latency is overlapped instead of exposed per tile, and no register or
+//     LSU instruction is spent on staging;
+//   * the compacted tile leaves through one bulk shared->global store (plus <= 6 scalar stores for
+//     the unaligned head and tail), again off the LSU path.
+// Proof obligations are unchanged and raise the same flags: strict order, range, one diagonal per
+// column (BUILD_NODIAG -> the chained-scan kernel takes over), structural symmetry by mirror
+// probes plus the global upper/lower count, over-long tiles (BUILD_WIDE -> sample-tiled kernel).
+#include "build.cuh"
+
+namespace pb {
+
+constexpr int K9_CONSUMERS = 512;
+constexpr int K9_THREADS = K9_CONSUMERS + 32;  // + producer warp
+constexpr int K9_TILE = 3584;                  // target samples per tile
+constexpr int K9_CAP = 4608;                   // staged samples per tile
+constexpr int K9_TCMAX = 1024;                 // columns per tile, upper bound
+constexpr int K9_REG = 8;
+constexpr int K9_LONG = 64;
+constexpr int K9_STAGES = 2;
+
+struct K9Stage {
+  int val[K9_CAP + 8];  // the 16-byte granular copy may fetch up to 3 samples on either side
+  int out[K9_CAP + 8];
+  int ap[K9_TCMAX + 8];
+};
+struct K9Smem {
+  K9Stage st[K9_STAGES];
+  unsigned long long full[K9_STAGES], empty[K9_STAGES];
+  int par[K9_STAGES][4];  // q0, q1, wide
+  int longs[K9_CAP / K9_LONG + 2];
+  int nlong;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "K9_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra K9_DONE;\n"
+      "bra K9_WAIT;\n"
+      "K9_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(K9_CONSUMERS) : "memory"); }
+
+// is c in the ascending column [a, b)?  first the slot a symmetric stencil predicts, then a search
+__device__ __forceinline__ bool k9_has_mirror(const int *__restrict__ Ai, const int *val, int sbase, int q0, int q1,
+                                              int a, int b, int idx, int len, int c) {
+  const bool in_tile = a >= q0 && b <= q1;
+  const int g = a + len - 1 - idx;
+  if (g >= a && g < b) {
+    const int v = in_tile ? val[g - sbase] : __ldg(Ai + g);
+    if (v == c) return true;
+  }
+  int lo = a, hi = b;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    const int v = in_tile ? val[mid - sbase] : __ldg(Ai + mid);
+    if (v < c) lo = mid + 1; else hi = mid;
+  }
+  if (lo >= b) return false;
+  return (in_tile ? val[lo - sbase] : __ldg(Ai + lo)) == c;
+}
+
+__global__ void __launch_bounds__(K9_THREADS, 2)
+build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M, int Q, int TC, int num_tiles,
+                  int *__restrict__ Mp, int *__restrict__ Mi, BuildStatus *__restrict__ st, int check_mirror) {
+  extern __shared__ __align__(128) unsigned char k9_raw[];
+  K9Smem &S = *reinterpret_cast<K9Smem *>(k9_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool producer = tid >= K9_CONSUMERS;
+
+  if (tid == 0) {
+    for (int s = 0; s < K9_STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    S.nlong = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (producer) {
+    if (lane != 0) return;
+    int k = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, k++) {
+      const int s = k & 1;
+      const int c0 = t * TC, c1 = min(M, c0 + TC), nc = c1 - c0;
+      const int q0 = __ldg(Ap + c0), q1 = __ldg(Ap + c1);
+      const int nq = q1 - q0;
+      if (k >= K9_STAGES) mbar_wait(&S.empty[s], ((k / K9_STAGES) - 1) & 1);
+      const bool wide = nq < 0 || nq > K9_CAP;
+      S.par[s][0] = q0; S.par[s][1] = q1; S.par[s][2] = wide;
+      unsigned bytes_ai = 0, bytes_ap = 0;
+      const int sbase = q0 & ~3;
+      if (!wide) {
+        const int n4 = (q1 - sbase + 3) >> 2, safe4 = (Q - sbase) >> 2;
+        bytes_ai = (unsigned)(n4 < safe4 ? n4 : safe4) * 16u;
+        if (nq == 0) bytes_ai = 0;
+        const int a4 = (nc + 1 + 3) >> 2, asafe4 = (M + 1 - c0) >> 2;
+        bytes_ap = (unsigned)(a4 < asafe4 ? a4 : asafe4) * 16u;
+      }
+      mbar_expect_tx(&S.full[s], bytes_ai + bytes_ap);
+      if (bytes_ai) bulk_g2s(S.st[s].val, Ai + sbase, bytes_ai, &S.full[s]);
+      if (bytes_ap) bulk_g2s(S.st[s].ap, Ap + c0, bytes_ap, &S.full[s]);
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumers
+  unsigned flags = 0;
+  long long diff = 0;
+  int k = 0;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, k++) {
+    const int s = k & 1;
+    K9Stage &B = S.st[s];
+    if (tid == 0) bulk_wait_read1();  // the store that last used out[s] has drained its smem reads
+    mbar_wait(&S.full[s], (k / K9_STAGES) & 1);
+    const int c0 = t * TC, c1 = min(M, c0 + TC), nc = c1 - c0;
+    const int q0 = S.par[s][0], q1 = S.par[s][1];
+    const bool wide = S.par[s][2] != 0;
+    const int nq = q1 - q0;
+    const int sbase = q0 & ~3;
+    if (!wide) {
+      // elements the 16-byte granular bulk copies could not fetch without leaving the arrays
+      const int got = (min((q1 - sbase + 3) >> 2, (Q - sbase) >> 2)) << 2;
+      for (int j = got + tid; j < q1 - sbase; j += K9_CONSUMERS) B.val[j] = ld_stream(Ai + sbase + j);
+      const int gota = (min((nc + 1 + 3) >> 2, (M + 1 - c0) >> 2)) << 2;
+      for (int j = gota + tid; j < nc + 1; j += K9_CONSUMERS) B.ap[j] = __ldg(Ap + c0 + j);
+    }
+    consumer_sync();
+    const long long base = (long long)q0 - c0;  // Mp[c0]
+    const int mis = (int)(base & 3);              // out[] is laid out with the alignment of Mi + base
+    int total = 0;
+    if (wide) {
+      if (tid == 0) atomicOr(&st->flags, BUILD_WIDE);
+    } else {
+      total = nq - nc;
+      for (int lc = tid; lc < nc; lc += K9_CONSUMERS) {
+        const int c = c0 + lc;
+        const int vs = B.ap[lc], ve = B.ap[lc + 1];
+        const int len = ve - vs;
+        Mp[c] = vs - c;
+        if (len <= 0) { flags |= len < 0 ? BUILD_RANGE : BUILD_NODIAG; continue; }
+        const int o0 = (vs - q0) - lc;
+        if (o0 < 0 || vs < q0 || ve > q1) { flags |= BUILD_NODIAG; continue; }
+        const int *sp = B.val + (vs - sbase);
+        int *op = B.out + mis + o0;
+        if (len <= K9_REG) {
+          int r[K9_REG];
+#pragma unroll
+          for (int i = 0; i < K9_REG; i++) r[i] = i < len ? sp[i] : 0x7fffffff;
+          int di = K9_REG, low = 0, lastv = 0;
+          bool bad = r[0] < 0;
+#pragma unroll
+          for (int i = 0; i < K9_REG; i++) {
+            if (i + 1 < K9_REG) bad |= (i + 1 < len) & (r[i] >= r[i + 1]);
+            if (r[i] == c) di = i;
+            low += r[i] < c;
+            if (i == len - 1) lastv = r[i];
+          }
+          if (bad) {
+            int prev = -1;
+            for (int i = 0; i < len; i++) {
+              if (sp[i] <= prev) flags |= sp[i] < 0 ? BUILD_RANGE : (sp[i] == prev ? BUILD_DUP : BUILD_UNSORTED);
+              prev = sp[i];
+            }
+          }
+          if (lastv >= M) flags |= BUILD_RANGE;
+          const int has = di < K9_REG;
+          if (!has) flags |= BUILD_NODIAG;
+          diff += (len - has - low) - low;
+          // drop the diagonal by shifting the registers, then store the first len-1 (or len) slots
+#pragma unroll
+          for (int i = 0; i < K9_REG; i++) {
+            const int v = (i >= di && i + 1 < K9_REG) ? r[i + 1] : r[i];
+            if (i < len - has) op[i] = v;
+          }
+          if (check_mirror && !bad && lastv < M) {
+            for (int i = low + has; i < len; i += 4) {
+              int a[4], b[4];
+#pragma unroll
+              for (int u = 0; u < 4; u++) {
+                const bool v = i + u < len;
+                const int rr = v ? sp[i + u] : 0;
+                a[u] = v ? __ldg(Ap + rr) : 0;
+                b[u] = v ? __ldg(Ap + rr + 1) : 0;
+              }
+#pragma unroll
+              for (int u = 0; u < 4; u++)
+                if (i + u < len && !k9_has_mirror(Ai, B.val, sbase, q0, q1, a[u], b[u], i + u, len, c)) flags |= BUILD_ASYM;
+            }
+          }
+        } else if (len <= K9_LONG) {
+          int prev = -1, low = 0, dpos = -1;
+          for (int i = 0; i < len; i++) {
+            const int r = sp[i];
+            if (r <= prev) flags |= (r < 0) ? BUILD_RANGE : (r == prev ? BUILD_DUP : BUILD_UNSORTED);
+            if (r == c) dpos = i;
+            low += r < c;
+            prev = r;
+          }
+          if (prev >= M) flags |= BUILD_RANGE;
+          if (dpos < 0) flags |= BUILD_NODIAG;
+          const int has = dpos >= 0;
+          diff += (len - has - low) - low;
+          for (int i = 0; i < len; i++)
+            if (i != dpos) op[i - (has && i > dpos)] = sp[i];
+          if (check_mirror && !(flags & (BUILD_RANGE | BUILD_UNSORTED)))
+            for (int i = low + has; i < len; i++) {
+              const int r = sp[i];
+              if (!k9_has_mirror(Ai, B.val, sbase, q0, q1, __ldg(Ap + r), __ldg(Ap + r + 1), i, len, c)) flags |= BUILD_ASYM;
+            }
+        } else {
+          S.longs[atomicAdd(&S.nlong, 1)] = lc;
+        }
+      }
+    }
+    fence_proxy_async();
+    consumer_sync();
+    const int nlong = S.nlong;
+    if (nlong > 0) {
+      for (int li = warp; li < nlong; li += K9_CONSUMERS / 32) {
+        const int lc = S.longs[li];
+        const int c = c0 + lc;
+        const int vs = B.ap[lc], ve = B.ap[lc + 1], len = ve - vs;
+        const int o0 = (vs - q0) - lc;
+        if (o0 < 0 || vs < q0 || ve > q1) { flags |= BUILD_NODIAG; continue; }
+        const int *sp = B.val + (vs - sbase);
+        int *op = B.out + mis + o0;
+        int dp = -1, low = 0;
+        unsigned f = 0;
+        for (int i0 = 0; i0 < len; i0 += 32) {
+          const int i = i0 + lane;
+          const int r = i < len ? sp[i] : 0x7fffffff;
+          int prev = __shfl_up_sync(0xffffffffu, r, 1);
+          if (lane == 0) prev = i0 > 0 ? sp[i0 - 1] : -1;
+          if (i < len) {
+            if (r <= prev) f |= (r < 0) ? BUILD_RANGE : (r == prev ? BUILD_DUP : BUILD_UNSORTED);
+            if (r >= M) f |= BUILD_RANGE;
+            if (r == c) dp = i;
+            low += r < c;
+          }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          low += __shfl_xor_sync(0xffffffffu, low, o);
+          dp = max(dp, __shfl_xor_sync(0xffffffffu, dp, o));
+          f |= __shfl_xor_sync(0xffffffffu, f, o);
+        }
+        const int has = dp >= 0;
+        if (!has) f |= BUILD_NODIAG;
+        for (int i = lane; i < len; i += 32)
+          if (i != dp) op[i - (has && i > dp)] = sp[i];
+        if (check_mirror && !(f & (BUILD_RANGE | BUILD_UNSORTED)))
+          for (int i = low + has + lane; i < len; i += 32) {
+            const int r = sp[i];
+            if (!k9_has_mirror(Ai, B.val, sbase, q0, q1, __ldg(Ap + r), __ldg(Ap + r + 1), i, len, c)) f |= BUILD_ASYM;
+          }
+        flags |= f;
+        if (lane == 0) diff += (len - has - low) - low;
+      }
+      fence_proxy_async();
+      consumer_sync();
+      if (tid == 0) S.nlong = 0;
+    }
+    // ---- the staged input is free again; the compacted tile leaves through the bulk-store path
+    if (tid == 0) mbar_arrive(&S.empty[s]);
+    if (total > 0) {
+      int *dst = Mi + base;
+      const int head = min((4 - mis) & 3, total);
+      const int n16 = (total - head) >> 2;
+      const int tail0 = head + 4 * n16;
+      if (tid == 0 && n16 > 0) bulk_s2g(dst + head, B.out + mis + head, (unsigned)n16 * 16u);
+      if (tid >= 32 && tid < 32 + head) st_stream(dst + (tid - 32), B.out[mis + tid - 32]);
+      if (tid >= 64 && tid < 64 + (total - tail0)) st_stream(dst + tail0 + (tid - 64), B.out[mis + tail0 + tid - 64]);
+    }
+    if (tid == 0) bulk_commit();  // one group per tile, even when empty: wait_group counts groups
+  }
+  if (tid == 0) {
+    bulk_wait_all();
+    if (blockIdx.x == (num_tiles - 1) % gridDim.x) {
+      Mp[M] = Q - M;
+      st->nnz_out = Q - M;
+    }
+  }
+  if (flags) atomicOr(&st->flags, flags);
+  if (check_mirror) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) diff += __shfl_xor_sync(0xffffffffu, diff, o);
+    if (lane == 0 && diff) atomicAdd(&st->diff_sum, (unsigned long long)diff);
+  }
+}
+
+int build_pipe_supported(const BuildArgs &a) {
+  // bulk copies need 16-byte aligned sources / destinations
+  return a.dim == 1 && ((reinterpret_cast<uintptr_t>(a.Ai) | reinterpret_cast<uintptr_t>(a.Ap) |
+                         reinterpret_cast<uintptr_t>(a.Mi)) & 15) == 0 && a.M > 0 && a.Q > 0;
+}
+
+int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s) {
+  PB_CUDA(cudaFuncSetAttribute(build_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K9Smem)));
+  // columns per tile from the average column length, a multiple of 32 so that Ap slices stay aligned
+  long long tc = (long long)K9_TILE * a.M / (a.Q > 0 ? a.Q : 1);
+  tc = (tc / 32) * 32;
+  if (tc < 32) tc = 32;
+  if (tc > K9_TCMAX) tc = K9_TCMAX;
+  const int TC = (int)tc;
+  const int num_tiles = (a.M + TC - 1) / TC;
+  PB_CUDA(cudaMemsetAsync(a.status, 0, sizeof(BuildStatus), s));
+  const int grid = num_tiles < 2 * num_sms ? num_tiles : 2 * num_sms;
+  if (a.ev_a) cudaEventRecord(a.ev_a, s);
+  build_pipe_kernel<<<grid, K9_THREADS, sizeof(K9Smem), s>>>(a.Ap, a.Ai, a.M, a.Q, TC, num_tiles, a.Mp, a.Mi, a.status,
+                                                            a.check_mirror);
+  if (a.ev_b) cudaEventRecord(a.ev_b, s);
+  PB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+}  // namespace pb

@@ -14,7 +14,7 @@
 #include "tree.cuh"
 
 struct parth_b200 {
-  int device = 0;
+  int device = 0, num_sms = pb::kNumSMsB200;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   std::string err;

@@ -59,7 +59,10 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
     a.tile_c = h.tile_c.p; a.desc = h.desc.p;
     for (;;) {
       if (h.build_mode <= 1) {
-        h.stats.kernels_launched += build_cols_launch(a, h.build_mode == 0, s);
+        if (h.build_mode == 0 && build_pipe_supported(a))
+          h.stats.kernels_launched += build_pipe_launch(a, h.num_sms, s);
+        else
+          h.stats.kernels_launched += build_cols_launch(a, h.build_mode == 0, s);
         read_status();
         if (h.build_mode == 0 && (st.flags & BUILD_NODIAG) && !(st.flags & ~(BUILD_NODIAG | BUILD_WIDE))) { h.build_mode = 1; continue; }
         if ((st.flags & BUILD_WIDE) && !(st.flags & ~(BUILD_NODIAG | BUILD_WIDE))) { h.build_mode = 2; continue; }
