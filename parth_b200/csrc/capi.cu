@@ -91,6 +91,8 @@ int parth_b200_clear(parth_b200 *h) {
   h->M_n_prev = h->nnz_prev = 0;
   h->map_len = 0;
   h->tree_init = false;
+  h->cur_sym_proven = h->prev_sym_proven = false;
+  h->diff_cached = false;
   h->num_levels = h->num_nodes = h->tree_M = 0;
   h->meta.clear();
   h->node_ptr.clear();
@@ -196,6 +198,8 @@ int parth_b200_set_mesh_dev(parth_b200 *h, int n, const int *dMp, const int *dMi
   h->nnzM = nnz;
   h->mesh_owned = false;
   h->map_len = 0;
+  h->cur_sym_proven = false;
+  h->diff_cached = false;
   PB_API_END
 }
 
@@ -216,6 +220,8 @@ int parth_b200_set_mesh(parth_b200 *h, int n, const int *Mp, const int *Mi) {
   h->nnzM = nnz;
   h->mesh_owned = true;
   h->map_len = 0;
+  h->cur_sym_proven = false;
+  h->diff_cached = false;
   PB_API_END
 }
 

@@ -181,6 +181,50 @@ __global__ void emit_row_edges_kernel(const int *__restrict__ rows, int n_rows,
   }
 }
 
+// Incremental symmetry proof (stage a).  The snapshot graph was proven symmetric and has the same
+// vertex set; rows[] are exactly the rows whose adjacency differs.  Then the new graph is
+// symmetric iff, for every changed row j: (1) every entry i of the new row has its mirror j in new
+// row i, and (2) every entry i that the row lost is gone from new row i as well.  (An unchanged row
+// x keeps its old entries, whose mirrors exist in the old graph: they can only be missing now if
+// row y changed and lost x -- which (2) catches from y's side.)  One warp per changed row.
+__device__ __forceinline__ bool row_contains(const int *__restrict__ Mi, int s, int e, int v) {
+  int lo = s, hi = e;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(Mi + mid) < v) lo = mid + 1; else hi = mid;
+  }
+  return lo < e && __ldg(Mi + lo) == v;
+}
+
+__global__ void sym_check_rows_kernel(const int *__restrict__ rows, int n_rows, const int *__restrict__ Mp,
+                                      const int *__restrict__ Mi, const int *__restrict__ Mp_prev,
+                                      const int *__restrict__ Mi_prev, int *__restrict__ asym) {
+  const int lane = threadIdx.x & 31;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (k >= n_rows) return;
+  const int j = rows[k];
+  const int s = Mp[j], e = Mp[j + 1];
+  bool bad = false;
+  for (int p = s + lane; p < e; p += 32) {
+    const int i = Mi[p];
+    if (!row_contains(Mi, Mp[i], Mp[i + 1], j)) bad = true;
+  }
+  for (int p = Mp_prev[j] + lane; p < Mp_prev[j + 1]; p += 32) {
+    const int i = Mi_prev[p];
+    if (!row_contains(Mi, s, e, i) && row_contains(Mi, Mp[i], Mp[i + 1], j)) bad = true;
+  }
+  if (bad) *asym = 1;
+}
+
+int launch_sym_check_rows(const int *rows, int n_rows, const int *Mp, const int *Mi, const int *Mp_prev,
+                          const int *Mi_prev, int *asym, cudaStream_t s) {
+  if (n_rows <= 0) return 0;
+  const long long threads = (long long)n_rows * 32;
+  sym_check_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rows, n_rows, Mp, Mi, Mp_prev, Mi_prev, asym);
+  PB_CUDA(cudaGetLastError());
+  return 1;
+}
+
 // ------------------------------------------------------------------ host launchers
 int launch_diff_rows(const int *Mp, const int *Mi, const int *Mp_prev, const int *Mi_prev, int M,
                      unsigned *row_bits, DetectCounters *cnt, cudaStream_t s) {

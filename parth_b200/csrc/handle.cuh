@@ -40,6 +40,13 @@ struct parth_b200 {
   int M_n_prev = 0, nnz_prev = 0;
   pb::DevBuf<int> Mp_prev, Mi_prev;
 
+  // ---- symmetry bookkeeping (stage a): a proven-symmetric snapshot lets the next build prove its
+  // graph by checking only the rows that changed; the row diff is then reused by change detection
+  bool cur_sym_proven = false, prev_sym_proven = false;
+  bool diff_cached = false;   // chg_bits / chg_rows describe (current graph vs snapshot)
+  int n_chg_rows = 0;
+  pb::DevBuf<int> chg_bits, chg_pre, chg_rows;
+
   // ---- DOF maps (reference ParthAPI.h:79-84)
   int map_len = 0;  // 0: no map
   pb::DevBuf<int> new_to_old, old_to_new;

@@ -5,6 +5,7 @@
 #include "build.cuh"
 #include "scan.cuh"
 #include "stages.cuh"
+#include "tree.cuh"
 
 namespace pb {
 
@@ -14,6 +15,36 @@ void read_ints(parth_b200 &h, const int *dsrc, int *dst, size_t n) {
   PB_CUDA(cudaStreamSynchronize(h.stream));
   for (size_t i = 0; i < n; i++) dst[i] = h.pin.p[i];
   h.stats.d2h_bytes += (long long)(sizeof(int) * n);
+}
+
+// Row diff of the freshly built graph (Mp_own / Mi_own) against the snapshot, cached for stage (b);
+// returns true when the changed rows prove the new graph symmetric.
+static bool prove_symmetry_from_changed_rows(parth_b200 &h, int M, int nnz_new) {
+  cudaStream_t s = h.stream;
+  (void)nnz_new;
+  const int n_words = (M + 31) / 32;
+  h.chg_bits.reserve((size_t)n_words + 1, s);
+  h.chg_pre.reserve((size_t)n_words + 2, s);
+  h.dcnt.reserve(1, s);
+  h.scan_ws.reserve(scan_ws_words((size_t)std::max(n_words, M) + 1), s);
+  h.stats.kernels_launched += launch_diff_rows(h.Mp_own.p, h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, M,
+                                               reinterpret_cast<unsigned *>(h.chg_bits.p), h.dcnt.p, s);
+  int cnt[4];
+  read_ints(h, reinterpret_cast<const int *>(h.dcnt.p), cnt, 4);
+  h.n_chg_rows = cnt[0];
+  h.diff_cached = true;
+  if (cnt[0] == 0) return true;  // identical to a proven graph
+  h.stats.kernels_launched += exclusive_scan<1>(h.chg_bits.p, h.chg_pre.p, n_words, h.scan_ws.p, s);
+  h.chg_rows.reserve((size_t)cnt[0] + 1, s);
+  h.stats.kernels_launched += launch_list_changed_rows(reinterpret_cast<unsigned *>(h.chg_bits.p), h.chg_pre.p, n_words,
+                                                       M, h.chg_rows.p, s);
+  if ((long long)cnt[0] * 20 > M) return false;  // > 5 % of the rows: the streaming proof is cheaper
+  int *asym = reinterpret_cast<int *>(h.dcnt.p) + 2;  // pad0 of DetectCounters, zeroed by launch_diff_rows
+  h.stats.kernels_launched += launch_sym_check_rows(h.chg_rows.p, cnt[0], h.Mp_own.p, h.Mi_own.p, h.Mp_prev.p,
+                                                    h.Mi_prev.p, asym, s);
+  int bad = 0;
+  read_ints(h, asym, &bad, 1);
+  return bad == 0;
 }
 
 void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, int dim) {
@@ -32,7 +63,15 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
 
   BuildArgs a{};
   a.Ap = dAp; a.Ai = dAi; a.V = h.V.p; a.dim = dim; a.M = M; a.Q = Q;
-  a.check_mirror = h.assume_symmetric ? 0 : 1;
+  // Incremental proof: when the snapshot graph is proven symmetric and has the same vertex set,
+  // symmetry of the new graph follows from the rows that changed (sym_check_rows_kernel), so the
+  // filter kernel skips its mirror probes; the row diff it needs is the one change detection wants
+  // anyway and is cached for it.
+  h.diff_cached = false;
+  h.cur_sym_proven = false;
+  const bool incremental = !h.assume_symmetric && dim == 1 && h.prev_sym_proven && M == h.M_n_prev &&
+                           h.Mp_prev.p && h.Mi_prev.p;
+  a.check_mirror = (h.assume_symmetric || incremental) ? 0 : 1;
   const int tiles = build_filter_tiles(M, Q);
   h.tile_c.reserve((size_t)tiles + 2, s);
   h.desc.reserve((size_t)tiles + 1, s);
@@ -87,10 +126,23 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   }
   if (st.flags & BUILD_RANGE)
     throw StatusError(PARTH_B200_ERR_INPUT, "set_matrix: row index out of range");
-  const bool proven = st.flags == 0 && (h.assume_symmetric || diff_ok);
+  bool proven = st.flags == 0 && (h.assume_symmetric || incremental || diff_ok);
+  if (proven && incremental) {
+    proven = prove_symmetry_from_changed_rows(h, M, st.nnz_out);
+    if (!proven && h.build_mode <= 1) {
+      // too many rows changed (or a mirror is missing): the full proof decides
+      a.check_mirror = 1;
+      if (h.build_mode == 0 && build_pipe_supported(a)) h.stats.kernels_launched += build_pipe_launch(a, h.num_sms, s);
+      else h.stats.kernels_launched += build_cols_launch(a, h.build_mode == 0, s);
+      read_status();
+      proven = st.flags == 0 && st.diff_sum == 0;
+      h.diff_cached = false;
+    }
+  }
   if (proven) {
     h.nnzM = st.nnz_out;
     h.stats.build_path = 1;
+    h.cur_sym_proven = !h.assume_symmetric;
   } else {
     // general path: any triangle, unsorted columns, duplicates
     h.cnt.reserve((size_t)M + 1, s);
@@ -113,6 +165,8 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
     h.stats.kernels_launched += build_general_gather_launch(a, h.ptr.p, h.tmp.p, s);
     h.nnzM = nnzM;
     h.stats.build_path = 2;
+    h.cur_sym_proven = true;  // the general path symmetrises by construction
+    h.diff_cached = false;
   }
   total.stop();
   h.Mp = h.Mp_own.p;

@@ -84,6 +84,8 @@ void stage_import_tree(parth_b200 &h, int M_n, int levels, int nodes, const int 
       PB_CUDA(cudaMemcpyAsync(h.Mi_prev.p, Mi_prev, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, s));
     h.M_n_prev = M_n;
     h.nnz_prev = nnz;
+    h.prev_sym_proven = false;  // caller-provided snapshot: nothing is known about it
+    h.diff_cached = false;
   }
   PB_CUDA(cudaStreamSynchronize(s));
 }
@@ -112,32 +114,43 @@ void stage_detect(parth_b200 &h) {
   StageTimer tm(h, h.ev0, h.ev1);
   h.n_changed = 0;
   const int n_words = (M + 31) / 32;
-  h.w0.reserve((size_t)n_words + 1, s);  // row bitmap
-  h.w1.reserve((size_t)n_words + 2, s);  // popc prefix
   h.dcnt.reserve(1, s);
   h.scan_ws.reserve(scan_ws_words((size_t)std::max(n_words, M) + 1), s);
-  unsigned *bits = reinterpret_cast<unsigned *>(h.w0.p);
-  if (h.map_len > 0)
-    h.stats.kernels_launched += launch_diff_rows_mapped(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, h.new_to_old.p,
-                                                        h.old_to_new.p, M, bits, h.dcnt.p, s);
-  else
-    h.stats.kernels_launched += launch_diff_rows(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt.p, s);
-  int cnt[4];
-  read_ints(h, reinterpret_cast<const int *>(h.dcnt.p), cnt, 4);
-  const int n_rows = cnt[0];
+  int n_rows = 0;
+  const int *rows = nullptr;
+  if (h.diff_cached && h.map_len == 0 && h.Mp == h.Mp_own.p) {
+    // stage (a) already diffed this graph against the snapshot for its symmetry proof
+    n_rows = h.n_chg_rows;
+    rows = h.chg_rows.p;
+  } else {
+    h.w0.reserve((size_t)n_words + 1, s);  // row bitmap
+    h.w1.reserve((size_t)n_words + 2, s);  // popc prefix
+    unsigned *bits = reinterpret_cast<unsigned *>(h.w0.p);
+    if (h.map_len > 0)
+      h.stats.kernels_launched += launch_diff_rows_mapped(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, h.new_to_old.p,
+                                                          h.old_to_new.p, M, bits, h.dcnt.p, s);
+    else
+      h.stats.kernels_launched += launch_diff_rows(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt.p, s);
+    int cnt[4];
+    read_ints(h, reinterpret_cast<const int *>(h.dcnt.p), cnt, 4);
+    n_rows = cnt[0];
+    if (n_rows > 0) {
+      h.stats.kernels_launched += exclusive_scan<1>(h.w0.p, h.w1.p, n_words, h.scan_ws.p, s);
+      h.w2.reserve((size_t)n_rows + 1, s);  // changed rows, ascending
+      h.stats.kernels_launched += launch_list_changed_rows(bits, h.w1.p, n_words, M, h.w2.p, s);
+    }
+    rows = h.w2.p;
+  }
   if (n_rows > 0) {
-    h.stats.kernels_launched += exclusive_scan<1>(h.w0.p, h.w1.p, n_words, h.scan_ws.p, s);
-    h.w2.reserve((size_t)n_rows + 1, s);  // changed rows, ascending
     h.w3.reserve((size_t)n_rows + 2, s);  // per-row edge counts -> offsets
-    h.stats.kernels_launched += launch_list_changed_rows(bits, h.w1.p, n_words, M, h.w2.p, s);
-    h.stats.kernels_launched += launch_count_row_edges(h.w2.p, n_rows, h.Mp, h.Mi, h.d_dof2node.p, h.w3.p, s);
+    h.stats.kernels_launched += launch_count_row_edges(rows, n_rows, h.Mp, h.Mi, h.d_dof2node.p, h.w3.p, s);
     h.w4.reserve((size_t)n_rows + 2, s);
     h.stats.kernels_launched += exclusive_scan<0>(h.w3.p, h.w4.p, n_rows, h.scan_ws.p, s);
     int n_edges = 0;
     read_ints(h, h.w4.p + n_rows, &n_edges, 1);
     if (n_edges > 0) {
       h.d_changed.reserve((size_t)n_edges * 2, s);
-      h.stats.kernels_launched += launch_emit_row_edges(h.w2.p, n_rows, h.Mp, h.Mi, h.d_dof2node.p, h.w4.p,
+      h.stats.kernels_launched += launch_emit_row_edges(rows, n_rows, h.Mp, h.Mi, h.d_dof2node.p, h.w4.p,
                                                         h.d_changed.p, s);
     }
     h.n_changed = n_edges;
@@ -252,6 +265,8 @@ void stage_snapshot(parth_b200 &h) {
     if (h.nnzM > 0)
       PB_CUDA(cudaMemcpyAsync(h.Mi_prev.p, h.Mi, sizeof(int) * (size_t)h.nnzM, cudaMemcpyDeviceToDevice, s));
   }
+  h.prev_sym_proven = h.cur_sym_proven;
+  h.diff_cached = false;
   h.Mp = h.Mp_prev.p;  // the current graph and the snapshot are now the same arrays
   h.Mi = h.Mi_prev.p;
   h.mesh_owned = true;

@@ -25,6 +25,8 @@ int launch_diff_rows(const int *Mp, const int *Mi, const int *Mp_prev, const int
 int launch_diff_rows_mapped(const int *Mp, const int *Mi, const int *Mp_prev, const int *Mi_prev,
                             const int *new_to_old, const int *old_to_new, int M, unsigned *row_bits,
                             DetectCounters *cnt, cudaStream_t s);
+int launch_sym_check_rows(const int *rows, int n_rows, const int *Mp, const int *Mi, const int *Mp_prev,
+                          const int *Mi_prev, int *asym, cudaStream_t s);
 int launch_list_changed_rows(const unsigned *row_bits, const int *word_prefix, int n_words, int M,
                              int *rows, cudaStream_t s);
 int launch_count_row_edges(const int *rows, int n_rows, const int *Mp, const int *Mi,

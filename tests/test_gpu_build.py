@@ -176,3 +176,64 @@ def test_large_grid_properties(gpu_api):
     inner[0] = False
     assert np.all((np.diff(Mi.astype(np.int64), prepend=-1) > 0) | ~inner)
     assert np.array_equal(np.bincount(Mi, minlength=N), np.diff(Mp))
+
+
+def _update_pair(gpu_api, port):
+    from tests import scenario_defs as sd
+    tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 16, 5)))
+    g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 5; g.reorder_type = 1
+    g.setCoarsePolicy(gpu_api.COARSE_REPORT)
+    o = port.CpuParth("port"); o.set_options(reorder_type=1, nd_levels=5)
+    g.import_tree(tree, Mp, Mi); o.import_tree(tree, Mp, Mi)
+    return g, o, Mp, Mi
+
+
+def test_incremental_symmetry_proof_over_consecutive_updates(gpu_api, port):
+    """after one proven build, symmetry of the next graph is proven from the changed rows only
+    (and the row diff is shared with change detection): symmetric updates stay on the filter path,
+    a missing or a misplaced mirror entry is still caught and symmetrised like the reference does"""
+    g, o, Mp, Mi = _update_pair(gpu_api, port)
+    M = len(Mp) - 1
+    rng = np.random.default_rng(5)
+
+    def step(Ap, Ai, expect_path):
+        g.setMatrix(M, Ap, Ai, 1); o.setMatrix(M, Ap, Ai, 1)
+        gm, om = g.mesh(), o.mesh()
+        assert np.array_equal(gm[0], om[0]) and np.array_equal(gm[1], om[1])
+        assert g.stats()["build_path"] == expect_path
+        st, perm = g.computePermutation(1)
+        ost, operm = o.computePermutation(1)
+        assert g.getNumChanges() == o.getNumChanges()
+        assert np.array_equal(g.changed_edges(), o.changed_edges())
+        assert g.getReuse() == o.getReuse()
+
+    cur = (Mp, Mi)
+    N, Ap, Ai = synth.graph_to_matrix(*cur)
+    step(Ap, Ai, 1)                                   # full proof (snapshot came from import_tree)
+    for k in range(3):                                # incremental proofs
+        cur = synth.add_edges(cur[0], cur[1], rng.integers(0, M, size=(4, 2)))
+        N, Ap, Ai = synth.graph_to_matrix(*cur)
+        step(Ap, Ai, 1)
+    step(Ap, Ai, 1)                                   # identical matrix again
+    # drop one strictly-lower entry of the CSC pattern: asymmetric, counts differ
+    col = 700
+    seg = Ai[Ap[col]:Ap[col + 1]]
+    kk = int(np.nonzero(seg > col)[0][0]) + Ap[col]
+    Ai2 = np.delete(Ai, kk); Ap2 = Ap.copy(); Ap2[col + 1:] -= 1
+    step(Ap2, Ai2, 2)
+    step(Ap, Ai, 1)                                   # back to a symmetric pattern
+    # move one entry so that the counts still match but a mirror is missing
+    Ai3 = Ai.copy()
+    col2 = 900
+    seg = Ai3[Ap[col2]:Ap[col2 + 1]]
+    j = int(np.nonzero(seg > col2)[0][-1])
+    new = seg[j] + 3
+    assert new < M and new not in seg
+    seg[j] = new
+    step(Ap, Ai3, 2)
+    # removed edges only (symmetric): stays on the filter path
+    src = np.repeat(np.arange(M), np.diff(cur[0]))
+    pick = rng.choice(len(cur[1]), 10, replace=False)
+    cur2 = synth.remove_edges(cur[0], cur[1], np.stack([src[pick], cur[1][pick]], axis=1))
+    N, Ap4, Ai4 = synth.graph_to_matrix(*cur2)
+    step(Ap4, Ai4, 1)
