@@ -60,7 +60,8 @@ int parth_b200_create(parth_b200 **out, int device) {
     PB_CUDA(cudaEventCreate(&h->ev2));
     PB_CUDA(cudaEventCreate(&h->ev3));
     h->pin.reserve(1 << 16);
-    h->bstatus.reserve(1);
+    for (auto &e : h->tev) PB_CUDA(cudaEventCreate(&e));
+    h->mail.reserve(32);
   } catch (const std::exception &ex) {
     g_create_error = ex.what();
     delete h;
@@ -78,6 +79,7 @@ int parth_b200_destroy(parth_b200 *h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev2) cudaEventDestroy(h->ev2);
   if (h->ev3) cudaEventDestroy(h->ev3);
+  for (auto &e : h->tev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return PARTH_B200_OK;
@@ -169,6 +171,7 @@ int parth_b200_set_matrix_dev(parth_b200 *h, int N, const int *dAp, const int *d
   h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
   h->sim_dim = dim;
   stage_build(*h, N, dAp, dAi, nnz, dim);
+  resolve_timers(*h);
   PB_API_END
 }
 
@@ -186,6 +189,7 @@ int parth_b200_set_matrix(parth_b200 *h, int N, const int *Ap, const int *Ai, in
   h->stats.d2h_bytes = 0;
   h->sim_dim = dim;
   stage_build(*h, N, h->dAp.p, h->dAi.p, nnz, dim);
+  resolve_timers(*h);
   PB_API_END
 }
 
@@ -292,7 +296,7 @@ int parth_b200_compute_permutation_dev(parth_b200 *h, int *dperm, int dim) {
   if (!dperm || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "computePermutation: bad argument");
   h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
   rc = stage_compute_permutation(*h, dperm, dim);
-  PB_CUDA(cudaStreamSynchronize(h->stream));
+  resolve_timers(*h);
   if (rc != PARTH_B200_OK) return rc;
   PB_API_END
 }
@@ -309,7 +313,7 @@ int parth_b200_compute_permutation(parth_b200 *h, int *perm, int dim) {
     PB_CUDA(cudaMemcpyAsync(perm, h->d_out.p, sizeof(int) * n_out, cudaMemcpyDeviceToHost, h->stream));
     h->stats.d2h_bytes += (long long)(sizeof(int) * n_out);
   }
-  PB_CUDA(cudaStreamSynchronize(h->stream));
+  resolve_timers(*h);
   if (rc != PARTH_B200_OK) return rc;
   PB_API_END
 }
@@ -320,7 +324,7 @@ int parth_b200_map_mesh_perm_to_matrix_perm_dev(parth_b200 *h, const int *dmesh_
   if (!dmesh_perm || !dout || n <= 0) throw StatusError(PARTH_B200_ERR_ARG, "mapMeshPermToMatrixPerm: bad argument");
   if (dim == -1) dim = h->sim_dim;
   stage_expand(*h, dmesh_perm, n, dim, dout);
-  PB_CUDA(cudaStreamSynchronize(h->stream));
+  resolve_timers(*h);
   PB_API_END
 }
 
@@ -334,7 +338,7 @@ int parth_b200_map_mesh_perm_to_matrix_perm(parth_b200 *h, const int *mesh_perm,
   PB_CUDA(cudaMemcpyAsync(h->w0.p, mesh_perm, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
   stage_expand(*h, h->w0.p, n, dim, h->d_out.p);
   PB_CUDA(cudaMemcpyAsync(out, h->d_out.p, sizeof(int) * (size_t)n * dim, cudaMemcpyDeviceToHost, h->stream));
-  PB_CUDA(cudaStreamSynchronize(h->stream));
+  resolve_timers(*h);
   h->stats.h2d_bytes = (long long)sizeof(int) * n;
   h->stats.d2h_bytes = (long long)sizeof(int) * n * dim;
   PB_API_END
@@ -399,7 +403,7 @@ int parth_b200_stage_integrate(parth_b200 *h) {
   PB_API_BEGIN
   if (!h->tree_init || h->map_len == 0) throw StatusError(PARTH_B200_ERR_ARG, "stage_integrate: needs a tree and a map");
   stage_integrate(*h);
-  PB_CUDA(cudaStreamSynchronize(h->stream));
+  resolve_timers(*h);
   PB_API_END
 }
 
@@ -407,6 +411,7 @@ int parth_b200_stage_detect(parth_b200 *h, int *nchanged) {
   PB_API_BEGIN
   if (!h->tree_init || !h->Mp) throw StatusError(PARTH_B200_ERR_ARG, "stage_detect: needs a tree and a mesh");
   stage_detect(*h);
+  resolve_timers(*h);
   if (nchanged) *nchanged = h->n_changed;
   PB_API_END
 }
@@ -415,7 +420,7 @@ int parth_b200_stage_permute_fine(parth_b200 *h, const int *nodes, int n) {
   PB_API_BEGIN
   if (!h->tree_init || !h->Mp || (n > 0 && !nodes)) throw StatusError(PARTH_B200_ERR_ARG, "stage_permute_fine: bad argument");
   stage_permute_fine(*h, std::vector<int>(nodes, nodes + n));
-  PB_CUDA(cudaStreamSynchronize(h->stream));
+  resolve_timers(*h);
   PB_API_END
 }
 
@@ -441,6 +446,7 @@ int parth_b200_symbolic(parth_b200 *h, const int *perm, int *parent, int *colcou
   if (!h->Mp || !lnz) throw StatusError(PARTH_B200_ERR_ARG, "symbolic: needs a mesh");
   long long v = 0;
   stage_symbolic(*h, perm, parent, colcount, &v);
+  resolve_timers(*h);
   *lnz = v;
   PB_API_END
 }

@@ -123,7 +123,7 @@ __global__ void diff_rows_mapped_kernel(const int *__restrict__ Mp, const int *_
 
 __global__ void list_changed_rows_kernel(const unsigned *__restrict__ row_bits,
                                          const int *__restrict__ word_prefix, int n_words, int M,
-                                         int *__restrict__ rows) {
+                                         int *__restrict__ rows, int cap) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n_words) return;
   unsigned m = row_bits[w];
@@ -131,7 +131,8 @@ __global__ void list_changed_rows_kernel(const unsigned *__restrict__ row_bits,
   while (m) {
     const int b = __ffs(m) - 1;
     m &= m - 1;
-    rows[o++] = (w << 5) + b;
+    if (o < cap) rows[o] = (w << 5) + b;
+    o++;
   }
 }
 
@@ -156,7 +157,7 @@ __global__ void count_row_edges_kernel(const int *__restrict__ rows, int n_rows,
 __global__ void emit_row_edges_kernel(const int *__restrict__ rows, int n_rows,
                                       const int *__restrict__ Mp, const int *__restrict__ Mi,
                                       const int *__restrict__ dof2node,
-                                      const int *__restrict__ offsets, int *__restrict__ edges) {
+                                      const int *__restrict__ offsets, int *__restrict__ edges, int cap) {
   const int lane = threadIdx.x & 31;
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (k >= n_rows) return;
@@ -174,8 +175,10 @@ __global__ void emit_row_edges_kernel(const int *__restrict__ rows, int n_rows,
     const unsigned m = __ballot_sync(0xffffffffu, hit);
     if (hit) {
       const int at = o + __popc(m & ((1u << lane) - 1u));
-      edges[2 * at] = i;
-      edges[2 * at + 1] = nb;
+      if (at < cap) {
+        edges[2 * at] = i;
+        edges[2 * at + 1] = nb;
+      }
     }
     o += __popc(m);
   }
@@ -196,31 +199,35 @@ __device__ __forceinline__ bool row_contains(const int *__restrict__ Mi, int s, 
   return lo < e && __ldg(Mi + lo) == v;
 }
 
-__global__ void sym_check_rows_kernel(const int *__restrict__ rows, int n_rows, const int *__restrict__ Mp,
-                                      const int *__restrict__ Mi, const int *__restrict__ Mp_prev,
-                                      const int *__restrict__ Mi_prev, int *__restrict__ asym) {
+// n_rows is read on the device (the host has not seen it yet); more than `cap` rows: nothing is
+// checked and the host falls back to the streaming proof
+__global__ void sym_check_rows_kernel(const int *__restrict__ rows, const int *__restrict__ n_rows_dev, int cap,
+                                      const int *__restrict__ Mp, const int *__restrict__ Mi,
+                                      const int *__restrict__ Mp_prev, const int *__restrict__ Mi_prev,
+                                      int *__restrict__ asym) {
   const int lane = threadIdx.x & 31;
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (k >= n_rows) return;
-  const int j = rows[k];
-  const int s = Mp[j], e = Mp[j + 1];
+  const int n_rows = *n_rows_dev;
+  if (n_rows > cap) return;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
   bool bad = false;
-  for (int p = s + lane; p < e; p += 32) {
-    const int i = Mi[p];
-    if (!row_contains(Mi, Mp[i], Mp[i + 1], j)) bad = true;
-  }
-  for (int p = Mp_prev[j] + lane; p < Mp_prev[j + 1]; p += 32) {
-    const int i = Mi_prev[p];
-    if (!row_contains(Mi, s, e, i) && row_contains(Mi, Mp[i], Mp[i + 1], j)) bad = true;
+  for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_rows; k += warps) {
+    const int j = rows[k];
+    const int s = Mp[j], e = Mp[j + 1];
+    for (int p = s + lane; p < e; p += 32) {
+      const int i = Mi[p];
+      if (!row_contains(Mi, Mp[i], Mp[i + 1], j)) bad = true;
+    }
+    for (int p = Mp_prev[j] + lane; p < Mp_prev[j + 1]; p += 32) {
+      const int i = Mi_prev[p];
+      if (!row_contains(Mi, s, e, i) && row_contains(Mi, Mp[i], Mp[i + 1], j)) bad = true;
+    }
   }
   if (bad) *asym = 1;
 }
 
-int launch_sym_check_rows(const int *rows, int n_rows, const int *Mp, const int *Mi, const int *Mp_prev,
-                          const int *Mi_prev, int *asym, cudaStream_t s) {
-  if (n_rows <= 0) return 0;
-  const long long threads = (long long)n_rows * 32;
-  sym_check_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rows, n_rows, Mp, Mi, Mp_prev, Mi_prev, asym);
+int launch_sym_check_rows(const int *rows, const int *n_rows_dev, int cap, const int *Mp, const int *Mi,
+                          const int *Mp_prev, const int *Mi_prev, int *asym, cudaStream_t s) {
+  sym_check_rows_kernel<<<2 * kNumSMsB200, 256, 0, s>>>(rows, n_rows_dev, cap, Mp, Mi, Mp_prev, Mi_prev, asym);
   PB_CUDA(cudaGetLastError());
   return 1;
 }
@@ -247,8 +254,8 @@ int launch_diff_rows_mapped(const int *Mp, const int *Mi, const int *Mp_prev, co
 }
 
 int launch_list_changed_rows(const unsigned *row_bits, const int *word_prefix, int n_words, int M,
-                             int *rows, cudaStream_t s) {
-  list_changed_rows_kernel<<<(n_words + 255) / 256, 256, 0, s>>>(row_bits, word_prefix, n_words, M, rows);
+                             int *rows, int cap, cudaStream_t s) {
+  list_changed_rows_kernel<<<(n_words + 255) / 256, 256, 0, s>>>(row_bits, word_prefix, n_words, M, rows, cap);
   PB_CUDA(cudaGetLastError());
   return 1;
 }
@@ -262,10 +269,10 @@ int launch_count_row_edges(const int *rows, int n_rows, const int *Mp, const int
 }
 
 int launch_emit_row_edges(const int *rows, int n_rows, const int *Mp, const int *Mi,
-                          const int *dof2node, const int *offsets, int *edges, cudaStream_t s) {
+                          const int *dof2node, const int *offsets, int *edges, int cap, cudaStream_t s) {
   const long long threads = (long long)n_rows * 32;
   emit_row_edges_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rows, n_rows, Mp, Mi, dof2node,
-                                                                         offsets, edges);
+                                                                         offsets, edges, cap);
   PB_CUDA(cudaGetLastError());
   return 1;
 }

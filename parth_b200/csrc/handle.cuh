@@ -17,6 +17,13 @@ struct parth_b200 {
   int device = 0, num_sms = pb::kNumSMsB200;
   cudaStream_t stream = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+  // deferred stage timers: events are recorded while the work is enqueued and read once, after the
+  // final synchronisation of the API call (no intermediate cudaEventSynchronize on the hot path)
+  static constexpr int kTimerPairs = 16;
+  cudaEvent_t tev[2 * kTimerPairs] = {};
+  struct PendingTimer { double *dst; double *dst2; int pair; bool accumulate; };
+  std::vector<PendingTimer> pending_timers;
+  int timer_next = 0;
   std::string err;
 
   // ---- options (reference ParthAPI.h:19-25, Integrator.h:24-28)
@@ -66,13 +73,19 @@ struct parth_b200 {
   int n_changed = 0;
   pb::DevBuf<int> d_changed;  // pairs
   std::vector<int> dirty_fine, dirty_coarse, dirty_fine_saved, dirty_coarse_saved;
-  double timers[5] = {0, 0, 0, 0, 0};
+  double timers[5] = {0, 0, 0, 0, 0};     // seconds, reference order (ParthAPI.h:87-91)
+  double timer_ms[5] = {0, 0, 0, 0, 0};   // the same spans in device milliseconds
 
   // ---- scratch
   pb::DevBuf<int> V, ns_tmp, tile_c, cnt, ptr, tmp, uniq;
   pb::DevBuf<unsigned long long> desc, scan_ws;
-  pb::DevBuf<pb::BuildStatus> bstatus;
-  pb::DevBuf<pb::DetectCounters> dcnt;
+  // device mailbox, read back with ONE copy: [0..5] BuildStatus, [8..11] DetectCounters
+  pb::DevBuf<int> mail;
+  pb::BuildStatus *bstatus_p() { return reinterpret_cast<pb::BuildStatus *>(mail.p); }
+  pb::DetectCounters *dcnt_p() { return reinterpret_cast<pb::DetectCounters *>(mail.p + 8); }
+  // node flags fetched together with the changed-edge count (stage b)
+  bool node_flags_valid = false;
+  std::vector<int> node_flags;
   pb::DevBuf<int> w0, w1, w2, w3, w4, w5;  // general-purpose int scratch
   // stage (c): node list, vertex offsets, per-vertex counts, sub-mesh CSR, pivots, AMD slabs
   pb::DevBuf<int> r_list, r_vtx, r_cnt, r_G, r_sub, r_perm, r_ws, r_chosen, r_g2l, r_l2g;

@@ -1,6 +1,7 @@
 // parth_b200/csrc/stage_build.cu -- host driver of stage (a): picks the filter path, checks its
 // proof flags, falls back to the general kernels (graph_build.cu).
 #include <algorithm>
+#include <cstring>
 
 #include "build.cuh"
 #include "scan.cuh"
@@ -17,40 +18,45 @@ void read_ints(parth_b200 &h, const int *dsrc, int *dst, size_t n) {
   h.stats.d2h_bytes += (long long)(sizeof(int) * n);
 }
 
-// Row diff of the freshly built graph (Mp_own / Mi_own) against the snapshot, cached for stage (b);
-// returns true when the changed rows prove the new graph symmetric.
-static bool prove_symmetry_from_changed_rows(parth_b200 &h, int M, int nnz_new) {
+// Enqueue (no read-back) the row diff of the freshly built graph (Mp_own / Mi_own) against the
+// snapshot, the ordered list of changed rows and the symmetry check over them.  The results land
+// in the mailbox (DetectCounters: changed_rows, dirty_tiles, pad0 = asymmetric) and are cached for
+// stage (b).  Rows beyond `cap` are not listed: the caller then falls back to the streaming proof.
+static int changed_rows_cap(int M) { return std::max(1024, M / 20); }
+
+static void enqueue_changed_row_proof(parth_b200 &h, int M) {
   cudaStream_t s = h.stream;
-  (void)nnz_new;
   const int n_words = (M + 31) / 32;
+  const int cap = changed_rows_cap(M);
   h.chg_bits.reserve((size_t)n_words + 1, s);
   h.chg_pre.reserve((size_t)n_words + 2, s);
-  h.dcnt.reserve(1, s);
+  h.chg_rows.reserve((size_t)cap + 1, s);
   h.scan_ws.reserve(scan_ws_words((size_t)std::max(n_words, M) + 1), s);
-  h.stats.kernels_launched += launch_diff_rows(h.Mp_own.p, h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, M,
-                                               reinterpret_cast<unsigned *>(h.chg_bits.p), h.dcnt.p, s);
-  int cnt[4];
-  read_ints(h, reinterpret_cast<const int *>(h.dcnt.p), cnt, 4);
-  h.n_chg_rows = cnt[0];
-  h.diff_cached = true;
-  if (cnt[0] == 0) return true;  // identical to a proven graph
+  unsigned *bits = reinterpret_cast<unsigned *>(h.chg_bits.p);
+  h.stats.kernels_launched += launch_diff_rows(h.Mp_own.p, h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt_p(), s);
   h.stats.kernels_launched += exclusive_scan<1>(h.chg_bits.p, h.chg_pre.p, n_words, h.scan_ws.p, s);
-  h.chg_rows.reserve((size_t)cnt[0] + 1, s);
-  h.stats.kernels_launched += launch_list_changed_rows(reinterpret_cast<unsigned *>(h.chg_bits.p), h.chg_pre.p, n_words,
-                                                       M, h.chg_rows.p, s);
-  if ((long long)cnt[0] * 20 > M) return false;  // > 5 % of the rows: the streaming proof is cheaper
-  int *asym = reinterpret_cast<int *>(h.dcnt.p) + 2;  // pad0 of DetectCounters, zeroed by launch_diff_rows
-  h.stats.kernels_launched += launch_sym_check_rows(h.chg_rows.p, cnt[0], h.Mp_own.p, h.Mi_own.p, h.Mp_prev.p,
-                                                    h.Mi_prev.p, asym, s);
-  int bad = 0;
-  read_ints(h, asym, &bad, 1);
-  return bad == 0;
+  h.stats.kernels_launched += launch_list_changed_rows(bits, h.chg_pre.p, n_words, M, h.chg_rows.p, cap, s);
+  h.stats.kernels_launched += launch_sym_check_rows(h.chg_rows.p, &h.dcnt_p()->changed_rows, cap, h.Mp_own.p, h.Mi_own.p,
+                                                    h.Mp_prev.p, h.Mi_prev.p, &h.dcnt_p()->pad0, s);
+}
+
+void resolve_timers(parth_b200 &h) {
+  PB_CUDA(cudaStreamSynchronize(h.stream));
+  for (auto &t : h.pending_timers) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h.tev[2 * t.pair], h.tev[2 * t.pair + 1]);
+    if (t.accumulate) *t.dst += ms; else *t.dst = ms;
+    if (t.dst2) *t.dst2 = ms;
+  }
+  h.pending_timers.clear();
+  h.timer_next = 0;
+  for (int i = 0; i < 5; i++) h.timers[i] = h.timer_ms[i] * 1e-3;
 }
 
 void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, int dim) {
   cudaStream_t s = h.stream;
   const int M = N / dim;
-  StageTimer total(h, h.ev0, h.ev1);
+  StageTimer total(h, &h.stats.build_ms);
 
   h.scan_ws.reserve(scan_ws_words((size_t)M + 1), s);
   int Q = nnz;
@@ -78,45 +84,48 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   // after a snapshot-by-swap the "own" buffers hold stale data and are free to be overwritten
   h.Mp_own.reserve((size_t)M + 1, s);
   h.Mi_own.reserve((size_t)(Q > 0 ? Q : 1), s);
-  a.tile_c = h.tile_c.p; a.desc = h.desc.p; a.status = h.bstatus.p;
+  a.tile_c = h.tile_c.p; a.desc = h.desc.p; a.status = h.bstatus_p();
   a.Mp = h.Mp_own.p; a.Mi = h.Mi_own.p;
 
   BuildStatus st{};
+  DetectCounters dc{};
   a.ev_a = h.ev2; a.ev_b = h.ev3;
-  static_assert(sizeof(BuildStatus) % sizeof(int) == 0, "BuildStatus is read back as ints");
-  auto read_status = [&]() {
-    read_ints(h, reinterpret_cast<const int *>(h.bstatus.p), reinterpret_cast<int *>(&st),
-              sizeof(BuildStatus) / sizeof(int));
+  a.status = h.bstatus_p();
+  static_assert(sizeof(BuildStatus) == 24 && sizeof(DetectCounters) == 16, "mailbox layout");
+  auto read_mail = [&]() {
+    int m[12];
+    read_ints(h, h.mail.p, m, 12);
+    std::memcpy(&st, m, sizeof(st));
+    std::memcpy(&dc, m + 8, sizeof(dc));
   };
-  bool diff_ok = true;
+  auto launch_filter = [&]() {
+    if (dim == 1 && h.build_mode <= 1) {
+      if (h.build_mode == 0 && build_pipe_supported(a)) h.stats.kernels_launched += build_pipe_launch(a, h.num_sms, s);
+      else h.stats.kernels_launched += build_cols_launch(a, h.build_mode == 0, s);
+    } else {
+      h.stats.kernels_launched += build_filter_launch(a, s);
+    }
+  };
+  auto diff_ok = [&]() { return (dim == 1 && h.build_mode <= 1) ? st.diff_sum == 0 : st.diff_mod == 0; };
   if (dim == 1) {
-    // column-aligned kernel; fall through its variants only when a flag asks for it, and remember
-    // the variant that worked so that steady-state updates launch it directly
     const int tiles7 = build_cols_tiles(Q);
     h.tile_c.reserve((size_t)std::max(tiles, tiles7) + 2, s);
     h.desc.reserve((size_t)std::max(tiles, tiles7) + 1, s);
     a.tile_c = h.tile_c.p; a.desc = h.desc.p;
-    for (;;) {
-      if (h.build_mode <= 1) {
-        if (h.build_mode == 0 && build_pipe_supported(a))
-          h.stats.kernels_launched += build_pipe_launch(a, h.num_sms, s);
-        else
-          h.stats.kernels_launched += build_cols_launch(a, h.build_mode == 0, s);
-        read_status();
-        if (h.build_mode == 0 && (st.flags & BUILD_NODIAG) && !(st.flags & ~(BUILD_NODIAG | BUILD_WIDE))) { h.build_mode = 1; continue; }
-        if ((st.flags & BUILD_WIDE) && !(st.flags & ~(BUILD_NODIAG | BUILD_WIDE))) { h.build_mode = 2; continue; }
-        diff_ok = st.diff_sum == 0;
-      } else {
-        h.stats.kernels_launched += build_filter_launch(a, s);
-        read_status();
-        diff_ok = st.diff_mod == 0;
-      }
-      break;
+  }
+  bool proven = false;
+  for (;;) {
+    // the filter kernel, then (incremental mode) the changed-row proof, then ONE read-back
+    launch_filter();
+    if (incremental) enqueue_changed_row_proof(h, M);
+    read_mail();
+    if (dim == 1 && h.build_mode <= 1) {
+      // remember the variant that works so that steady-state updates launch it directly
+      const unsigned only = st.flags & ~(BUILD_NODIAG | BUILD_WIDE);
+      if (h.build_mode == 0 && (st.flags & BUILD_NODIAG) && !only) { h.build_mode = 1; continue; }
+      if ((st.flags & BUILD_WIDE) && !only) { h.build_mode = 2; continue; }
     }
-  } else {
-    h.stats.kernels_launched += build_filter_launch(a, s);
-    read_status();
-    diff_ok = st.diff_mod == 0;
+    break;
   }
   h.stats.build_kernel_ms = 0;
   if (Q > 0) {  // the filter kernel of the last launch alone (events recorded around it)
@@ -126,17 +135,23 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   }
   if (st.flags & BUILD_RANGE)
     throw StatusError(PARTH_B200_ERR_INPUT, "set_matrix: row index out of range");
-  bool proven = st.flags == 0 && (h.assume_symmetric || incremental || diff_ok);
-  if (proven && incremental) {
-    proven = prove_symmetry_from_changed_rows(h, M, st.nnz_out);
-    if (!proven && h.build_mode <= 1) {
-      // too many rows changed (or a mirror is missing): the full proof decides
-      a.check_mirror = 1;
-      if (h.build_mode == 0 && build_pipe_supported(a)) h.stats.kernels_launched += build_pipe_launch(a, h.num_sms, s);
-      else h.stats.kernels_launched += build_cols_launch(a, h.build_mode == 0, s);
-      read_status();
-      proven = st.flags == 0 && st.diff_sum == 0;
-      h.diff_cached = false;
+  if (st.flags == 0) {
+    if (h.assume_symmetric) proven = true;
+    else if (!incremental) proven = diff_ok();
+    else {
+      h.n_chg_rows = dc.changed_rows;
+      h.diff_cached = dc.changed_rows <= changed_rows_cap(M);
+      if (dc.changed_rows == 0) proven = true;                       // identical to a proven graph
+      else if (h.diff_cached && dc.pad0 == 0) proven = true;         // every changed row is mirrored
+      else if (h.diff_cached && dc.pad0 != 0) proven = false;        // a mirror is missing: symmetrise below
+      else {
+        // more than 5 % of the rows changed: the streaming proof is cheaper than probing them
+        a.check_mirror = 1;
+        launch_filter();
+        read_mail();
+        proven = st.flags == 0 && diff_ok();
+        h.diff_cached = false;
+      }
     }
   }
   if (proven) {
@@ -151,8 +166,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
     h.stats.kernels_launched += build_general_count_launch(a, h.cnt.p, h.ptr.p, h.scan_ws.p, s);
     int total_pairs = 0;
     read_ints(h, h.ptr.p + M, &total_pairs, 1);
-    read_ints(h, reinterpret_cast<const int *>(h.bstatus.p), reinterpret_cast<int *>(&st),
-              sizeof(BuildStatus) / sizeof(int));
+    read_mail();
     if (st.flags & BUILD_RANGE)
       throw StatusError(PARTH_B200_ERR_INPUT, "set_matrix: row index out of range");
     h.tmp.reserve((size_t)(total_pairs > 0 ? total_pairs : 1), s);
@@ -174,7 +188,6 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   h.M_n = M;
   h.mesh_owned = true;
   h.map_len = 0;
-  h.stats.build_ms = total.ms();
 }
 
 }  // namespace pb

@@ -419,8 +419,7 @@ std::vector<int> regroup_finish(parth_b200 &h, int total, const int *key, const 
   }
   h.d_dofs2.reserve((size_t)std::max(new_total, 1), s);
   h.d_labels2.reserve((size_t)std::max(new_total, 1), s);
-  h.dcnt.reserve(1, s);
-  int *d_flag = reinterpret_cast<int *>(h.dcnt.p);
+  int *d_flag = h.mail.p + 16;
   PB_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), s));
   if (total_surv > 0) {
     regroup_place_surv_kernel<<<nblk(total_surv), 256, 0, s>>>(d_sptr, d_aptr, d_nptr, nn, total_surv, h.r_cnt.p, h.r_G.p,
@@ -460,8 +459,7 @@ void stage_set_map(parth_b200 &h, const int *map, int len) {
   h.old_to_new.reserve((size_t)Mp, s);
   PB_CUDA(cudaMemcpyAsync(h.new_to_old.p, map, sizeof(int) * (size_t)M, cudaMemcpyHostToDevice, s));
   h.stats.h2d_bytes += (long long)sizeof(int) * M;
-  h.dcnt.reserve(1, s);
-  int *d_bad = reinterpret_cast<int *>(h.dcnt.p);
+  int *d_bad = h.mail.p + 16;
   PB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
   fill_kernel<<<nblk(Mp), 256, 0, s>>>(h.old_to_new.p, Mp, -1);
   invert_map_kernel<<<nblk(M), 256, 0, s>>>(h.new_to_old.p, M, Mp, h.old_to_new.p, d_bad);
@@ -493,7 +491,7 @@ void stage_set_map(parth_b200 &h, const int *map, int len) {
 // ------------------------------------------------------------------ (a6)
 void stage_integrate(parth_b200 &h) {
   cudaStream_t s = h.stream;
-  StageTimer tm(h, h.ev0, h.ev1);
+  StageTimer tm(h, &h.stats.integrate_ms, false, &h.timer_ms[1]);
   const int nn = h.num_nodes, M = h.M_n;
   const int total = h.node_ptr[nn];
   h.w0.reserve((size_t)std::max(total, M) + 2, s);  // keep
@@ -564,7 +562,6 @@ void stage_integrate(parth_b200 &h) {
   PB_CUDA(cudaMemsetAsync(h.d_mesh_perm.p, 0, sizeof(int) * (size_t)M, s));
   assemble_all(h);
   tm.stop();
-  h.stats.integrate_ms = tm.ms();
 }
 
 // ------------------------------------------------------------------ (f2)

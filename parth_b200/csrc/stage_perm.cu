@@ -108,13 +108,15 @@ void stage_export_tree(parth_b200 &h, int *meta, int *node_ptr, int *dofs, int *
 
 // ------------------------------------------------------------------ (b) change detection
 // Integrator::computeChangedEdges (Integrator.cpp:259-338).  Result: h.d_changed / h.n_changed.
+// The node flags of findRegionConnections are computed in the same enqueue and fetched with the
+// edge count in ONE read-back (h.node_flags); stage_dirty_sets consumes them.
 void stage_detect(parth_b200 &h) {
   cudaStream_t s = h.stream;
-  const int M = h.M_n;
-  StageTimer tm(h, h.ev0, h.ev1);
+  const int M = h.M_n, nn = h.num_nodes;
+  StageTimer tm(h, &h.stats.detect_ms, false, &h.timer_ms[2]);
   h.n_changed = 0;
+  h.node_flags_valid = false;
   const int n_words = (M + 31) / 32;
-  h.dcnt.reserve(1, s);
   h.scan_ws.reserve(scan_ws_words((size_t)std::max(n_words, M) + 1), s);
   int n_rows = 0;
   const int *rows = nullptr;
@@ -128,35 +130,43 @@ void stage_detect(parth_b200 &h) {
     unsigned *bits = reinterpret_cast<unsigned *>(h.w0.p);
     if (h.map_len > 0)
       h.stats.kernels_launched += launch_diff_rows_mapped(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, h.new_to_old.p,
-                                                          h.old_to_new.p, M, bits, h.dcnt.p, s);
+                                                          h.old_to_new.p, M, bits, h.dcnt_p(), s);
     else
-      h.stats.kernels_launched += launch_diff_rows(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt.p, s);
+      h.stats.kernels_launched += launch_diff_rows(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt_p(), s);
     int cnt[4];
-    read_ints(h, reinterpret_cast<const int *>(h.dcnt.p), cnt, 4);
+    read_ints(h, reinterpret_cast<const int *>(h.dcnt_p()), cnt, 4);
     n_rows = cnt[0];
     if (n_rows > 0) {
       h.stats.kernels_launched += exclusive_scan<1>(h.w0.p, h.w1.p, n_words, h.scan_ws.p, s);
       h.w2.reserve((size_t)n_rows + 1, s);  // changed rows, ascending
-      h.stats.kernels_launched += launch_list_changed_rows(bits, h.w1.p, n_words, M, h.w2.p, s);
+      h.stats.kernels_launched += launch_list_changed_rows(bits, h.w1.p, n_words, M, h.w2.p, n_rows, s);
     }
     rows = h.w2.p;
   }
   if (n_rows > 0) {
     h.w3.reserve((size_t)n_rows + 2, s);  // per-row edge counts -> offsets
-    h.stats.kernels_launched += launch_count_row_edges(rows, n_rows, h.Mp, h.Mi, h.d_dof2node.p, h.w3.p, s);
     h.w4.reserve((size_t)n_rows + 2, s);
+    h.w5.reserve((size_t)nn * 2 + 2, s);  // [0] edge count, [2 .. 2+nn) within-node flags, then LCA flags
+    h.stats.kernels_launched += launch_count_row_edges(rows, n_rows, h.Mp, h.Mi, h.d_dof2node.p, h.w3.p, s);
     h.stats.kernels_launched += exclusive_scan<0>(h.w3.p, h.w4.p, n_rows, h.scan_ws.p, s);
-    int n_edges = 0;
-    read_ints(h, h.w4.p + n_rows, &n_edges, 1);
-    if (n_edges > 0) {
-      h.d_changed.reserve((size_t)n_edges * 2, s);
+    if (h.d_changed.cap < 2 * 65536) h.d_changed.reserve(2 * 65536, s);
+    std::vector<int> fl((size_t)nn * 2 + 2);
+    for (int attempt = 0; attempt < 2; attempt++) {
+      const int cap = (int)(h.d_changed.cap / 2);
+      PB_CUDA(cudaMemsetAsync(h.w5.p, 0, sizeof(int) * ((size_t)nn * 2 + 2), s));
       h.stats.kernels_launched += launch_emit_row_edges(rows, n_rows, h.Mp, h.Mi, h.d_dof2node.p, h.w4.p,
-                                                        h.d_changed.p, s);
+                                                        h.d_changed.p, cap, s);
+      h.stats.kernels_launched += launch_mark_dirty_nodes_dev(h.d_changed.p, h.w4.p + n_rows, cap, h.d_dof2node.p,
+                                                              h.d_meta.p, h.w5.p + 2, h.w5.p + 2 + nn, h.w5.p, s);
+      read_ints(h, h.w5.p, fl.data(), fl.size());
+      if (fl[0] <= cap) break;
+      h.d_changed.reserve((size_t)fl[0] * 2 + 64, s);  // the list did not fit: grow and emit again
     }
-    h.n_changed = n_edges;
+    h.n_changed = fl[0];
+    h.node_flags.assign(fl.begin() + 2, fl.end());
+    h.node_flags_valid = true;
   }
   tm.stop();
-  h.stats.detect_ms = tm.ms();
 }
 
 // ------------------------------------------------------------------ (b) dirty sets on 2^(L+1)-1 nodes
@@ -194,13 +204,20 @@ static long long subtree_size(const parth_b200 &h, int x) {
 void stage_dirty_sets(parth_b200 &h, const std::vector<int> &pre_fine) {
   cudaStream_t s = h.stream;
   const int nn = h.num_nodes;
-  StageTimer tm(h, h.ev0, h.ev1);
-  h.w5.reserve((size_t)nn * 2, s);
-  PB_CUDA(cudaMemsetAsync(h.w5.p, 0, sizeof(int) * (size_t)nn * 2, s));
-  h.stats.kernels_launched += launch_mark_dirty_nodes(h.d_changed.p, h.n_changed, h.d_dof2node.p, h.d_meta.p,
-                                                      h.w5.p, h.w5.p + nn, s);
-  std::vector<int> flags((size_t)nn * 2);
-  read_ints(h, h.w5.p, flags.data(), (size_t)nn * 2);
+  StageTimer tm(h, &h.stats.dirty_ms);
+  std::vector<int> flags;
+  if (h.node_flags_valid && (int)h.node_flags.size() == nn * 2) {
+    flags.swap(h.node_flags);  // fetched together with the edge list by stage_detect
+    h.node_flags_valid = false;
+  } else {
+    // the edge list or the tree changed since detection (relocation): classify again
+    h.w5.reserve((size_t)nn * 2 + 2, s);
+    PB_CUDA(cudaMemsetAsync(h.w5.p, 0, sizeof(int) * (size_t)nn * 2, s));
+    h.stats.kernels_launched += launch_mark_dirty_nodes(h.d_changed.p, h.n_changed, h.d_dof2node.p, h.d_meta.p,
+                                                        h.w5.p, h.w5.p + nn, s);
+    flags.resize((size_t)nn * 2);
+    read_ints(h, h.w5.p, flags.data(), (size_t)nn * 2);
+  }
   const int *within = flags.data(), *lca = flags.data() + nn;
 
   h.dirty_fine = pre_fine;
@@ -241,15 +258,13 @@ void stage_dirty_sets(parth_b200 &h, const std::vector<int> &pre_fine) {
   for (int x : h.dirty_fine) nodes += h.node_ptr[x + 1] - h.node_ptr[x];
   h.reuse = h.tree_M != 0 ? 1 - (nodes * 1.0 / h.tree_M) : 0.0;
   tm.stop();
-  h.stats.dirty_ms = tm.ms();
 }
 
 // ------------------------------------------------------------------ (e) expansion
 void stage_expand(parth_b200 &h, const int *dmesh_perm, int n, int dim, int *dout) {
-  StageTimer tm(h, h.ev0, h.ev1);
+  StageTimer tm(h, &h.stats.expand_ms);
   h.stats.kernels_launched += launch_expand(dmesh_perm, n, dim, dout, h.stream);
   tm.stop();
-  h.stats.expand_ms = tm.ms();
 }
 
 // (a19) snapshot, ParthAPI.cpp:270-278: a buffer swap when the graph is ours, a copy when borrowed
@@ -315,6 +330,7 @@ static int global_perm(parth_b200 &h) {
   if (h.aggressive) {
     const int thr = (int)std::pow(2, h.relocate_lvl + 1) - 1;  // getLastHMDNodeInLevel(relocate_lvl)
     stage_relocate(h, thr, pre_fine);
+    h.node_flags_valid = false;  // the edge list and the tree have changed
   }
   stage_dirty_sets(h, pre_fine);
   const bool full = h.reuse < 0.2;
@@ -335,7 +351,7 @@ static int global_perm(parth_b200 &h) {
 
 // ParthAPI::computePermutation (ParthAPI.cpp:191-279); dperm: device buffer of M_n*dim ints
 int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
-  for (double &t : h.timers) t = 0;
+  for (double &t : h.timer_ms) t = 0;
   h.reuse = 0;
   h.n_changed = 0;
   h.sim_dim = dim;
@@ -345,30 +361,22 @@ int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
   if (h.M_n != h.M_n_prev && h.map_len == 0) h.tree_init = false;
   int rc = PARTH_B200_OK;
   if (!h.tree_init) {
-    cold_start(h);
-    h.timers[0] = 0;  // host callback: not device time
-    stage_expand(h, h.d_mesh_perm.p, h.M_n, dim, dperm);
-    h.timers[4] = h.stats.expand_ms * 1e-3;
+    cold_start(h);  // host callback: init_time stays 0 (not device time)
+    StageTimer tm(h, &h.stats.expand_ms, false, &h.timer_ms[4]);
+    h.stats.kernels_launched += launch_expand(h.d_mesh_perm.p, h.M_n, dim, dperm, h.stream);
+    tm.stop();
     h.reuse = 0;
   } else {
-    if (h.map_len > 0) {
-      stage_integrate(h);
-      h.timers[1] = h.stats.integrate_ms * 1e-3;
-    }
+    if (h.map_len > 0) stage_integrate(h);
     stage_detect(h);
-    h.timers[2] = h.stats.detect_ms * 1e-3;
-    cudaEventRecord(h.ev2, h.stream);
+    StageTimer tc(h, &h.timer_ms[3]);
     if (h.n_changed == 0) {
       h.reuse = 1;
     } else {
       rc = global_perm(h);
     }
     if (rc == PARTH_B200_OK) stage_expand(h, h.d_mesh_perm.p, h.M_n, dim, dperm);
-    cudaEventRecord(h.ev3, h.stream);
-    cudaEventSynchronize(h.ev3);
-    float t = 0;
-    cudaEventElapsedTime(&t, h.ev2, h.ev3);
-    h.timers[3] = t * 1e-3;
+    tc.stop();
   }
   stage_snapshot(h);
   return rc;

@@ -92,22 +92,17 @@ bool device_orders_with_amd(const parth_b200 &h) {
 void stage_permute_fine(parth_b200 &h, const std::vector<int> &nodes) {
   if (nodes.empty()) return;
   cudaStream_t s = h.stream;
-  cudaEvent_t e0, e1;
-  PB_CUDA(cudaEventCreate(&e0));
-  PB_CUDA(cudaEventCreate(&e1));
-  cudaEventRecord(e0, s);
+  StageTimer tm(h, &h.stats.reorder_ms, /*accumulate=*/true);
   Batch b = extract_fine(h, nodes);
   std::vector<int> gnnz = batch_graph_nnz(h, b);
   if (!device_orders_with_amd(h))
     for (int g = 0; g < b.count; g++)
       if (gnnz[g] > 0) {
-        cudaEventDestroy(e0); cudaEventDestroy(e1);
         throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
                           "permute_fine: METIS_NodeND leaf ordering is not available on the device "
                           "(use ReorderingType AMD or the REPAIR coarse policy)");
       }
   if (h.reorder_type == PARTH_B200_MORTON_CODE && !h.force_amd) {
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
     // the reference prints "Morton code is not implemented yet" and leaves perm unset (HMD.cpp:82-83)
     throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "permute_fine: MORTON_CODE is not implemented in the reference");
   }
@@ -115,13 +110,7 @@ void stage_permute_fine(parth_b200 &h, const std::vector<int> &nodes) {
   h.stats.kernels_launched += launch_apply_order(h.r_list.p, h.r_vtx.p, b.count, b.total, h.d_node_ptr.p,
                                                  h.d_meta.p, h.d_dofs.p, h.r_perm.p, h.d_labels.p,
                                                  h.d_mesh_perm.p, s);
-  cudaEventRecord(e1, s);
-  cudaEventSynchronize(e1);
-  float t = 0;
-  cudaEventElapsedTime(&t, e0, e1);
-  h.stats.reorder_ms += t;
-  cudaEventDestroy(e0);
-  cudaEventDestroy(e1);
+  tm.stop();
 }
 
 // HMD::createMultiSubMesh for one node (coarse == 0) / HMD::getCoarseMesh (coarse == 1)

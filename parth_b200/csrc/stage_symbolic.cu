@@ -245,7 +245,7 @@ __global__ void colcount_kernel(const int *__restrict__ pre, const int *__restri
 void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *colcount_out, long long *lnz_out) {
   cudaStream_t s = h.stream;
   const int n = h.M_n;
-  StageTimer tm(h, h.ev0, h.ev1);
+  StageTimer tm(h, &h.stats.symbolic_ms);
   const bool tree_aware = perm_host == nullptr && h.tree_init && h.tree_M == n;
   if (perm_host == nullptr && !tree_aware)
     throw StatusError(PARTH_B200_ERR_ARG, "symbolic: no permutation given and no current mesh_perm");
@@ -448,7 +448,6 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
   PB_CUDA(cudaStreamSynchronize(s));
   *lnz_out = (long long)total;
   tm.stop();
-  h.stats.symbolic_ms = tm.ms();
 }
 
 }  // namespace pb

@@ -13,21 +13,24 @@ struct StatusError : std::runtime_error {
   StatusError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
 };
 
-// RAII device-time bracket on the handle's stream (events ev0/ev1); read with ms() after a sync.
+// Device-time bracket on the handle's stream.  The elapsed time lands in *dst when
+// resolve_timers() runs (after the API call's final synchronisation).
 struct StageTimer {
   parth_b200 &h;
-  cudaEvent_t a, b;
-  StageTimer(parth_b200 &hh, cudaEvent_t ea, cudaEvent_t eb) : h(hh), a(ea), b(eb) {
-    cudaEventRecord(a, h.stream);
+  int pair;
+  double *dst, *dst2;
+  bool accumulate;
+  StageTimer(parth_b200 &hh, double *d, bool acc = false, double *d2 = nullptr) : h(hh), dst(d), dst2(d2), accumulate(acc) {
+    pair = h.timer_next < parth_b200::kTimerPairs ? h.timer_next++ : -1;
+    if (pair >= 0) cudaEventRecord(h.tev[2 * pair], h.stream);
   }
-  void stop() { cudaEventRecord(b, h.stream); }
-  double ms() {
-    float t = 0;
-    cudaEventSynchronize(b);
-    cudaEventElapsedTime(&t, a, b);
-    return t;
+  void stop() {
+    if (pair < 0) return;
+    cudaEventRecord(h.tev[2 * pair + 1], h.stream);
+    h.pending_timers.push_back({dst, dst2, pair, accumulate});
   }
 };
+void resolve_timers(parth_b200 &h);  // synchronises the stream
 
 // small synchronous read-back of n ints through pinned memory
 void read_ints(parth_b200 &h, const int *dsrc, int *dst, size_t n);

@@ -95,6 +95,23 @@ __global__ void mark_dirty_nodes_kernel(const int *__restrict__ edges, int n_edg
   lca_flag[common_separator_dev(meta, small, big)] = 1;
 }
 
+__global__ void mark_dirty_nodes_dev_kernel(const int *__restrict__ edges, const int *__restrict__ n_edges_dev, int cap,
+                                            const int *__restrict__ dof2node, const int *__restrict__ meta,
+                                            int *__restrict__ within_flag, int *__restrict__ lca_flag,
+                                            int *__restrict__ count_out) {
+  const int n_all = *n_edges_dev;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *count_out = n_all;
+  const int n_edges = n_all < cap ? n_all : cap;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += gridDim.x * blockDim.x) {
+    int na = __ldg(dof2node + edges[2 * e]), nb = __ldg(dof2node + edges[2 * e + 1]);
+    int big = na, small = nb;
+    if (small > big) { int t = big; big = small; small = t; }
+    if (small == big) { within_flag[small] = 1; continue; }
+    if (is_separator_dev(small, big)) continue;
+    lca_flag[common_separator_dev(meta, small, big)] = 1;
+  }
+}
+
 // ------------------------------------------------------------------ host launchers
 int launch_assemble_all(const int *node_ptr, const int *meta, const int *visit, int nodes,
                         const int *dofs, const int *labels, int total, int *mesh_perm,
@@ -130,6 +147,14 @@ int launch_expand(const int *mesh_perm, int M_n, int dim, int *out, cudaStream_t
   else if (dim == 2) expand_kernel<2><<<blocks, 256, 0, s>>>(mesh_perm, n_out, dim, out);
   else if (dim == 3) expand_kernel<3><<<blocks, 256, 0, s>>>(mesh_perm, n_out, dim, out);
   else expand_kernel<0><<<blocks, 256, 0, s>>>(mesh_perm, n_out, dim, out);
+  PB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int launch_mark_dirty_nodes_dev(const int *edges, const int *n_edges_dev, int cap, const int *dof2node,
+                                const int *meta, int *within_flag, int *lca_flag, int *count_out, cudaStream_t s) {
+  mark_dirty_nodes_dev_kernel<<<kNumSMsB200, 256, 0, s>>>(edges, n_edges_dev, cap, dof2node, meta, within_flag, lca_flag,
+                                                         count_out);
   PB_CUDA(cudaGetLastError());
   return 1;
 }

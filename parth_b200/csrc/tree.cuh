@@ -13,6 +13,9 @@ int launch_dof2node(const int *node_ptr, int nodes, const int *dofs, int total, 
 int launch_expand(const int *mesh_perm, int M_n, int dim, int *out, cudaStream_t s);
 int launch_mark_dirty_nodes(const int *edges, int n_edges, const int *dof2node, const int *meta,
                             int *within_flag, int *lca_flag, cudaStream_t s);
+// same with the edge count read on the device (n_edges_dev, clamped to cap); also copies the count to *count_out
+int launch_mark_dirty_nodes_dev(const int *edges, const int *n_edges_dev, int cap, const int *dof2node,
+                                const int *meta, int *within_flag, int *lca_flag, int *count_out, cudaStream_t s);
 
 // detect.cu
 struct DetectCounters {
@@ -25,13 +28,13 @@ int launch_diff_rows(const int *Mp, const int *Mi, const int *Mp_prev, const int
 int launch_diff_rows_mapped(const int *Mp, const int *Mi, const int *Mp_prev, const int *Mi_prev,
                             const int *new_to_old, const int *old_to_new, int M, unsigned *row_bits,
                             DetectCounters *cnt, cudaStream_t s);
-int launch_sym_check_rows(const int *rows, int n_rows, const int *Mp, const int *Mi, const int *Mp_prev,
-                          const int *Mi_prev, int *asym, cudaStream_t s);
+int launch_sym_check_rows(const int *rows, const int *n_rows_dev, int cap, const int *Mp, const int *Mi,
+                          const int *Mp_prev, const int *Mi_prev, int *asym, cudaStream_t s);
 int launch_list_changed_rows(const unsigned *row_bits, const int *word_prefix, int n_words, int M,
-                             int *rows, cudaStream_t s);
+                             int *rows, int cap, cudaStream_t s);
 int launch_count_row_edges(const int *rows, int n_rows, const int *Mp, const int *Mi,
                            const int *dof2node, int *counts, cudaStream_t s);
 int launch_emit_row_edges(const int *rows, int n_rows, const int *Mp, const int *Mi,
-                          const int *dof2node, const int *offsets, int *edges, cudaStream_t s);
+                          const int *dof2node, const int *offsets, int *edges, int cap, cudaStream_t s);
 
 }  // namespace pb
