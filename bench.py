@@ -11,7 +11,7 @@ the DOFs dirtied per update (workloads.PoissonUpdateStream; SURVEY.md section 8d
 
 `value` : updates/s with the inputs resident in HBM (device-pointer entry points)
 `e2e`   : updates/s through the host-pointer C ABI (pinned host CSC in, host permutation out)
-`roofline`: dominant kernel (build_filter_kernel) algorithmic bytes / its CUDA-event time
+`roofline`: dominant kernel (build_pipe_kernel) algorithmic bytes / its CUDA-event time
 `cpu_baseline`: the reference CPU implementation timed on this box's host cores (rank 0, N = 1)
 N > 1: every rank updates its own mesh (independent objects, no data-path collective): weak scaling.
 """
@@ -281,7 +281,9 @@ def run_ours(args):
                    "parallelism": f"{world} independent meshes (one per GPU), no data-path collective"},
         "gnnz_per_s": value * nnzA / 1e9,
         "roofline": {"bound": "hbm", "kernel": "build_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "algorithmic_bytes": alg, "kernel_ms": kms,
+                     "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_bench_ncu_summary.md
+                     "traffic": 440306944 if args.n == 200 else None, "algorithmic_bytes": alg, "kernel_ms": kms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s"},
         "stage_ms": {"build": float(st[0]), "detect": float(st[1]), "dirty_sets": float(st[2]),
                      "reorder": float(st[3]), "expand": float(st[4])},
