@@ -54,6 +54,7 @@ enum {
   PARTH_B200_COARSE_REPORT = 2    /* leave the permutation, report PARTH_B200_NEEDS_REDISSECT */
 };
 #define PARTH_B200_NEEDS_REDISSECT 100 /* positive, non-error status of compute_permutation */
+#define PARTH_B200_NEEDS_EXCHANGE 101  /* sharded mode: gather the re-ordered nodes, then call finish */
 
 const char *parth_b200_version(void);
 const char *parth_b200_last_error(const parth_b200 *h);
@@ -157,10 +158,26 @@ int parth_b200_synchronize(parth_b200 *h);
 /* the stream all work of this handle runs on (cudaStream_t) */
 void *parth_b200_stream(parth_b200 *h);
 
-/* multi-GPU: shard the row-block stages; rank/world as in torch.distributed.  The data-path
- * exchange (gather of dirty permutation slices) is driven by the caller over NCCL, see
- * INTEGRATION.md; row-block stages need no collective. */
+/* Multi-GPU, one process per GPU, every rank holding the same graph and tree.  Independent dirty
+ * separator-tree nodes are the unit that shards: after
+ * parth_b200_set_shard(h, rank, world) with world > 1, the nodes an update has to re-order
+ * (Integrator::permuteFineHMDNodes, Integrator.cpp:851-893) are dealt to the ranks largest-first
+ * onto the least loaded rank -- the same plan on every rank -- and compute_permutation orders only
+ * this rank's share, then returns PARTH_B200_NEEDS_EXCHANGE without expanding.  The caller gathers
+ * the per-node label slices over NCCL (pack -> all-gather -> unpack; parth_b200/sharded.py) and
+ * calls parth_b200_finish_permutation*.  Nothing else of the update needs a collective: build,
+ * detection and the dirty sets are computed redundantly and identically on every rank. */
 int parth_b200_set_shard(parth_b200 *h, int rank, int world);
+/* two-call protocol: nodes == NULL returns the count.  owner[i] = rank that ordered nodes[i],
+ * sizes[i] = its number of DOFs (= length of its label slice) */
+int parth_b200_exchange_plan(parth_b200 *h, int *n_nodes, int *nodes, int *owner, int *sizes);
+/* labels of the listed nodes, concatenated in list order, to / from a device buffer; unpack also
+ * re-scatters the nodes' slices of mesh_perm (mesh_perm[label + offset] = DOF) */
+int parth_b200_pack_labels_dev(parth_b200 *h, const int *nodes, int n, int *dbuf);
+int parth_b200_unpack_labels_dev(parth_b200 *h, const int *nodes, int n, const int *dbuf);
+/* expansion + snapshot that compute_permutation skipped; perm / dperm hold M_n*dim ints */
+int parth_b200_finish_permutation(parth_b200 *h, int *perm, int dim);
+int parth_b200_finish_permutation_dev(parth_b200 *h, int *dperm, int dim);
 
 #ifdef __cplusplus
 }

@@ -16,6 +16,7 @@ LIB_PATH = os.path.join(HERE, "libparth_b200.so")
 
 OK = 0
 NEEDS_REDISSECT = 100
+NEEDS_EXCHANGE = 101
 METIS, AMD, MORTON_CODE = 0, 1, 2
 COARSE_REPAIR, COARSE_CALLBACK, COARSE_REPORT = 0, 1, 2
 
@@ -77,6 +78,11 @@ SYMBOLS = {
     "parth_b200_synchronize": (C.c_int, [_vp]),
     "parth_b200_stream": (_vp, [_vp]),
     "parth_b200_set_shard": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "parth_b200_exchange_plan": (C.c_int, [_vp, _ip, _ip, _ip, _ip]),
+    "parth_b200_pack_labels_dev": (C.c_int, [_vp, _ip, C.c_int, _vp]),
+    "parth_b200_unpack_labels_dev": (C.c_int, [_vp, _ip, C.c_int, _vp]),
+    "parth_b200_finish_permutation": (C.c_int, [_vp, _ip, C.c_int]),
+    "parth_b200_finish_permutation_dev": (C.c_int, [_vp, _vp, C.c_int]),
 }
 
 
@@ -300,13 +306,38 @@ class ParthAPI:
             perm = out
         else:
             perm = np.empty(max(n * dim, 1), np.int32)
-        rc = self._check(self.lib.parth_b200_compute_permutation(self.h, _p(perm), int(dim)), allow=(NEEDS_REDISSECT,))
+        rc = self._check(self.lib.parth_b200_compute_permutation(self.h, _p(perm), int(dim)), allow=(NEEDS_REDISSECT, NEEDS_EXCHANGE))
         return rc, perm[:n * dim]
 
     def computePermutationDev(self, dperm_ptr, dim=3):
         self._push_options()
         return self._check(self.lib.parth_b200_compute_permutation_dev(self.h, C.c_void_p(dperm_ptr), int(dim)),
-                           allow=(NEEDS_REDISSECT,))
+                           allow=(NEEDS_REDISSECT, NEEDS_EXCHANGE))
+
+    # ---- multi-GPU exchange (see parth_b200/sharded.py)
+    def exchange_plan(self):
+        n = C.c_int()
+        self._check(self.lib.parth_b200_exchange_plan(self.h, C.byref(n), None, None, None))
+        nodes, owner, sizes = (np.empty(max(n.value, 1), np.int32) for _ in range(3))
+        self._check(self.lib.parth_b200_exchange_plan(self.h, C.byref(n), _p(nodes), _p(owner), _p(sizes)))
+        return nodes[:n.value].copy(), owner[:n.value].copy(), sizes[:n.value].copy()
+
+    def pack_labels_dev(self, nodes, dbuf_ptr):
+        nodes = _i32(nodes)
+        self._check(self.lib.parth_b200_pack_labels_dev(self.h, _p(nodes), len(nodes), C.c_void_p(dbuf_ptr)))
+
+    def unpack_labels_dev(self, nodes, dbuf_ptr):
+        nodes = _i32(nodes)
+        self._check(self.lib.parth_b200_unpack_labels_dev(self.h, _p(nodes), len(nodes), C.c_void_p(dbuf_ptr)))
+
+    def finishPermutationDev(self, dperm_ptr, dim=3):
+        self._check(self.lib.parth_b200_finish_permutation_dev(self.h, C.c_void_p(dperm_ptr), int(dim)))
+
+    def finishPermutation(self, dim=3, out=None):
+        n, _ = self.mesh_dims()
+        perm = out if out is not None else np.empty(max(n * dim, 1), np.int32)
+        self._check(self.lib.parth_b200_finish_permutation(self.h, _p(perm), int(dim)))
+        return perm[:n * dim]
 
     def mapMeshPermToMatrixPerm(self, mesh_perm, dim=-1):
         mesh_perm = _i32(mesh_perm)

@@ -360,7 +360,7 @@ __device__ static void amd_eliminate(int n, int *Pe, int *Iw, int *Len, int iwle
 // (HMD.cpp:62-72).
 __global__ void amd_batch_kernel(int count, const int *__restrict__ vtx_ptr, const int *__restrict__ G,
                                  const int *__restrict__ sub_Mi, const long long *__restrict__ ws_ptr,
-                                 int *__restrict__ ws, int *__restrict__ perm_out) {
+                                 int *__restrict__ ws, int *__restrict__ perm_out, int smem_ints) {
   const int g = blockIdx.x;
   if (g >= count || threadIdx.x != 0) return;
   const int v0 = vtx_ptr[g], n = vtx_ptr[g + 1] - v0;
@@ -371,7 +371,14 @@ __global__ void amd_batch_kernel(int count, const int *__restrict__ vtx_ptr, con
   int *P = perm_out + v0;
   if (nz == 0) { for (int i = 0; i < n; i++) P[i] = i; return; }
   const int *Ci = sub_Mi + e0;
-  int *slab = ws + ws_ptr[g];
+  // quotient-graph staging: the whole work-space of a graph lives in shared memory when it fits
+  // (separators and small leaves: ~10x lower latency per dependent access), else in its slab
+  extern __shared__ int amd_smem[];
+  const long long need = 2 * (long long)n + (long long)nz + nz / 5 + 7 * (long long)n + 16;
+  const bool in_smem = need + n <= (long long)smem_ints;
+  int *slab = in_smem ? amd_smem : ws + ws_ptr[g];
+  int *const Pout = P;
+  if (in_smem) P = amd_smem + need;  // the pivot / Last array too; copied out at the end
   int *Len = slab, *Pinv = slab + n, *S = slab + 2 * (size_t)n;
   // symmetric pattern sizes (amd_aat) with P as the Tp workspace
   int *Tp = P;
@@ -434,12 +441,18 @@ __global__ void amd_batch_kernel(int count, const int *__restrict__ vtx_ptr, con
       Iw[Sp[i]++] = j; Iw[Sp[j]++] = i;
     }
   amd_eliminate(n, Pe, Iw, Len, iwlen, pfree, Nv, Pinv, P, Head, Elen, Degree, W);
+  if (in_smem) for (int i = 0; i < n; i++) Pout[i] = P[i];
 }
 
 int launch_amd_batch(int count, const int *vtx_ptr, const int *G, const int *sub_Mi,
                      const long long *ws_ptr, int *ws, int *perm_out, cudaStream_t s) {
   if (count <= 0) return 0;
-  amd_batch_kernel<<<count, 32, 0, s>>>(count, vtx_ptr, G, sub_Mi, ws_ptr, ws, perm_out);
+  int dev = 0, max_smem = 0;
+  PB_CUDA(cudaGetDevice(&dev));
+  PB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  const int smem_bytes = max_smem - 1024;
+  PB_CUDA(cudaFuncSetAttribute(amd_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  amd_batch_kernel<<<count, 32, smem_bytes, s>>>(count, vtx_ptr, G, sub_Mi, ws_ptr, ws, perm_out, smem_bytes / 4);
   PB_CUDA(cudaGetLastError());
   return 1;
 }

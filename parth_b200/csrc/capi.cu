@@ -318,6 +318,53 @@ int parth_b200_compute_permutation(parth_b200 *h, int *perm, int dim) {
   PB_API_END
 }
 
+int parth_b200_exchange_plan(parth_b200 *h, int *n_nodes, int *nodes, int *owner, int *sizes) {
+  if (!h || !n_nodes) return PARTH_B200_ERR_ARG;
+  *n_nodes = (int)h->xchg_nodes.size();
+  for (size_t i = 0; i < h->xchg_nodes.size(); i++) {
+    if (nodes) nodes[i] = h->xchg_nodes[i];
+    if (owner) owner[i] = h->xchg_owner[i];
+    if (sizes) sizes[i] = h->node_ptr[h->xchg_nodes[i] + 1] - h->node_ptr[h->xchg_nodes[i]];
+  }
+  return PARTH_B200_OK;
+}
+
+int parth_b200_pack_labels_dev(parth_b200 *h, const int *nodes, int n, int *dbuf) {
+  PB_API_BEGIN
+  if (!h->tree_init || n < 0 || (n > 0 && (!nodes || !dbuf))) throw StatusError(PARTH_B200_ERR_ARG, "pack_labels: bad argument");
+  stage_pack_labels(*h, nodes, n, dbuf, false);
+  PB_CUDA(cudaStreamSynchronize(h->stream));
+  PB_API_END
+}
+
+int parth_b200_unpack_labels_dev(parth_b200 *h, const int *nodes, int n, const int *dbuf) {
+  PB_API_BEGIN
+  if (!h->tree_init || n < 0 || (n > 0 && (!nodes || !dbuf))) throw StatusError(PARTH_B200_ERR_ARG, "unpack_labels: bad argument");
+  stage_pack_labels(*h, nodes, n, const_cast<int *>(dbuf), true);
+  PB_CUDA(cudaStreamSynchronize(h->stream));
+  PB_API_END
+}
+
+int parth_b200_finish_permutation_dev(parth_b200 *h, int *dperm, int dim) {
+  PB_API_BEGIN
+  if (!dperm || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "finish_permutation: bad argument");
+  stage_finish_permutation(*h, dperm, dim);
+  resolve_timers(*h);
+  PB_API_END
+}
+
+int parth_b200_finish_permutation(parth_b200 *h, int *perm, int dim) {
+  PB_API_BEGIN
+  if (!perm || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "finish_permutation: bad argument");
+  const size_t n_out = (size_t)h->M_n * dim;
+  h->d_out.reserve(n_out > 0 ? n_out : 1, h->stream);
+  stage_finish_permutation(*h, h->d_out.p, dim);
+  PB_CUDA(cudaMemcpyAsync(perm, h->d_out.p, sizeof(int) * n_out, cudaMemcpyDeviceToHost, h->stream));
+  h->stats.d2h_bytes += (long long)(sizeof(int) * n_out);
+  resolve_timers(*h);
+  PB_API_END
+}
+
 int parth_b200_map_mesh_perm_to_matrix_perm_dev(parth_b200 *h, const int *dmesh_perm, int n,
                                                 int *dout, int dim) {
   PB_API_BEGIN

@@ -116,6 +116,29 @@ __global__ void apply_order_kernel(const int *__restrict__ list, const int *__re
   mesh_perm[j + __ldg(meta + nd * 7 + 4)] = __ldg(dofs + a + k);
 }
 
+__global__ void pack_labels_kernel(const int *__restrict__ list, const int *__restrict__ vtx_ptr, int count, int total,
+                                   const int *__restrict__ node_ptr, const int *__restrict__ labels,
+                                   int *__restrict__ buf) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= total) return;
+  const int g = graph_of_vertex(vtx_ptr, count, v);
+  buf[v] = labels[__ldg(node_ptr + __ldg(list + g)) + (v - __ldg(vtx_ptr + g))];
+}
+
+__global__ void unpack_labels_kernel(const int *__restrict__ list, const int *__restrict__ vtx_ptr, int count, int total,
+                                     const int *__restrict__ node_ptr, const int *__restrict__ meta,
+                                     const int *__restrict__ dofs, const int *__restrict__ buf,
+                                     int *__restrict__ labels, int *__restrict__ mesh_perm) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= total) return;
+  const int g = graph_of_vertex(vtx_ptr, count, v);
+  const int nd = __ldg(list + g);
+  const int k = __ldg(node_ptr + nd) + (v - __ldg(vtx_ptr + g));
+  const int lab = buf[v];
+  labels[k] = lab;
+  mesh_perm[lab + __ldg(meta + nd * 7 + 4)] = __ldg(dofs + k);
+}
+
 // ------------------------------------------------------------------ host launchers
 static inline unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 256); }
 
@@ -166,6 +189,24 @@ int launch_marker_fill(const int *l2g, int n, const int *Mp, const int *Mi, cons
                        const int *g2l, const int *G, int *sub_Mi, cudaStream_t s) {
   if (n <= 0) return 0;
   marker_fill_kernel<<<blocks_for(n), 256, 0, s>>>(l2g, n, Mp, Mi, chosen, g2l, G, sub_Mi);
+  PB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int launch_pack_labels(const int *list, const int *vtx_ptr, int count, int total, const int *node_ptr,
+                       const int *labels, int *buf, cudaStream_t s) {
+  if (total <= 0) return 0;
+  pack_labels_kernel<<<blocks_for(total), 256, 0, s>>>(list, vtx_ptr, count, total, node_ptr, labels, buf);
+  PB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+int launch_unpack_labels(const int *list, const int *vtx_ptr, int count, int total, const int *node_ptr,
+                         const int *meta, const int *dofs, const int *buf, int *labels, int *mesh_perm,
+                         cudaStream_t s) {
+  if (total <= 0) return 0;
+  unpack_labels_kernel<<<blocks_for(total), 256, 0, s>>>(list, vtx_ptr, count, total, node_ptr, meta, dofs, buf, labels,
+                                                        mesh_perm);
   PB_CUDA(cudaGetLastError());
   return 1;
 }

@@ -32,6 +32,8 @@ struct parth_b200 {
   int coarse_policy = PARTH_B200_COARSE_REPAIR, assume_symmetric = 0;
   int build_mode = 0;  // dim == 1 filter kernel that proved itself last time: 0 closed-form offsets, 1 chained scan, 2 sample-tiled
   int rank = 0, world = 1;
+  std::vector<int> xchg_nodes, xchg_owner;  // sharded mode: plan of the last update
+  bool xchg_pending = false;
   bool builtin_decomposer = false, force_amd = false;
   parth_b200_decomposer decomposer = nullptr;
   void *decomposer_user = nullptr;

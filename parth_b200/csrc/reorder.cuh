@@ -28,6 +28,13 @@ int launch_apply_order(const int *list, const int *vtx_ptr, int count, int total
                        const int *meta, const int *dofs, const int *perm, int *labels, int *mesh_perm,
                        cudaStream_t s);
 
+// label slices of the listed nodes <-> one concatenated buffer (multi-GPU exchange)
+int launch_pack_labels(const int *list, const int *vtx_ptr, int count, int total, const int *node_ptr,
+                       const int *labels, int *buf, cudaStream_t s);
+int launch_unpack_labels(const int *list, const int *vtx_ptr, int count, int total, const int *node_ptr,
+                         const int *meta, const int *dofs, const int *buf, int *labels, int *mesh_perm,
+                         cudaStream_t s);
+
 // ---- amd.cu
 int launch_amd_batch(int count, const int *vtx_ptr, const int *G, const int *sub_Mi,
                      const long long *ws_ptr, int *ws, int *perm_out, cudaStream_t s);

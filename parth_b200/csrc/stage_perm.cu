@@ -341,8 +341,8 @@ static int global_perm(parth_b200 &h) {
   }
   if (!h.dirty_coarse.empty()) {
     if (h.coarse_policy == PARTH_B200_COARSE_REPORT) return PARTH_B200_NEEDS_REDISSECT;
-    // fine nodes first, as the reference does (Integrator.cpp:659)
-    if (!full) stage_permute_fine(h, h.dirty_fine);
+    // the reference orders the fine nodes first (Integrator.cpp:659); REPAIR re-orders them again
+    // together with the touched separators after the relocation, so once is enough
     return stage_coarse(h);
   }
   stage_permute_fine(h, h.dirty_fine);
@@ -352,6 +352,9 @@ static int global_perm(parth_b200 &h) {
 // ParthAPI::computePermutation (ParthAPI.cpp:191-279); dperm: device buffer of M_n*dim ints
 int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
   for (double &t : h.timer_ms) t = 0;
+  h.xchg_pending = false;
+  h.xchg_nodes.clear();
+  h.xchg_owner.clear();
   h.reuse = 0;
   h.n_changed = 0;
   h.sim_dim = dim;
@@ -375,11 +378,24 @@ int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
     } else {
       rc = global_perm(h);
     }
+    if (rc == PARTH_B200_OK && h.xchg_pending) {
+      // sharded mode: the other ranks' nodes are still missing; the caller gathers them, then
+      // stage_finish_permutation expands and snapshots
+      tc.stop();
+      return PARTH_B200_NEEDS_EXCHANGE;
+    }
     if (rc == PARTH_B200_OK) stage_expand(h, h.d_mesh_perm.p, h.M_n, dim, dperm);
     tc.stop();
   }
   stage_snapshot(h);
   return rc;
+}
+
+void stage_finish_permutation(parth_b200 &h, int *dperm, int dim) {
+  if (!h.xchg_pending) throw StatusError(PARTH_B200_ERR_ARG, "finish_permutation: no exchange pending");
+  h.xchg_pending = false;
+  stage_expand(h, h.d_mesh_perm.p, h.M_n, dim, dperm);
+  stage_snapshot(h);
 }
 
 }  // namespace pb

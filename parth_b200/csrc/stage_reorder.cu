@@ -88,8 +88,35 @@ bool device_orders_with_amd(const parth_b200 &h) {
 
 }  // namespace
 
+// sharded mode: deal the nodes to the ranks, largest first onto the least loaded rank (ties: lower
+// node id, lower rank) -- a pure function of the replicated tree, so every rank derives the same plan
+static std::vector<int> my_share(parth_b200 &h, const std::vector<int> &nodes) {
+  std::vector<int> order(nodes.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+  auto size_of = [&](int nd) { return h.node_ptr[nd + 1] - h.node_ptr[nd]; };
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    const int sa = size_of(nodes[a]), sb = size_of(nodes[b]);
+    return sa != sb ? sa > sb : nodes[a] < nodes[b];
+  });
+  std::vector<long long> load((size_t)h.world, 0);
+  h.xchg_nodes = nodes;
+  h.xchg_owner.assign(nodes.size(), 0);
+  for (int i : order) {
+    int best = 0;
+    for (int r = 1; r < h.world; r++) if (load[r] < load[best]) best = r;
+    h.xchg_owner[i] = best;
+    load[best] += size_of(nodes[i]);
+  }
+  h.xchg_pending = true;
+  std::vector<int> mine;
+  for (size_t i = 0; i < nodes.size(); i++) if (h.xchg_owner[i] == h.rank) mine.push_back(nodes[i]);
+  return mine;
+}
+
 // Integrator::permuteFineHMDNodes
-void stage_permute_fine(parth_b200 &h, const std::vector<int> &nodes) {
+void stage_permute_fine(parth_b200 &h, const std::vector<int> &all_nodes) {
+  if (all_nodes.empty()) return;
+  const std::vector<int> nodes = (h.world > 1 && !h.force_amd) ? my_share(h, all_nodes) : all_nodes;
   if (nodes.empty()) return;
   cudaStream_t s = h.stream;
   StageTimer tm(h, &h.stats.reorder_ms, /*accumulate=*/true);
@@ -162,6 +189,28 @@ void stage_submesh(parth_b200 &h, int node, int coarse, int *n_out, int *nnz_out
   if (Mp) read_ints(h, h.r_G.p, Mp, (size_t)n + 1);
   if (Mi && nnz > 0) read_ints(h, h.r_sub.p, Mi, (size_t)nnz);
   if (l2g && n > 0) read_ints(h, h.r_l2g.p, l2g, (size_t)n);
+}
+
+// multi-GPU exchange helpers: label slices of the listed nodes <-> a concatenated device buffer
+void stage_pack_labels(parth_b200 &h, const int *nodes_in, int n, int *dbuf, bool unpack) {
+  if (n <= 0) return;
+  std::vector<int> nodes(nodes_in, nodes_in + n);
+  cudaStream_t s = h.stream;
+  std::vector<int> vtx((size_t)n + 1, 0);
+  for (int g = 0; g < n; g++) {
+    if (nodes[g] < 0 || nodes[g] >= h.num_nodes) throw StatusError(PARTH_B200_ERR_ARG, "pack_labels: node id out of range");
+    vtx[g + 1] = vtx[g] + (h.node_ptr[nodes[g] + 1] - h.node_ptr[nodes[g]]);
+  }
+  h.r_list.reserve((size_t)n + 1, s);
+  h.r_vtx.reserve((size_t)n + 2, s);
+  PB_CUDA(cudaMemcpyAsync(h.r_list.p, nodes.data(), sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaMemcpyAsync(h.r_vtx.p, vtx.data(), sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+  if (unpack)
+    h.stats.kernels_launched += launch_unpack_labels(h.r_list.p, h.r_vtx.p, n, vtx[n], h.d_node_ptr.p, h.d_meta.p,
+                                                     h.d_dofs.p, dbuf, h.d_labels.p, h.d_mesh_perm.p, s);
+  else
+    h.stats.kernels_launched += launch_pack_labels(h.r_list.p, h.r_vtx.p, n, vtx[n], h.d_node_ptr.p, h.d_labels.p, dbuf, s);
 }
 
 // Dirty COARSE nodes.  The reference re-dissects the sub-tree with METIS_ComputeVertexSeparator

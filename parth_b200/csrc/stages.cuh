@@ -60,6 +60,8 @@ void stage_relocate(parth_b200 &h, int threshold_node, std::vector<int> &dirty_f
 // stage_reorder.cu: (a12-a14) extraction + ordering of dirty fine nodes, coarse-node policy
 void stage_permute_fine(parth_b200 &h, const std::vector<int> &nodes);
 int stage_coarse(parth_b200 &h);
+void stage_pack_labels(parth_b200 &h, const int *nodes, int n, int *dbuf, bool unpack);
+void stage_finish_permutation(parth_b200 &h, int *dperm, int dim);
 void stage_submesh(parth_b200 &h, int node, int coarse, int *n, int *nnz, int *Mp, int *Mi, int *l2g);
 void stage_amd_batch(parth_b200 &h, int count, const int *graph_ptr, const int *Mp, const int *Mi, int *perm);
 
