@@ -269,3 +269,49 @@ def dof_to_node(meta, node_ptr, dofs):
     out = np.empty(len(dofs), np.int32)
     out[dofs] = node_of
     return out
+
+
+def lattice_pattern(n, dirs, diagonal=True, dtype=np.int32):
+    """Symmetric pattern on an n^3 lattice: vertex (x,y,z) ~ (x,y,z) +/- d for every d in `dirs`
+    (index z + y*n + x*n^2).  Returns (N, Ap, Ai) with ascending columns.  Memory-lean: one offset
+    at a time, so it also serves the 512^3 config."""
+    N = n * n * n
+    ind = np.arange(N, dtype=np.int64)
+    z = (ind % n).astype(np.int32)
+    y = ((ind // n) % n).astype(np.int32)
+    x = (ind // (n * n)).astype(np.int32)
+    offs = []
+    for (dx, dy, dz) in dirs:
+        for s in (-1, 1):
+            offs.append((s * (dz + dy * n + dx * n * n), s * dx, s * dy, s * dz))
+    if diagonal:
+        offs.append((0, 0, 0, 0))
+    offs.sort()
+    masks = []
+    cnt = np.zeros(N, np.int32)
+    for (o, dx, dy, dz) in offs:
+        m = np.ones(N, bool)
+        for c, d in ((x, dx), (y, dy), (z, dz)):
+            if d > 0:
+                m &= c < n - d
+            elif d < 0:
+                m &= c >= -d
+        masks.append(m)
+        cnt += m
+    Ap = np.zeros(N + 1, np.int64)
+    np.cumsum(cnt, out=Ap[1:])
+    Ai = np.empty(int(Ap[-1]), dtype)
+    pos = Ap[:-1].copy()
+    for (o, _, _, _), m in zip(offs, masks):
+        Ai[pos[m]] = (ind[m] + o).astype(dtype)
+        pos[m] += 1
+    return N, Ap.astype(np.int32) if Ap[-1] < 2 ** 31 else Ap, Ai
+
+
+KUHN_DIRS = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (0, 1, 1), (1, 0, 1), (1, 1, 1)]
+GRID_DIRS = [(1, 0, 0), (0, 1, 0), (0, 0, 1)]
+
+
+def geometric_tree_fast(n, levels):
+    """geometric_tree without per-node python lists of ids: same output, usable at 512^3"""
+    return geometric_tree(n, levels)
