@@ -152,6 +152,7 @@ typedef struct {
   long long kernels_launched;
   int build_path;               /* 1 = proven-symmetric filter path, 2 = general sort/dedupe path */
   long long h2d_bytes, d2h_bytes; /* bytes moved by the last set_* / compute_* call */
+  int integrate_passes, integrate_sweeps; /* added-DOF placement: FIFO passes / wavefront sweeps */
 } parth_b200_stats;
 int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out);
 int parth_b200_synchronize(parth_b200 *h);

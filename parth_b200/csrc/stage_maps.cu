@@ -518,7 +518,9 @@ void stage_integrate(parth_b200 &h) {
     cbuf.reserve(8, s);
     PlaceCounters *d_cnt = reinterpret_cast<PlaceCounters *>(cbuf.p);
     int sweep = 0;
+    h.stats.integrate_passes = 0;
     for (int pass = 1;; pass++) {
+      h.stats.integrate_passes = pass;
       PB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(PlaceCounters), s));
       count_unplaced_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.r_g2l.p, d_cnt);
       h.stats.kernels_launched++;
@@ -538,6 +540,7 @@ void stage_integrate(parth_b200 &h) {
       }
       if (c[1] == 0) break;  // a pass that placed nothing ends the loop
     }
+    h.stats.integrate_sweeps = sweep;
     // ---- leftovers: last empty leaf, else the last node (Integrator.cpp:204-217)
     h.w2.reserve((size_t)total + 2, s);
     h.scan_ws.reserve(scan_ws_words((size_t)total + 1), s);

@@ -63,6 +63,22 @@ __global__ void expand_kernel(const int *__restrict__ mesh_perm, long long n_out
   out[o] = __ldg(mesh_perm + i) * d + r;
 }
 
+// vectorised form: one thread expands 4 consecutive mesh indices into DIM 128-bit stores
+// (4*DIM contiguous ints, 16-byte aligned), so every store instruction moves full vectors
+template <int DIM>
+__global__ void expand_vec_kernel(const int4 *__restrict__ mesh_perm4, int n4, int4 *__restrict__ out4) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int4 v = ld_stream4(mesh_perm4 + i);
+  const int src[4] = {v.x, v.y, v.z, v.w};
+  int o[4 * DIM];
+#pragma unroll
+  for (int k = 0; k < 4 * DIM; k++) o[k] = src[k / DIM] * DIM + (k % DIM);
+#pragma unroll
+  for (int q = 0; q < DIM; q++)
+    st_stream4(out4 + (size_t)i * DIM + q, make_int4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
+}
+
 // HMD::isSeparator (HMD.cpp:366-379)
 __device__ __forceinline__ bool is_separator_dev(int sep, int node) {
   int a = (node - 1) / 2;
@@ -142,6 +158,25 @@ int launch_dof2node(const int *node_ptr, int nodes, const int *dofs, int total, 
 int launch_expand(const int *mesh_perm, int M_n, int dim, int *out, cudaStream_t s) {
   long long n_out = (long long)M_n * dim;
   if (n_out <= 0) return 0;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(mesh_perm) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  if (aligned && dim >= 1 && dim <= 4 && M_n >= 4) {
+    const int n4 = M_n / 4;
+    const unsigned vb = (unsigned)((n4 + 255) / 256);
+    const int4 *in4 = reinterpret_cast<const int4 *>(mesh_perm);
+    int4 *out4 = reinterpret_cast<int4 *>(out);
+    if (dim == 1) expand_vec_kernel<1><<<vb, 256, 0, s>>>(in4, n4, out4);
+    else if (dim == 2) expand_vec_kernel<2><<<vb, 256, 0, s>>>(in4, n4, out4);
+    else if (dim == 3) expand_vec_kernel<3><<<vb, 256, 0, s>>>(in4, n4, out4);
+    else expand_vec_kernel<4><<<vb, 256, 0, s>>>(in4, n4, out4);
+    PB_CUDA(cudaGetLastError());
+    const int rest = M_n - 4 * n4;  // at most 3 mesh indices left: the scalar kernel on the tail
+    if (rest > 0) {
+      expand_kernel<0><<<1, 32, 0, s>>>(mesh_perm + 4 * n4, (long long)rest * dim, dim, out + (long long)4 * n4 * dim);
+      PB_CUDA(cudaGetLastError());
+      return 2;
+    }
+    return 1;
+  }
   unsigned blocks = (unsigned)((n_out + 255) / 256);
   if (dim == 1) expand_kernel<1><<<blocks, 256, 0, s>>>(mesh_perm, n_out, dim, out);
   else if (dim == 2) expand_kernel<2><<<blocks, 256, 0, s>>>(mesh_perm, n_out, dim, out);

@@ -84,7 +84,7 @@ def config3():
                       "removed_added": int((new_to_old == -1).sum()), "build_ms": sb["build_ms"],
                       "build_kernel_ms": sb["build_kernel_ms"], "build_path": sb["build_path"],
                       "build_GBs": alg / sb["build_kernel_ms"] / 1e6, "build_frac": alg / sb["build_kernel_ms"] / 1e6 / PEAK,
-                      "integrate_ms": s["integrate_ms"], "detect_ms": s["detect_ms"], "expand_ms": s["expand_ms"],
+                      "integrate_ms": s["integrate_ms"], "integrate_passes": s["integrate_passes"], "integrate_sweeps": s["integrate_sweeps"], "detect_ms": s["detect_ms"], "expand_ms": s["expand_ms"],
                       "changes": g.getNumChanges(), "reuse": g.getReuse(), "status": int(st), "oracle_status": int(ost),
                       "cpu_port_s": cpu_s, "gen_s": gen_s}), flush=True)
 
