@@ -59,7 +59,7 @@ static void grid(int n, bool extra, int &N, std::vector<int> &Ap, std::vector<in
       }
   if (extra) {  // a handful of new couplings, as in the reference's {0..4}_matrix.mtx fixtures
     for (int k = 0; k < 4; k++) {
-      int a = id(1 + k, 2, 3), b = id(n - 2 - k, n - 3, n - 4);
+      int a = id(3 + k, 3, 3), b = id(3 + k, 5, 3);  // two cells apart: a local change
       col[a].push_back(b);
       col[b].push_back(a);
     }

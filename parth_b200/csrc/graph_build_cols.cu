@@ -322,25 +322,33 @@ build_cols_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
 constexpr int K8_THREADS = 256;
 constexpr int K8_REG = 8;  // columns up to this length are handled entirely in registers
 
-// mirror probe of the upper entry (c, r): is c in column r?  First the position a symmetric
-// stencil predicts (mirror index from the end), then a binary search.
+// mirror probe of the upper entry (c, r): is c in column r?  [a, b) is column r in sample space;
+// for dim > 1 its samples sit at Ai[raw + k*dim] / dim.  First the position a symmetric stencil
+// predicts (mirror index from the end), then a binary search.
+template <bool DIM1>
 __device__ __forceinline__ bool has_mirror(const int *__restrict__ Ai, const int *s_val, int sbase, int q0, int q1,
-                                           int a, int b, int idx_from_start, int len, int c) {
+                                           int a, int b, long long raw, int dim, int idx_from_start, int len, int c) {
   const bool in_tile = a >= q0 && b <= q1;
-  const int g = b - 1 - idx_from_start + (len - (b - a));  // same distance from the end, corrected for the length
-  if (g >= a && g < b) {
-    const int v = in_tile ? s_val[g - sbase] : __ldg(Ai + g);
-    if (v == c) return true;
+  auto val = [&](int pos) -> int {
+    if (in_tile) return s_val[pos - sbase];
+    return DIM1 ? __ldg(Ai + pos) : __ldg(Ai + raw + (long long)(pos - a) * dim) / dim;
+  };
+  const int g = a + len - 1 - idx_from_start;
+  if (g >= a && g < b && val(g) == c) return true;
+  int lo = a, hi = b;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (val(mid) < c) lo = mid + 1; else hi = mid;
   }
-  int found;
-  col_lower_bound(Ai, s_val, sbase, q0, q1, a, b, c, &found);
-  return found == c;
+  return lo < b && val(lo) == c;
 }
 
+template <bool DIM1>
 __global__ void __launch_bounds__(K8_THREADS)
-build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M, int Q,
-                       const int *__restrict__ tile_c, int num_tiles, int *__restrict__ Mp,
+build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, const int *__restrict__ V, int dim, int M,
+                       int Q, const int *__restrict__ tile_c, int num_tiles, int *__restrict__ Mp,
                        int *__restrict__ Mi, BuildStatus *__restrict__ st, int check_mirror) {
+  // V: exclusive prefix of the samples per (block-)column; for dim == 1 it is Ap itself
   __shared__ __align__(16) int s_val[K7_CAP + 4];
   __shared__ __align__(16) int s_out[K7_CAP];
   __shared__ int s_long[K7_CAP / K7_LONG + 2];
@@ -350,9 +358,9 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, i
   const int tile = blockIdx.x;
   const int c0 = tile_c[tile], c1 = tile_c[tile + 1];
   int nc = c1 - c0;
-  const int q0 = __ldg(Ap + c0), q1 = __ldg(Ap + c1);
+  const int q0 = __ldg(V + c0), q1 = __ldg(V + c1);
   int nq = q1 - q0;
-  const int sbase = q0 & ~3;
+  const int sbase = DIM1 ? (q0 & ~3) : q0;
   unsigned flags = 0;
   if (nq > K7_CAP || nq < 0 || nc > K7_MAXROUNDS * K8_THREADS) {
     if (tid == 0) atomicOr(&st->flags, BUILD_WIDE);
@@ -360,7 +368,16 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, i
   }
   if (tid == 0) s_nlong = 0;
   // ---- A
-  {
+  if (!DIM1) {
+    // block-column c is matrix column c*dim sampled at every dim-th entry (ParthAPI.cpp:371-374);
+    // one thread gathers one column (all sectors of that column are used by its own later loads)
+    for (int lc = tid; lc < nc; lc += K8_THREADS) {
+      const int c = c0 + lc;
+      const int vs = __ldg(V + c), len = __ldg(V + c + 1) - vs;
+      const int *col = Ai + __ldg(Ap + (long long)c * dim);
+      for (int k = 0; k < len; k++) s_val[vs - sbase + k] = __ldg(col + (long long)k * dim) / dim;
+    }
+  } else {
     const int n4 = (q0 + nq - sbase + 3) >> 2;
     const int4 *src = reinterpret_cast<const int4 *>(Ai + sbase);
     if ((reinterpret_cast<uintptr_t>(Ai) & 15) == 0) {
@@ -383,7 +400,7 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, i
   // ---- B: one thread per column, proof + copy in one go
   for (int lc = tid; lc < nc; lc += K8_THREADS) {
     const int c = c0 + lc;
-    const int vs = __ldg(Ap + c), ve = __ldg(Ap + c + 1);
+    const int vs = __ldg(V + c), ve = __ldg(V + c + 1);
     const int len = ve - vs;
     Mp[c] = vs - c;
     if (len <= 0) {
@@ -428,16 +445,19 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, i
         // upper entries, four at a time: the Ap pairs first (all loads in flight), then the probes
         for (int i = low + has; i < len; i += 4) {
           int rr[4], a[4], b[4];
+          long long raw[4];
 #pragma unroll
           for (int u = 0; u < 4; u++) {
             const bool v = i + u < len;
             rr[u] = v ? sp[i + u] : 0;
-            a[u] = v ? __ldg(Ap + rr[u]) : 0;
-            b[u] = v ? __ldg(Ap + rr[u] + 1) : 0;
+            a[u] = v ? __ldg(V + rr[u]) : 0;
+            b[u] = v ? __ldg(V + rr[u] + 1) : 0;
+            raw[u] = (!DIM1 && v) ? __ldg(Ap + (long long)rr[u] * dim) : 0;
           }
 #pragma unroll
           for (int u = 0; u < 4; u++)
-            if (i + u < len && !has_mirror(Ai, s_val, sbase, q0, q0 + nq, a[u], b[u], i + u, len, c)) flags |= BUILD_ASYM;
+            if (i + u < len && !has_mirror<DIM1>(Ai, s_val, sbase, q0, q0 + nq, a[u], b[u], raw[u], dim, i + u, len, c))
+              flags |= BUILD_ASYM;
         }
       }
     } else if (len <= K7_LONG) {
@@ -458,7 +478,9 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, i
       if (check_mirror && !(flags & (BUILD_RANGE | BUILD_UNSORTED)))
         for (int i = low + has; i < len; i++) {
           const int r = sp[i];
-          if (!has_mirror(Ai, s_val, sbase, q0, q0 + nq, __ldg(Ap + r), __ldg(Ap + r + 1), i, len, c)) flags |= BUILD_ASYM;
+          if (!has_mirror<DIM1>(Ai, s_val, sbase, q0, q0 + nq, __ldg(V + r), __ldg(V + r + 1),
+                                DIM1 ? 0 : __ldg(Ap + (long long)r * dim), dim, i, len, c))
+            flags |= BUILD_ASYM;
         }
     } else {
       s_long[atomicAdd(&s_nlong, 1)] = lc;
@@ -470,7 +492,7 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, i
   for (int li = warp; li < nlong; li += K8_THREADS / 32) {
     const int lc = s_long[li];
     const int c = c0 + lc;
-    const int vs = __ldg(Ap + c), ve = __ldg(Ap + c + 1), len = ve - vs;
+    const int vs = __ldg(V + c), ve = __ldg(V + c + 1), len = ve - vs;
     const int *sp = s_val + (vs - sbase);
     const int o0 = (vs - q0) - lc;
     if (o0 < 0) { flags |= BUILD_NODIAG; continue; }
@@ -502,7 +524,9 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, i
     if (check_mirror && !(f & (BUILD_RANGE | BUILD_UNSORTED)))
       for (int i = low + has + lane; i < len; i += 32) {
         const int r = sp[i];
-        if (!has_mirror(Ai, s_val, sbase, q0, q0 + nq, __ldg(Ap + r), __ldg(Ap + r + 1), i, len, c)) f |= BUILD_ASYM;
+        if (!has_mirror<DIM1>(Ai, s_val, sbase, q0, q0 + nq, __ldg(V + r), __ldg(V + r + 1),
+                              DIM1 ? 0 : __ldg(Ap + (long long)r * dim), dim, i, len, c))
+          f |= BUILD_ASYM;
       }
     flags |= f;
     if (lane == 0) diff += (len - has - low) - low;
@@ -528,17 +552,21 @@ int build_cols_tiles(int Q) { return (Q + K7_TILE - 1) / K7_TILE; }
 
 int build_cols_launch(const BuildArgs &a, bool spec, cudaStream_t s) {
   const int num_tiles = build_cols_tiles(a.Q);
+  const int *V = a.dim == 1 ? a.Ap : a.V;
   PB_CUDA(cudaMemsetAsync(a.status, 0, sizeof(BuildStatus), s));
   if (num_tiles == 0) {
     PB_CUDA(cudaMemsetAsync(a.Mp, 0, sizeof(int) * ((size_t)a.M + 1), s));
     return 0;
   }
   if (!spec) PB_CUDA(cudaMemsetAsync(a.desc, 0, sizeof(unsigned long long) * (size_t)num_tiles, s));
-  build_cols_partition_kernel<<<(num_tiles + 256) / 256, 256, 0, s>>>(a.Ap, a.M, num_tiles, a.tile_c);
+  build_cols_partition_kernel<<<(num_tiles + 256) / 256, 256, 0, s>>>(V, a.M, num_tiles, a.tile_c);
   if (a.ev_a) cudaEventRecord(a.ev_a, s);
-  if (spec)
-    build_cols_spec_kernel<<<num_tiles, K8_THREADS, 0, s>>>(a.Ap, a.Ai, a.M, a.Q, a.tile_c, num_tiles, a.Mp, a.Mi,
-                                                          a.status, a.check_mirror);
+  if (spec && a.dim == 1)
+    build_cols_spec_kernel<true><<<num_tiles, K8_THREADS, 0, s>>>(a.Ap, a.Ai, V, 1, a.M, a.Q, a.tile_c, num_tiles, a.Mp,
+                                                                a.Mi, a.status, a.check_mirror);
+  else if (spec)
+    build_cols_spec_kernel<false><<<num_tiles, K8_THREADS, 0, s>>>(a.Ap, a.Ai, V, a.dim, a.M, a.Q, a.tile_c, num_tiles,
+                                                                 a.Mp, a.Mi, a.status, a.check_mirror);
   else
     build_cols_kernel<false><<<num_tiles, K7_THREADS, 0, s>>>(a.Ap, a.Ai, a.M, a.Q, a.tile_c, num_tiles, a.Mp, a.Mi,
                                                             a.status, a.desc, a.check_mirror);

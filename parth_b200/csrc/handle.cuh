@@ -30,6 +30,7 @@ struct parth_b200 {
   int reorder_type = PARTH_B200_METIS, nd_levels = 8, lagging = 1, aggressive = 0;
   int relocate_lvl = 2, lag_lvl = 5, verbose = 1, sim_dim = 1;
   int coarse_policy = PARTH_B200_COARSE_REPAIR, assume_symmetric = 0;
+  int build_mode_n = 0;  // dim > 1: 0 closed-form offsets (column-aligned), 1 sample-tiled chained scan
   int build_mode = 0;  // dim == 1 filter kernel that proved itself last time: 0 closed-form offsets, 1 chained scan, 2 sample-tiled
   int rank = 0, world = 1;
   std::vector<int> xchg_nodes, xchg_owner;  // sharded mode: plan of the last update

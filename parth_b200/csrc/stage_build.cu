@@ -75,7 +75,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   // anyway and is cached for it.
   h.diff_cached = false;
   h.cur_sym_proven = false;
-  const bool incremental = !h.assume_symmetric && dim == 1 && h.prev_sym_proven && M == h.M_n_prev &&
+  const bool incremental = !h.assume_symmetric && h.prev_sym_proven && M == h.M_n_prev &&
                            h.Mp_prev.p && h.Mi_prev.p;
   a.check_mirror = (h.assume_symmetric || incremental) ? 0 : 1;
   const int tiles = build_filter_tiles(M, Q);
@@ -102,12 +102,15 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
     if (dim == 1 && h.build_mode <= 1) {
       if (h.build_mode == 0 && build_pipe_supported(a)) h.stats.kernels_launched += build_pipe_launch(a, h.num_sms, s);
       else h.stats.kernels_launched += build_cols_launch(a, h.build_mode == 0, s);
+    } else if (dim > 1 && h.build_mode_n == 0) {
+      h.stats.kernels_launched += build_cols_launch(a, true, s);  // closed-form offsets, strided samples
     } else {
       h.stats.kernels_launched += build_filter_launch(a, s);
     }
   };
-  auto diff_ok = [&]() { return (dim == 1 && h.build_mode <= 1) ? st.diff_sum == 0 : st.diff_mod == 0; };
-  if (dim == 1) {
+  auto cols_family = [&]() { return (dim == 1 && h.build_mode <= 1) || (dim > 1 && h.build_mode_n == 0); };
+  auto diff_ok = [&]() { return cols_family() ? st.diff_sum == 0 : st.diff_mod == 0; };
+  {
     const int tiles7 = build_cols_tiles(Q);
     h.tile_c.reserve((size_t)std::max(tiles, tiles7) + 2, s);
     h.desc.reserve((size_t)std::max(tiles, tiles7) + 1, s);
@@ -124,6 +127,9 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
       const unsigned only = st.flags & ~(BUILD_NODIAG | BUILD_WIDE);
       if (h.build_mode == 0 && (st.flags & BUILD_NODIAG) && !only) { h.build_mode = 1; continue; }
       if ((st.flags & BUILD_WIDE) && !only) { h.build_mode = 2; continue; }
+    } else if (dim > 1 && h.build_mode_n == 0) {
+      const unsigned only = st.flags & ~(BUILD_NODIAG | BUILD_WIDE);
+      if ((st.flags & (BUILD_NODIAG | BUILD_WIDE)) && !only) { h.build_mode_n = 1; continue; }  // sample-tiled, chained scan
     }
     break;
   }
