@@ -97,6 +97,110 @@ __global__ void etree_wave_kernel(const int *__restrict__ ranges, int n_ranges, 
   }
 }
 
+// ---------------------------------------------------------------- fast path (valid separator tree)
+// One CTA per separator-tree node.  The node's own slice of anc[] lives in shared memory; a
+// neighbour in a child sub-tree enters through flat[k], the root of its already finished
+// component (kept up to date by the two flatten kernels after every wave), so a walk costs one
+// global load plus a few shared-memory steps.  Adjacency is prefetched 128 columns at a time by
+// the whole CTA; warp 0 then walks the columns in order, lanes over the neighbours of one column.
+constexpr int E2_THREADS = 128;
+constexpr int E2_CHUNK = 128;
+constexpr int E2_DEG = 32;
+constexpr int E2_OUT = 1 << 30;  // tag: the entry is a component root outside the node's own slice
+
+__global__ void __launch_bounds__(E2_THREADS)
+etree_node_kernel(const int *__restrict__ ranges, const int *__restrict__ perm, const int *__restrict__ inv,
+                  const int *__restrict__ Mp, const int *__restrict__ Mi, const int *__restrict__ flat,
+                  volatile int *anc, int *parent, int smem_cap) {
+  extern __shared__ int e2_anc[];
+  __shared__ int s_nbr[E2_CHUNK][E2_DEG];
+  __shared__ int s_cnt[E2_CHUNK];
+  const int b = ranges[2 * blockIdx.x], e = ranges[2 * blockIdx.x + 1];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const bool in_smem = e - b <= smem_cap;
+  if (in_smem) for (int i = tid; i < e - b; i += E2_THREADS) e2_anc[i] = -1;
+  volatile int *own = in_smem ? (volatile int *)e2_anc : anc + b;  // own[x - b]
+  __syncthreads();
+  for (int c0 = b; c0 < e; c0 += E2_CHUNK) {
+    {  // prefetch: thread t -> column c0 + t
+      const int j = c0 + tid;
+      int cnt = 0;
+      if (j < e) {
+        const int old = __ldg(perm + j);
+        const int s = __ldg(Mp + old), t = __ldg(Mp + old + 1);
+        if (t - s > E2_DEG) cnt = -1;  // long row: walked straight from global memory
+        else
+          for (int p = s; p < t; p++) {
+            const int k = __ldg(inv + __ldg(Mi + p));
+            if (k >= j) continue;
+            s_nbr[tid][cnt++] = k >= b ? k : (__ldg(flat + k) | E2_OUT);
+          }
+      }
+      s_cnt[tid] = cnt;
+    }
+    __syncthreads();
+    if (tid < 32) {
+      const int lim = min(E2_CHUNK, e - c0);
+      for (int t = 0; t < lim; t++) {
+        const int j = c0 + t;
+        const int cnt = s_cnt[t];
+        auto walk = [&](int k, bool outside) {
+          if (outside) {
+            const int a = anc[k];
+            if (a == j) return;
+            anc[k] = j;
+            if (a == -1) { parent[k] = j; return; }
+            k = a;  // a column of this node
+          }
+          for (;;) {
+            const int a = own[k - b];
+            if (a == j) break;
+            own[k - b] = j;
+            if (a == -1) { parent[k] = j; break; }
+            k = a;
+          }
+        };
+        if (cnt >= 0) {
+          if (lane < cnt) {
+            const int v = s_nbr[t][lane];
+            walk(v & ~E2_OUT, (v & E2_OUT) != 0);
+          }
+        } else {
+          const int old = __ldg(perm + j);
+          for (int p = __ldg(Mp + old) + lane; p < __ldg(Mp + old + 1); p += 32) {
+            const int k = __ldg(inv + __ldg(Mi + p));
+            if (k >= j) continue;
+            if (k >= b) walk(k, false); else walk(__ldg(flat + k), true);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+  }
+  if (in_smem) for (int i = tid; i < e - b; i += E2_THREADS) anc[b + i] = e2_anc[i];
+}
+
+// after wave w: (i) every column of a wave-w node learns the root of its component ...
+__global__ void flatten_own_kernel(const int *__restrict__ perm, const int *__restrict__ dof2node,
+                                   const int *__restrict__ nodewave, int w, int n, const int *__restrict__ anc,
+                                   int *__restrict__ flat) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n || __ldg(nodewave + __ldg(dof2node + __ldg(perm + j))) != w) return;
+  int r = j;
+  for (int a = anc[r]; a != -1; a = anc[r]) r = a;
+  flat[j] = r;
+}
+// ... (ii) and every column of an earlier wave follows its old root one hop further
+__global__ void flatten_below_kernel(const int *__restrict__ perm, const int *__restrict__ dof2node,
+                                     const int *__restrict__ nodewave, int w, int n, const int *__restrict__ anc,
+                                     int *__restrict__ flat) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n || __ldg(nodewave + __ldg(dof2node + __ldg(perm + j))) >= w) return;
+  const int a = anc[flat[j]];
+  if (a != -1) flat[j] = flat[a];
+}
+
 // ---------------------------------------------------------------- Euler tour of the etree
 // children CSR by parent; roots hang under the virtual vertex n
 __global__ void child_count_kernel(const int *__restrict__ parent, int n, int *__restrict__ cnt) {
@@ -274,6 +378,8 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
 
   // ---- waves of column ranges
   std::vector<std::vector<int>> waves;  // flattened (begin, end) pairs per wave
+  std::vector<int> node_wave;            // per separator-tree node (fast path only)
+  bool fast = false;
   if (!tree_aware) {
     waves.push_back({0, n});
   } else {
@@ -332,6 +438,7 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
         waves[w].push_back(h.meta[x * 7 + 4]);
         waves[w].push_back(h.meta[x * 7 + 4] + sz);
       }
+      if (nv == 0) { fast = true; node_wave = wave; }
     }
   }
   {
@@ -347,6 +454,33 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
       PB_CUDA(cudaStreamSynchronize(s));
     }
     size_t at = 0;
+    if (fast) {
+      // valid separator tree: shared-memory node kernel + component flattening between the waves
+      DevBuf<int> flatroot, d_wave;
+      flatroot.reserve((size_t)n, s);
+      d_wave.reserve(node_wave.size(), s);
+      PB_CUDA(cudaMemcpyAsync(d_wave.p, node_wave.data(), sizeof(int) * node_wave.size(), cudaMemcpyHostToDevice, s));
+      PB_CUDA(cudaStreamSynchronize(s));
+      int dev = 0, max_smem = 0;
+      PB_CUDA(cudaGetDevice(&dev));
+      PB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+      const int dyn = max_smem - 20 * 1024;  // static part: prefetched adjacency lists
+      PB_CUDA(cudaFuncSetAttribute(etree_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+      int wi = 0;
+      for (auto &w : waves) {
+        const int nr = (int)w.size() / 2;
+        if (nr > 0) {
+          etree_node_kernel<<<nr, E2_THREADS, dyn, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi, flatroot.p, anc.p, parent.p,
+                                                        dyn / 4);
+          flatten_own_kernel<<<nblk(n), 256, 0, s>>>(perm.p, h.d_dof2node.p, d_wave.p, wi, n, anc.p, flatroot.p);
+          flatten_below_kernel<<<nblk(n), 256, 0, s>>>(perm.p, h.d_dof2node.p, d_wave.p, wi, n, anc.p, flatroot.p);
+          h.stats.kernels_launched += 3;
+        }
+        at += w.size();
+        wi++;
+      }
+      PB_CUDA(cudaStreamSynchronize(s));
+    } else
     for (auto &w : waves) {
       const int nr = (int)w.size() / 2;
       if (nr > 0) {
