@@ -153,6 +153,9 @@ typedef struct {
   int build_path;               /* 1 = proven-symmetric filter path, 2 = general sort/dedupe path */
   long long h2d_bytes, d2h_bytes; /* bytes moved by the last set_* / compute_* call */
   int integrate_passes, integrate_sweeps; /* added-DOF placement: FIFO passes / wavefront sweeps */
+  double symbolic_etree_ms;               /* etree part of symbolic_ms */
+  double diff_kernel_ms;                  /* diff_rows_kernel alone (last build or detection that ran it) */
+  int symbolic_path;                      /* 2 = per-node shared-memory kernel, 1 = wave-scheduled walk, 0 = one range */
 } parth_b200_stats;
 int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out);
 int parth_b200_synchronize(parth_b200 *h);

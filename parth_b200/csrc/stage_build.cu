@@ -33,7 +33,11 @@ static void enqueue_changed_row_proof(parth_b200 &h, int M) {
   h.chg_rows.reserve((size_t)cap + 1, s);
   h.scan_ws.reserve(scan_ws_words((size_t)std::max(n_words, M) + 1), s);
   unsigned *bits = reinterpret_cast<unsigned *>(h.chg_bits.p);
-  h.stats.kernels_launched += launch_diff_rows(h.Mp_own.p, h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt_p(), s);
+  {
+    StageTimer td(h, &h.stats.diff_kernel_ms);
+    h.stats.kernels_launched += launch_diff_rows(h.Mp_own.p, h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt_p(), s);
+    td.stop();
+  }
   h.stats.kernels_launched += exclusive_scan<1>(h.chg_bits.p, h.chg_pre.p, n_words, h.scan_ws.p, s);
   h.stats.kernels_launched += launch_list_changed_rows(bits, h.chg_pre.p, n_words, M, h.chg_rows.p, cap, s);
   h.stats.kernels_launched += launch_sym_check_rows(h.chg_rows.p, &h.dcnt_p()->changed_rows, cap, h.Mp_own.p, h.Mi_own.p,

@@ -196,78 +196,92 @@ __global__ void regroup_place_join_kernel(const int *__restrict__ sptr, const in
 }
 
 // ---------------------------------------------------------------- (a6) added-DOF placement
-// state[d] for an added DOF d: placed_pass (0 = not placed) and dec (sweep in which its decision
-// for the current pass was taken).  A decision taken in sweep s is visible from sweep s+1 on.
-struct PlaceCounters { int undecided; int placed_in_pass; int pad0, pad1; };
+// Exact wavefront schedule of the reference's FIFO placement (Integrator.cpp:118-202).  Inside one
+// pass an added DOF d depends on the still-unplaced added neighbours with a smaller id (they precede
+// it in the queue); this is a DAG.  pass_init counts those predecessors and seeds the frontier with
+// the DOFs that have none; every sweep decides the DOFs of the current frontier (they only look at
+// decisions of earlier sweeps, i.e. earlier launches), releases their successors and appends the
+// ones that became ready to the next frontier.  Work per pass = edges among the unplaced DOFs.
+// state: placed_pass[d] (0 = not placed), indeg[d]; cnt[s] = size of the frontier of sweep s.
+struct PlaceCounters { int unplaced; int placed_in_pass; int pad0, pad1; };
 
-__global__ void place_sweep_kernel(const int *__restrict__ added, int n_added, const int *__restrict__ Mp,
-                                   const int *__restrict__ Mi, const int *__restrict__ n2o,
-                                   const int *__restrict__ meta, int *nd2n, int *placed_pass, int *dec,
-                                   int pass, int pass_start, int sweep, PlaceCounters *cnt) {
+__global__ void place_pass_init_kernel(const int *__restrict__ added, int n_added, const int *__restrict__ Mp,
+                                       const int *__restrict__ Mi, const int *__restrict__ n2o,
+                                       const int *__restrict__ placed_pass, int *__restrict__ indeg,
+                                       int *__restrict__ frontier, int *__restrict__ fcnt, PlaceCounters *cnt) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= n_added) return;
   const int d = added[q];
-  if (placed_pass[d] != 0) return;   // placed in an earlier pass or earlier in this one
-  if (dec[d] >= pass_start) return;  // deferred in this pass already
-  const int s = Mp[d], e = Mp[d + 1];
-  // ready <=> every still-unplaced-at-pass-start added neighbour with a smaller id has decided
-  for (int p = s; p < e; p++) {
+  if (placed_pass[d] != 0) return;
+  atomicAdd(&cnt->unplaced, 1);
+  int deg = 0;
+  for (int p = Mp[d]; p < Mp[d + 1]; p++) {
     const int nb = Mi[p];
-    if (nb >= d || __ldg(n2o + nb) != -1) continue;
-    const int pp = placed_pass[nb];
-    if (pp != 0 && pp < pass) continue;
-    const int dn = dec[nb];
-    if (!(dn >= pass_start && dn < sweep)) return;  // not decided yet (or decided in this very sweep)
+    deg += nb < d && __ldg(n2o + nb) == -1 && placed_pass[nb] == 0;
   }
-  // visible node of a neighbour, -1 if none
-  auto visible = [&](int nb) -> int {
-    if (__ldg(n2o + nb) != -1) return nd2n[nb];
-    const int pp = placed_pass[nb];
-    if (pp != 0 && (pp < pass || nb < d)) return nd2n[nb];
-    return -1;
-  };
-  int first = -1, result = -1;
-  bool many = false;
-  for (int p = s; p < e; p++) {
-    const int r = visible(Mi[p]);
-    if (r == -1) continue;
-    if (first == -1) first = r;
-    else if (r != first) many = true;
-  }
-  if (first == -1) {  // no placed neighbour: next ring
-    dec[d] = sweep;
-    atomicSub(&cnt->undecided, 1);
-    return;
-  }
-  if (!many) result = first;
-  else {
-    // minimum over all pairs of distinct neighbour nodes of {descendant if ancestor-related, else LCA}
-    int mn = 1 << 30;
-    for (int p = s; p < e; p++) {
-      const int ra = visible(Mi[p]);
-      if (ra == -1) continue;
-      for (int p2 = p + 1; p2 < e; p2++) {
-        const int rb = visible(Mi[p2]);
-        if (rb == -1 || rb == ra) continue;
-        const int big = ra > rb ? ra : rb, small = ra > rb ? rb : ra;
-        const int c = is_sep_d(small, big) ? big : lca_d(meta, small, big);
-        mn = c < mn ? c : mn;
-      }
-    }
-    result = mn;
-  }
-  nd2n[d] = result;
-  __threadfence();
-  placed_pass[d] = pass;
-  dec[d] = sweep;
-  atomicSub(&cnt->undecided, 1);
-  atomicAdd(&cnt->placed_in_pass, 1);
+  indeg[d] = deg;
+  if (deg == 0) frontier[atomicAdd(fcnt, 1)] = d;
 }
 
-__global__ void count_unplaced_kernel(const int *__restrict__ added, int n_added, const int *__restrict__ placed_pass,
-                                      PlaceCounters *cnt) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < n_added && placed_pass[added[q]] == 0) atomicAdd(&cnt->undecided, 1);
+__global__ void place_sweep_kernel(const int *__restrict__ frontier, const int *__restrict__ fcnt_in,
+                                   int *__restrict__ next, int *__restrict__ fcnt_out, const int *__restrict__ Mp,
+                                   const int *__restrict__ Mi, const int *__restrict__ n2o,
+                                   const int *__restrict__ meta, int *nd2n, int *placed_pass, int *indeg, int pass,
+                                   PlaceCounters *cnt) {
+  const int nf = *fcnt_in;
+  for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nf; q += gridDim.x * blockDim.x) {
+    const int d = frontier[q];
+    const int s = Mp[d], e = Mp[d + 1];
+    // visible node of a neighbour, -1 if none: survivors always; added DOFs placed in an earlier
+    // pass, or in this pass if they precede d in the queue (then they were decided in an earlier sweep)
+    auto visible = [&](int nb) -> int {
+      if (__ldg(n2o + nb) != -1) return nd2n[nb];
+      const int pp = placed_pass[nb];
+      if (pp != 0 && (pp < pass || nb < d)) return nd2n[nb];
+      return -1;
+    };
+    int first = -1, result = -1;
+    bool many = false;
+    for (int p = s; p < e; p++) {
+      const int r = visible(Mi[p]);
+      if (r == -1) continue;
+      if (first == -1) first = r;
+      else if (r != first) many = true;
+    }
+    if (first != -1) {
+      if (!many) result = first;
+      else {
+        // minimum over all pairs of distinct neighbour nodes of {descendant if ancestor-related, else LCA}
+        int mn = 1 << 30;
+        for (int p = s; p < e; p++) {
+          const int ra = visible(Mi[p]);
+          if (ra == -1) continue;
+          for (int p2 = p + 1; p2 < e; p2++) {
+            const int rb = visible(Mi[p2]);
+            if (rb == -1 || rb == ra) continue;
+            const int big = ra > rb ? ra : rb, small = ra > rb ? rb : ra;
+            const int c = is_sep_d(small, big) ? big : lca_d(meta, small, big);
+            mn = c < mn ? c : mn;
+          }
+        }
+        result = mn;
+      }
+    }
+    // release the successors first: their test "unplaced at pass start" must still see d as unplaced
+    // or placed in THIS pass, both of which hold before and after the write below
+    for (int p = s; p < e; p++) {
+      const int nb = Mi[p];
+      if (nb <= d || __ldg(n2o + nb) != -1) continue;
+      const int pp = placed_pass[nb];
+      if (pp != 0 && pp != pass) continue;            // placed in an earlier pass: not in this DAG
+      if (atomicSub(indeg + nb, 1) == 1) next[atomicAdd(fcnt_out, 1)] = nb;
+    }
+    if (first != -1) {  // no placed neighbour: stays unplaced, next ring
+      nd2n[d] = result;
+      placed_pass[d] = pass;
+      atomicAdd(&cnt->placed_in_pass, 1);
+    }
+  }
 }
 
 __global__ void finish_added_kernel(const int *__restrict__ added, int n_added, int spare, int *__restrict__ nd2n,
@@ -510,37 +524,46 @@ void stage_integrate(parth_b200 &h) {
   if (n_added > 0) {
     // ---- ring placement (Integrator.cpp:118-202)
     h.r_g2l.reserve((size_t)M + 1, s);  // placed_pass
-    h.r_l2g.reserve((size_t)M + 1, s);  // dec
+    h.r_l2g.reserve((size_t)M + 1, s);  // indeg
     PB_CUDA(cudaMemsetAsync(h.r_g2l.p, 0, sizeof(int) * (size_t)M, s));
-    fill_kernel<<<nblk(M), 256, 0, s>>>(h.r_l2g.p, M, -1);
-    h.stats.kernels_launched++;
-    pb::DevBuf<int> cbuf;
+    constexpr int kBatch = 16;          // sweeps enqueued per read-back
+    const int max_sweeps = n_added + kBatch + 2;
+    pb::DevBuf<int> cbuf, fr, fcnt;
     cbuf.reserve(8, s);
+    fr.reserve((size_t)2 * n_added + 2, s);
+    fcnt.reserve((size_t)max_sweeps + kBatch + 4, s);
     PlaceCounters *d_cnt = reinterpret_cast<PlaceCounters *>(cbuf.p);
-    int sweep = 0;
-    h.stats.integrate_passes = 0;
+    int *F[2] = {fr.p, fr.p + n_added};
+    std::vector<int> fc((size_t)kBatch);
+    const unsigned grid = std::min<unsigned>(nblk(n_added), 4u * (unsigned)h.num_sms);
+    h.stats.integrate_passes = h.stats.integrate_sweeps = 0;
     for (int pass = 1;; pass++) {
       h.stats.integrate_passes = pass;
       PB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(PlaceCounters), s));
-      count_unplaced_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.r_g2l.p, d_cnt);
+      PB_CUDA(cudaMemsetAsync(fcnt.p, 0, sizeof(int) * ((size_t)max_sweeps + kBatch + 4), s));
+      place_pass_init_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.Mp, h.Mi, h.new_to_old.p, h.r_g2l.p,
+                                                          h.r_l2g.p, F[0], fcnt.p, d_cnt);
       h.stats.kernels_launched++;
-      const int pass_start = sweep;
+      int sweep = 0;
+      bool done = false;
+      while (!done) {
+        for (int rep = 0; rep < kBatch; rep++, sweep++) {
+          place_sweep_kernel<<<grid, 256, 0, s>>>(F[sweep & 1], fcnt.p + sweep, F[(sweep + 1) & 1], fcnt.p + sweep + 1,
+                                                  h.Mp, h.Mi, h.new_to_old.p, h.d_meta.p, nd2n, h.r_g2l.p, h.r_l2g.p,
+                                                  pass, d_cnt);
+          h.stats.kernels_launched++;
+        }
+        // an empty frontier ends the pass (the dependency graph is acyclic)
+        read_ints(h, fcnt.p + sweep - kBatch + 1, fc.data(), (size_t)kBatch);
+        for (int v : fc) if (v == 0) done = true;
+        if (sweep > max_sweeps) throw StatusError(PARTH_B200_ERR_INTERNAL, "integrate: placement did not terminate");
+      }
+      h.stats.integrate_sweeps += sweep;
       int c[4] = {0, 0, 0, 0};
       read_ints(h, reinterpret_cast<const int *>(d_cnt), c, 4);
-      if (c[0] == 0) break;
-      while (c[0] > 0) {
-        // a few sweeps per read-back: a sweep with nothing ready is a cheap no-op
-        for (int rep = 0; rep < 4; rep++) {
-          place_sweep_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.Mp, h.Mi, h.new_to_old.p, h.d_meta.p,
-                                                          nd2n, h.r_g2l.p, h.r_l2g.p, pass, pass_start, sweep, d_cnt);
-          h.stats.kernels_launched++;
-          sweep++;
-        }
-        read_ints(h, reinterpret_cast<const int *>(d_cnt), c, 4);
-      }
-      if (c[1] == 0) break;  // a pass that placed nothing ends the loop
+      if (c[0] == 0 || c[1] == 0) break;  // nothing left, or a pass that placed nothing ends the loop
+      if (c[1] == c[0]) break;            // everything that was left has been placed
     }
-    h.stats.integrate_sweeps = sweep;
     // ---- leftovers: last empty leaf, else the last node (Integrator.cpp:204-217)
     h.w2.reserve((size_t)total + 2, s);
     h.scan_ws.reserve(scan_ws_words((size_t)total + 1), s);

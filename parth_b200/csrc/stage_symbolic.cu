@@ -377,6 +377,7 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
   }
 
   // ---- waves of column ranges
+  StageTimer t_etree(h, &h.stats.symbolic_etree_ms);
   std::vector<std::vector<int>> waves;  // flattened (begin, end) pairs per wave
   std::vector<int> node_wave;            // per separator-tree node (fast path only)
   bool fast = false;
@@ -490,6 +491,8 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
       }
       at += w.size();
     }
+    h.stats.symbolic_path = fast ? 2 : (tree_aware ? 1 : 0);
+    t_etree.stop();
     int err = 0;
     read_ints(h, flag.p + 4, &err, 1);  // also keeps `ranges` alive until the waves are done
     if (err) throw StatusError(PARTH_B200_ERR_INTERNAL, "symbolic: etree walk did not terminate");

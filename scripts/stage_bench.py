@@ -32,7 +32,12 @@ for assume in (False, True):
               f"detect={s2['detect_ms']:.3f} dirty={s2['dirty_ms']:.3f} reorder={s2['reorder_ms']:.3f} expand={s2['expand_ms']:.3f} "
               f"compute_wall={1e3*(t1-t0):.3f} changes={g.getNumChanges()} reuse={g.getReuse():.5f} dirty={g.dirty()[1].tolist()}")
 if what == "all":
-    t0 = time.perf_counter()
-    parent, cc, lnz = g.symbolic(None)
-    t1 = time.perf_counter()
-    print(f"symbolic: nnz(L)={lnz} device={g.stats()['symbolic_ms']:.1f} ms wall={1e3*(t1-t0):.1f} ms")
+    for fresh in (False, True):
+        if fresh:  # pristine tree + graph: the separator property holds everywhere
+            g.import_tree(st.tree(), st.Mp, st.Mi); g.setMesh(st.N, st.Mp, st.Mi)
+        t0 = time.perf_counter()
+        parent, cc, lnz = g.symbolic(None)
+        t1 = time.perf_counter()
+        s = g.stats()
+        print(f"symbolic (fresh={fresh}): nnz(L)={lnz} device={s['symbolic_ms']:.1f} ms etree={s['symbolic_etree_ms']:.1f} ms "
+              f"path={s['symbolic_path']} wall={1e3*(t1-t0):.1f} ms")

@@ -53,3 +53,13 @@ def test_product_never_imports_the_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b|cpu_parth|liboracle|libparth_ref", s, flags=re.M):
                     bad.append(f)
     assert not bad, bad
+
+
+def test_cpp_drop_in_example_compiles_and_links():
+    """the header-only PARTH::ParthAPI (include/parth/parth.h) and the quick_start flow of the
+    reference (examples/api_demos/quick_start.cpp:72-118) build against the library with g++ alone"""
+    from parth_b200 import build
+    build.build()
+    exe = build.build_example("quick_start")
+    import os
+    assert os.path.exists(exe)
