@@ -65,6 +65,7 @@ struct parth_b200 {
 
   // ---- separator tree
   bool tree_init = false;
+  bool meta_heap = false;  // stored parent / level fields agree with heap arithmetic (checked at import)
   int num_levels = 0, num_nodes = 0, tree_M = 0;
   std::vector<int> meta;      // host mirror, nodes*7
   std::vector<int> node_ptr;  // host mirror, nodes+1

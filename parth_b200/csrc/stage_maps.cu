@@ -45,7 +45,18 @@ __device__ __forceinline__ bool is_sep_d(int sep, int node) {
   return a == sep;
 }
 
+// heap-consistent tree (parent == (i-1)/2 and level == depth for every node, which is what
+// HMD::Decompose produces, HMD.cpp:303-337): findCommonSeparator in pure integer arithmetic
+__device__ __forceinline__ int lca_heap_d(int a, int b) {
+  int da = 31 - __clz(a + 1), db = 31 - __clz(b + 1);
+  while (da > db) { a = (a - 1) >> 1; da--; }
+  while (db > da) { b = (b - 1) >> 1; db--; }
+  while (a != b) { a = (a - 1) >> 1; b = (b - 1) >> 1; }
+  return a;
+}
+
 __device__ __forceinline__ int lca_d(const int *__restrict__ meta, int first, int second) {
+  if (meta == nullptr) return lca_heap_d(first, second);
   int hi = first, lo = second;
   if (__ldg(meta + hi * 7 + 5) < __ldg(meta + lo * 7 + 5)) { hi = second; lo = first; }
   while (__ldg(meta + hi * 7 + 5) != __ldg(meta + lo * 7 + 5)) hi = __ldg(meta + hi * 7 + 3);
@@ -240,32 +251,44 @@ __global__ void place_sweep_kernel(const int *__restrict__ frontier, const int *
       if (pp != 0 && (pp < pass || nb < d)) return nd2n[nb];
       return -1;
     };
-    int first = -1, result = -1;
-    bool many = false;
+    // distinct visible neighbour nodes (a mesh vertex touches a handful of nodes at most)
+    constexpr int kMaxDistinct = 16;
+    int uniq[kMaxDistinct];
+    int nu = 0;
+    bool overflow = false;
     for (int p = s; p < e; p++) {
       const int r = visible(Mi[p]);
       if (r == -1) continue;
-      if (first == -1) first = r;
-      else if (r != first) many = true;
+      bool seen = false;
+      for (int u = 0; u < nu; u++) seen |= uniq[u] == r;
+      if (seen) continue;
+      if (nu < kMaxDistinct) uniq[nu++] = r; else overflow = true;
     }
-    if (first != -1) {
-      if (!many) result = first;
-      else {
-        // minimum over all pairs of distinct neighbour nodes of {descendant if ancestor-related, else LCA}
-        int mn = 1 << 30;
+    const int first = nu > 0 ? uniq[0] : -1;
+    int result = -1;
+    if (nu == 1 && !overflow) result = first;
+    else if (nu > 1) {
+      // minimum over all pairs of distinct neighbour nodes of {descendant if ancestor-related, else LCA}
+      int mn = 1 << 30;
+      auto pair_node = [&](int ra, int rb) {
+        const int big = ra > rb ? ra : rb, small = ra > rb ? rb : ra;
+        const int c = is_sep_d(small, big) ? big : lca_d(meta, small, big);
+        mn = c < mn ? c : mn;
+      };
+      if (!overflow) {
+        for (int a = 0; a < nu; a++)
+          for (int b2 = a + 1; b2 < nu; b2++) pair_node(uniq[a], uniq[b2]);
+      } else {
         for (int p = s; p < e; p++) {
           const int ra = visible(Mi[p]);
           if (ra == -1) continue;
           for (int p2 = p + 1; p2 < e; p2++) {
             const int rb = visible(Mi[p2]);
-            if (rb == -1 || rb == ra) continue;
-            const int big = ra > rb ? ra : rb, small = ra > rb ? rb : ra;
-            const int c = is_sep_d(small, big) ? big : lca_d(meta, small, big);
-            mn = c < mn ? c : mn;
+            if (rb != -1 && rb != ra) pair_node(ra, rb);
           }
         }
-        result = mn;
       }
+      result = mn;
     }
     // release the successors first: their test "unplaced at pass start" must still see d as unplaced
     // or placed in THIS pass, both of which hold before and after the write below
@@ -549,8 +572,8 @@ void stage_integrate(parth_b200 &h) {
       while (!done) {
         for (int rep = 0; rep < kBatch; rep++, sweep++) {
           place_sweep_kernel<<<grid, 256, 0, s>>>(F[sweep & 1], fcnt.p + sweep, F[(sweep + 1) & 1], fcnt.p + sweep + 1,
-                                                  h.Mp, h.Mi, h.new_to_old.p, h.d_meta.p, nd2n, h.r_g2l.p, h.r_l2g.p,
-                                                  pass, d_cnt);
+                                                  h.Mp, h.Mi, h.new_to_old.p, h.meta_heap ? nullptr : h.d_meta.p, nd2n,
+                                                  h.r_g2l.p, h.r_l2g.p, pass, d_cnt);
           h.stats.kernels_launched++;
         }
         // an empty frontier ends the pass (the dependency graph is acyclic)

@@ -31,6 +31,14 @@ static void compute_visit(parth_b200 &h, std::vector<int> &visit) {
 void upload_tree_meta(parth_b200 &h) {
   cudaStream_t s = h.stream;
   const int nodes = h.num_nodes;
+  h.meta_heap = true;
+  for (int x = 0; x < nodes && h.meta_heap; x++) {
+    if (h.meta[x * 7 + 2] == -1) continue;
+    int depth = 0;
+    for (int y = x; y > 0; y = (y - 1) >> 1) depth++;
+    if (h.meta[x * 7 + 2] != x || h.meta[x * 7 + 5] != depth || (x > 0 && h.meta[x * 7 + 3] != (x - 1) / 2))
+      h.meta_heap = false;
+  }
   h.d_meta.reserve((size_t)nodes * 7, s);
   h.d_node_ptr.reserve((size_t)nodes + 1, s);
   h.d_visit.reserve((size_t)nodes, s);

@@ -54,14 +54,15 @@ def config3():
     gen_s = time.time() - t0
     g = api.ParthAPI(); g.verbose = False; g.ND_levels = L; g.reorder_type = api.AMD; g.lagging = False
     g.setCoarsePolicy(api.COARSE_REPORT)
-    g.import_tree(tree, Mp, Mi)
     dAp, dAi = torch.from_numpy(Ap3).cuda(), torch.from_numpy(Ai3).cuda()
-    g.setMatrixDev(N3, dAp.data_ptr(), dAi.data_ptr(), len(Ai3), dim)
-    sb = g.stats()
-    g.setNewToOldDOFMap(new_to_old)
-    gMp, gMi = g.mesh()
-    st, perm = g.computePermutation(dim)
-    s = g.stats()
+    for rep in range(3):  # same update three times from a freshly imported tree; the last one is reported
+        g.import_tree(tree, Mp, Mi)
+        g.setMatrixDev(N3, dAp.data_ptr(), dAi.data_ptr(), len(Ai3), dim)
+        sb = g.stats()
+        g.setNewToOldDOFMap(new_to_old)
+        gMp, gMi = g.mesh()
+        st, perm = g.computePermutation(dim)
+        s = g.stats()
     # oracle on the same inputs (the port's build takes a while at 2.7e8 nnz; it is the checker)
     t1 = time.time()
     o = cpu_parth.CpuParth("port"); o.set_options(reorder_type=1, nd_levels=L, lagging=False)
