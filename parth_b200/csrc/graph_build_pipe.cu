@@ -185,15 +185,18 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
           int r[K9_REG];
 #pragma unroll
           for (int i = 0; i < K9_REG; i++) r[i] = i < len ? sp[i] : 0x7fffffff;
-          int di = K9_REG, low = 0, lastv = 0;
+          int di = K9_REG, low = 0;
           bool bad = r[0] < 0;
 #pragma unroll
           for (int i = 0; i < K9_REG; i++) {
             if (i + 1 < K9_REG) bad |= (i + 1 < len) & (r[i] >= r[i + 1]);
             if (r[i] == c) di = i;
-            low += r[i] < c;
-            if (i == len - 1) lastv = r[i];
           }
+          if (check_mirror) {  // lower / upper split: only the full symmetry proof needs it
+#pragma unroll
+            for (int i = 0; i < K9_REG; i++) low += r[i] < c;
+          }
+          const int lastv = sp[len - 1];
           if (bad) {
             int prev = -1;
             for (int i = 0; i < len; i++) {
@@ -204,7 +207,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
           if (lastv >= M) flags |= BUILD_RANGE;
           const int has = di < K9_REG;
           if (!has) flags |= BUILD_NODIAG;
-          diff += (len - has - low) - low;
+          if (check_mirror) diff += (len - has - low) - low;
           // drop the diagonal by shifting the registers, then store the first len-1 (or len) slots
 #pragma unroll
           for (int i = 0; i < K9_REG; i++) {

@@ -310,8 +310,3 @@ def lattice_pattern(n, dirs, diagonal=True, dtype=np.int32):
 
 KUHN_DIRS = [(1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (0, 1, 1), (1, 0, 1), (1, 1, 1)]
 GRID_DIRS = [(1, 0, 0), (0, 1, 0), (0, 0, 1)]
-
-
-def geometric_tree_fast(n, levels):
-    """geometric_tree without per-node python lists of ids: same output, usable at 512^3"""
-    return geometric_tree(n, levels)

@@ -81,3 +81,26 @@ def test_kat_values_of_survey_appendix_b4():
     assert g["kat48_125_126_lag0"]["dirty_coarse"].tolist() == [62]
     assert float(g["kat48_255_256_lag0"]["reuse"]) == pytest.approx(0.992188, abs=1e-6)
     assert int(g["kat48_1_3_lag1"]["num_changes"]) == 0 and int(g["kat48_3_3_lag0"]["num_changes"]) == 0
+
+
+def test_synthetic_generators_agree():
+    """host-side generators used by bench.py / the config suite (no oracle involved)"""
+    import numpy as np
+    from parth_b200 import synth, workloads
+    N, Ap, Ai = synth.lattice_pattern(9, synth.GRID_DIRS)
+    N2, Ap2, Ai2 = synth.poisson3d(9)
+    assert N == N2 and np.array_equal(Ap, Ap2) and np.array_equal(Ai, Ai2)
+    # Kuhn lattice: symmetric, ascending columns, 14 neighbours + diagonal in the interior
+    N, Ap, Ai = synth.lattice_pattern(6, synth.KUHN_DIRS)
+    col = np.repeat(np.arange(N), np.diff(Ap))
+    assert np.diff(Ap).max() == 15
+    assert set(zip(col.tolist(), Ai.tolist())) == set(zip(Ai.tolist(), col.tolist()))
+    assert all(np.all(np.diff(Ai[Ap[c]:Ap[c + 1]]) > 0) for c in range(N))
+    # insert_entries keeps columns ascending and adds exactly the requested entries
+    Ap3, Ai3 = workloads.insert_entries(Ap2, Ai2, [5, 700, 5], [700, 5, 300])
+    assert Ap3[-1] == Ap2[-1] + 3 and 700 in Ai3[Ap3[5]:Ap3[6]] and 300 in Ai3[Ap3[5]:Ap3[6]] and 5 in Ai3[Ap3[700]:Ap3[701]]
+    assert all(np.all(np.diff(Ai3[Ap3[c]:Ap3[c + 1]]) > 0) for c in (5, 700))
+    st = workloads.PoissonUpdateStream(n=12, levels=4, edges_per_update=20)
+    Apk, Aik = st.matrix(3)
+    s, e = st.edges_of(3)
+    assert Apk[-1] == st.Ap[-1] + 2 * len(e)
