@@ -37,7 +37,10 @@ int launch_unpack_labels(const int *list, const int *vtx_ptr, int count, int tot
 
 // ---- amd.cu
 int launch_amd_batch(int count, const int *vtx_ptr, const int *G, const int *sub_Mi,
-                     const long long *ws_ptr, int *ws, int *perm_out, cudaStream_t s);
+                     const long long *ws_ptr, int *ws, int *perm_out, long long max_stage_ints, bool any_unstaged,
+                     cudaStream_t s);
 long long amd_slab_ints(int n, int nnz);
+int amd_stage_capacity_ints();                  // ints of shared memory one CTA can stage a graph in
+long long amd_stage_need_ints(int n, int nnz);  // ints a (symmetric) graph needs to be staged
 
 }  // namespace pb

@@ -52,15 +52,25 @@ Batch extract_fine(parth_b200 &h, const std::vector<int> &nodes) {
 void order_batch(parth_b200 &h, const Batch &b, const std::vector<int> &graph_nnz) {
   cudaStream_t s = h.stream;
   std::vector<long long> wsptr((size_t)b.count + 1, 0);
-  for (int g = 0; g < b.count; g++)
-    wsptr[g + 1] = wsptr[g] + (graph_nnz[g] > 0 ? amd_slab_ints(b.vtx[g + 1] - b.vtx[g], graph_nnz[g]) : 0);
+  // graphs that fit are ordered out of shared memory (their slab is only the fallback for rows that
+  // turn out not to be symmetric); the staging area is sized by the largest of them
+  const long long cap = amd_stage_capacity_ints();
+  long long max_stage = 0;
+  bool any_unstaged = false;
+  for (int g = 0; g < b.count; g++) {
+    const int n = b.vtx[g + 1] - b.vtx[g];
+    wsptr[g + 1] = wsptr[g] + (graph_nnz[g] > 0 ? amd_slab_ints(n, graph_nnz[g]) : 0);
+    if (n <= 0) continue;
+    const long long need = amd_stage_need_ints(n, graph_nnz[g]);
+    if (need <= cap) max_stage = std::max(max_stage, need); else any_unstaged = true;
+  }
   h.r_wsptr.reserve((size_t)b.count + 1, s);
   h.r_ws.reserve((size_t)std::max<long long>(wsptr[b.count], 1), s);
   h.r_perm.reserve((size_t)std::max(b.total, 1), s);
   PB_CUDA(cudaMemcpyAsync(h.r_wsptr.p, wsptr.data(), sizeof(long long) * ((size_t)b.count + 1), cudaMemcpyHostToDevice, s));
   PB_CUDA(cudaStreamSynchronize(s));
   h.stats.kernels_launched += launch_amd_batch(b.count, h.r_vtx.p, h.r_G.p, h.r_sub.p, h.r_wsptr.p, h.r_ws.p,
-                                               h.r_perm.p, s);
+                                               h.r_perm.p, max_stage, any_unstaged, s);
 }
 
 std::vector<int> batch_graph_nnz(parth_b200 &h, const Batch &b) {
