@@ -61,7 +61,7 @@ amd_batch_kernel(int count, const int *__restrict__ vtx_ptr, const int *__restri
     return;
   }
   const int *Ci = sub_Mi + e0;
-  __shared__ int sh[4];
+  __shared__ int sh[36];
   extern __shared__ int amd_smem[];
   const bool sym = amdk::rows_are_symmetric(n, Cp, e0, Ci, &sh[0]);
   const long long need = amd_smem_need(n, sym ? (long long)nz : 2 * (long long)nz);

@@ -836,9 +836,138 @@ PB_DEVFN void finish_serial(const Ws &w) {
   for (int i = 0; i < n; i++) Last[Next[i]] = i;
 }
 
+// ------------------------------------------------------------------ epilogue, whole CTA
+// The same result as finish_serial: per-vertex passes run on all threads; the steps whose outcome
+// depends on the visiting order (children lists in ascending id, slots of absorbed variables in
+// ascending id) advance one warp-wide chunk at a time on warp 0; only the depth-first numbering of
+// the assembly tree (one node per pivot) stays on one thread.  sh: >= 4 + 32 ints shared by the CTA.
+PB_DEVFN void finish_cta(const Ws &w, int *sh) {
+  const int n = w.n, tid = thread_id(), nt = num_threads(), lane = lane_id();
+  int *const Pe = w.Pe, *const Nv = w.Nv, *const Head = w.Head, *const Elen = w.Elen;
+  int *const W = w.W, *const Next = w.Next, *const Last = w.Last, *const Root = w.Degree, *const Tail = w.Len;
+  for (int i = tid; i < n; i += nt) { Pe[i] = flip(Pe[i]); Elen[i] = flip(Elen[i]); }
+  sync_cta();
+  // absorbed variables point at the element that finally holds them
+  for (int i = tid; i < n; i += nt) {
+    int r = NONE;
+    if (Nv[i] == 0) {
+      r = Pe[i];
+      int guard = 0;
+      while (r != NONE && Nv[r] == 0 && ++guard <= n) r = Pe[r];
+    }
+    Root[i] = r;
+  }
+  sync_cta();
+  int *const Child = Head, *const Sibling = Next, *const Order = W, *const Stack = Last;
+  for (int i = tid; i < n; i += nt) {
+    if (Nv[i] == 0) Pe[i] = Root[i];
+    Child[i] = NONE; Sibling[i] = NONE; Tail[i] = NONE; Order[i] = NONE;
+  }
+  sync_cta();
+  // children of every element in ascending id (amd_postorder pushes them in descending order)
+  if (tid < WARP) {
+    for (int base = 0; base < n; base += WARP) {
+      const int j = base + lane;
+      int par = NONE;
+      bool act = false;
+      if (j < n && Nv[j] > 0) { par = Pe[j]; act = par != NONE; }
+      const unsigned grp = match_any(act ? par : -1 - lane);
+      const unsigned lower = grp & lanemask_lt(), higher = grp & lanemask_gt();
+      const int succ = (act && higher) ? lowest(higher) : -1;
+      const int j_succ = shfl(j, succ >= 0 ? succ : lane);
+      int oldtail = NONE;
+      if (act && !lower) oldtail = Tail[par];
+      sync_warp();
+      if (act) {
+        if (!lower) { if (oldtail == NONE) Child[par] = j; else Sibling[oldtail] = j; }
+        if (succ >= 0) Sibling[j] = j_succ;
+        if (!higher) Tail[par] = j;
+      }
+      sync_warp();
+    }
+  }
+  sync_cta();
+  // the largest child (last one among equals) goes to the end of its list
+  for (int i = tid; i < n; i += nt)
+    if (Nv[i] > 0 && Child[i] != NONE) {
+      int fprev = NONE, maxfr = NONE, bigfprev = NONE, bigf = NONE;
+      for (int f = Child[i]; f != NONE; f = Sibling[f]) {
+        const int fr = Elen[f];
+        if (fr >= maxfr) { maxfr = fr; bigfprev = fprev; bigf = f; }
+        fprev = f;
+      }
+      const int fnext = Sibling[bigf];
+      if (fnext != NONE) {
+        if (bigfprev == NONE) Child[i] = fnext; else Sibling[bigfprev] = fnext;
+        Sibling[bigf] = NONE;
+        Sibling[fprev] = bigf;
+      }
+    }
+  sync_cta();
+  // post-order of the forest, roots in ascending id
+  if (tid < WARP) {
+    int k = 0;
+    for (int base = 0; base < n; base += WARP) {
+      const int i = base + lane;
+      unsigned b = ballot(i < n && Nv[i] > 0 && Pe[i] == NONE);
+      while (b) {
+        const int r = base + lowest(b);
+        b &= b - 1;
+        if (lane == 0) k = post_tree_serial(r, k, Child, Sibling, Order, Stack);
+        k = shfl(k, 0);
+      }
+    }
+  }
+  sync_cta();
+  // slots: elements in post-order, each behind the variables it absorbed (ascending id)
+  for (int q = tid; q < n; q += nt) { Head[q] = NONE; Next[q] = NONE; }
+  sync_cta();
+  for (int e = tid; e < n; e += nt) { const int q = Order[e]; if (q != NONE) Head[q] = e; }
+  sync_cta();
+  const int nwarps = (nt + WARP - 1) / WARP, warp = tid / WARP;
+  int running = 0;
+  for (int base = 0; base < n; base += nt) {
+    const int q = base + tid;
+    int e = NONE, v = 0;
+    if (q < n) { e = Head[q]; if (e != NONE) v = Nv[e]; }
+    const int incl = warp_incl_scan(v);
+    if (lane == WARP - 1) sh[4 + warp] = incl;
+    sync_cta();
+    int off = 0, tot = 0;
+    for (int x = 0; x < nwarps; x++) { const int sx = sh[4 + x]; if (x < warp) off += sx; tot += sx; }
+    if (e != NONE) Next[e] = running + off + incl - v;
+    running += tot;
+    sync_cta();
+  }
+  if (tid < WARP) {
+    int nel = running;
+    for (int base = 0; base < n; base += WARP) {
+      const int i = base + lane;
+      int e = NONE;
+      bool absorbed = false, dense = false;
+      if (i < n && Nv[i] == 0) { e = Pe[i]; absorbed = e != NONE; dense = e == NONE; }
+      const unsigned grp = match_any(absorbed ? e : -1 - lane);
+      int slot = 0;
+      if (absorbed) slot = Next[e];
+      sync_warp();
+      if (absorbed) {
+        Next[i] = slot + popc(grp & lanemask_lt());
+        if ((grp & lanemask_lt()) == 0) Next[e] = slot + popc(grp);
+      }
+      const unsigned bd = ballot(dense);
+      if (dense) Next[i] = nel + popc(bd & lanemask_lt());
+      nel += popc(bd);
+      sync_warp();
+    }
+  }
+  sync_cta();
+  for (int i = tid; i < n; i += nt) Last[Next[i]] = i;
+  sync_cta();
+}
+
 // ------------------------------------------------------------------ one graph, one CTA
 // slab: 8n + iwlen ints (Len, Next, Pe, Nv, Head, Elen, Degree, W, Iw); P: n ints, receives the
-// permutation (P[k] = k-th pivot); sh: 4 ints shared by the CTA.  iwlen >= nzaat + n is the
+// permutation (P[k] = k-th pivot); sh: 4 + 32 ints shared by the CTA.  iwlen >= nzaat + n is the
 // caller's job (nzaat = nz for symmetric rows, <= 2 nz otherwise).
 PB_DEVFN void order_graph(int n, const int *Cp, int e0, const int *Ci, bool symmetric, int *slab,
                           long long slab_ints, int *P, int *sh) {
@@ -874,8 +1003,7 @@ PB_DEVFN void order_graph(int n, const int *Cp, int e0, const int *Ci, bool symm
   if (thread_id() < WARP) eliminate_warp(w, pfree, nel);
   sync_cta();
   PB_T0R();
-  if (thread_id() == 0) finish_serial(w);
-  sync_cta();
+  finish_cta(w, sh);
   PB_T(7);
 }
 

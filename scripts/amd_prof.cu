@@ -13,7 +13,7 @@ using namespace pb;
 
 __global__ void __launch_bounds__(256) prof_kernel(int n, const int *Cp, const int *Ci, int *slab, long long slab_ints,
                                                    int *P, int smem_ints, int force_global) {
-  __shared__ int sh[4];
+  __shared__ int sh[36];
   extern __shared__ int amd_smem[];
   const int nz = Cp[n];
   const bool sym = amdk::rows_are_symmetric(n, Cp, 0, Ci, &sh[0]);

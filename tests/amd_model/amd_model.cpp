@@ -21,7 +21,7 @@ int amd_model_order(int n, const int *Mp, const int *Mi, int *perm, int nthreads
     return 1;
   }
   CtaShared cta(nthreads);
-  int sh[4] = {0, 0, 0, 0};
+  int sh[36] = {0};
   int sym_out = 0;
   const long long slab_ints = 8LL * n + 2LL * nz + n + extra_iw;
   std::vector<int> slab((size_t)slab_ints + 16, -12345);
