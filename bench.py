@@ -40,17 +40,41 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=200, help="grid edge (200 -> 8 M DOF)")
-    ap.add_argument("--variant", default="lag", choices=["lag", "nolag"],
-                    help="lag: reference defaults (lagging on); nolag: the dirty node is re-ordered")
+    ap.add_argument("--variant", default="lag", choices=["lag", "nolag", "aggr"],
+                    help="lag: reference defaults (lagging on: the dirty level-7 node is dropped, reuse 1); "
+                         "aggr: aggressive reuse on (relocation into the separator + AMD of the touched nodes, "
+                         "bit-exact with the reference); nolag: lagging off, the dirty coarse node is REPAIRed")
+    ap.add_argument("--no-variants", action="store_true", help="skip the secondary variants (reported under 'variants')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
+VARIANT_TEXT = {
+    "lag": "lagging=true (reference defaults: the dirty level-7 node is lag-dropped, reuse 1)",
+    "aggr": "reference defaults + aggressive reuse (relocate level 8), ReorderingType AMD: broken edges are relocated "
+            "into the common separator and the touched nodes are re-ordered with AMD",
+    "nolag": "lagging=false: the dirty coarse node is repaired on the device (relocation + AMD) where the reference "
+             "re-dissects it with METIS",
+}
+
+
 def workload_name(n, variant):
     return (f"poisson3d_{n}^3 dim=1 ({n**3/1e6:.1f}M DOF), warm reuse update, 1000 cousin-leaf edges under one "
-            f"level-7 node per update (~0.8% of DOFs dirty), 8 ND levels, geometric tree fixture, "
-            f"{'lagging=true (reference default)' if variant == 'lag' else 'lagging=false (dirty node re-ordered)'}")
+            f"level-7 node per update (~0.8% of DOFs dirty), 8 ND levels, geometric tree fixture, " + VARIANT_TEXT[variant])
+
+
+def apply_variant(h, variant, api=None):
+    """the option set of a variant on either implementation (our ParthAPI mirror or oracle.CpuParth)"""
+    if api is not None:  # our arm
+        h.lagging = variant != "nolag"
+        h.activate_aggressive_reuse = variant == "aggr"
+        h.relocate_lvl = 8 if variant == "aggr" else 2
+        h.reorder_type = api.AMD if variant == "aggr" else api.METIS
+        h.setCoarsePolicy(api.COARSE_REPAIR)
+    else:
+        h.set_options(reorder_type=1 if variant == "aggr" else 0, nd_levels=8, lagging=variant != "nolag",
+                      aggressive=variant == "aggr", relocate_lvl=8 if variant == "aggr" else 2)
 
 
 # ------------------------------------------------------------------ clocks
@@ -108,7 +132,7 @@ def cpu_update_stream(kind, stream, variant, steps, warmup, first=0):
     """times `steps` updates (after `warmup`) of a CPU implementation on the stream's matrices"""
     from oracle import cpu_parth
     h = cpu_parth.CpuParth(kind)
-    h.set_options(reorder_type=0, nd_levels=stream.levels, lagging=(variant == "lag"))
+    apply_variant(h, variant)
     h.import_tree(stream.tree(), stream.Mp, stream.Mi)
     times, info = [], {}
     for k in range(warmup + steps):
@@ -191,13 +215,15 @@ def run_ours(args):
     dev_mats = [(a.to(dev), b.to(dev)) for a, b in host_mats]
     nnzA = int(host_mats[0][0][-1])
 
-    g = api.ParthAPI(local)
-    g.verbose = False
-    g.ND_levels = stream.levels
-    g.lagging = args.variant == "lag"
-    g.setCoarsePolicy(api.COARSE_REPAIR)
-    g.import_tree(stream.tree(), stream.Mp, stream.Mi)
-    ext = torch.cuda.ExternalStream(g.stream(), device=dev)
+    def make_handle(variant):
+        g = api.ParthAPI(local)
+        g.verbose = False
+        g.ND_levels = stream.levels
+        apply_variant(g, variant, api)
+        g.import_tree(stream.tree(), stream.Mp, stream.Mi)
+        return g
+
+    g = make_handle(args.variant)
     dperm = torch.empty(M, dtype=torch.int32, device=dev)
     hperm = torch.empty(M, dtype=torch.int32).pin_memory()
 
@@ -206,27 +232,27 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident(k):
+    def step_resident(g, k):
         Ap, Ai = dev_mats[k % D]
         g.setMatrixDev(N, Ap.data_ptr(), Ai.data_ptr(), nnzA, 1)
         s1 = g.stats()
         g.computePermutationDev(dperm.data_ptr(), 1)
         return s1
 
-    def step_e2e(k):
+    def step_e2e(g, k):
         Ap, Ai = host_mats[k % D]
         g.setMatrix(N, Ap.numpy(), Ai.numpy(), 1)
         g.computePermutation(1, out=hperm.numpy())
 
-    def timed(fn, k0, steps):
+    def timed(g, fn, k0, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         kernel_ms, stages = [], []
         launches0 = g.stats()["kernels_launched"]
-        with torch.cuda.stream(ext):
+        with torch.cuda.stream(torch.cuda.ExternalStream(g.stream(), device=dev)):
             e0.record()
             for k in range(k0, k0 + steps):
-                s = fn(k)
+                s = fn(g, k)
                 if s is not None:
                     kernel_ms.append(s["build_kernel_ms"])
                     st = g.stats()
@@ -239,14 +265,17 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), kernel_ms, stages, g.stats()["kernels_launched"] - launches0
 
+    def update_info(g):
+        return dict(reuse=g.getReuse(), changes=g.getNumChanges(), dirty=[x.tolist() for x in g.dirty()])
+
     # ---- resident arm
     sampler = ClockSampler(local)
     sampler.start()  # samples every 50 ms from the warm-up to the end of the end-to-end arm
     for k in range(args.warmup):
-        step_resident(k)
-    ms, kernel_ms, stages, launches = timed(step_resident, args.warmup, args.steps)
+        step_resident(g, k)
+    ms, kernel_ms, stages, launches = timed(g, step_resident, args.warmup, args.steps)
     diff_ms = g.stats()["diff_kernel_ms"]
-    info = dict(reuse=g.getReuse(), changes=g.getNumChanges(), dirty=[x.tolist() for x in g.dirty()])
+    info = update_info(g)
     value = world * args.steps / (ms * 1e-3)
 
     # ---- end-to-end arm (host buffers in, host permutation out)
@@ -254,11 +283,31 @@ def run_ours(args):
     if not args.no_e2e:
         k0 = args.warmup + args.steps
         for k in range(2):
-            step_e2e(k0 + k)
-        ms_e, _, _, _ = timed(lambda k: step_e2e(k), k0 + 2, args.steps)
+            step_e2e(g, k0 + k)
+        ms_e, _, _, _ = timed(g, step_e2e, k0 + 2, args.steps)
         e2e = {"value": world * args.steps / (ms_e * 1e-3), "unit": UNIT,
                "h2d_bytes_per_step": 4 * (N + 1 + nnzA), "d2h_bytes_per_step": 4 * M,
                "ms_per_step": ms_e / args.steps}
+
+    # ---- the other variants of the same workload (resident arm, a few steps each): what the update
+    # costs when the dirty nodes really are re-ordered (stage c: extraction + batched AMD)
+    variants = {}
+    if not args.no_variants:
+        for v in ("lag", "aggr", "nolag"):
+            if v == args.variant:
+                continue
+            gv = make_handle(v)
+            vs = max(2, min(args.steps, 5))
+            for k in range(2):
+                step_resident(gv, k)
+            ms_v, _, st_v, l_v = timed(gv, step_resident, 2, vs)
+            sv = np.mean(np.array(st_v), axis=0)
+            variants[v] = {"what": VARIANT_TEXT[v], "updates_per_s": world * vs / (ms_v * 1e-3), "ms_per_step": ms_v / vs,
+                           "steps": vs, "gpu_launches": int(l_v),
+                           "stage_ms": {"build": float(sv[0]), "detect": float(sv[1]), "dirty_sets": float(sv[2]),
+                                        "reorder": float(sv[3]), "expand": float(sv[4])},
+                           "last_update": update_info(gv)}
+            del gv
 
     clocks = sampler.stop()
     Mn, nnzM = g.mesh_dims()
@@ -292,7 +341,7 @@ def run_ours(args):
                             "note": "runs inside setMatrix (incremental symmetry proof) and is reused by change detection"},
         "stage_ms": {"build": float(st[0]), "detect": float(st[1]), "dirty_sets": float(st[2]),
                      "reorder": float(st[3]), "expand": float(st[4])},
-        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "last_update": info,
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "last_update": info, "variants": variants,
     }
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

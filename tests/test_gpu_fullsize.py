@@ -80,6 +80,33 @@ def test_config2_200cubed_properties(gpu_api):
     assert int((parent == -1).sum()) == 1 and cc.min() >= 1
 
 
+def test_config2_aggressive_reuse_update_matches_oracle_at_full_size(gpu_api, port):
+    """the bench's `aggr` variant: relocation of the broken cousin-leaf edges into the level-7 separator,
+    extraction + AMD of the touched nodes, assembly -- every integer result equal to the oracle's at 8 M DOF"""
+    from parth_b200 import workloads
+    st = workloads.PoissonUpdateStream(n=200, levels=8)
+    N = st.N
+    g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 8; g.reorder_type = gpu_api.AMD
+    g.activate_aggressive_reuse = True; g.relocate_lvl = 8
+    g.setCoarsePolicy(gpu_api.COARSE_REPORT)
+    o = port.CpuParth("port")
+    o.set_options(reorder_type=1, nd_levels=8, lagging=True, aggressive=True, relocate_lvl=8)
+    g.import_tree(st.tree(), st.Mp, st.Mi); o.import_tree(st.tree(), st.Mp, st.Mi)
+    for k in (0, 1):
+        Ap, Ai = st.matrix(k)
+        g.setMatrix(N, Ap, Ai, 1); o.setMatrix(N, Ap, Ai, 1)
+        rc, perm = g.computePermutation(1)
+        orc, operm = o.computePermutation(1)
+        assert rc == 0 and orc == 0
+        assert g.getNumChanges() == o.getNumChanges() and g.getReuse() == o.getReuse()
+        gf, gc = g.dirty(); of, oc = o.dirty()
+        assert gf.tolist() == of.tolist() and gc.tolist() == oc.tolist()
+        assert len(gf) > 0                                      # fine nodes really were re-ordered
+        assert np.array_equal(perm, operm)
+    gt, ot = g.export_tree(), o.export_tree()
+    assert np.array_equal(gt["labels"], ot.labels) and np.array_equal(gt["dofs"], ot.dofs)
+
+
 def test_config3_full_size_against_oracle():
     out = _suite("3")
     assert out["ok"] and out["M"] == 2000376 and out["removed_added"] > 90000
