@@ -321,13 +321,18 @@ build_cols_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
 // BUILD_NODIAG (the output is then discarded and the chained kernel runs).
 constexpr int K8_THREADS = 256;
 constexpr int K8_REG = 8;  // columns up to this length are handled entirely in registers
+constexpr int K8_RAWCAP = 1024;  // dim > 1: columns per tile whose raw starts are staged
 
 // mirror probe of the upper entry (c, r): is c in column r?  [a, b) is column r in sample space;
 // for dim > 1 its samples sit at Ai[raw + k*dim] / dim.  First the position a symmetric stencil
 // predicts (mirror index from the end), then a binary search.
-template <bool DIM1>
+// DIM: compile-time block size (1, 2, 3) or 0 = run-time `dim`: the divisions by a constant
+// become a multiply + shift
+template <int DIM>
 __device__ __forceinline__ bool has_mirror(const int *__restrict__ Ai, const int *s_val, int sbase, int q0, int q1,
-                                           int a, int b, long long raw, int dim, int idx_from_start, int len, int c) {
+                                           int a, int b, long long raw, int dim_rt, int idx_from_start, int len, int c) {
+  constexpr bool DIM1 = DIM == 1;
+  const int dim = DIM ? DIM : dim_rt;
   const bool in_tile = a >= q0 && b <= q1;
   auto val = [&](int pos) -> int {
     if (in_tile) return s_val[pos - sbase];
@@ -343,16 +348,19 @@ __device__ __forceinline__ bool has_mirror(const int *__restrict__ Ai, const int
   return lo < b && val(lo) == c;
 }
 
-template <bool DIM1>
+template <int DIM>
 __global__ void __launch_bounds__(K8_THREADS)
-build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, const int *__restrict__ V, int dim, int M,
+build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, const int *__restrict__ V, int dim_rt, int M,
                        int Q, const int *__restrict__ tile_c, int num_tiles, int *__restrict__ Mp,
                        int *__restrict__ Mi, BuildStatus *__restrict__ st, int check_mirror) {
+  constexpr bool DIM1 = DIM == 1;
+  const int dim = DIM ? DIM : dim_rt;
   // V: exclusive prefix of the samples per (block-)column; for dim == 1 it is Ap itself
   __shared__ __align__(16) int s_val[K7_CAP + 4];
   __shared__ __align__(16) int s_out[K7_CAP];
   __shared__ int s_long[K7_CAP / K7_LONG + 2];
   __shared__ int s_nlong;
+  __shared__ int s_raw[DIM1 ? 1 : K8_RAWCAP], s_vs[DIM1 ? 1 : K8_RAWCAP];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x;
@@ -369,13 +377,34 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, c
   if (tid == 0) s_nlong = 0;
   // ---- A
   if (!DIM1) {
-    // block-column c is matrix column c*dim sampled at every dim-th entry (ParthAPI.cpp:371-374);
-    // one thread gathers one column (all sectors of that column are used by its own later loads)
-    for (int lc = tid; lc < nc; lc += K8_THREADS) {
-      const int c = c0 + lc;
-      const int vs = __ldg(V + c), len = __ldg(V + c + 1) - vs;
-      const int *col = Ai + __ldg(Ap + (long long)c * dim);
-      for (int k = 0; k < len; k++) s_val[vs - sbase + k] = __ldg(col + (long long)k * dim) / dim;
+    // block-column c is matrix column c*dim sampled at every dim-th entry (ParthAPI.cpp:371-374).
+    // Two steps so that every load of the tile is independent of the others: (1) one thread per
+    // column fetches the column's raw start and labels the column's samples with its index;
+    // (2) one thread per SAMPLE gathers Ai[raw + k*dim] -- neighbouring threads read the same
+    // column, so a request covers that column's sectors once.
+    int *s_colof = s_out;  // free until phase B
+    if (nc <= K8_RAWCAP) {
+      for (int lc = tid; lc < nc; lc += K8_THREADS) {
+        const int c = c0 + lc;
+        const int vs = __ldg(V + c) - q0, len = __ldg(V + c + 1) - q0 - vs;
+        s_raw[lc] = __ldg(Ap + (long long)c * dim);
+        s_vs[lc] = vs;
+        for (int k = 0; k < len; k++) s_colof[vs + k] = lc;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int ls = tid; ls < nq; ls += K8_THREADS) {
+        const int lc = s_colof[ls];
+        s_val[ls] = ld_stream(Ai + (long long)s_raw[lc] + (long long)(ls - s_vs[lc]) * dim) / dim;
+      }
+    } else {
+      // a tile of mostly empty columns: one thread gathers one column
+      for (int lc = tid; lc < nc; lc += K8_THREADS) {
+        const int c = c0 + lc;
+        const int vs = __ldg(V + c), len = __ldg(V + c + 1) - vs;
+        const int *col = Ai + __ldg(Ap + (long long)c * dim);
+        for (int k = 0; k < len; k++) s_val[vs - sbase + k] = __ldg(col + (long long)k * dim) / dim;
+      }
     }
   } else {
     const int n4 = (q0 + nq - sbase + 3) >> 2;
@@ -456,7 +485,7 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, c
           }
 #pragma unroll
           for (int u = 0; u < 4; u++)
-            if (i + u < len && !has_mirror<DIM1>(Ai, s_val, sbase, q0, q0 + nq, a[u], b[u], raw[u], dim, i + u, len, c))
+            if (i + u < len && !has_mirror<DIM>(Ai, s_val, sbase, q0, q0 + nq, a[u], b[u], raw[u], dim, i + u, len, c))
               flags |= BUILD_ASYM;
         }
       }
@@ -478,7 +507,7 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, c
       if (check_mirror && !(flags & (BUILD_RANGE | BUILD_UNSORTED)))
         for (int i = low + has; i < len; i++) {
           const int r = sp[i];
-          if (!has_mirror<DIM1>(Ai, s_val, sbase, q0, q0 + nq, __ldg(V + r), __ldg(V + r + 1),
+          if (!has_mirror<DIM>(Ai, s_val, sbase, q0, q0 + nq, __ldg(V + r), __ldg(V + r + 1),
                                 DIM1 ? 0 : __ldg(Ap + (long long)r * dim), dim, i, len, c))
             flags |= BUILD_ASYM;
         }
@@ -524,7 +553,7 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, c
     if (check_mirror && !(f & (BUILD_RANGE | BUILD_UNSORTED)))
       for (int i = low + has + lane; i < len; i += 32) {
         const int r = sp[i];
-        if (!has_mirror<DIM1>(Ai, s_val, sbase, q0, q0 + nq, __ldg(V + r), __ldg(V + r + 1),
+        if (!has_mirror<DIM>(Ai, s_val, sbase, q0, q0 + nq, __ldg(V + r), __ldg(V + r + 1),
                               DIM1 ? 0 : __ldg(Ap + (long long)r * dim), dim, i, len, c))
           f |= BUILD_ASYM;
       }
@@ -561,12 +590,14 @@ int build_cols_launch(const BuildArgs &a, bool spec, cudaStream_t s) {
   if (!spec) PB_CUDA(cudaMemsetAsync(a.desc, 0, sizeof(unsigned long long) * (size_t)num_tiles, s));
   build_cols_partition_kernel<<<(num_tiles + 256) / 256, 256, 0, s>>>(V, a.M, num_tiles, a.tile_c);
   if (a.ev_a) cudaEventRecord(a.ev_a, s);
-  if (spec && a.dim == 1)
-    build_cols_spec_kernel<true><<<num_tiles, K8_THREADS, 0, s>>>(a.Ap, a.Ai, V, 1, a.M, a.Q, a.tile_c, num_tiles, a.Mp,
-                                                                a.Mi, a.status, a.check_mirror);
-  else if (spec)
-    build_cols_spec_kernel<false><<<num_tiles, K8_THREADS, 0, s>>>(a.Ap, a.Ai, V, a.dim, a.M, a.Q, a.tile_c, num_tiles,
-                                                                 a.Mp, a.Mi, a.status, a.check_mirror);
+#define PB_SPEC(D)                                                                                              \
+  build_cols_spec_kernel<D><<<num_tiles, K8_THREADS, 0, s>>>(a.Ap, a.Ai, V, a.dim, a.M, a.Q, a.tile_c, num_tiles, a.Mp, \
+                                                             a.Mi, a.status, a.check_mirror)
+  if (spec && a.dim == 1) PB_SPEC(1);
+  else if (spec && a.dim == 2) PB_SPEC(2);
+  else if (spec && a.dim == 3) PB_SPEC(3);
+  else if (spec) PB_SPEC(0);
+#undef PB_SPEC
   else
     build_cols_kernel<false><<<num_tiles, K7_THREADS, 0, s>>>(a.Ap, a.Ai, a.M, a.Q, a.tile_c, num_tiles, a.Mp, a.Mi,
                                                             a.status, a.desc, a.check_mirror);
