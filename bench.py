@@ -29,6 +29,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one build_pipe_kernel launch from `ncu --set full` (profiles/), keyed by
+# (grid edge, fused stage b)
+TRAFFIC = {(200, False): 440306944}
+
 METRIC = "reuse-update perms/s at 8M DOF 1% change"
 UNIT = "updates/s"
 
@@ -317,7 +321,11 @@ def run_ours(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg = workloads.build_bytes(N, nnzA, Mn, nnzM, 1)
+    # the pipeline kernel also does stage (b) (it compares every tile with the snapshot in shared
+    # memory and writes the changed-row bitmap), so its algorithmic bytes are the two stages' sum
+    fused = bool(g.stats().get("build_fused_detect", 0))
+    alg_build, alg_detect = workloads.build_bytes(N, nnzA, Mn, nnzM, 1), workloads.detect_bytes(Mn, nnzM)
+    alg = alg_build + (alg_detect if fused else 0)
     kms = float(np.mean(kernel_ms)) if kernel_ms else float("nan")
     achieved = alg / (kms * 1e-3) / 1e9
     st = np.mean(np.array(stages), axis=0) if stages else np.zeros(5)
@@ -330,15 +338,20 @@ def run_ours(args):
                    "l2": "inputs larger than L2: 478 MB build + 446 MB detect per step, a different matrix every step",
                    "parallelism": f"{world} independent meshes (one per GPU), no data-path collective"},
         "gnnz_per_s": value * nnzA / 1e9,
-        "roofline": {"bound": "hbm", "kernel": "build_pipe_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak,
-                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch, profiles/r01_bench_ncu_summary.md
-                     "traffic": 440306944 if args.n == 200 else None, "algorithmic_bytes": alg, "kernel_ms": kms,
+        "roofline": {"bound": "hbm", "kernel": "build_pipe_kernel" + (" (stage a + fused stage b)" if fused else ""),
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/)
+                     "traffic": TRAFFIC.get((args.n, fused)), "algorithmic_bytes": alg,
+                     "algorithmic_bytes_stage_a": alg_build, "algorithmic_bytes_stage_b": alg_detect if fused else 0,
+                     "kernel_ms": kms,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s"},
-        "roofline_detect": {"bound": "hbm", "kernel": "diff_rows_kernel", "algorithmic_bytes": workloads.detect_bytes(Mn, nnzM),
-                            "kernel_ms": diff_ms, "achieved": workloads.detect_bytes(Mn, nnzM) / (diff_ms * 1e-3) / 1e9 if diff_ms else None,
-                            "frac": workloads.detect_bytes(Mn, nnzM) / (diff_ms * 1e-3) / 1e9 / peak if diff_ms else None,
-                            "note": "runs inside setMatrix (incremental symmetry proof) and is reused by change detection"},
+        "roofline_detect": ({"kernel": "diff_rows_kernel", "kernel_ms": diff_ms,
+                             "note": "stage b is fused into the build kernel; this launch only visits tiles the build "
+                                     "kernel could not stage (none here)"} if fused else
+                            {"bound": "hbm", "kernel": "diff_rows_kernel", "algorithmic_bytes": alg_detect,
+                             "kernel_ms": diff_ms, "achieved": alg_detect / (diff_ms * 1e-3) / 1e9 if diff_ms else None,
+                             "frac": alg_detect / (diff_ms * 1e-3) / 1e9 / peak if diff_ms else None,
+                             "note": "runs inside setMatrix (incremental symmetry proof) and is reused by change detection"}),
         "stage_ms": {"build": float(st[0]), "detect": float(st[1]), "dirty_sets": float(st[2]),
                      "reorder": float(st[3]), "expand": float(st[4])},
         "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "last_update": info, "variants": variants,

@@ -156,6 +156,7 @@ typedef struct {
   double symbolic_etree_ms;               /* etree part of symbolic_ms */
   double diff_kernel_ms;                  /* diff_rows_kernel alone (last build or detection that ran it) */
   int symbolic_path;                      /* 2 = per-node shared-memory kernel, 1 = wave-scheduled walk, 0 = one range */
+  int build_fused_detect;                 /* 1 = the last build kernel also compared its tiles with the snapshot (stage b fused into stage a) */
 } parth_b200_stats;
 int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out);
 int parth_b200_synchronize(parth_b200 *h);

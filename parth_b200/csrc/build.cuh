@@ -24,6 +24,15 @@ struct BuildArgs {
   unsigned long long *desc;
   int check_mirror;
   cudaEvent_t ev_a, ev_b;  // optional: bracket the filter kernel alone (roofline timing)
+  // optional (pipeline kernel only): fused change detection against the snapshot graph.  Every
+  // tile is compared with the same rows of the snapshot while both are in shared memory and the
+  // changed-row bitmap (row_bits, one bit per row) + counters are written by the build kernel;
+  // tile_dirty[t] = 2 marks the tiles left to diff_rows_kernel.
+  const int *Mp_prev, *Mi_prev;
+  int nnz_prev;
+  int *tile_dirty;
+  unsigned *row_bits;
+  struct DetectCounters *dcnt;
 };
 
 int build_filter_tiles(int M, int Q);
@@ -33,6 +42,8 @@ int build_cols_launch(const BuildArgs &a, bool spec, cudaStream_t s);
 // graph_build_pipe.cu (dim == 1, aligned arrays): persistent bulk-copy pipeline, closed-form offsets
 int build_pipe_supported(const BuildArgs &a);
 int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s);
+int build_pipe_tile_cols(const BuildArgs &a);  // columns per tile of the pipeline kernel
+int build_pipe_num_tiles(const BuildArgs &a);
 int build_filter_launch(const BuildArgs &a, cudaStream_t s);
 int build_sample_prefix_launch(const int *Ap, int M, int dim, int *ns_tmp, int *V,
                                unsigned long long *scan_ws, cudaStream_t s);

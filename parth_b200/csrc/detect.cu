@@ -38,11 +38,41 @@ __device__ __forceinline__ bool problematic_d(const int *__restrict__ dof2node, 
 __global__ void __launch_bounds__(K2_THREADS)
 diff_rows_kernel(const int *__restrict__ Mp, const int *__restrict__ Mi,
                  const int *__restrict__ Mp_prev, const int *__restrict__ Mi_prev, int M,
-                 unsigned *__restrict__ row_bits, DetectCounters *__restrict__ cnt) {
+                 unsigned *__restrict__ row_bits, DetectCounters *__restrict__ cnt,
+                 const int *__restrict__ tile_state, int tile_cols) {
   __shared__ int s_bad;
   const int tid = threadIdx.x, lane = tid & 31;
   const int r0 = blockIdx.x * K2_ROWS;
   const int r1 = r0 + K2_ROWS < M ? r0 + K2_ROWS : M;
+  if (tile_state) {
+    // fused mode: the graph build compared its tiles with the snapshot and wrote their bitmap
+    // words; only tiles it could not stage (state 2) are compared here, word by word.  A small
+    // grid strides over the row blocks (normally there is nothing to do).
+    const int n_blocks = (M + K2_ROWS - 1) / K2_ROWS;
+    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
+      const int b0 = blk * K2_ROWS;
+      const int b1 = b0 + K2_ROWS < M ? b0 + K2_ROWS : M;
+      int any = 0;
+      for (int t = b0 / tile_cols; t <= (b1 - 1) / tile_cols; t++) any |= __ldg(tile_state + t) == 2;
+      if (!any) continue;
+      int changed_here = 0;
+      for (int base = b0 + (tid & ~31); base < b1; base += K2_THREADS) {
+        if (__ldg(tile_state + base / tile_cols) != 2) continue;  // warp-uniform: tiles are multiples of 32 rows
+        const int i = base + lane;
+        bool ch = false;
+        if (i < b1) {
+          const int s = Mp[i], e = Mp[i + 1], sp = Mp_prev[i], ep = Mp_prev[i + 1];
+          ch = (e - s) != (ep - sp);
+          for (int k = 0; !ch && k < e - s; k++) ch = Mi[s + k] != Mi_prev[sp + k];
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, ch);
+        if (lane == 0) { row_bits[base >> 5] = m; changed_here += __popc(m); }
+      }
+      if (lane == 0 && changed_here) atomicAdd(&cnt->changed_rows, changed_here);
+      if (tid == 0) atomicAdd(&cnt->dirty_tiles, 1);
+    }
+    return;
+  }
   if (tid == 0) s_bad = 0;
   __syncthreads();
   const int p0 = Mp[r0], pp0 = Mp_prev[r0];
@@ -234,10 +264,13 @@ int launch_sym_check_rows(const int *rows, const int *n_rows_dev, int cap, const
 
 // ------------------------------------------------------------------ host launchers
 int launch_diff_rows(const int *Mp, const int *Mi, const int *Mp_prev, const int *Mi_prev, int M,
-                     unsigned *row_bits, DetectCounters *cnt, cudaStream_t s) {
-  PB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(DetectCounters), s));
-  const int blocks = (M + K2_ROWS - 1) / K2_ROWS;
-  diff_rows_kernel<<<blocks, K2_THREADS, 0, s>>>(Mp, Mi, Mp_prev, Mi_prev, M, row_bits, cnt);
+                     unsigned *row_bits, DetectCounters *cnt, const int *tile_dirty, int tile_cols, cudaStream_t s) {
+  // fused mode (tile_cols > 0): the counters already hold the build kernel's share
+  if (tile_cols <= 0) PB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(DetectCounters), s));
+  int blocks = (M + K2_ROWS - 1) / K2_ROWS;
+  if (tile_cols > 0 && blocks > 2 * kNumSMsB200) blocks = 2 * kNumSMsB200;
+  diff_rows_kernel<<<blocks, K2_THREADS, 0, s>>>(Mp, Mi, Mp_prev, Mi_prev, M, row_bits, cnt,
+                                                 tile_cols > 0 ? tile_dirty : nullptr, tile_cols);
   PB_CUDA(cudaGetLastError());
   return 1;
 }

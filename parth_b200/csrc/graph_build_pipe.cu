@@ -17,6 +17,7 @@
 // column (BUILD_NODIAG -> the chained-scan kernel takes over), structural symmetry by mirror
 // probes plus the global upper/lower count, over-long tiles (BUILD_WIDE -> sample-tiled kernel).
 #include "build.cuh"
+#include "tree.cuh"
 
 namespace pb {
 
@@ -34,12 +35,19 @@ struct K9Stage {
   int out[K9_CAP + 8];
   int ap[K9_TCMAX + 8];
 };
+static_assert(sizeof(K9Stage) % 16 == 0, "bulk copies need 16-byte aligned stage buffers");
 struct K9Smem {
   K9Stage st[K9_STAGES];
   unsigned long long full[K9_STAGES], empty[K9_STAGES];
   int par[K9_STAGES][4];  // q0, q1, wide
   int longs[K9_CAP / K9_LONG + 2];
   int nlong;
+  // fused change detection: the snapshot's rows of the tile being worked on (single stage: it is
+  // fetched while the tile is walked and consumed right after)
+  alignas(16) int pval[K9_CAP + 8];
+  alignas(16) int pap[K9_TCMAX + 8];
+  alignas(8) unsigned long long pfull, pempty;
+  int ppar[4];  // Mp_prev[c0], staged?, Mp_prev[c1] - Mp_prev[c0]
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -75,11 +83,29 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned by
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
                : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(K9_CONSUMERS) : "memory"); }
+// barrier + OR over the consumer threads
+__device__ __forceinline__ bool consumer_any(bool p) {
+  int r;
+  asm volatile(
+      "{\n"
+      ".reg .pred q, o;\n"
+      "setp.ne.s32 q, %1, 0;\n"
+      "bar.red.or.pred o, 1, %2, q;\n"
+      "selp.s32 %0, 1, 0, o;\n"
+      "}\n"
+      : "=r"(r)
+      : "r"((int)p), "n"(K9_CONSUMERS)
+      : "memory");
+  return r != 0;
+}
 
 // is c in the ascending column [a, b)?  first the slot a symmetric stencil predicts, then a search
 __device__ __forceinline__ bool k9_has_mirror(const int *__restrict__ Ai, const int *val, int sbase, int q0, int q1,
@@ -102,7 +128,9 @@ __device__ __forceinline__ bool k9_has_mirror(const int *__restrict__ Ai, const 
 
 __global__ void __launch_bounds__(K9_THREADS, 2)
 build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M, int Q, int TC, int num_tiles,
-                  int *__restrict__ Mp, int *__restrict__ Mi, BuildStatus *__restrict__ st, int check_mirror) {
+                  int *__restrict__ Mp, int *__restrict__ Mi, BuildStatus *__restrict__ st, int check_mirror,
+                  const int *__restrict__ Mp_prev, const int *__restrict__ Mi_prev, int nnz_prev,
+                  int *__restrict__ tile_state, unsigned *__restrict__ row_bits, DetectCounters *__restrict__ dcnt) {
   extern __shared__ __align__(128) unsigned char k9_raw[];
   K9Smem &S = *reinterpret_cast<K9Smem *>(k9_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -110,6 +138,8 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
 
   if (tid == 0) {
     for (int s = 0; s < K9_STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    mbar_init(&S.pfull, 1);
+    mbar_init(&S.pempty, 1);
     S.nlong = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -138,6 +168,25 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
       mbar_expect_tx(&S.full[s], bytes_ai + bytes_ap);
       if (bytes_ai) bulk_g2s(S.st[s].val, Ai + sbase, bytes_ai, &S.full[s]);
       if (bytes_ap) bulk_g2s(S.st[s].ap, Ap + c0, bytes_ap, &S.full[s]);
+      if (Mp_prev) {
+        // the same rows of the snapshot, once the consumers are done with the previous tile's
+        const int pp0 = __ldg(Mp_prev + c0), pp1 = __ldg(Mp_prev + c1);
+        const int lenp = pp1 - pp0;
+        const bool fits = !wide && pp0 >= 0 && pp1 <= nnz_prev && lenp >= 0 && lenp <= K9_CAP;
+        if (k >= 1) mbar_wait(&S.pempty, (k - 1) & 1);
+        S.ppar[0] = pp0; S.ppar[1] = fits; S.ppar[2] = lenp;
+        unsigned bytes_pv = 0, bytes_pa = 0;
+        if (fits) {
+          const int pbase = pp0 & ~3;
+          const int n4 = (pp1 - pbase + 3) >> 2, safe4 = (nnz_prev - pbase) >> 2;
+          bytes_pv = lenp > 0 ? (unsigned)(n4 < safe4 ? n4 : safe4) * 16u : 0u;
+          const int a4 = (nc + 1 + 3) >> 2, asafe4 = (M + 1 - c0) >> 2;
+          bytes_pa = (unsigned)(a4 < asafe4 ? a4 : asafe4) * 16u;
+        }
+        mbar_expect_tx(&S.pfull, bytes_pv + bytes_pa);
+        if (bytes_pv) bulk_g2s(S.pval, Mi_prev + (pp0 & ~3), bytes_pv, &S.pfull);
+        if (bytes_pa) bulk_g2s(S.pap, Mp_prev + c0, bytes_pa, &S.pfull);
+      }
     }
     return;
   }
@@ -302,6 +351,62 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
       consumer_sync();
       if (tid == 0) S.nlong = 0;
     }
+    if (Mp_prev) {
+      // ---- fused change detection (stage b): this tile against the same rows of the snapshot,
+      // both sides in shared memory.  Constant row-pointer shift + identical entries <=> no row of
+      // the tile changed; otherwise one thread per row compares (Integrator.cpp:269-288) and the
+      // changed-row bitmap words of the tile are written here.  tile_state: 0 clean, 1 rows
+      // compared here, 2 left to diff_rows_kernel (snapshot tile too large / over-long columns).
+      mbar_wait(&S.pfull, k & 1);
+      const int pp0 = S.ppar[0], lenp = S.ppar[2];
+      const bool resolved = S.ppar[1] != 0 && nlong == 0 && !wide;
+      if (!resolved) {
+        if (tid == 0) tile_state[t] = 2;
+      } else {
+        const int pbase = pp0 & ~3, off = pp0 - pbase;
+        const int gotp = lenp > 0 ? (min((pp0 + lenp - pbase + 3) >> 2, (nnz_prev - pbase) >> 2)) << 2 : 0;
+        const int gotpa = (min((nc + 1 + 3) >> 2, (M + 1 - c0) >> 2)) << 2;
+        auto prev_ptr = [&](int lc) { return lc < gotpa ? S.pap[lc] : __ldg(Mp_prev + c0 + lc); };
+        auto prev_val = [&](int j) { return off + j < gotp ? S.pval[off + j] : __ldg(Mi_prev + pp0 + j); };
+        const int *ov = B.out + mis;
+        bool bad = lenp != total;
+        if (!bad) {
+          const int shift = (int)base - pp0;
+          if (off + lenp <= gotp && nc + 1 <= gotpa) {
+            // everything was staged (always, except next to the end of the arrays): bare compare
+            const int want = shift + c0;
+            for (int lc = tid; lc <= nc; lc += K9_CONSUMERS) bad |= (B.ap[lc] - lc) - S.pap[lc] != want;
+            const int *pv = S.pval + off;
+#pragma unroll 2
+            for (int i = tid; i < total; i += K9_CONSUMERS) bad |= pv[i] != ov[i];
+          } else {
+            for (int lc = tid; lc <= nc; lc += K9_CONSUMERS) bad |= (B.ap[lc] - (c0 + lc)) - prev_ptr(lc) != shift;
+            for (int i = tid; i < total; i += K9_CONSUMERS) bad |= prev_val(i) != ov[i];
+          }
+        }
+        if (consumer_any(bad)) {
+          int changed_here = 0;
+          for (int lb = tid & ~31; lb < nc; lb += K9_CONSUMERS) {
+            const int lc = lb + lane;
+            bool ch = false;
+            if (lc < nc) {
+              const int vs = B.ap[lc], nlen = B.ap[lc + 1] - vs - 1, o0 = (vs - q0) - lc;
+              const int ps = prev_ptr(lc) - pp0, plen = prev_ptr(lc + 1) - pp0 - ps;
+              ch = nlen != plen;
+              for (int i = 0; !ch && i < nlen; i++) ch = ov[o0 + i] != prev_val(ps + i);
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ch);
+            if (lane == 0) { row_bits[(c0 + lb) >> 5] = m; changed_here += __popc(m); }
+          }
+          if (lane == 0 && changed_here) atomicAdd(&dcnt->changed_rows, changed_here);
+          if (tid == 0) { atomicAdd(&dcnt->dirty_tiles, 1); tile_state[t] = 1; }
+        } else {
+          for (int w = tid; w < (nc + 31) >> 5; w += K9_CONSUMERS) row_bits[(c0 >> 5) + w] = 0u;
+        }
+      }
+      consumer_sync();
+      if (tid == 0) mbar_arrive(&S.pempty);
+    }
     // ---- the staged input is free again; the compacted tile leaves through the bulk-store path
     if (tid == 0) mbar_arrive(&S.empty[s]);
     if (total > 0) {
@@ -336,20 +441,36 @@ int build_pipe_supported(const BuildArgs &a) {
                          reinterpret_cast<uintptr_t>(a.Mi)) & 15) == 0 && a.M > 0 && a.Q > 0;
 }
 
-int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s) {
-  PB_CUDA(cudaFuncSetAttribute(build_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K9Smem)));
+int build_pipe_tile_cols(const BuildArgs &a) {
   // columns per tile from the average column length, a multiple of 32 so that Ap slices stay aligned
   long long tc = (long long)K9_TILE * a.M / (a.Q > 0 ? a.Q : 1);
   tc = (tc / 32) * 32;
   if (tc < 32) tc = 32;
   if (tc > K9_TCMAX) tc = K9_TCMAX;
-  const int TC = (int)tc;
+  return (int)tc;
+}
+
+int build_pipe_num_tiles(const BuildArgs &a) {
+  const int TC = build_pipe_tile_cols(a);
+  return (a.M + TC - 1) / TC;
+}
+
+int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s) {
+  PB_CUDA(cudaFuncSetAttribute(build_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K9Smem)));
+  const int TC = build_pipe_tile_cols(a);
   const int num_tiles = (a.M + TC - 1) / TC;
   PB_CUDA(cudaMemsetAsync(a.status, 0, sizeof(BuildStatus), s));
+  const bool fused = a.Mp_prev && a.Mi_prev && a.tile_dirty && a.row_bits && a.dcnt;
+  if (fused) {
+    PB_CUDA(cudaMemsetAsync(a.tile_dirty, 0, sizeof(int) * (size_t)num_tiles, s));
+    PB_CUDA(cudaMemsetAsync(a.dcnt, 0, sizeof(DetectCounters), s));
+  }
   const int grid = num_tiles < 2 * num_sms ? num_tiles : 2 * num_sms;
   if (a.ev_a) cudaEventRecord(a.ev_a, s);
   build_pipe_kernel<<<grid, K9_THREADS, sizeof(K9Smem), s>>>(a.Ap, a.Ai, a.M, a.Q, TC, num_tiles, a.Mp, a.Mi, a.status,
-                                                            a.check_mirror);
+                                                            a.check_mirror, fused ? a.Mp_prev : nullptr,
+                                                            fused ? a.Mi_prev : nullptr, a.nnz_prev,
+                                                            fused ? a.tile_dirty : nullptr, a.row_bits, a.dcnt);
   if (a.ev_b) cudaEventRecord(a.ev_b, s);
   PB_CUDA(cudaGetLastError());
   return 1;

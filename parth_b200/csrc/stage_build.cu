@@ -24,7 +24,7 @@ void read_ints(parth_b200 &h, const int *dsrc, int *dst, size_t n) {
 // stage (b).  Rows beyond `cap` are not listed: the caller then falls back to the streaming proof.
 static int changed_rows_cap(int M) { return std::max(1024, M / 20); }
 
-static void enqueue_changed_row_proof(parth_b200 &h, int M) {
+static void enqueue_changed_row_proof(parth_b200 &h, int M, const int *tile_dirty, int tile_cols) {
   cudaStream_t s = h.stream;
   const int n_words = (M + 31) / 32;
   const int cap = changed_rows_cap(M);
@@ -35,7 +35,7 @@ static void enqueue_changed_row_proof(parth_b200 &h, int M) {
   unsigned *bits = reinterpret_cast<unsigned *>(h.chg_bits.p);
   {
     StageTimer td(h, &h.stats.diff_kernel_ms);
-    h.stats.kernels_launched += launch_diff_rows(h.Mp_own.p, h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt_p(), s);
+    h.stats.kernels_launched += launch_diff_rows(h.Mp_own.p, h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt_p(), tile_dirty, tile_cols, s);
     td.stop();
   }
   h.stats.kernels_launched += exclusive_scan<1>(h.chg_bits.p, h.chg_pre.p, n_words, h.scan_ws.p, s);
@@ -102,9 +102,26 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
     std::memcpy(&st, m, sizeof(st));
     std::memcpy(&dc, m + 8, sizeof(dc));
   };
+  // fused change detection: the pipeline kernel compares each tile with the snapshot on the fly
+  int fused_cols = 0;
   auto launch_filter = [&]() {
+    fused_cols = 0;
+    a.Mp_prev = a.Mi_prev = nullptr;
+    a.tile_dirty = nullptr;
+    a.row_bits = nullptr;
+    a.dcnt = nullptr;
     if (dim == 1 && h.build_mode <= 1) {
-      if (h.build_mode == 0 && build_pipe_supported(a)) h.stats.kernels_launched += build_pipe_launch(a, h.num_sms, s);
+      if (h.build_mode == 0 && build_pipe_supported(a)) {
+        if (incremental && !a.check_mirror) {
+          h.tile_dirty.reserve((size_t)build_pipe_num_tiles(a) + 1, s);
+          a.Mp_prev = h.Mp_prev.p; a.Mi_prev = h.Mi_prev.p; a.nnz_prev = h.nnz_prev; a.tile_dirty = h.tile_dirty.p;
+          h.chg_bits.reserve((size_t)(M + 31) / 32 + 1, s);
+          a.row_bits = reinterpret_cast<unsigned *>(h.chg_bits.p);
+          a.dcnt = h.dcnt_p();
+          fused_cols = build_pipe_tile_cols(a);
+        }
+        h.stats.kernels_launched += build_pipe_launch(a, h.num_sms, s);
+      }
       else h.stats.kernels_launched += build_cols_launch(a, h.build_mode == 0, s);
     } else if (dim > 1 && h.build_mode_n == 0) {
       h.stats.kernels_launched += build_cols_launch(a, true, s);  // closed-form offsets, strided samples
@@ -124,7 +141,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   for (;;) {
     // the filter kernel, then (incremental mode) the changed-row proof, then ONE read-back
     launch_filter();
-    if (incremental) enqueue_changed_row_proof(h, M);
+    if (incremental) enqueue_changed_row_proof(h, M, fused_cols ? h.tile_dirty.p : nullptr, fused_cols);
     read_mail();
     if (dim == 1 && h.build_mode <= 1) {
       // remember the variant that works so that steady-state updates launch it directly
@@ -167,6 +184,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   if (proven) {
     h.nnzM = st.nnz_out;
     h.stats.build_path = 1;
+    h.stats.build_fused_detect = fused_cols > 0 ? 1 : 0;
     h.cur_sym_proven = !h.assume_symmetric;
   } else {
     // general path: any triangle, unsorted columns, duplicates
@@ -189,6 +207,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
     h.stats.kernels_launched += build_general_gather_launch(a, h.ptr.p, h.tmp.p, s);
     h.nnzM = nnzM;
     h.stats.build_path = 2;
+    h.stats.build_fused_detect = 0;
     h.cur_sym_proven = true;  // the general path symmetrises by construction
     h.diff_cached = false;
   }

@@ -23,8 +23,10 @@ struct DetectCounters {
   int dirty_tiles;    // row tiles that needed the per-row comparison
   int pad0, pad1;
 };
+// tile_dirty / tile_cols: optional per-tile verdict of the fused comparison in the pipeline build
+// kernel (tile t = rows [t*tile_cols, (t+1)*tile_cols)); tile_cols == 0: compare everything
 int launch_diff_rows(const int *Mp, const int *Mi, const int *Mp_prev, const int *Mi_prev, int M,
-                     unsigned *row_bits, DetectCounters *cnt, cudaStream_t s);
+                     unsigned *row_bits, DetectCounters *cnt, const int *tile_dirty, int tile_cols, cudaStream_t s);
 int launch_diff_rows_mapped(const int *Mp, const int *Mi, const int *Mp_prev, const int *Mi_prev,
                             const int *new_to_old, const int *old_to_new, int M, unsigned *row_bits,
                             DetectCounters *cnt, cudaStream_t s);

@@ -54,15 +54,22 @@ int main(int argc, char **argv) {
   cudaFuncSetAttribute(prof_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   for (int rep = 0; rep < 2; rep++) {
     long long zero[16] = {0};
+#ifdef PB_AMD_PROF
     cudaMemcpyToSymbol(amdk::g_amd_prof, zero, sizeof(zero));
+#endif
     cudaEvent_t a, b; cudaEventCreate(&a); cudaEventCreate(&b);
     cudaEventRecord(a);
     prof_kernel<<<1, 256, smem>>>(n, dCp, dCi, slab, slab_ints, P, smem / 4, force_global);
     cudaEventRecord(b);
     cudaError_t e = cudaDeviceSynchronize();
     float ms = 0; cudaEventElapsedTime(&ms, a, b);
-    long long pr[16];
+    long long pr[16] = {0};
+#ifdef PB_AMD_PROF
     cudaMemcpyFromSymbol(pr, amdk::g_amd_prof, sizeof(pr));
+#else
+    pr[8] = 1;
+    (void)zero;
+#endif
     if (rep == 0) continue;
     const char *nm[8] = {"P0 pick", "P1 Lme", "P2 |Le-Lme|", "P3 degrees", "P4 supervar", "P5 reinsert", "init", "tail"};
     printf("%s k=%d n=%d nz=%d  %s  %.3f ms (%s)  pivots=%lld  avg|Lme|=%.1f avg elenme=%.2f\n", d3 ? "3d" : "2d", k, n, nz,

@@ -120,3 +120,40 @@ def test_cold_start_through_decomposer_callback(gpu_api):
     assert np.array_equal(perm, (mp[:, None] * 3 + np.arange(3)).reshape(-1))
     st, perm2 = g.computePermutation(3)  # warm, nothing changed
     assert g.getReuse() == 1.0 and np.array_equal(perm, perm2)
+
+
+def test_fused_detection_with_over_long_columns_matches_oracle(gpu_api, port):
+    """steady-state updates run change detection inside the pipeline build kernel (stage b fused into
+    stage a); tiles holding a column longer than 64 are left to diff_rows_kernel.  Both routes, and
+    the tiles whose entry count changed, must give the oracle's changed edges / dirty sets / permutation."""
+    tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 16, 5)))
+    from parth_b200 import synth
+    rng = np.random.default_rng(9)
+    n = len(Mp) - 1
+    hub = int(tree.node_dofs(0)[0])                                  # a root-separator DOF: edges to it never break the tree
+    others = [int(x) for x in rng.choice(n, 120, replace=False) if int(x) != hub]
+    cur = synth.add_edges(Mp, Mi, [(hub, x) for x in others[:100]])   # column of the hub: > 64 entries
+    g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 5; g.reorder_type = 1
+    g.setCoarsePolicy(gpu_api.COARSE_REPORT)
+    o = port.CpuParth("port"); o.set_options(reorder_type=1, nd_levels=5)
+    g.import_tree(tree, *cur); o.import_tree(tree, *cur)
+    fused_seen = 0
+    for step in range(6):
+        if step in (1, 3):    # the hub gains neighbours (long column, tile left to the row diff)
+            cur = synth.add_edges(cur[0], cur[1], [(hub, x) for x in others[100 + 5 * step:105 + 5 * step]])
+        if step in (2, 3, 4):  # short rows change (compared inside the build kernel)
+            a = int(tree.node_dofs(1 + step)[0]); b = int(tree.node_dofs(1 + step)[-1])
+            cur = synth.add_edges(cur[0], cur[1], [(a, b)])
+        N, Ap, Ai = synth.graph_to_matrix(*cur)
+        g.setMatrix(N, Ap, Ai, 1); o.setMatrix(N, Ap, Ai, 1)
+        fused_seen += g.stats()["build_fused_detect"]
+        st, perm = g.computePermutation(1)
+        ost, operm = o.computePermutation(1)
+        assert g.getNumChanges() == o.getNumChanges(), step
+        assert np.array_equal(g.changed_edges(), o.changed_edges()), step
+        assert g.getReuse() == o.getReuse(), step
+        gf, gc = g.dirty(); of, oc = o.dirty()
+        assert gf.tolist() == of.tolist() and gc.tolist() == oc.tolist(), step
+        if ost == 0:
+            assert st == 0 and np.array_equal(perm, operm), step
+    assert fused_seen >= 4
