@@ -109,6 +109,9 @@ int parth_b200_use_builtin_decomposer(parth_b200 *h, int on);
 
 /* ParthAPI::computePermutation, ParthAPI.cpp:191-279.  perm must hold M_n*dim ints. */
 int parth_b200_compute_permutation(parth_b200 *h, int *perm, int dim);
+/* device-pointer variant: STREAM-ORDERED.  dperm is written by work enqueued on the handle's stream
+ * (parth_b200_stream); it is valid for later work on that stream, or on the host after
+ * parth_b200_synchronize.  No synchronisation is done just to return. */
 int parth_b200_compute_permutation_dev(parth_b200 *h, int *dperm, int dim);
 /* ParthAPI::mapMeshPermToMatrixPerm, ParthAPI.cpp:285-337 (dim == -1: sim_dim) */
 int parth_b200_map_mesh_perm_to_matrix_perm(parth_b200 *h, const int *mesh_perm, int n, int *out,

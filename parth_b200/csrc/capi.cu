@@ -61,6 +61,7 @@ int parth_b200_create(parth_b200 **out, int device) {
     PB_CUDA(cudaEventCreate(&h->ev3));
     h->pin.reserve(1 << 16);
     for (auto &e : h->tev) PB_CUDA(cudaEventCreate(&e));
+    for (int i = parth_b200::kTimerPairs - 1; i >= 0; i--) h->free_pairs.push_back(i);
     h->mail.reserve(32);
   } catch (const std::exception &ex) {
     g_create_error = ex.what();
@@ -160,6 +161,12 @@ int parth_b200_synchronize(parth_b200 *h) {
 
 int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out) {
   if (!h || !out) return PARTH_B200_ERR_ARG;
+  if (!h->pending_timers.empty()) {  // device-pointer calls leave their timers to be read here
+    PB_API_BEGIN
+    resolve_timers(*h);
+    *out = h->stats;
+    PB_API_END
+  }
   *out = h->stats;
   return PARTH_B200_OK;
 }
@@ -170,8 +177,7 @@ int parth_b200_set_matrix_dev(parth_b200 *h, int N, const int *dAp, const int *d
   if (!dAp || !dAi || N <= 0 || dim <= 0 || nnz < 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: bad argument");
   h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
   h->sim_dim = dim;
-  stage_build(*h, N, dAp, dAi, nnz, dim);
-  resolve_timers(*h);
+  stage_build(*h, N, dAp, dAi, nnz, dim);  // ends on its mailbox read-back: nothing is in flight
   PB_API_END
 }
 
@@ -295,8 +301,9 @@ int parth_b200_compute_permutation_dev(parth_b200 *h, int *dperm, int dim) {
   PB_API_BEGIN
   if (!dperm || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "computePermutation: bad argument");
   h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
+  // stream-ordered: dperm is valid for work enqueued on the handle's stream after this call (or
+  // after parth_b200_synchronize); the stage timers are read at the next synchronisation point
   rc = stage_compute_permutation(*h, dperm, dim);
-  resolve_timers(*h);
   if (rc != PARTH_B200_OK) return rc;
   PB_API_END
 }
@@ -421,6 +428,12 @@ int parth_b200_get_dirty_nodes(parth_b200 *h, int *fine, int *nfine, int *coarse
 
 int parth_b200_get_timers(parth_b200 *h, double t[5]) {
   if (!h || !t) return PARTH_B200_ERR_ARG;
+  if (!h->pending_timers.empty()) {
+    PB_API_BEGIN
+    resolve_timers(*h);
+    for (int i = 0; i < 5; i++) t[i] = h->timers[i];
+    PB_API_END
+  }
   for (int i = 0; i < 5; i++) t[i] = h->timers[i];
   return PARTH_B200_OK;
 }

@@ -19,11 +19,11 @@ struct parth_b200 {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // deferred stage timers: events are recorded while the work is enqueued and read once, after the
   // final synchronisation of the API call (no intermediate cudaEventSynchronize on the hot path)
-  static constexpr int kTimerPairs = 16;
+  static constexpr int kTimerPairs = 48;
   cudaEvent_t tev[2 * kTimerPairs] = {};
   struct PendingTimer { double *dst; double *dst2; int pair; bool accumulate; };
-  std::vector<PendingTimer> pending_timers;
-  int timer_next = 0;
+  std::vector<PendingTimer> pending_timers;  // stopped, not yet read
+  std::vector<int> free_pairs;               // event pairs nobody holds (filled at creation)
   std::string err;
 
   // ---- options (reference ParthAPI.h:19-25, Integrator.h:24-28)

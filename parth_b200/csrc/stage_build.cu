@@ -16,6 +16,7 @@ void read_ints(parth_b200 &h, const int *dsrc, int *dst, size_t n) {
   PB_CUDA(cudaStreamSynchronize(h.stream));
   for (size_t i = 0; i < n; i++) dst[i] = h.pin.p[i];
   h.stats.d2h_bytes += (long long)(sizeof(int) * n);
+  collect_timers(h);  // everything recorded so far has completed: free
 }
 
 // Enqueue (no read-back) the row diff of the freshly built graph (Mp_own / Mi_own) against the
@@ -44,17 +45,21 @@ static void enqueue_changed_row_proof(parth_b200 &h, int M, const int *tile_dirt
                                                     h.Mp_prev.p, h.Mi_prev.p, &h.dcnt_p()->pad0, s);
 }
 
-void resolve_timers(parth_b200 &h) {
-  PB_CUDA(cudaStreamSynchronize(h.stream));
+void collect_timers(parth_b200 &h) {
   for (auto &t : h.pending_timers) {
     float ms = 0;
     cudaEventElapsedTime(&ms, h.tev[2 * t.pair], h.tev[2 * t.pair + 1]);
     if (t.accumulate) *t.dst += ms; else *t.dst = ms;
     if (t.dst2) *t.dst2 = ms;
+    h.free_pairs.push_back(t.pair);
   }
   h.pending_timers.clear();
-  h.timer_next = 0;
   for (int i = 0; i < 5; i++) h.timers[i] = h.timer_ms[i] * 1e-3;
+}
+
+void resolve_timers(parth_b200 &h) {
+  PB_CUDA(cudaStreamSynchronize(h.stream));
+  collect_timers(h);
 }
 
 void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, int dim) {

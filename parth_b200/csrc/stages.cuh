@@ -13,24 +13,29 @@ struct StatusError : std::runtime_error {
   StatusError(int c, const std::string &m) : std::runtime_error(m), code(c) {}
 };
 
-// Device-time bracket on the handle's stream.  The elapsed time lands in *dst when
-// resolve_timers() runs (after the API call's final synchronisation).
+// Device-time bracket on the handle's stream.  The elapsed time lands in *dst the next time the
+// host has synchronised with the stream anyway (read_ints, the host-pointer entry points) or asks
+// for the statistics: the device-pointer entry points never synchronise just for a timer.
 struct StageTimer {
   parth_b200 &h;
   int pair;
   double *dst, *dst2;
   bool accumulate;
   StageTimer(parth_b200 &hh, double *d, bool acc = false, double *d2 = nullptr) : h(hh), dst(d), dst2(d2), accumulate(acc) {
-    pair = h.timer_next < parth_b200::kTimerPairs ? h.timer_next++ : -1;
+    pair = -1;
+    if (!h.free_pairs.empty()) { pair = h.free_pairs.back(); h.free_pairs.pop_back(); }
     if (pair >= 0) cudaEventRecord(h.tev[2 * pair], h.stream);
   }
   void stop() {
     if (pair < 0) return;
     cudaEventRecord(h.tev[2 * pair + 1], h.stream);
     h.pending_timers.push_back({dst, dst2, pair, accumulate});
+    pair = -1;
   }
+  ~StageTimer() { if (pair >= 0) h.free_pairs.push_back(pair); }  // abandoned (exception): give the pair back
 };
-void resolve_timers(parth_b200 &h);  // synchronises the stream
+void resolve_timers(parth_b200 &h);  // synchronises the stream, then collect_timers
+void collect_timers(parth_b200 &h);  // reads the stopped timers; call only right after a stream synchronisation
 
 // small synchronous read-back of n ints through pinned memory
 void read_ints(parth_b200 &h, const int *dsrc, int *dst, size_t n);
