@@ -167,12 +167,19 @@ __global__ void list_changed_rows_kernel(const unsigned *__restrict__ row_bits,
 }
 
 // computeTheAddedRemovedEdgesForDOF (Integrator.cpp:23-42): one warp per changed row
-__global__ void count_row_edges_kernel(const int *__restrict__ rows, int n_rows,
+// n_rows_dev != nullptr: the row count is read on the device (speculative enqueue behind the build,
+// the host has not seen it yet); n_rows is then the capacity: slots beyond the count get 0, and
+// more rows than slots leave everything 0 (the host falls back to the normal path)
+__global__ void count_row_edges_kernel(const int *__restrict__ rows, int n_rows, const int *__restrict__ n_rows_dev,
                                        const int *__restrict__ Mp, const int *__restrict__ Mi,
                                        const int *__restrict__ dof2node, int *__restrict__ counts) {
   const int lane = threadIdx.x & 31;
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (k >= n_rows) return;
+  if (n_rows_dev) {
+    const int have = *n_rows_dev;
+    if (have > n_rows || k >= have) { if (lane == 0) counts[k] = 0; return; }
+  }
   const int i = rows[k];
   int c = 0;
   for (int p = Mp[i] + lane; p < Mp[i + 1]; p += 32) {
@@ -184,13 +191,17 @@ __global__ void count_row_edges_kernel(const int *__restrict__ rows, int n_rows,
   if (lane == 0) counts[k] = c;
 }
 
-__global__ void emit_row_edges_kernel(const int *__restrict__ rows, int n_rows,
+__global__ void emit_row_edges_kernel(const int *__restrict__ rows, int n_rows, const int *__restrict__ n_rows_dev,
                                       const int *__restrict__ Mp, const int *__restrict__ Mi,
                                       const int *__restrict__ dof2node,
                                       const int *__restrict__ offsets, int *__restrict__ edges, int cap) {
   const int lane = threadIdx.x & 31;
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (k >= n_rows) return;
+  if (n_rows_dev) {
+    const int have = *n_rows_dev;
+    if (have > n_rows || k >= have) return;
+  }
   const int i = rows[k];
   int o = offsets[k];
   const int s = Mp[i], e = Mp[i + 1];
@@ -293,18 +304,19 @@ int launch_list_changed_rows(const unsigned *row_bits, const int *word_prefix, i
   return 1;
 }
 
-int launch_count_row_edges(const int *rows, int n_rows, const int *Mp, const int *Mi,
+int launch_count_row_edges(const int *rows, int n_rows, const int *n_rows_dev, const int *Mp, const int *Mi,
                            const int *dof2node, int *counts, cudaStream_t s) {
   const long long threads = (long long)n_rows * 32;
-  count_row_edges_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rows, n_rows, Mp, Mi, dof2node, counts);
+  count_row_edges_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rows, n_rows, n_rows_dev, Mp, Mi, dof2node,
+                                                                          counts);
   PB_CUDA(cudaGetLastError());
   return 1;
 }
 
-int launch_emit_row_edges(const int *rows, int n_rows, const int *Mp, const int *Mi,
+int launch_emit_row_edges(const int *rows, int n_rows, const int *n_rows_dev, const int *Mp, const int *Mi,
                           const int *dof2node, const int *offsets, int *edges, int cap, cudaStream_t s) {
   const long long threads = (long long)n_rows * 32;
-  emit_row_edges_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rows, n_rows, Mp, Mi, dof2node,
+  emit_row_edges_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(rows, n_rows, n_rows_dev, Mp, Mi, dof2node,
                                                                          offsets, edges, cap);
   PB_CUDA(cudaGetLastError());
   return 1;

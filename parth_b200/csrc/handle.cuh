@@ -90,6 +90,10 @@ struct parth_b200 {
   // node flags fetched together with the changed-edge count (stage b)
   bool node_flags_valid = false;
   std::vector<int> node_flags;
+  // stage (b) results computed speculatively behind the build (steady state): edge count + node flags
+  bool spec_valid = false;
+  int spec_n_changed = 0;
+  std::vector<int> spec_flags;
   pb::DevBuf<int> w0, w1, w2, w3, w4, w5;  // general-purpose int scratch
   // stage (c): node list, vertex offsets, per-vertex counts, sub-mesh CSR, pivots, AMD slabs
   pb::DevBuf<int> r_list, r_vtx, r_cnt, r_G, r_sub, r_perm, r_ws, r_chosen, r_g2l, r_l2g;

@@ -45,6 +45,35 @@ static void enqueue_changed_row_proof(parth_b200 &h, int M, const int *tile_dirt
                                                     h.Mp_prev.p, h.Mi_prev.p, &h.dcnt_p()->pad0, s);
 }
 
+// Stage (b)'s edge kernels (computeTheAddedRemovedEdgesForDOF, findRegionConnections), enqueued
+// speculatively behind the changed-row list so that their result (edge count + node flags in w5)
+// travels with the build's mailbox: computePermutation then needs no read-back of its own.  The row
+// count is still on the device; up to kSpecRows changed rows are covered, more fall back to
+// stage_detect's normal path.
+constexpr int kSpecRows = 8192;
+
+static bool enqueue_speculative_detection(parth_b200 &h, int M) {
+  if (!h.tree_init || h.num_nodes <= 0 || h.tree_M != M || h.map_len != 0) return false;
+  cudaStream_t s = h.stream;
+  const int nn = h.num_nodes;
+  h.w3.reserve((size_t)kSpecRows + 2, s);
+  h.w4.reserve((size_t)kSpecRows + 2, s);
+  h.w5.reserve((size_t)nn * 2 + 2, s);
+  if (h.d_changed.cap < 2 * 65536) h.d_changed.reserve(2 * 65536, s);
+  h.scan_ws.reserve(scan_ws_words((size_t)kSpecRows + 1), s);
+  const int *n_rows_dev = &h.dcnt_p()->changed_rows;
+  h.stats.kernels_launched += launch_count_row_edges(h.chg_rows.p, kSpecRows, n_rows_dev, h.Mp_own.p, h.Mi_own.p,
+                                                     h.d_dof2node.p, h.w3.p, s);
+  h.stats.kernels_launched += exclusive_scan<0>(h.w3.p, h.w4.p, kSpecRows, h.scan_ws.p, s);
+  PB_CUDA(cudaMemsetAsync(h.w5.p, 0, sizeof(int) * ((size_t)nn * 2 + 2), s));
+  const int cap = (int)(h.d_changed.cap / 2);
+  h.stats.kernels_launched += launch_emit_row_edges(h.chg_rows.p, kSpecRows, n_rows_dev, h.Mp_own.p, h.Mi_own.p,
+                                                    h.d_dof2node.p, h.w4.p, h.d_changed.p, cap, s);
+  h.stats.kernels_launched += launch_mark_dirty_nodes_dev(h.d_changed.p, h.w4.p + kSpecRows, cap, h.d_dof2node.p,
+                                                          h.d_meta.p, h.w5.p + 2, h.w5.p + 2 + nn, h.w5.p, s);
+  return true;
+}
+
 void collect_timers(parth_b200 &h) {
   for (auto &t : h.pending_timers) {
     float ms = 0;
@@ -84,6 +113,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   // anyway and is cached for it.
   h.diff_cached = false;
   h.cur_sym_proven = false;
+  h.spec_valid = false;
   const bool incremental = !h.assume_symmetric && h.prev_sym_proven && M == h.M_n_prev &&
                            h.Mp_prev.p && h.Mi_prev.p;
   a.check_mirror = (h.assume_symmetric || incremental) ? 0 : 1;
@@ -101,9 +131,20 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   a.ev_a = h.ev2; a.ev_b = h.ev3;
   a.status = h.bstatus_p();
   static_assert(sizeof(BuildStatus) == 24 && sizeof(DetectCounters) == 16, "mailbox layout");
+  bool spec_enqueued = false;
+  std::vector<int> spec_out;
   auto read_mail = [&]() {
+    // ONE synchronisation: the mailbox and, when the edge kernels ran speculatively, their result
     int m[12];
-    read_ints(h, h.mail.p, m, 12);
+    const size_t n_spec = spec_enqueued ? (size_t)h.num_nodes * 2 + 2 : 0;
+    h.pin.reserve(16 + n_spec);
+    PB_CUDA(cudaMemcpyAsync(h.pin.p, h.mail.p, sizeof(int) * 12, cudaMemcpyDeviceToHost, s));
+    if (n_spec) PB_CUDA(cudaMemcpyAsync(h.pin.p + 16, h.w5.p, sizeof(int) * n_spec, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < 12; i++) m[i] = h.pin.p[i];
+    spec_out.assign(h.pin.p + 16, h.pin.p + 16 + n_spec);
+    h.stats.d2h_bytes += (long long)(sizeof(int) * (12 + n_spec));
+    collect_timers(h);
     std::memcpy(&st, m, sizeof(st));
     std::memcpy(&dc, m + 8, sizeof(dc));
   };
@@ -146,7 +187,11 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   for (;;) {
     // the filter kernel, then (incremental mode) the changed-row proof, then ONE read-back
     launch_filter();
-    if (incremental) enqueue_changed_row_proof(h, M, fused_cols ? h.tile_dirty.p : nullptr, fused_cols);
+    spec_enqueued = false;
+    if (incremental) {
+      enqueue_changed_row_proof(h, M, fused_cols ? h.tile_dirty.p : nullptr, fused_cols);
+      spec_enqueued = enqueue_speculative_detection(h, M);
+    }
     read_mail();
     if (dim == 1 && h.build_mode <= 1) {
       // remember the variant that works so that steady-state updates launch it directly
@@ -185,6 +230,12 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
         h.diff_cached = false;
       }
     }
+  }
+  if (proven && incremental && spec_enqueued && h.diff_cached && dc.changed_rows <= kSpecRows &&
+      (int)spec_out.size() == h.num_nodes * 2 + 2 && spec_out[0] <= (int)(h.d_changed.cap / 2)) {
+    h.spec_valid = true;
+    h.spec_n_changed = spec_out[0];
+    h.spec_flags.assign(spec_out.begin() + 2, spec_out.end());
   }
   if (proven) {
     h.nnzM = st.nnz_out;

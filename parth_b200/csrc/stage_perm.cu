@@ -124,6 +124,16 @@ void stage_detect(parth_b200 &h) {
   StageTimer tm(h, &h.stats.detect_ms, false, &h.timer_ms[2]);
   h.n_changed = 0;
   h.node_flags_valid = false;
+  if (h.spec_valid && h.diff_cached && h.map_len == 0 && h.Mp == h.Mp_own.p && (int)h.spec_flags.size() == nn * 2) {
+    // stage (a) enqueued the edge kernels right behind its row diff and fetched their result with
+    // its own mailbox: nothing to launch, nothing to wait for
+    h.spec_valid = false;
+    h.n_changed = h.spec_n_changed;
+    if (h.n_chg_rows > 0) { h.node_flags.swap(h.spec_flags); h.node_flags_valid = true; }
+    tm.stop();
+    return;
+  }
+  h.spec_valid = false;
   const int n_words = (M + 31) / 32;
   h.scan_ws.reserve(scan_ws_words((size_t)std::max(n_words, M) + 1), s);
   int n_rows = 0;
@@ -155,14 +165,14 @@ void stage_detect(parth_b200 &h) {
     h.w3.reserve((size_t)n_rows + 2, s);  // per-row edge counts -> offsets
     h.w4.reserve((size_t)n_rows + 2, s);
     h.w5.reserve((size_t)nn * 2 + 2, s);  // [0] edge count, [2 .. 2+nn) within-node flags, then LCA flags
-    h.stats.kernels_launched += launch_count_row_edges(rows, n_rows, h.Mp, h.Mi, h.d_dof2node.p, h.w3.p, s);
+    h.stats.kernels_launched += launch_count_row_edges(rows, n_rows, nullptr, h.Mp, h.Mi, h.d_dof2node.p, h.w3.p, s);
     h.stats.kernels_launched += exclusive_scan<0>(h.w3.p, h.w4.p, n_rows, h.scan_ws.p, s);
     if (h.d_changed.cap < 2 * 65536) h.d_changed.reserve(2 * 65536, s);
     std::vector<int> fl((size_t)nn * 2 + 2);
     for (int attempt = 0; attempt < 2; attempt++) {
       const int cap = (int)(h.d_changed.cap / 2);
       PB_CUDA(cudaMemsetAsync(h.w5.p, 0, sizeof(int) * ((size_t)nn * 2 + 2), s));
-      h.stats.kernels_launched += launch_emit_row_edges(rows, n_rows, h.Mp, h.Mi, h.d_dof2node.p, h.w4.p,
+      h.stats.kernels_launched += launch_emit_row_edges(rows, n_rows, nullptr, h.Mp, h.Mi, h.d_dof2node.p, h.w4.p,
                                                         h.d_changed.p, cap, s);
       h.stats.kernels_launched += launch_mark_dirty_nodes_dev(h.d_changed.p, h.w4.p + n_rows, cap, h.d_dof2node.p,
                                                               h.d_meta.p, h.w5.p + 2, h.w5.p + 2 + nn, h.w5.p, s);

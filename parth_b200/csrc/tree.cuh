@@ -34,9 +34,9 @@ int launch_sym_check_rows(const int *rows, const int *n_rows_dev, int cap, const
                           const int *Mp_prev, const int *Mi_prev, int *asym, cudaStream_t s);
 int launch_list_changed_rows(const unsigned *row_bits, const int *word_prefix, int n_words, int M,
                              int *rows, int cap, cudaStream_t s);
-int launch_count_row_edges(const int *rows, int n_rows, const int *Mp, const int *Mi,
+int launch_count_row_edges(const int *rows, int n_rows, const int *n_rows_dev, const int *Mp, const int *Mi,
                            const int *dof2node, int *counts, cudaStream_t s);
-int launch_emit_row_edges(const int *rows, int n_rows, const int *Mp, const int *Mi,
+int launch_emit_row_edges(const int *rows, int n_rows, const int *n_rows_dev, const int *Mp, const int *Mi,
                           const int *dof2node, const int *offsets, int *edges, int cap, cudaStream_t s);
 
 }  // namespace pb
