@@ -160,6 +160,7 @@ typedef struct {
   double diff_kernel_ms;                  /* diff_rows_kernel alone (last build or detection that ran it) */
   int symbolic_path;                      /* 2 = per-node shared-memory kernel, 1 = wave-scheduled walk, 0 = one range */
   int build_fused_detect;                 /* 1 = the last build kernel also compared its tiles with the snapshot (stage b fused into stage a) */
+  double proof_kernel_ms;                 /* dim > 1: full symmetry proof on the compacted graph (0 when the proof was incremental or in-kernel) */
 } parth_b200_stats;
 int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out);
 int parth_b200_synchronize(parth_b200 *h);

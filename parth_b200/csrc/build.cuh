@@ -39,6 +39,8 @@ int build_filter_tiles(int M, int Q);
 // graph_build_cols.cu (dim == 1): spec = closed-form offsets (every column holds its diagonal)
 int build_cols_tiles(int Q);
 int build_cols_launch(const BuildArgs &a, bool spec, cudaStream_t s);
+// full symmetry proof on the compacted output graph (used for dim > 1 instead of in-kernel probes)
+int sym_proof_csr_launch(const int *Mp, const int *Mi, int M, int nnz_cap, BuildStatus *st, cudaStream_t s);
 // graph_build_pipe.cu (dim == 1, aligned arrays): persistent bulk-copy pipeline, closed-form offsets
 int build_pipe_supported(const BuildArgs &a);
 int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s);

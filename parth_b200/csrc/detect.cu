@@ -48,6 +48,7 @@ diff_rows_kernel(const int *__restrict__ Mp, const int *__restrict__ Mi,
     // fused mode: the graph build compared its tiles with the snapshot and wrote their bitmap
     // words; only tiles it could not stage (state 2) are compared here, word by word.  A small
     // grid strides over the row blocks (normally there is nothing to do).
+    if (cnt->pad1 == 0) return;  // the build kernel staged every tile (the normal case)
     const int n_blocks = (M + K2_ROWS - 1) / K2_ROWS;
     for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
       const int b0 = blk * K2_ROWS;

@@ -577,6 +577,76 @@ build_cols_spec_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, c
   }
 }
 
+// ------------------------------------------------------------------ full symmetry proof on the output
+// dim > 1: the mirror probes of the filter kernel would walk strided global columns of the INPUT
+// (three dependent loads per probe, 3x the sectors); the compacted mesh graph it has just written is
+// the same pattern in 1/dim^2 of the bytes and mostly L2 resident.  Every
+// upper entry (c, r > c) looks for c in row r -- first the slot a symmetric stencil predicts, then a
+// binary search -- and the global upper/lower counts must match (injection + equal counts =>
+// bijection), exactly the proof of the in-kernel probes.  Raises BUILD_ASYM / adds to diff_sum.
+__global__ void __launch_bounds__(256)
+sym_proof_csr_kernel(const int *__restrict__ Mp, const int *__restrict__ Mi, int M, int nnz_cap,
+                     BuildStatus *__restrict__ st) {
+  // one thread per row: neighbouring threads probe neighbouring rows (mesh numberings are local),
+  // so the row-pointer loads coalesce and the probed entries share sectors across the warp
+  long long diff = 0;
+  unsigned flags = 0;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < M) {
+    const int s = __ldg(Mp + c), e = __ldg(Mp + c + 1);
+    if (s < 0 || e < s || e > nnz_cap) {
+      flags |= BUILD_RANGE;  // only after a failed build
+    } else {
+      const int len = e - s;
+      for (int p0 = s; p0 < e; p0 += 4) {
+        int r[4], a[4], b[4];
+        bool up[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          r[u] = p0 + u < e ? __ldg(Mi + p0 + u) : -1;
+          up[u] = false;
+          if (p0 + u < e) {
+            if ((unsigned)r[u] >= (unsigned)M) flags |= BUILD_RANGE;
+            else if (r[u] < c) diff--;
+            else { diff++; up[u] = true; }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) { a[u] = up[u] ? __ldg(Mp + r[u]) : 0; b[u] = up[u] ? __ldg(Mp + r[u] + 1) : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          if (!up[u]) continue;
+          if (a[u] < 0 || b[u] < a[u] || b[u] > nnz_cap) { flags |= BUILD_RANGE; continue; }
+          const int g = a[u] + len - 1 - (p0 + u - s);
+          if (g >= a[u] && g < b[u] && __ldg(Mi + g) == c) continue;
+          int lo = a[u], hi = b[u];
+          while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(Mi + mid) < c) lo = mid + 1; else hi = mid;
+          }
+          if (!(lo < b[u] && __ldg(Mi + lo) == c)) flags |= BUILD_ASYM;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    diff += __shfl_xor_sync(0xffffffffu, diff, o);
+    flags |= __shfl_xor_sync(0xffffffffu, flags, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (flags) atomicOr(&st->flags, flags);
+    if (diff) atomicAdd(&st->diff_sum, (unsigned long long)diff);
+  }
+}
+
+int sym_proof_csr_launch(const int *Mp, const int *Mi, int M, int nnz_cap, BuildStatus *st, cudaStream_t s) {
+  if (M <= 0) return 0;
+  sym_proof_csr_kernel<<<(M + 255) / 256, 256, 0, s>>>(Mp, Mi, M, nnz_cap, st);
+  PB_CUDA(cudaGetLastError());
+  return 1;
+}
+
 int build_cols_tiles(int Q) { return (Q + K7_TILE - 1) / K7_TILE; }
 
 int build_cols_launch(const BuildArgs &a, bool spec, cudaStream_t s) {

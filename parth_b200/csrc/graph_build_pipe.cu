@@ -361,7 +361,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
       const int pp0 = S.ppar[0], lenp = S.ppar[2];
       const bool resolved = S.ppar[1] != 0 && nlong == 0 && !wide;
       if (!resolved) {
-        if (tid == 0) tile_state[t] = 2;
+        if (tid == 0) { tile_state[t] = 2; atomicAdd(&dcnt->pad1, 1); }  // pad1 = tiles left to diff_rows_kernel
       } else {
         const int pbase = pp0 & ~3, off = pp0 - pbase;
         const int gotp = lenp > 0 ? (min((pp0 + lenp - pbase + 3) >> 2, (nnz_prev - pbase) >> 2)) << 2 : 0;

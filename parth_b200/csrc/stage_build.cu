@@ -95,6 +95,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   cudaStream_t s = h.stream;
   const int M = N / dim;
   StageTimer total(h, &h.stats.build_ms);
+  h.stats.proof_kernel_ms = 0;
 
   h.scan_ws.reserve(scan_ws_words((size_t)M + 1), s);
   int Q = nnz;
@@ -170,7 +171,16 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
       }
       else h.stats.kernels_launched += build_cols_launch(a, h.build_mode == 0, s);
     } else if (dim > 1 && h.build_mode_n == 0) {
-      h.stats.kernels_launched += build_cols_launch(a, true, s);  // closed-form offsets, strided samples
+      // closed-form offsets, strided samples; the full symmetry proof runs on the compact output
+      const int want_proof = a.check_mirror;
+      a.check_mirror = 0;
+      h.stats.kernels_launched += build_cols_launch(a, true, s);
+      a.check_mirror = want_proof;
+      if (want_proof) {
+        StageTimer tp(h, &h.stats.proof_kernel_ms);
+        h.stats.kernels_launched += sym_proof_csr_launch(a.Mp, a.Mi, M, Q, a.status, s);
+        tp.stop();
+      }
     } else {
       h.stats.kernels_launched += build_filter_launch(a, s);
     }

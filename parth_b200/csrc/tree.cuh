@@ -21,7 +21,8 @@ int launch_mark_dirty_nodes_dev(const int *edges, const int *n_edges_dev, int ca
 struct DetectCounters {
   int changed_rows;   // rows whose adjacency differs from the snapshot
   int dirty_tiles;    // row tiles that needed the per-row comparison
-  int pad0, pad1;
+  int pad0;           // incremental symmetry proof: a mirror entry is missing
+  int pad1;           // fused detection: tiles the build kernel left to diff_rows_kernel
 };
 // tile_dirty / tile_cols: optional per-tile verdict of the fused comparison in the pipeline build
 // kernel (tile t = rows [t*tile_cols, (t+1)*tile_cols)); tile_cols == 0: compare everything

@@ -83,8 +83,9 @@ def config3():
     alg = workloads.build_bytes(N3, len(Ai3), len(gMp) - 1, len(gMi), dim)
     print(json.dumps({"config": 3, "ok": ok, "N": N3, "nnzA": int(len(Ai3)), "M": int(len(gMp) - 1), "nnzM": int(len(gMi)),
                       "removed_added": int((new_to_old == -1).sum()), "build_ms": sb["build_ms"],
-                      "build_kernel_ms": sb["build_kernel_ms"], "build_path": sb["build_path"],
-                      "build_GBs": alg / sb["build_kernel_ms"] / 1e6, "build_frac": alg / sb["build_kernel_ms"] / 1e6 / PEAK,
+                      "build_kernel_ms": sb["build_kernel_ms"], "proof_kernel_ms": sb["proof_kernel_ms"], "build_path": sb["build_path"],
+                      "build_GBs": alg / (sb["build_kernel_ms"] + sb["proof_kernel_ms"]) / 1e6,
+                      "build_frac": alg / (sb["build_kernel_ms"] + sb["proof_kernel_ms"]) / 1e6 / PEAK,
                       "integrate_ms": s["integrate_ms"], "integrate_passes": s["integrate_passes"], "integrate_sweeps": s["integrate_sweeps"], "detect_ms": s["detect_ms"], "expand_ms": s["expand_ms"],
                       "changes": g.getNumChanges(), "reuse": g.getReuse(), "status": int(st), "oracle_status": int(ost),
                       "cpu_port_s": cpu_s, "gen_s": gen_s}), flush=True)
