@@ -80,6 +80,27 @@ def test_config2_200cubed_properties(gpu_api):
     assert int((parent == -1).sum()) == 1 and cc.min() >= 1
 
 
+def test_config2_many_changed_rows_leave_the_speculative_path(gpu_api):
+    """> 8192 changed rows: the edge kernels enqueued speculatively behind the build cover at most 8192 rows, so
+    detection must fall back to its normal path -- and give the same, fully predictable, edge list"""
+    from parth_b200 import workloads
+    st = workloads.PoissonUpdateStream(n=200, levels=8, edges_per_update=6000)
+    N = st.N
+    g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 8
+    g.import_tree(st.tree(), st.Mp, st.Mi)
+    for k in (0, 1, 2):   # 0: full proof, 1 and 2: incremental proof + fused detection
+        Ap, Ai = st.matrix(k)
+        g.setMatrix(N, Ap, Ai, 1)
+        fused = g.stats()["build_fused_detect"]
+        rc, perm = g.computePermutation(1)
+        _, e = st.edges_of(k)
+        exp = np.stack([np.minimum(e[:, 0], e[:, 1]), np.maximum(e[:, 0], e[:, 1])], axis=1)
+        exp = exp[np.lexsort((exp[:, 1], exp[:, 0]))]
+        assert rc == 0 and np.array_equal(g.changed_edges(), exp), k
+        assert g.getNumChanges() == len(exp) and len(exp) > 4096
+    assert fused == 1
+
+
 def test_config2_aggressive_reuse_update_matches_oracle_at_full_size(gpu_api, port):
     """the bench's `aggr` variant: relocation of the broken cousin-leaf edges into the level-7 separator,
     extraction + AMD of the touched nodes, assembly -- every integer result equal to the oracle's at 8 M DOF"""
