@@ -755,7 +755,8 @@ PB_DEVFN void eliminate_warp(const Ws &w, int pfree, int nel) {
 }
 
 // ------------------------------------------------------------------ assembly-tree post-order
-// amd_2's epilogue + amd_postorder / amd_post_tree; one thread.
+// amd_post_tree: depth-first numbering of one tree of the assembly forest (one thread; the rest of
+// amd_2's epilogue and of amd_postorder runs on the whole CTA, finish_cta below)
 PB_DEVFN int post_tree_serial(int root, int k, int *Child, const int *Sibling, int *Order, int *Stack) {
   int head = 0;
   Stack[0] = root;
@@ -774,70 +775,8 @@ PB_DEVFN int post_tree_serial(int root, int k, int *Child, const int *Sibling, i
   return k;
 }
 
-PB_DEVFN void finish_serial(const Ws &w) {
-  const int n = w.n;
-  int *const Pe = w.Pe, *const Nv = w.Nv, *const Head = w.Head, *const Elen = w.Elen;
-  int *const W = w.W, *const Next = w.Next, *const Last = w.Last;
-  for (int i = 0; i < n; i++) Pe[i] = flip(Pe[i]);
-  for (int i = 0; i < n; i++) Elen[i] = flip(Elen[i]);
-  for (int i = 0; i < n; i++) {
-    if (Nv[i] == 0) {
-      int j = Pe[i];
-      if (j == NONE) continue;
-      while (Nv[j] == 0) j = Pe[j];
-      const int e = j;
-      j = i;
-      while (Nv[j] == 0) { const int jnext = Pe[j]; Pe[j] = e; j = jnext; }
-    }
-  }
-  // amd_postorder(n, Parent = Pe, Nv, Fsize = Elen, Order = W, Child = Head, Sibling = Next, Stack = Last)
-  int *const Child = Head, *const Sibling = Next, *const Order = W, *const Stack = Last;
-  for (int j = 0; j < n; j++) { Child[j] = NONE; Sibling[j] = NONE; }
-  for (int j = n - 1; j >= 0; j--)
-    if (Nv[j] > 0) {
-      const int parent = Pe[j];
-      if (parent != NONE) { Sibling[j] = Child[parent]; Child[parent] = j; }
-    }
-  for (int i = 0; i < n; i++)
-    if (Nv[i] > 0 && Child[i] != NONE) {
-      int fprev = NONE, maxfr = NONE, bigfprev = NONE, bigf = NONE;
-      for (int f = Child[i]; f != NONE; f = Sibling[f]) {
-        const int fr = Elen[f];
-        if (fr >= maxfr) { maxfr = fr; bigfprev = fprev; bigf = f; }
-        fprev = f;
-      }
-      const int fnext = Sibling[bigf];
-      if (fnext != NONE) {
-        if (bigfprev == NONE) Child[i] = fnext; else Sibling[bigfprev] = fnext;
-        Sibling[bigf] = NONE;
-        Sibling[fprev] = bigf;
-      }
-    }
-  for (int i = 0; i < n; i++) Order[i] = NONE;
-  int k = 0;
-  for (int i = 0; i < n; i++)
-    if (Pe[i] == NONE && Nv[i] > 0) k = post_tree_serial(i, k, Child, Sibling, Order, Stack);
-  for (int q = 0; q < n; q++) { Head[q] = NONE; Next[q] = NONE; }
-  for (int e = 0; e < n; e++) { const int q = W[e]; if (q != NONE) Head[q] = e; }
-  int nel = 0;
-  for (int q = 0; q < n; q++) {
-    const int e = Head[q];
-    if (e == NONE) break;
-    Next[e] = nel;
-    nel += Nv[e];
-  }
-  for (int i = 0; i < n; i++) {
-    if (Nv[i] == 0) {
-      const int e = Pe[i];
-      if (e != NONE) { Next[i] = Next[e]; Next[e]++; }
-      else Next[i] = nel++;
-    }
-  }
-  for (int i = 0; i < n; i++) Last[Next[i]] = i;
-}
-
 // ------------------------------------------------------------------ epilogue, whole CTA
-// The same result as finish_serial: per-vertex passes run on all threads; the steps whose outcome
+// amd_2's epilogue + amd_postorder.  Per-vertex passes run on all threads; the steps whose outcome
 // depends on the visiting order (children lists in ascending id, slots of absorbed variables in
 // ascending id) advance one warp-wide chunk at a time on warp 0; only the depth-first numbering of
 // the assembly tree (one node per pivot) stays on one thread.  sh: >= 4 + 32 ints shared by the CTA.
