@@ -14,6 +14,7 @@
 //                     2*4*[(M+1)+nnzM].  Only blocks that fail do the per-row comparison.
 //   list_changed_rows ordered compaction of the changed-row bitmap (popc scan outside)
 //   count/emit        per changed row (few): problematic-edge count, exclusive scan, ordered emit
+#include "scan.cuh"
 #include "tree.cuh"
 
 namespace pb {
@@ -38,42 +39,11 @@ __device__ __forceinline__ bool problematic_d(const int *__restrict__ dof2node, 
 __global__ void __launch_bounds__(K2_THREADS)
 diff_rows_kernel(const int *__restrict__ Mp, const int *__restrict__ Mi,
                  const int *__restrict__ Mp_prev, const int *__restrict__ Mi_prev, int M,
-                 unsigned *__restrict__ row_bits, DetectCounters *__restrict__ cnt,
-                 const int *__restrict__ tile_state, int tile_cols) {
+                 unsigned *__restrict__ row_bits, DetectCounters *__restrict__ cnt) {
   __shared__ int s_bad;
   const int tid = threadIdx.x, lane = tid & 31;
   const int r0 = blockIdx.x * K2_ROWS;
   const int r1 = r0 + K2_ROWS < M ? r0 + K2_ROWS : M;
-  if (tile_state) {
-    // fused mode: the graph build compared its tiles with the snapshot and wrote their bitmap
-    // words; only tiles it could not stage (state 2) are compared here, word by word.  A small
-    // grid strides over the row blocks (normally there is nothing to do).
-    if (cnt->pad1 == 0) return;  // the build kernel staged every tile (the normal case)
-    const int n_blocks = (M + K2_ROWS - 1) / K2_ROWS;
-    for (int blk = blockIdx.x; blk < n_blocks; blk += gridDim.x) {
-      const int b0 = blk * K2_ROWS;
-      const int b1 = b0 + K2_ROWS < M ? b0 + K2_ROWS : M;
-      int any = 0;
-      for (int t = b0 / tile_cols; t <= (b1 - 1) / tile_cols; t++) any |= __ldg(tile_state + t) == 2;
-      if (!any) continue;
-      int changed_here = 0;
-      for (int base = b0 + (tid & ~31); base < b1; base += K2_THREADS) {
-        if (__ldg(tile_state + base / tile_cols) != 2) continue;  // warp-uniform: tiles are multiples of 32 rows
-        const int i = base + lane;
-        bool ch = false;
-        if (i < b1) {
-          const int s = Mp[i], e = Mp[i + 1], sp = Mp_prev[i], ep = Mp_prev[i + 1];
-          ch = (e - s) != (ep - sp);
-          for (int k = 0; !ch && k < e - s; k++) ch = Mi[s + k] != Mi_prev[sp + k];
-        }
-        const unsigned m = __ballot_sync(0xffffffffu, ch);
-        if (lane == 0) { row_bits[base >> 5] = m; changed_here += __popc(m); }
-      }
-      if (lane == 0 && changed_here) atomicAdd(&cnt->changed_rows, changed_here);
-      if (tid == 0) atomicAdd(&cnt->dirty_tiles, 1);
-    }
-    return;
-  }
   if (tid == 0) s_bad = 0;
   __syncthreads();
   const int p0 = Mp[r0], pp0 = Mp_prev[r0];
@@ -246,7 +216,8 @@ __device__ __forceinline__ bool row_contains(const int *__restrict__ Mi, int s, 
 __global__ void sym_check_rows_kernel(const int *__restrict__ rows, const int *__restrict__ n_rows_dev, int cap,
                                       const int *__restrict__ Mp, const int *__restrict__ Mi,
                                       const int *__restrict__ Mp_prev, const int *__restrict__ Mi_prev,
-                                      int *__restrict__ asym) {
+                                      int *__restrict__ asym, const int *__restrict__ dof2node,
+                                      int *__restrict__ counts, int spec_cap) {
   const int lane = threadIdx.x & 31;
   const int n_rows = *n_rows_dev;
   if (n_rows > cap) return;
@@ -255,9 +226,17 @@ __global__ void sym_check_rows_kernel(const int *__restrict__ rows, const int *_
   for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_rows; k += warps) {
     const int j = rows[k];
     const int s = Mp[j], e = Mp[j + 1];
+    const bool want_count = counts != nullptr && k < spec_cap;  // computeTheAddedRemovedEdgesForDOF, fused in
+    int c = 0;
     for (int p = s + lane; p < e; p += 32) {
       const int i = Mi[p];
       if (!row_contains(Mi, Mp[i], Mp[i + 1], j)) bad = true;
+      if (want_count) c += (j < i) && problematic_d(dof2node, j, i);
+    }
+    if (want_count) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+      if (lane == 0) counts[k] = c;
     }
     for (int p = Mp_prev[j] + lane; p < Mp_prev[j + 1]; p += 32) {
       const int i = Mi_prev[p];
@@ -268,21 +247,153 @@ __global__ void sym_check_rows_kernel(const int *__restrict__ rows, const int *_
 }
 
 int launch_sym_check_rows(const int *rows, const int *n_rows_dev, int cap, const int *Mp, const int *Mi,
-                          const int *Mp_prev, const int *Mi_prev, int *asym, cudaStream_t s) {
-  sym_check_rows_kernel<<<2 * kNumSMsB200, 256, 0, s>>>(rows, n_rows_dev, cap, Mp, Mi, Mp_prev, Mi_prev, asym);
+                          const int *Mp_prev, const int *Mi_prev, int *asym, const int *dof2node, int *counts,
+                          int spec_cap, cudaStream_t s) {
+  sym_check_rows_kernel<<<2 * kNumSMsB200, 256, 0, s>>>(rows, n_rows_dev, cap, Mp, Mi, Mp_prev, Mi_prev, asym, dof2node,
+                                                        counts, spec_cap);
   PB_CUDA(cudaGetLastError());
   return 1;
 }
 
+// ------------------------------------------------------------------ fused steady state
+// The pipeline build kernel (graph_build_pipe.cu) has written the changed-row bitmap and, per tile,
+// the number of changed rows (-1: tile left unresolved -> the host falls back to diff_rows_kernel).
+// Kernels A1 + A2: ascending list of the changed rows.  A scan over the tile counts (one CTA)
+// replaces the scan over the whole bitmap; only the bitmap words of dirty tiles are read.
+constexpr int KA_THREADS = 1024;
+
+__device__ __forceinline__ int block_excl_scan_1024(int v, int *s_warp, int *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, w, d);
+      if (lane >= d) w += t;
+    }
+    s_warp[lane] = w;  // inclusive over warps
+  }
+  __syncthreads();
+  *total = s_warp[31];
+  const int base = warp > 0 ? s_warp[warp - 1] : 0;
+  __syncthreads();  // s_warp may be reused by the caller
+  return base + incl - v;
+}
+
+// A2 (grid, one warp per tile): the changed rows of a dirty tile, ascending, at the tile's offset
+// (tile_off = device-wide exclusive scan of the tile counts; with unresolved tiles (-1) in it the
+// offsets are meaningless, the host discards the list -- only the bounds are guarded)
+__global__ void rows_from_tiles_kernel(const int *__restrict__ tile_cnt, const int *__restrict__ tile_off,
+                                       int num_tiles, int tile_cols, const unsigned *__restrict__ row_bits, int M,
+                                       int *__restrict__ rows, int cap) {
+  const int lane = threadIdx.x & 31;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= num_tiles || __ldg(tile_cnt + t) <= 0) return;
+  const int wpt = tile_cols >> 5, n_words = (M + 31) >> 5;
+  const int w0 = (int)(((long long)t * tile_cols) >> 5);
+  int o = __ldg(tile_off + t);
+  for (int wb = 0; wb < wpt; wb += 32) {
+    const int w = w0 + wb + lane;
+    unsigned m = (wb + lane < wpt && w < n_words) ? row_bits[w] : 0u;
+    const int c = __popc(m);
+    int incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int x = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += x;
+    }
+    int at = o + incl - c;
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      if (at >= 0 && at < cap) rows[at] = (w << 5) + b;
+      at++;
+    }
+    o += __shfl_sync(0xffffffffu, incl, 31);
+  }
+}
+
+// Kernel C1 (one CTA): exclusive scan of the per-row edge counts -> offsets, total -> out[0]; clears
+// the node flags.  Covers up to kSpecRows changed rows; more (or unresolved tiles) -> out[0] = -1 and
+// the host uses the multi-kernel path.
+__global__ void __launch_bounds__(KA_THREADS)
+scan_counts_kernel(const DetectCounters *__restrict__ cnt, const int *__restrict__ counts, int *__restrict__ offsets,
+                   int nn, int *__restrict__ out) {
+  __shared__ int s_warp[32];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * nn; i += KA_THREADS) out[2 + i] = 0;
+  const int n = cnt->changed_rows;
+  if (n > kSpecRows || cnt->pad1 > 0) {
+    if (tid == 0) out[0] = -1;
+    return;
+  }
+  constexpr int IPT = kSpecRows / KA_THREADS;
+  int c[IPT], sum = 0;
+#pragma unroll
+  for (int u = 0; u < IPT; u++) { const int k = tid * IPT + u; c[u] = k < n ? counts[k] : 0; sum += c[u]; }
+  int total;
+  int o = block_excl_scan_1024(sum, s_warp, &total);
+#pragma unroll
+  for (int u = 0; u < IPT; u++) { offsets[tid * IPT + u] = o; o += c[u]; }
+  if (tid == 0) out[0] = total;
+}
+
+// Kernel C2 (grid, one warp per changed row): ordered emission of the row's changed edges
+// (emit_row_edges_kernel's body) and, while the endpoints are in registers, the dirty-node flags of
+// Integrator::findRegionConnections (mark_dirty_nodes)
+__global__ void emit_mark_kernel(const int *__restrict__ rows, const DetectCounters *__restrict__ cnt,
+                                 const int *__restrict__ offsets, const int *__restrict__ Mp,
+                                 const int *__restrict__ Mi, const int *__restrict__ dof2node,
+                                 const int *__restrict__ meta, int *__restrict__ edges, int cap_edges, int nn,
+                                 int *__restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n = cnt->changed_rows;
+  if (n > kSpecRows || cnt->pad1 > 0 || k >= n) return;
+  const int i = rows[k];
+  const int ni = __ldg(dof2node + i);
+  int at0 = offsets[k];
+  const int s = Mp[i], e = Mp[i + 1];
+  for (int b = s; b < e; b += 32) {
+    const int p = b + lane;
+    bool hit = false;
+    int nb = 0, nnb = 0;
+    if (p < e) {
+      nb = Mi[p];
+      if (i < nb) {
+        nnb = __ldg(dof2node + nb);
+        const int small = ni < nnb ? ni : nnb, big = ni < nnb ? nnb : ni;
+        hit = !(small == big || is_separator_d(small, big));  // Integrator::problematicEdgeCondition
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) {
+      const int at = at0 + __popc(m & ((1u << lane) - 1u));
+      if (at < cap_edges) {
+        edges[2 * at] = i;
+        edges[2 * at + 1] = nb;
+        // a problematic edge joins two nodes that are neither equal nor ancestor-related: its LCA is dirty
+        out[2 + nn + common_separator_dev(meta, ni < nnb ? ni : nnb, ni < nnb ? nnb : ni)] = 1;
+      }
+    }
+    at0 += __popc(m);
+  }
+}
+
 // ------------------------------------------------------------------ host launchers
 int launch_diff_rows(const int *Mp, const int *Mi, const int *Mp_prev, const int *Mi_prev, int M,
-                     unsigned *row_bits, DetectCounters *cnt, const int *tile_dirty, int tile_cols, cudaStream_t s) {
-  // fused mode (tile_cols > 0): the counters already hold the build kernel's share
-  if (tile_cols <= 0) PB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(DetectCounters), s));
-  int blocks = (M + K2_ROWS - 1) / K2_ROWS;
-  if (tile_cols > 0 && blocks > 2 * kNumSMsB200) blocks = 2 * kNumSMsB200;
-  diff_rows_kernel<<<blocks, K2_THREADS, 0, s>>>(Mp, Mi, Mp_prev, Mi_prev, M, row_bits, cnt,
-                                                 tile_cols > 0 ? tile_dirty : nullptr, tile_cols);
+                     unsigned *row_bits, DetectCounters *cnt, cudaStream_t s) {
+  PB_CUDA(cudaMemsetAsync(cnt, 0, sizeof(DetectCounters), s));
+  const int blocks = (M + K2_ROWS - 1) / K2_ROWS;
+  diff_rows_kernel<<<blocks, K2_THREADS, 0, s>>>(Mp, Mi, Mp_prev, Mi_prev, M, row_bits, cnt);
   PB_CUDA(cudaGetLastError());
   return 1;
 }
@@ -321,6 +432,26 @@ int launch_emit_row_edges(const int *rows, int n_rows, const int *n_rows_dev, co
                                                                          offsets, edges, cap);
   PB_CUDA(cudaGetLastError());
   return 1;
+}
+
+int launch_rows_from_tiles(const int *tile_cnt, int *tile_off, unsigned long long *scan_ws, int num_tiles, int tile_cols,
+                           const unsigned *row_bits, int M, int *rows, int cap, cudaStream_t s) {
+  exclusive_scan<0>(tile_cnt, tile_off, num_tiles, scan_ws, s);
+  rows_from_tiles_kernel<<<(unsigned)(((long long)num_tiles * 32 + 255) / 256), 256, 0, s>>>(tile_cnt, tile_off, num_tiles,
+                                                                                            tile_cols, row_bits, M, rows, cap);
+  PB_CUDA(cudaGetLastError());
+  return 2;
+}
+
+int launch_emit_mark(const int *rows, const DetectCounters *cnt, const int *counts, const int *Mp, const int *Mi,
+                     const int *dof2node, const int *meta, int *edges, int cap_edges, int nn, int *out, cudaStream_t s) {
+  // counts doubles as the offsets array: the scan reads its counts into registers before it writes
+  int *offsets = const_cast<int *>(counts);
+  scan_counts_kernel<<<1, KA_THREADS, 0, s>>>(cnt, counts, offsets, nn, out);
+  emit_mark_kernel<<<(kSpecRows * 32) / 256, 256, 0, s>>>(rows, cnt, offsets, Mp, Mi, dof2node, meta, edges, cap_edges, nn,
+                                                          out);
+  PB_CUDA(cudaGetLastError());
+  return 2;
 }
 
 }  // namespace pb

@@ -352,13 +352,14 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
       // ---- fused change detection (stage b): this tile against the same rows of the snapshot,
       // both sides in shared memory.  Constant row-pointer shift + identical entries <=> no row of
       // the tile changed; otherwise one thread per row compares (Integrator.cpp:269-288) and the
-      // changed-row bitmap words of the tile are written here.  tile_state: 0 clean, 1 rows
-      // compared here, 2 left to diff_rows_kernel (snapshot tile too large / over-long columns).
+      // changed-row bitmap words of the tile are written here.  tile_state[t] (zeroed before the
+      // launch): number of changed rows of the tile, or -1 = not compared here (snapshot tile too
+      // large / over-long columns; counted in dcnt->pad1, the host then runs diff_rows_kernel).
       mbar_wait(&S.pfull, k & 1);
       const int pp0 = S.ppar[0], lenp = S.ppar[2];
       const bool resolved = S.ppar[1] != 0 && nlong == 0 && !wide;
       if (!resolved) {
-        if (tid == 0) { tile_state[t] = 2; atomicAdd(&dcnt->pad1, 1); }  // pad1 = tiles left to diff_rows_kernel
+        if (tid == 0) { tile_state[t] = -1; atomicAdd(&dcnt->pad1, 1); }
       } else {
         const int pbase = pp0 & ~3, off = pp0 - pbase;
         const int gotp = lenp > 0 ? (min((pp0 + lenp - pbase + 3) >> 2, (nnz_prev - pbase) >> 2)) << 2 : 0;
@@ -395,8 +396,8 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
             const unsigned m = __ballot_sync(0xffffffffu, ch);
             if (lane == 0) { row_bits[(c0 + lb) >> 5] = m; changed_here += __popc(m); }
           }
-          if (lane == 0 && changed_here) atomicAdd(&dcnt->changed_rows, changed_here);
-          if (tid == 0) { atomicAdd(&dcnt->dirty_tiles, 1); tile_state[t] = 1; }
+          if (lane == 0 && changed_here) { atomicAdd(&dcnt->changed_rows, changed_here); atomicAdd(&tile_state[t], changed_here); }
+          if (tid == 0) atomicAdd(&dcnt->dirty_tiles, 1);
         } else {
           for (int w = tid; w < (nc + 31) >> 5; w += K9_CONSUMERS) row_bits[(c0 >> 5) + w] = 0u;
         }

@@ -81,7 +81,7 @@ struct parth_b200 {
   double timer_ms[5] = {0, 0, 0, 0, 0};   // the same spans in device milliseconds
 
   // ---- scratch
-  pb::DevBuf<int> V, ns_tmp, tile_c, cnt, ptr, tmp, uniq, tile_dirty;
+  pb::DevBuf<int> V, ns_tmp, tile_c, cnt, ptr, tmp, uniq, tile_dirty, tile_off;
   pb::DevBuf<unsigned long long> desc, scan_ws;
   // device mailbox, read back with ONE copy: [0..5] BuildStatus, [8..11] DetectCounters
   pb::DevBuf<int> mail;

@@ -25,7 +25,16 @@ void read_ints(parth_b200 &h, const int *dsrc, int *dst, size_t n) {
 // stage (b).  Rows beyond `cap` are not listed: the caller then falls back to the streaming proof.
 static int changed_rows_cap(int M) { return std::max(1024, M / 20); }
 
-static void enqueue_changed_row_proof(parth_b200 &h, int M, const int *tile_dirty, int tile_cols) {
+static bool spec_ready(const parth_b200 &h, int M) {
+  return h.tree_init && h.num_nodes > 0 && h.tree_M == M && h.map_len == 0;
+}
+
+// fused_cols > 0: the pipeline build kernel has already written the bitmap, the counters and the
+// per-tile counts (h.tile_dirty); three launches finish stages (a) and (b): the row list from the
+// tile counts, the symmetry check with the per-row edge counts fused in, and one CTA that scans the
+// counts, emits the changed edges in order and marks the dirty nodes.  Returns true when the
+// stage (b) result (w5) was enqueued as well.
+static bool enqueue_changed_row_proof(parth_b200 &h, int M, int fused_cols, int num_tiles) {
   cudaStream_t s = h.stream;
   const int n_words = (M + 31) / 32;
   const int cap = changed_rows_cap(M);
@@ -34,15 +43,37 @@ static void enqueue_changed_row_proof(parth_b200 &h, int M, const int *tile_dirt
   h.chg_rows.reserve((size_t)cap + 1, s);
   h.scan_ws.reserve(scan_ws_words((size_t)std::max(n_words, M) + 1), s);
   unsigned *bits = reinterpret_cast<unsigned *>(h.chg_bits.p);
+  if (fused_cols > 0) {
+    const bool spec = spec_ready(h, M);
+    const int nn = h.num_nodes;
+    if (spec) {
+      h.w3.reserve((size_t)kSpecRows + 2, s);
+      h.w5.reserve((size_t)nn * 2 + 2, s);
+      if (h.d_changed.cap < 2 * 65536) h.d_changed.reserve(2 * 65536, s);
+    }
+    h.tile_off.reserve((size_t)num_tiles + 2, s);
+    h.stats.kernels_launched += launch_rows_from_tiles(h.tile_dirty.p, h.tile_off.p, h.scan_ws.p, num_tiles, fused_cols, bits,
+                                                       M, h.chg_rows.p, cap, s);
+    h.stats.kernels_launched += launch_sym_check_rows(h.chg_rows.p, &h.dcnt_p()->changed_rows, cap, h.Mp_own.p,
+                                                      h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, &h.dcnt_p()->pad0,
+                                                      spec ? h.d_dof2node.p : nullptr, spec ? h.w3.p : nullptr,
+                                                      kSpecRows, s);
+    if (spec)
+      h.stats.kernels_launched += launch_emit_mark(h.chg_rows.p, h.dcnt_p(), h.w3.p, h.Mp_own.p, h.Mi_own.p,
+                                                   h.d_dof2node.p, h.d_meta.p, h.d_changed.p,
+                                                   (int)(h.d_changed.cap / 2), nn, h.w5.p, s);
+    return spec;
+  }
   {
     StageTimer td(h, &h.stats.diff_kernel_ms);
-    h.stats.kernels_launched += launch_diff_rows(h.Mp_own.p, h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt_p(), tile_dirty, tile_cols, s);
+    h.stats.kernels_launched += launch_diff_rows(h.Mp_own.p, h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt_p(), s);
     td.stop();
   }
   h.stats.kernels_launched += exclusive_scan<1>(h.chg_bits.p, h.chg_pre.p, n_words, h.scan_ws.p, s);
   h.stats.kernels_launched += launch_list_changed_rows(bits, h.chg_pre.p, n_words, M, h.chg_rows.p, cap, s);
   h.stats.kernels_launched += launch_sym_check_rows(h.chg_rows.p, &h.dcnt_p()->changed_rows, cap, h.Mp_own.p, h.Mi_own.p,
-                                                    h.Mp_prev.p, h.Mi_prev.p, &h.dcnt_p()->pad0, s);
+                                                    h.Mp_prev.p, h.Mi_prev.p, &h.dcnt_p()->pad0, nullptr, nullptr, 0, s);
+  return false;
 }
 
 // Stage (b)'s edge kernels (computeTheAddedRemovedEdgesForDOF, findRegionConnections), enqueued
@@ -50,10 +81,8 @@ static void enqueue_changed_row_proof(parth_b200 &h, int M, const int *tile_dirt
 // travels with the build's mailbox: computePermutation then needs no read-back of its own.  The row
 // count is still on the device; up to kSpecRows changed rows are covered, more fall back to
 // stage_detect's normal path.
-constexpr int kSpecRows = 8192;
-
 static bool enqueue_speculative_detection(parth_b200 &h, int M) {
-  if (!h.tree_init || h.num_nodes <= 0 || h.tree_M != M || h.map_len != 0) return false;
+  if (!spec_ready(h, M)) return false;
   cudaStream_t s = h.stream;
   const int nn = h.num_nodes;
   h.w3.reserve((size_t)kSpecRows + 2, s);
@@ -96,6 +125,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   const int M = N / dim;
   StageTimer total(h, &h.stats.build_ms);
   h.stats.proof_kernel_ms = 0;
+  h.stats.diff_kernel_ms = 0;
 
   h.scan_ws.reserve(scan_ws_words((size_t)M + 1), s);
   int Q = nnz;
@@ -199,10 +229,18 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
     launch_filter();
     spec_enqueued = false;
     if (incremental) {
-      enqueue_changed_row_proof(h, M, fused_cols ? h.tile_dirty.p : nullptr, fused_cols);
-      spec_enqueued = enqueue_speculative_detection(h, M);
+      spec_enqueued = enqueue_changed_row_proof(h, M, fused_cols, fused_cols ? build_pipe_num_tiles(a) : 0);
+      if (!fused_cols) spec_enqueued = enqueue_speculative_detection(h, M);
     }
     read_mail();
+    if (incremental && fused_cols && st.flags == 0 && dc.pad1 > 0) {
+      // some tiles could not be compared inside the build kernel (over-long columns, snapshot tile
+      // larger than the staging buffer): the streaming row diff takes over for this update
+      fused_cols = 0;
+      enqueue_changed_row_proof(h, M, 0, 0);
+      spec_enqueued = enqueue_speculative_detection(h, M);
+      read_mail();
+    }
     if (dim == 1 && h.build_mode <= 1) {
       // remember the variant that works so that steady-state updates launch it directly
       const unsigned only = st.flags & ~(BUILD_NODIAG | BUILD_WIDE);
@@ -242,7 +280,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
     }
   }
   if (proven && incremental && spec_enqueued && h.diff_cached && dc.changed_rows <= kSpecRows &&
-      (int)spec_out.size() == h.num_nodes * 2 + 2 && spec_out[0] <= (int)(h.d_changed.cap / 2)) {
+      (int)spec_out.size() == h.num_nodes * 2 + 2 && spec_out[0] >= 0 && spec_out[0] <= (int)(h.d_changed.cap / 2)) {
     h.spec_valid = true;
     h.spec_n_changed = spec_out[0];
     h.spec_flags.assign(spec_out.begin() + 2, spec_out.end());

@@ -150,7 +150,7 @@ void stage_detect(parth_b200 &h) {
       h.stats.kernels_launched += launch_diff_rows_mapped(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, h.new_to_old.p,
                                                           h.old_to_new.p, M, bits, h.dcnt_p(), s);
     else
-      h.stats.kernels_launched += launch_diff_rows(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt_p(), nullptr, 0, s);
+      h.stats.kernels_launched += launch_diff_rows(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, M, bits, h.dcnt_p(), s);
     int cnt[4];
     read_ints(h, reinterpret_cast<const int *>(h.dcnt_p()), cnt, 4);
     n_rows = cnt[0];

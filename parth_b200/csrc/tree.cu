@@ -79,22 +79,6 @@ __global__ void expand_vec_kernel(const int4 *__restrict__ mesh_perm4, int n4, i
     st_stream4(out4 + (size_t)i * DIM + q, make_int4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]));
 }
 
-// HMD::isSeparator (HMD.cpp:366-379)
-__device__ __forceinline__ bool is_separator_dev(int sep, int node) {
-  int a = (node - 1) / 2;
-  while (a > sep && a > 0) a = (a - 1) / 2;
-  return a == sep;
-}
-
-// HMD::findCommonSeparator (HMD.cpp:381-419) on the stored level / parent fields
-__device__ __forceinline__ int common_separator_dev(const int *__restrict__ meta, int first, int second) {
-  int hi = first, lo = second;
-  if (__ldg(meta + hi * 7 + 5) < __ldg(meta + lo * 7 + 5)) { hi = second; lo = first; }
-  while (__ldg(meta + hi * 7 + 5) != __ldg(meta + lo * 7 + 5)) hi = __ldg(meta + hi * 7 + 3);
-  while (hi != lo) { hi = __ldg(meta + hi * 7 + 3); lo = __ldg(meta + lo * 7 + 3); }
-  return hi;
-}
-
 // Integrator::findRegionConnections + first loop of filterChanges (Integrator.cpp:685-747):
 // every changed DOF edge marks either its node (same node) or the LCA of its two nodes.
 __global__ void mark_dirty_nodes_kernel(const int *__restrict__ edges, int n_edges,

@@ -124,29 +124,32 @@ def test_cold_start_through_decomposer_callback(gpu_api):
 
 def test_fused_detection_with_over_long_columns_matches_oracle(gpu_api, port):
     """steady-state updates run change detection inside the pipeline build kernel (stage b fused into
-    stage a); tiles holding a column longer than 64 are left to diff_rows_kernel.  Both routes, and
-    the tiles whose entry count changed, must give the oracle's changed edges / dirty sets / permutation."""
+    stage a); an update whose tiles hold a column longer than 64 falls back to diff_rows_kernel.  Both
+    routes, and the tiles whose entry count changed, must give the oracle's changed edges / dirty sets /
+    permutation."""
     tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 16, 5)))
     from parth_b200 import synth
     rng = np.random.default_rng(9)
     n = len(Mp) - 1
     hub = int(tree.node_dofs(0)[0])                                  # a root-separator DOF: edges to it never break the tree
-    others = [int(x) for x in rng.choice(n, 120, replace=False) if int(x) != hub]
-    cur = synth.add_edges(Mp, Mi, [(hub, x) for x in others[:100]])   # column of the hub: > 64 entries
+    others = [int(x) for x in rng.choice(n, 140, replace=False) if int(x) != hub]
+    cur = (Mp, Mi)
     g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 5; g.reorder_type = 1
     g.setCoarsePolicy(gpu_api.COARSE_REPORT)
     o = port.CpuParth("port"); o.set_options(reorder_type=1, nd_levels=5)
     g.import_tree(tree, *cur); o.import_tree(tree, *cur)
-    fused_seen = 0
-    for step in range(6):
-        if step in (1, 3):    # the hub gains neighbours (long column, tile left to the row diff)
-            cur = synth.add_edges(cur[0], cur[1], [(hub, x) for x in others[100 + 5 * step:105 + 5 * step]])
-        if step in (2, 3, 4):  # short rows change (compared inside the build kernel)
+    fused = []
+    for step in range(8):
+        if step in (1, 2, 3, 6):  # short rows change (compared inside the build kernel)
             a = int(tree.node_dofs(1 + step)[0]); b = int(tree.node_dofs(1 + step)[-1])
             cur = synth.add_edges(cur[0], cur[1], [(a, b)])
+        if step == 4:             # the hub appears: its column has > 64 entries from now on
+            cur = synth.add_edges(cur[0], cur[1], [(hub, x) for x in others[:100]])
+        if step in (5, 6):        # ... and keeps changing
+            cur = synth.add_edges(cur[0], cur[1], [(hub, x) for x in others[100 + 5 * step:105 + 5 * step]])
         N, Ap, Ai = synth.graph_to_matrix(*cur)
         g.setMatrix(N, Ap, Ai, 1); o.setMatrix(N, Ap, Ai, 1)
-        fused_seen += g.stats()["build_fused_detect"]
+        fused.append(g.stats()["build_fused_detect"])
         st, perm = g.computePermutation(1)
         ost, operm = o.computePermutation(1)
         assert g.getNumChanges() == o.getNumChanges(), step
@@ -156,4 +159,5 @@ def test_fused_detection_with_over_long_columns_matches_oracle(gpu_api, port):
         assert gf.tolist() == of.tolist() and gc.tolist() == oc.tolist(), step
         if ost == 0:
             assert st == 0 and np.array_equal(perm, operm), step
-    assert fused_seen >= 4
+    assert fused[1:4] == [1, 1, 1]        # steady state without long columns: fused
+    assert fused[4:] == [0, 0, 0, 0]      # a tile with an over-long column: the row diff took over
