@@ -60,6 +60,15 @@ int parth_b200_create(parth_b200 **out, int device) {
     PB_CUDA(cudaEventCreate(&h->ev2));
     PB_CUDA(cudaEventCreate(&h->ev3));
     h->pin.reserve(1 << 16);
+    {
+      // keep freed work-space in the device's default pool instead of returning it to the driver
+      cudaMemPool_t pool = nullptr;
+      if (cudaDeviceGetDefaultMemPool(&pool, h->device) == cudaSuccess && pool) {
+        unsigned long long keep_all = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep_all);
+      }
+      (void)cudaGetLastError();
+    }
     for (auto &e : h->tev) PB_CUDA(cudaEventCreate(&e));
     for (int i = parth_b200::kTimerPairs - 1; i >= 0; i--) h->free_pairs.push_back(i);
     h->mail.reserve(32);

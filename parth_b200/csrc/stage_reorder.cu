@@ -4,6 +4,9 @@
 // HMD::createMultiSubMesh (HMD.cpp:538-612), HMD::getCoarseMesh (HMD.cpp:465-481),
 // HMD::AMDNodeNDPermutation (HMD.cpp:58-75).
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 #include "reorder.cuh"
 #include "scan.cuh"
@@ -64,13 +67,24 @@ void order_batch(parth_b200 &h, const Batch &b, const std::vector<int> &graph_nn
     const long long need = amd_stage_need_ints(n, graph_nnz[g]);
     if (need <= cap) max_stage = std::max(max_stage, need); else any_unstaged = true;
   }
+  const bool trace = std::getenv("PARTH_B200_TRACE") != nullptr;
+  auto tick = [&]() { if (trace) cudaStreamSynchronize(s); return std::chrono::steady_clock::now(); };
+  const auto ta = tick();
+  const size_t cap_before = h.r_ws.cap;
   h.r_wsptr.reserve((size_t)b.count + 1, s);
   h.r_ws.reserve((size_t)std::max<long long>(wsptr[b.count], 1), s);
   h.r_perm.reserve((size_t)std::max(b.total, 1), s);
   PB_CUDA(cudaMemcpyAsync(h.r_wsptr.p, wsptr.data(), sizeof(long long) * ((size_t)b.count + 1), cudaMemcpyHostToDevice, s));
   PB_CUDA(cudaStreamSynchronize(s));
+  const auto tb = tick();
   h.stats.kernels_launched += launch_amd_batch(b.count, h.r_vtx.p, h.r_G.p, h.r_sub.p, h.r_wsptr.p, h.r_ws.p,
                                                h.r_perm.p, max_stage, any_unstaged, s);
+  if (trace) {
+    const auto tc = tick();
+    std::fprintf(stderr, "[parth_b200] order_batch: work-space %zu -> %zu ints (%.3f ms), kernels %.3f ms, staged need %lld ints%s\n",
+                 cap_before, h.r_ws.cap, std::chrono::duration<double, std::milli>(tb - ta).count(),
+                 std::chrono::duration<double, std::milli>(tc - tb).count(), max_stage, any_unstaged ? " + slab graphs" : "");
+  }
 }
 
 std::vector<int> batch_graph_nnz(parth_b200 &h, const Batch &b) {
@@ -130,8 +144,12 @@ void stage_permute_fine(parth_b200 &h, const std::vector<int> &all_nodes) {
   if (nodes.empty()) return;
   cudaStream_t s = h.stream;
   StageTimer tm(h, &h.stats.reorder_ms, /*accumulate=*/true);
+  const bool trace = std::getenv("PARTH_B200_TRACE") != nullptr;
+  auto now = [&]() { cudaStreamSynchronize(s); return std::chrono::steady_clock::now(); };
+  auto t0 = trace ? now() : std::chrono::steady_clock::time_point();
   Batch b = extract_fine(h, nodes);
   std::vector<int> gnnz = batch_graph_nnz(h, b);
+  auto t1 = trace ? now() : t0;
   if (!device_orders_with_amd(h))
     for (int g = 0; g < b.count; g++)
       if (gnnz[g] > 0) {
@@ -144,10 +162,19 @@ void stage_permute_fine(parth_b200 &h, const std::vector<int> &all_nodes) {
     throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "permute_fine: MORTON_CODE is not implemented in the reference");
   }
   order_batch(h, b, gnnz);
+  auto t2 = trace ? now() : t0;
   h.stats.kernels_launched += launch_apply_order(h.r_list.p, h.r_vtx.p, b.count, b.total, h.d_node_ptr.p,
                                                  h.d_meta.p, h.d_dofs.p, h.r_perm.p, h.d_labels.p,
                                                  h.d_mesh_perm.p, s);
   tm.stop();
+  if (trace) {
+    auto t3 = now();
+    auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
+    int nmax = 0, zmax = 0;
+    for (int g = 0; g < b.count; g++) { nmax = std::max(nmax, b.vtx[g + 1] - b.vtx[g]); zmax = std::max(zmax, gnnz[g]); }
+    std::fprintf(stderr, "[parth_b200] permute_fine: %d graphs (max n %d, max nnz %d): extract %.3f ms, order %.3f ms, apply %.3f ms\n",
+                 b.count, nmax, zmax, ms(t0, t1), ms(t1, t2), ms(t2, t3));
+  }
 }
 
 // HMD::createMultiSubMesh for one node (coarse == 0) / HMD::getCoarseMesh (coarse == 1)

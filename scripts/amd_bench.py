@@ -43,7 +43,7 @@ def kuhn(k):
 def main():
     cases = [("grid2d_40", grid2d(40), 1), ("grid2d_128", grid2d(128), 1), ("grid3d_16", synth.grid_graph(16), 1),
              ("grid3d_31", synth.grid_graph(31), 1), ("kuhn_25", kuhn(25), 1), ("grid3d_31 x64", synth.grid_graph(31), 64),
-             ("grid2d_40 x148", grid2d(40), 148)]
+             ("grid2d_40 x148", grid2d(40), 148), ("grid2d_128 x66", grid2d(128), 66), ("grid2d_128 x148", grid2d(128), 148)]
     if len(sys.argv) > 1:
         cases = [c for c in cases if c[0].split()[0] in sys.argv[1:]]
     g = api.ParthAPI()
