@@ -167,7 +167,7 @@ PB_DEVFN int build_general_serial(const Ws &w, const int *Cp, int e0, const int 
 // links to the old head, the highest one becomes the head.
 PB_DEV void deglist_push_chunk(const Ws &w, int i, int deg, bool act) {
   const int lane = lane_id();
-  const unsigned grp = match_any(act ? deg : -1 - lane);
+  const unsigned grp = match_any(act ? deg : NONE);
   int old = NONE;
   if (act) old = w.Head[deg];
   const unsigned lower = grp & lanemask_lt(), higher = grp & lanemask_gt();
@@ -390,7 +390,7 @@ PB_DEV bool p3_degree(const Ws &w, int i, int p1, int eln, int ln, int nvi, int 
 // list h is empty, else in Last[] of that list's head variable.
 PB_DEV void hash_push_chunk(const Ws &w, int i, int hash_i, bool alive) {
   const int lane = lane_id();
-  const unsigned grp = match_any(alive ? hash_i : -1 - lane);
+  const unsigned grp = match_any(alive ? hash_i : NONE);
   int hj = NONE;
   if (alive) hj = w.Head[hash_i];
   const unsigned lower = grp & lanemask_lt(), higher = grp & lanemask_gt();
@@ -406,24 +406,57 @@ PB_DEV void hash_push_chunk(const Ws &w, int i, int hash_i, bool alive) {
   sync_warp();
 }
 
+// The whole element fits one chunk: the buckets are empty before (they are emptied at the end of
+// every pivot), so a hash that only one lane holds is a bucket of one -- nothing to compare, nothing
+// to store, nothing to clear.  Only hashes shared by several lanes are chained; returns the lanes
+// that have company (P4 walks those buckets).
+PB_DEV unsigned hash_push_single_chunk(const Ws &w, int i, int hash_i, bool alive) {
+  const int lane = lane_id();
+  const unsigned grp = match_any(alive ? hash_i : NONE);
+  const bool shared = alive && (grp & (grp - 1)) != 0;
+  const unsigned any_shared = ballot(shared);
+  if (!any_shared) return 0u;
+  int hj = NONE;
+  if (shared) hj = w.Head[hash_i];
+  const unsigned lower = grp & lanemask_lt(), higher = grp & lanemask_gt();
+  const int pred = (shared && lower) ? highest(lower) : -1;
+  const int i_pred = shfl(i, pred >= 0 ? pred : lane);
+  int oldb = NONE;
+  if (shared && pred < 0) oldb = hj <= NONE ? flip(hj) : w.Last[hj];
+  sync_warp();
+  if (shared) {
+    w.Next[i] = pred >= 0 ? i_pred : oldb;
+    if (!higher) { if (hj <= NONE) w.Head[hash_i] = flip(i); else w.Last[hj] = i; }
+  }
+  sync_warp();
+  return any_shared;
+}
+
 // P4 for one chunk: buckets with one member are emptied in parallel; the others are walked one
 // after the other in lane (= Lme) order, marking and comparing lists with all lanes
-PB_DEV void p4_supervariables(const Ws &w, int i, bool alive, int hash_i, int &wflg) {
+PB_DEV void p4_supervariables(const Ws &w, int i, bool alive, int hash_i, int &wflg, bool known, unsigned known_mm) {
   const int lane = lane_id(), n = w.n;
   int *const Pe = w.Pe, *const Nv = w.Nv, *const Head = w.Head, *const Elen = w.Elen;
   int *const W = w.W, *const Len = w.Len, *const Next = w.Next, *const Last = w.Last, *const Iw = w.Iw;
-  bool multi = false;
-  int j0 = NONE;
-  if (alive) {
-    j0 = Head[hash_i];
-    const int bh = j0 == NONE ? NONE : (j0 < NONE ? flip(j0) : Last[j0]);
-    multi = bh != NONE && Next[bh] != NONE;
+  unsigned mm;
+  if (known) {
+    // single-chunk mode: only buckets shared by several lanes exist (hash_push_single_chunk)
+    mm = known_mm;
+    if (!mm) return;
+  } else {
+    bool multi = false;
+    int j0 = NONE;
+    if (alive) {
+      j0 = Head[hash_i];
+      const int bh = j0 == NONE ? NONE : (j0 < NONE ? flip(j0) : Last[j0]);
+      multi = bh != NONE && Next[bh] != NONE;
+    }
+    mm = ballot(multi);
+    sync_warp();
+    if (alive && !multi) { if (j0 < NONE) Head[hash_i] = NONE; else if (j0 > NONE) Last[j0] = NONE; }
+    if (!mm) return;
+    sync_warp();
   }
-  unsigned mm = ballot(multi);
-  sync_warp();
-  if (alive && !multi) { if (j0 < NONE) Head[hash_i] = NONE; else if (j0 > NONE) Last[j0] = NONE; }
-  if (!mm) return;
-  sync_warp();
   while (mm) {
     const int src = lowest(mm);
     mm &= mm - 1;
@@ -486,6 +519,21 @@ PB_DEV int stream_source(int t, int nlists, int excl_k, int len_k, int pe_k, int
   return src;
 }
 
+// one chunk of the flattened P1 stream: src = Iw position of this lane's entry (or -1)
+PB_DEV void p1_take_chunk(const Ws &w, int src, int &pfree, int &degme) {
+  const int lane = lane_id();
+  int i = 0, nvi = 0;
+  if (src >= 0) { i = w.Iw[src]; nvi = w.Nv[i]; }
+  const bool cand = nvi > 0;
+  const unsigned grp = match_any(cand ? i : NONE);
+  const bool keep = cand && (grp & lanemask_lt()) == 0;
+  const unsigned b = ballot(keep);
+  if (keep) { w.Nv[i] = -nvi; w.Iw[pfree + popc(b & lanemask_lt())] = i; }
+  degme += warp_sum(keep ? nvi : 0);
+  pfree += popc(b);
+  deglist_remove_chunk(w, i, keep);
+}
+
 PB_DEVFN void eliminate_warp(const Ws &w, int pfree, int nel) {
   const int lane = lane_id(), n = w.n, iwlen = w.iwlen;
   int *const Pe = w.Pe, *const Nv = w.Nv, *const Head = w.Head, *const Elen = w.Elen;
@@ -544,33 +592,39 @@ PB_DEVFN void eliminate_warp(const Ws &w, int pfree, int nel) {
       pme1 = pfree;
       const int slenme = len_me - elenme;
       const int nlists = elenme + 1;
-      bool flat = nlists <= WARP;
+      bool flat = nlists <= WARP, done = false;
       int e_k = NONE, pe_k = 0, len_k = 0, incl = 0, total = 0;
-      if (flat) {
+      if (elenme == 1) {
+        // the common case (one adjacent element): both list descriptors are read by every lane,
+        // no scan and no shuffles to find a lane's source
+        const int e0 = Iw[p];
+        const int pe0 = Pe[e0], len0 = Len[e0];
+        const int tot = len0 + slenme;
+        if ((long long)pfree + tot <= (long long)iwlen) {
+          for (int base = 0; base < tot; base += WARP) {
+            const int t = base + lane;
+            p1_take_chunk(w, t < len0 ? pe0 + t : (t < tot ? p + 1 + (t - len0) : -1), pfree, degme);
+          }
+          if (lane == 0) { Pe[e0] = flip(me); W[e0] = 0; }
+          done = true;
+        }
+      }
+      if (!done && flat) {
         if (lane < elenme) { e_k = Iw[p + lane]; pe_k = Pe[e_k]; len_k = Len[e_k]; }
         else if (lane == elenme) { pe_k = p + elenme; len_k = slenme; }
         incl = warp_incl_scan(len_k);
         total = shfl(incl, WARP - 1);
         flat = (long long)pfree + total <= (long long)iwlen;
       }
-      if (flat) {
+      if (done) {
+        // Lme is complete
+      } else if (flat) {
         // every feeding list at once: the concatenation of the lists is read 32 entries at a
         // time; a variable met twice keeps its first place (lowest lane, or an earlier chunk)
         const int excl = incl - len_k;
         int q0 = 0;
-        for (int base = 0; base < total; base += WARP) {
-          const int src = stream_source(base + lane, nlists, excl, len_k, pe_k, base, q0);
-          int i = 0, nvi = 0;
-          if (src >= 0) { i = Iw[src]; nvi = Nv[i]; }
-          const bool cand = nvi > 0;
-          const unsigned grp = match_any(cand ? i : -1 - lane);
-          const bool keep = cand && (grp & lanemask_lt()) == 0;
-          const unsigned b = ballot(keep);
-          if (keep) { Nv[i] = -nvi; Iw[pfree + popc(b & lanemask_lt())] = i; }
-          degme += warp_sum(keep ? nvi : 0);
-          pfree += popc(b);
-          deglist_remove_chunk(w, i, keep);
-        }
+        for (int base = 0; base < total; base += WARP)
+          p1_take_chunk(w, stream_source(base + lane, nlists, excl, len_k, pe_k, base, q0), pfree, degme);
         if (lane < elenme) { Pe[e_k] = flip(me); W[e_k] = 0; }
       } else {
         // list by list, with workspace compaction when the room runs out
@@ -648,13 +702,13 @@ PB_DEVFN void eliminate_warp(const Ws &w, int pfree, int nel) {
       degme -= dm;
       nvpiv += dm;
       nel += dm;
-      hash_push_chunk(w, i, hash_i, alive);
+      const unsigned shared_mm = hash_push_single_chunk(w, i, hash_i, alive);
       if (degme > lemax) lemax = degme;
       wflg += lemax;
       wflg = reset_stamp_warp(wflg, wbig, W, n);
       sync_warp();
       PB_T(3);
-      p4_supervariables(w, i, alive, hash_i, wflg);
+      p4_supervariables(w, i, alive, hash_i, wflg, true, shared_mm);
       sync_warp();
       PB_T(4);
       const int nleft = n - nel;
@@ -718,7 +772,7 @@ PB_DEVFN void eliminate_warp(const Ws &w, int pfree, int nel) {
           alive = Nv[i] < 0;
           if (alive) hash_i = Last[i];
         }
-        p4_supervariables(w, i, alive, hash_i, wflg);
+        p4_supervariables(w, i, alive, hash_i, wflg, false, 0u);
         sync_warp();
       }
       PB_T(4);
@@ -810,7 +864,7 @@ PB_DEVFN void finish_cta(const Ws &w, int *sh) {
       int par = NONE;
       bool act = false;
       if (j < n && Nv[j] > 0) { par = Pe[j]; act = par != NONE; }
-      const unsigned grp = match_any(act ? par : -1 - lane);
+      const unsigned grp = match_any(act ? par : NONE);
       const unsigned lower = grp & lanemask_lt(), higher = grp & lanemask_gt();
       const int succ = (act && higher) ? lowest(higher) : -1;
       const int j_succ = shfl(j, succ >= 0 ? succ : lane);
@@ -885,7 +939,7 @@ PB_DEVFN void finish_cta(const Ws &w, int *sh) {
       int e = NONE;
       bool absorbed = false, dense = false;
       if (i < n && Nv[i] == 0) { e = Pe[i]; absorbed = e != NONE; dense = e == NONE; }
-      const unsigned grp = match_any(absorbed ? e : -1 - lane);
+      const unsigned grp = match_any(absorbed ? e : NONE);
       int slot = 0;
       if (absorbed) slot = Next[e];
       sync_warp();

@@ -6,6 +6,9 @@
 //     lane as an OS thread and implements the collectives with barriers, which lets the CPU suite
 //     check the cooperative algorithm bit for bit against the oracle without a GPU.
 // Every collective is called by ALL lanes of a warp (full mask), never from divergent code.
+// Measured on B200 (scripts/warp_ops_probe.cu, dependent chain): shfl 36, ballot 27, redux.add 51,
+// redux.min 22, LDS 34 cycles; match_any costs ~11 cycles PER DISTINCT VALUE (64 cycles for 4 groups,
+// 373 for 32 distinct values) -- so idle lanes pass one shared dummy key, never a per-lane one.
 #pragma once
 #ifdef __CUDACC__
 
