@@ -5,7 +5,7 @@
 namespace pb {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
+constexpr int kScanItems = 16;
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 // ws: [0] = dynamic tile counter (as u64), [1..] tile descriptors; must be zeroed before launch.
@@ -23,15 +23,31 @@ scan_excl_kernel(const int *in, int *out, int n, unsigned long long *ws) {
   const long long base = (long long)tile * kScanTile;
   int v[kScanItems];
   int sum = 0;
-#pragma unroll
-  for (int k = 0; k < kScanItems; k++) {
-    long long i = base + (long long)threadIdx.x * kScanItems + k;
-    int x = i < n ? in[i] : 0;
+  // full tiles of 16-byte aligned arrays move as 128-bit vectors (a thread owns 16 consecutive ints)
+  const bool vec = base + kScanTile <= (long long)n &&
+                   ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  auto f = [](int x, bool inside) {
     if (MODE == 1) x = __popc((unsigned)x);
     if (MODE == 2) x = x != 0;
-    if (MODE == 3) x = (i < n) && x == -1;
-    v[k] = x;
-    sum += x;
+    if (MODE == 3) x = inside && x == -1;
+    return x;
+  };
+  if (vec) {
+    const int4 *src = reinterpret_cast<const int4 *>(in + base) + threadIdx.x * (kScanItems / 4);
+#pragma unroll
+    for (int q = 0; q < kScanItems / 4; q++) {
+      const int4 x = ld_stream4(src + q);
+      v[4 * q] = f(x.x, true); v[4 * q + 1] = f(x.y, true); v[4 * q + 2] = f(x.z, true); v[4 * q + 3] = f(x.w, true);
+    }
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) sum += v[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+      long long i = base + (long long)threadIdx.x * kScanItems + k;
+      v[k] = f(i < n ? in[i] : 0, i < n);
+      sum += v[k];
+    }
   }
   int total;
   int excl = block_excl_scan<kScanThreads>(sum, s_scan, &total);
@@ -41,12 +57,26 @@ scan_excl_kernel(const int *in, int *out, int n, unsigned long long *ws) {
   }
   __syncthreads();
   long long run = s_base + excl;
+  if (vec) {
+    int4 *dst = reinterpret_cast<int4 *>(out + base) + threadIdx.x * (kScanItems / 4);
 #pragma unroll
-  for (int k = 0; k < kScanItems; k++) {
-    long long i = base + (long long)threadIdx.x * kScanItems + k;
-    if (i < n) out[i] = (int)run;
-    run += v[k];
-    if (i == n - 1) out[n] = (int)run;
+    for (int q = 0; q < kScanItems / 4; q++) {
+      int4 o;
+      o.x = (int)run; run += v[4 * q];
+      o.y = (int)run; run += v[4 * q + 1];
+      o.z = (int)run; run += v[4 * q + 2];
+      o.w = (int)run; run += v[4 * q + 3];
+      dst[q] = o;
+    }
+    if (base + kScanTile == (long long)n && threadIdx.x == kScanThreads - 1) out[n] = (int)run;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; k++) {
+      long long i = base + (long long)threadIdx.x * kScanItems + k;
+      if (i < n) out[i] = (int)run;
+      run += v[k];
+      if (i == n - 1) out[n] = (int)run;
+    }
   }
   if (n == 0 && tile == 0 && threadIdx.x == 0) out[0] = 0;
 }
