@@ -210,7 +210,11 @@ def run_ours(args):
 
     stream = workloads.PoissonUpdateStream(n=args.n, levels=8)
     N, M = stream.N, stream.N
-    D = min(args.steps + args.warmup, 12)  # distinct matrices, cycled; consecutive ones always differ
+    # distinct matrices, cycled; consecutive ones always differ.  The variants that repair the tree (aggr, nolag)
+    # must never meet a matrix twice (its broken edges would already be repaired: nothing to re-order), so they get
+    # one matrix per update they run; the headline variant changes nothing in the tree and cycles through 12.
+    need = args.warmup + args.steps + min(args.steps, 8) + (0 if args.no_e2e else 2 + args.steps)
+    D = min(args.steps + args.warmup, 12) if args.variant == "lag" else min(need, 64)
     first = rank * 17  # each rank updates its own sequence of nodes
     host_mats = []
     for k in range(D):
