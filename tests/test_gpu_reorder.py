@@ -77,3 +77,25 @@ def test_metis_leaf_ordering_is_refused_not_faked(gpu_api):
     with pytest.raises(gpu_api.ParthError) as e:
         g.stage_permute_fine([31])
     assert e.value.code == -6
+
+
+def test_amd_batch_stress_is_deterministic_and_exact(gpu_api, port):
+    """compute-sanitizer is not available on the GPU pool: the warp-level synchronisation discipline of
+    the cooperative AMD kernel is stressed instead -- 160 graphs of mixed shapes (staged in shared memory
+    and slab resident, chunked elements, dense rows, supervariable-rich meshes) in one batch, three
+    runs, every permutation equal to the oracle's every time"""
+    rng = np.random.default_rng(77)
+    graphs = []
+    for t in range(150):
+        n = int(rng.integers(2, 700))
+        m = int(rng.integers(0, 6 * n))
+        graphs.append(_random_sym_graph(rng, n, m))
+    graphs += [synth.grid_graph(k) for k in (4, 7, 10, 13, 20, 27)]
+    graphs += [_random_sym_graph(rng, 3000, 40000), _random_sym_graph(rng, 9000, 30000)]
+    graphs += [synth.grid_graph(34), synth.grid_graph(40)]     # 39 304 / 64 000 vertices: slab resident
+    want = [port.amd(Mp, Mi) for Mp, Mi in graphs]
+    g = gpu_api.ParthAPI()
+    for rep in range(3):
+        got = g.amd_batch(graphs)
+        for k, (p, w) in enumerate(zip(got, want)):
+            assert np.array_equal(p, w), (rep, k, len(w))
