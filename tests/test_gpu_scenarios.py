@@ -161,3 +161,42 @@ def test_fused_detection_with_over_long_columns_matches_oracle(gpu_api, port):
             assert st == 0 and np.array_equal(perm, operm), step
     assert fused[1:4] == [1, 1, 1]        # steady state without long columns: fused
     assert fused[4:] == [0, 0, 0, 0]      # a tile with an over-long column: the row diff took over
+
+
+@pytest.mark.parametrize("seed,lagging", [(1, True), (2, False), (3, True)])
+def test_random_update_sequences_match_oracle(gpu_api, port, seed, lagging):
+    """a random walk of updates (edges inserted and removed anywhere, sometimes nothing at all) through
+    setMatrix + computePermutation: the fused build/detect kernel, the speculative edge kernels and the
+    snapshot swap must reproduce the oracle's changed edges, dirty sets and reuse at every step"""
+    tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 16, 5)))
+    from parth_b200 import synth
+    rng = np.random.default_rng(1000 + seed)
+    n = len(Mp) - 1
+    g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 5; g.reorder_type = 1; g.lagging = lagging
+    g.setCoarsePolicy(gpu_api.COARSE_REPORT)
+    o = port.CpuParth("port"); o.set_options(reorder_type=1, nd_levels=5, lagging=lagging)
+    g.import_tree(tree, Mp, Mi); o.import_tree(tree, Mp, Mi)
+    cur, extra = (Mp, Mi), []
+    for step in range(10):
+        kind = int(rng.integers(0, 4))
+        if kind == 0 and extra:                                   # remove some of the inserted edges
+            k = int(rng.integers(1, len(extra) + 1))
+            cur = synth.remove_edges(cur[0], cur[1], extra[:k]); extra = extra[k:]
+        elif kind in (1, 2):                                      # insert random edges
+            e = rng.integers(0, n, size=(int(rng.integers(1, 40)), 2))
+            e = [(int(a), int(b)) for a, b in e if a != b]
+            cur = synth.add_edges(cur[0], cur[1], e); extra += e
+        N, Ap, Ai = synth.graph_to_matrix(*cur)                   # kind 3: the same matrix again
+        g.setMatrix(N, Ap, Ai, 1); o.setMatrix(N, Ap, Ai, 1)
+        st, perm = g.computePermutation(1)
+        ost, operm = o.computePermutation(1)
+        assert g.getNumChanges() == o.getNumChanges(), step
+        assert np.array_equal(g.changed_edges(), o.changed_edges()), step
+        assert g.getReuse() == o.getReuse(), step
+        gf, gc = g.dirty(); of, oc = o.dirty()
+        assert gf.tolist() == of.tolist() and gc.tolist() == oc.tolist(), step
+        if ost == 0:
+            assert st == 0 and np.array_equal(perm, operm), step
+        else:
+            # the oracle stops at a dirty coarse node (METIS); keep both sides on the same tree
+            g.import_tree(tree, *cur); o.import_tree(tree, *cur)
