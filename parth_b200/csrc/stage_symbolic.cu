@@ -106,71 +106,124 @@ __global__ void etree_wave_kernel(const int *__restrict__ ranges, int n_ranges, 
 constexpr int E2_THREADS = 128;
 constexpr int E2_CHUNK = 128;
 constexpr int E2_DEG = 32;
-constexpr int E2_OUT = 1 << 30;  // tag: the entry is a component root outside the node's own slice
 
+// first[r] = the smallest column of the wave that is adjacent to the finished component with root r
+// (a component of a child sub-tree).  It is where Liu's walk attaches r (parent[r] = first[r]), and
+// every later column that touches the component may continue from first[r] instead of from r: the
+// walks of a node then never leave its own slice (shared memory) -- the dependent global loads of
+// anc[r] were the critical path of the top separators.
+__global__ void first_touch_kernel(const int *__restrict__ ranges, const int *__restrict__ perm,
+                                   const int *__restrict__ inv, const int *__restrict__ Mp,
+                                   const int *__restrict__ Mi, const int *__restrict__ flat, int *__restrict__ first) {
+  const int b = ranges[2 * blockIdx.y], e = ranges[2 * blockIdx.y + 1];
+  const int j = b + blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= e) return;
+  const int old = __ldg(perm + j);
+  for (int p = __ldg(Mp + old); p < __ldg(Mp + old + 1); p++) {
+    const int k = __ldg(inv + __ldg(Mi + p));
+    if (k < b) atomicMin(first + __ldg(flat + k), j);
+  }
+}
+
+// SLOT = unsigned short: slices of up to 65 534 columns keep their ancestor links as 16-bit offsets
+// (0 = none, x - b + 1 otherwise), which halves the shared memory per CTA -- two leaves of a 200^3
+// grid share an SM instead of taking turns.  SLOT = int: absolute column ids, -1 = none, also the
+// layout of the global fallback for slices that do not fit.
+template <typename SLOT, bool SMEM>
 __global__ void __launch_bounds__(E2_THREADS)
 etree_node_kernel(const int *__restrict__ ranges, const int *__restrict__ perm, const int *__restrict__ inv,
                   const int *__restrict__ Mp, const int *__restrict__ Mi, const int *__restrict__ flat,
-                  volatile int *anc, int *parent, int smem_cap) {
-  extern __shared__ int e2_anc[];
-  __shared__ int s_nbr[E2_CHUNK][E2_DEG];
-  __shared__ int s_cnt[E2_CHUNK];
+                  const int *__restrict__ first, volatile int *anc, int *parent, int smem_cap) {
+  extern __shared__ __align__(16) unsigned char e2_raw[];
+  __shared__ int s_nbr[2][E2_CHUNK][E2_DEG];
+  __shared__ int s_cnt[2][E2_CHUNK];
+  constexpr bool SHORT = sizeof(SLOT) == 2;
   const int b = ranges[2 * blockIdx.x], e = ranges[2 * blockIdx.x + 1];
   const int tid = threadIdx.x, lane = tid & 31;
-  const bool in_smem = e - b <= smem_cap;
-  if (in_smem) for (int i = tid; i < e - b; i += E2_THREADS) e2_anc[i] = -1;
-  volatile int *own = in_smem ? (volatile int *)e2_anc : anc + b;  // own[x - b]
-  __syncthreads();
-  for (int c0 = b; c0 < e; c0 += E2_CHUNK) {
-    {  // prefetch: thread t -> column c0 + t
-      const int j = c0 + tid;
-      int cnt = 0;
-      if (j < e) {
-        const int old = __ldg(perm + j);
-        const int s = __ldg(Mp + old), t = __ldg(Mp + old + 1);
-        if (t - s > E2_DEG) cnt = -1;  // long row: walked straight from global memory
-        else
-          for (int p = s; p < t; p++) {
-            const int k = __ldg(inv + __ldg(Mi + p));
-            if (k >= j) continue;
-            s_nbr[tid][cnt++] = k >= b ? k : (__ldg(flat + k) | E2_OUT);
+  // SMEM: every slice of the wave fits the shared memory of the launch (the host checks); else the
+  // links live in the global anc[] array
+  constexpr bool in_smem = SMEM;
+  (void)smem_cap;
+  volatile SLOT *sm = reinterpret_cast<volatile SLOT *>(e2_raw);
+  if (in_smem) for (int i = tid; i < e - b; i += E2_THREADS) sm[i] = SHORT ? (SLOT)0 : (SLOT)-1;
+  volatile int *gl = anc + b;
+  auto own_get = [&](int x) -> int {  // ancestor link of own column x (absolute id, -1 = none)
+    if constexpr (!SMEM) return gl[x - b];
+    else if constexpr (SHORT) { const int v = (int)sm[x - b]; return v == 0 ? -1 : v - 1 + b; }
+    else return (int)sm[x - b];
+  };
+  auto own_set = [&](int x, int j) {
+    if constexpr (!SMEM) gl[x - b] = j;
+    else if constexpr (SHORT) sm[x - b] = (SLOT)(j - b + 1);
+    else sm[x - b] = (SLOT)j;
+  };
+
+  // adjacency of column c0 + t, resolved to columns of this node's own slice, into buffer `buf`.
+  // Loads are issued eight neighbours at a time (independent chains Mi -> inv -> flat -> first).
+  auto prefetch = [&](int c0, int buf, int t) {
+    const int j = c0 + t;
+    int cnt = 0;
+    if (j < e) {
+      const int old = __ldg(perm + j);
+      const int s = __ldg(Mp + old), deg = __ldg(Mp + old + 1) - s;
+      if (deg > E2_DEG) cnt = -1;  // long row: walked straight from global memory
+      else
+        for (int q0 = 0; q0 < deg; q0 += 8) {
+          int k[8], r[8], f[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) k[u] = q0 + u < deg ? __ldg(inv + __ldg(Mi + s + q0 + u)) : 0x7fffffff;
+#pragma unroll
+          for (int u = 0; u < 8; u++) r[u] = k[u] < b ? __ldg(flat + k[u]) : -1;
+#pragma unroll
+          for (int u = 0; u < 8; u++) f[u] = r[u] >= 0 ? __ldg(first + r[u]) : -1;
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            if (k[u] >= j) continue;
+            if (k[u] >= b) { s_nbr[buf][t][cnt++] = k[u]; continue; }
+            // a finished component below this node: attach it at its first toucher, else enter
+            // the node's own forest through that column
+            if (f[u] == j) { parent[r[u]] = j; anc[r[u]] = j; }
+            else if (f[u] >= b && f[u] < j) s_nbr[buf][t][cnt++] = f[u];  // always true on a valid separator tree
           }
-      }
-      s_cnt[tid] = cnt;
+        }
     }
-    __syncthreads();
-    if (tid < 32) {
+    s_cnt[buf][t] = cnt;
+  };
+
+  prefetch(b, 0, tid);
+  __syncthreads();
+  int ci = 0;
+  for (int c0 = b; c0 < e; c0 += E2_CHUNK, ci++) {
+    const int buf = ci & 1;
+    if (tid >= 32) {
+      // three warps fetch the next chunk while warp 0 walks this one
+      if (c0 + E2_CHUNK < e)
+        for (int t = tid - 32; t < E2_CHUNK; t += E2_THREADS - 32) prefetch(c0 + E2_CHUNK, buf ^ 1, t);
+    } else {
       const int lim = min(E2_CHUNK, e - c0);
       for (int t = 0; t < lim; t++) {
         const int j = c0 + t;
-        const int cnt = s_cnt[t];
-        auto walk = [&](int k, bool outside) {
-          if (outside) {
-            const int a = anc[k];
-            if (a == j) return;
-            anc[k] = j;
-            if (a == -1) { parent[k] = j; return; }
-            k = a;  // a column of this node
-          }
+        const int cnt = s_cnt[buf][t];
+        auto walk = [&](int k) {
           for (;;) {
-            const int a = own[k - b];
+            const int a = own_get(k);
             if (a == j) break;
-            own[k - b] = j;
+            own_set(k, j);
             if (a == -1) { parent[k] = j; break; }
             k = a;
           }
         };
         if (cnt >= 0) {
-          if (lane < cnt) {
-            const int v = s_nbr[t][lane];
-            walk(v & ~E2_OUT, (v & E2_OUT) != 0);
-          }
+          if (lane < cnt) walk(s_nbr[buf][t][lane]);
         } else {
           const int old = __ldg(perm + j);
           for (int p = __ldg(Mp + old) + lane; p < __ldg(Mp + old + 1); p += 32) {
             const int k = __ldg(inv + __ldg(Mi + p));
             if (k >= j) continue;
-            if (k >= b) walk(k, false); else walk(__ldg(flat + k), true);
+            if (k >= b) { walk(k); continue; }
+            const int r = __ldg(flat + k), f = __ldg(first + r);
+            if (f == j) { parent[r] = j; anc[r] = j; }
+            else if (f >= b && f < j) walk(f);
           }
         }
         __syncwarp();
@@ -178,7 +231,7 @@ etree_node_kernel(const int *__restrict__ ranges, const int *__restrict__ perm, 
     }
     __syncthreads();
   }
-  if (in_smem) for (int i = tid; i < e - b; i += E2_THREADS) anc[b + i] = e2_anc[i];
+  if (in_smem) for (int i = tid; i < e - b; i += E2_THREADS) anc[b + i] = own_get(b + i);
 }
 
 // after wave w: (i) every column of a wave-w node learns the root of its component ...
@@ -457,22 +510,47 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
     size_t at = 0;
     if (fast) {
       // valid separator tree: shared-memory node kernel + component flattening between the waves
-      DevBuf<int> flatroot, d_wave;
+      DevBuf<int> flatroot, d_wave, first;
       flatroot.reserve((size_t)n, s);
+      first.reserve((size_t)n, s);
+      fill_i32<<<nblk(n), 256, 0, s>>>(first.p, n, 0x7fffffff);
+      h.stats.kernels_launched++;
       d_wave.reserve(node_wave.size(), s);
       PB_CUDA(cudaMemcpyAsync(d_wave.p, node_wave.data(), sizeof(int) * node_wave.size(), cudaMemcpyHostToDevice, s));
       PB_CUDA(cudaStreamSynchronize(s));
       int dev = 0, max_smem = 0;
       PB_CUDA(cudaGetDevice(&dev));
       PB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-      const int dyn = max_smem - 20 * 1024;  // static part: prefetched adjacency lists
-      PB_CUDA(cudaFuncSetAttribute(etree_node_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+      const int dyn = max_smem - 36 * 1024;  // static part: two buffers of prefetched adjacency lists
+      PB_CUDA(cudaFuncSetAttribute(etree_node_kernel<int, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+      PB_CUDA(cudaFuncSetAttribute(etree_node_kernel<unsigned short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
       int wi = 0;
       for (auto &w : waves) {
         const int nr = (int)w.size() / 2;
         if (nr > 0) {
-          etree_node_kernel<<<nr, E2_THREADS, dyn, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi, flatroot.p, anc.p, parent.p,
-                                                        dyn / 4);
+          if (wi > 0) {  // leaves have no finished component below them
+            int longest = 0;
+            for (int r = 0; r < nr; r++) longest = std::max(longest, w[2 * r + 1] - w[2 * r]);
+            first_touch_kernel<<<dim3(nblk(longest), (unsigned)nr), 256, 0, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi,
+                                                                                flatroot.p, first.p);
+            h.stats.kernels_launched++;
+          }
+          // shared memory sized by the wave's largest slice (the smaller, the more CTAs per SM)
+          int longest = 0;
+          for (int r = 0; r < nr; r++) longest = std::max(longest, w[2 * r + 1] - w[2 * r]);
+          // 16-bit slots cost ~30 % per column walk: they pay only when the wave has more nodes than the GPU has SMs
+          if (nr > h.num_sms && longest <= 65534 && 2 * longest <= dyn) {
+            const int bytes = ((2 * longest + 1023) / 1024) * 1024;
+            etree_node_kernel<unsigned short, true><<<nr, E2_THREADS, bytes, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi,
+                                                                                flatroot.p, first.p, anc.p, parent.p, bytes / 2);
+          } else if (4 * longest <= dyn) {
+            const int bytes = ((4 * longest + 1023) / 1024) * 1024;
+            etree_node_kernel<int, true><<<nr, E2_THREADS, bytes, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi, flatroot.p,
+                                                                     first.p, anc.p, parent.p, bytes / 4);
+          } else {  // a slice larger than shared memory: links in global memory for this wave
+            etree_node_kernel<int, false><<<nr, E2_THREADS, 0, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi, flatroot.p,
+                                                                  first.p, anc.p, parent.p, 0);
+          }
           flatten_own_kernel<<<nblk(n), 256, 0, s>>>(perm.p, h.d_dof2node.p, d_wave.p, wi, n, anc.p, flatroot.p);
           flatten_below_kernel<<<nblk(n), 256, 0, s>>>(perm.p, h.d_dof2node.p, d_wave.p, wi, n, anc.p, flatroot.p);
           h.stats.kernels_launched += 3;
