@@ -128,6 +128,37 @@ def test_config2_aggressive_reuse_update_matches_oracle_at_full_size(gpu_api, po
     assert np.array_equal(gt["labels"], ot.labels) and np.array_equal(gt["dofs"], ot.dofs)
 
 
+def test_config2_edges_inside_leaves_follow_the_reference_at_full_size(gpu_api, port):
+    """the reference reports only edges whose two nodes are neither equal nor ancestor-related
+    (Integrator::problematicEdgeCondition, Integrator.cpp:895-921): edges inserted INSIDE leaves change rows but
+    dirty nothing -- num_changes 0, reuse 1, permutation kept.  (Leaves are re-ordered through the aggressive
+    relocation, test above.)  The device must agree with the oracle on exactly that, at 8 M DOF."""
+    from parth_b200 import workloads
+    st = workloads.PoissonUpdateStream(n=200, levels=8)
+    N = st.N
+    rng = np.random.default_rng(21)
+    first_leaf = 2 ** 8 - 1
+    edges = []
+    for leaf in (first_leaf + 3, first_leaf + 100, first_leaf + 255):
+        d = st.node_dofs(leaf)
+        a, b = rng.choice(d, 40), rng.choice(d, 40)
+        edges += [(int(x), int(y)) for x, y in zip(a, b) if x != y and abs(int(x) - int(y)) not in (1, 200, 40000)]
+    e = np.unique(np.array(edges, np.int64), axis=0)
+    Ap, Ai = workloads.insert_entries(st.Ap, st.Ai, np.concatenate([e[:, 0], e[:, 1]]), np.concatenate([e[:, 1], e[:, 0]]))
+    g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 8; g.reorder_type = gpu_api.AMD; g.lagging = False
+    g.setCoarsePolicy(gpu_api.COARSE_REPORT)
+    o = port.CpuParth("port"); o.set_options(reorder_type=1, nd_levels=8, lagging=False)
+    g.import_tree(st.tree(), st.Mp, st.Mi); o.import_tree(st.tree(), st.Mp, st.Mi)
+    g.setMatrix(N, Ap, Ai, 1); o.setMatrix(N, Ap, Ai, 1)
+    rc, perm = g.computePermutation(1)
+    orc, operm = o.computePermutation(1)
+    gf, gc = g.dirty(); of, oc = o.dirty()
+    assert rc == 0 and orc == 0
+    assert gf.tolist() == of.tolist() == [] and gc.tolist() == oc.tolist() == []
+    assert g.getNumChanges() == o.getNumChanges() == 0 and g.getReuse() == o.getReuse() == 1.0
+    assert np.array_equal(perm, operm)
+
+
 def test_config3_full_size_against_oracle():
     out = _suite("3")
     assert out["ok"] and out["M"] == 2000376 and out["removed_added"] > 90000
