@@ -156,9 +156,12 @@ class ParthAPI:
         return rc
 
     def _push_options(self):
-        self._check(self.lib.parth_b200_set_options(self.h, int(self.reorder_type), int(self.ND_levels),
-                                                    int(self.lagging), int(self.activate_aggressive_reuse),
-                                                    int(self.relocate_lvl), int(self.lag_lvl), int(self.verbose)))
+        # the public fields may be written directly (like the reference's): push them when they changed
+        opts = (int(self.reorder_type), int(self.ND_levels), int(self.lagging), int(self.activate_aggressive_reuse),
+                int(self.relocate_lvl), int(self.lag_lvl), int(self.verbose))
+        if opts != getattr(self, "_pushed", None):
+            self._check(self.lib.parth_b200_set_options(self.h, *opts))
+            self._pushed = opts
 
     # ---- options (ParthAPI.cpp:13-45)
     def setReorderingType(self, t):
