@@ -146,6 +146,10 @@ int parth_b200_amd_batch(parth_b200 *h, int count, const int *graph_ptr /*count+
  * permutation perm[new]=old (NULL: current mesh_perm).  Replaces cholmod_analyze_p as used in
  * reference src/utils/ParthTestUtils.cpp:15-59; etree as src/utils/etree.cpp:39-115. */
 int parth_b200_symbolic(parth_b200 *h, const int *perm, int *parent, int *colcount, int64_t *lnz);
+/* same with device pointers: the etree and the column counts stay on the device for the consumer of the
+ * ordering (the symbolic phase of a device sparse Cholesky: reference src/LinSysSolver/LinSysSolver.hpp:92-113,
+ * CHOLMODSolver.cpp:108-151 recompute them on the host).  dperm NULL: current mesh_perm. */
+int parth_b200_symbolic_dev(parth_b200 *h, const int *dperm, int *dparent, int *dcolcount, int64_t *lnz);
 
 /* instrumentation: device time of the last call's stages (CUDA events on the handle's stream)
  * and the number of kernels launched by the library since creation */

@@ -76,6 +76,7 @@ SYMBOLS = {
     "parth_b200_stage_submesh": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip]),
     "parth_b200_amd_batch": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _ip]),
     "parth_b200_symbolic": (C.c_int, [_vp, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
+    "parth_b200_symbolic_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
     "parth_b200_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "parth_b200_synchronize": (C.c_int, [_vp]),
     "parth_b200_stream": (_vp, [_vp]),
@@ -436,6 +437,13 @@ class ParthAPI:
         perm = np.empty(max(int(gp[-1]), 1), np.int32)
         self._check(self.lib.parth_b200_amd_batch(self.h, len(graphs), _p(gp), _p(Mp), _p(Mi), _p(perm)))
         return [perm[gp[i]:gp[i + 1]].copy() for i in range(len(graphs))]
+
+    def symbolicDev(self, dperm_ptr, dparent_ptr, dcolcount_ptr):
+        """stage (d) with device pointers (0 = NULL): returns nnz(L); etree / column counts stay on the device"""
+        lnz = C.c_int64()
+        self._check(self.lib.parth_b200_symbolic_dev(self.h, C.c_void_p(dperm_ptr or None), C.c_void_p(dparent_ptr or None),
+                                                     C.c_void_p(dcolcount_ptr or None), C.byref(lnz)))
+        return int(lnz.value)
 
     def symbolic(self, perm=None):
         n, _ = self.mesh_dims()

@@ -520,4 +520,16 @@ int parth_b200_symbolic(parth_b200 *h, const int *perm, int *parent, int *colcou
   PB_API_END
 }
 
+// device-pointer variant: dperm (may be NULL: current mesh_perm), dparent and dcolcount (each may be
+// NULL) live on the device; lnz is returned on the host
+int parth_b200_symbolic_dev(parth_b200 *h, const int *dperm, int *dparent, int *dcolcount, int64_t *lnz) {
+  PB_API_BEGIN
+  if (!h->Mp || !lnz) throw StatusError(PARTH_B200_ERR_ARG, "symbolic: needs a mesh");
+  long long v = 0;
+  stage_symbolic(*h, dperm, dparent, dcolcount, &v, /*on_device=*/true);
+  resolve_timers(*h);
+  *lnz = v;
+  PB_API_END
+}
+
 }  // extern "C"

@@ -399,7 +399,11 @@ __global__ void colcount_kernel(const int *__restrict__ pre, const int *__restri
 
 }  // namespace
 
-void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *colcount_out, long long *lnz_out) {
+void stage_symbolic(parth_b200 &h, const int *perm_in, int *parent_out, int *colcount_out, long long *lnz_out,
+                    bool on_device) {
+  const int *perm_host = perm_in;
+  const cudaMemcpyKind in_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+  const cudaMemcpyKind out_kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   cudaStream_t s = h.stream;
   const int n = h.M_n;
   StageTimer tm(h, &h.stats.symbolic_ms);
@@ -413,8 +417,8 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
   flag.reserve(8, s);
   PB_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int) * 8, s));
   if (perm_host) {
-    PB_CUDA(cudaMemcpyAsync(perm.p, perm_host, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, s));
-    h.stats.h2d_bytes += (long long)sizeof(int) * n;
+    PB_CUDA(cudaMemcpyAsync(perm.p, perm_host, sizeof(int) * (size_t)n, in_kind, s));
+    if (!on_device) h.stats.h2d_bytes += (long long)sizeof(int) * n;
   } else {
     PB_CUDA(cudaMemcpyAsync(perm.p, h.d_mesh_perm.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToDevice, s));
   }
@@ -576,7 +580,7 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
     if (err) throw StatusError(PARTH_B200_ERR_INTERNAL, "symbolic: etree walk did not terminate");
   }
   if (parent_out) {
-    PB_CUDA(cudaMemcpyAsync(parent_out, parent.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaMemcpyAsync(parent_out, parent.p, sizeof(int) * (size_t)n, out_kind, s));
     h.stats.d2h_bytes += (long long)sizeof(int) * n;
   }
 
@@ -657,7 +661,7 @@ void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent_out, int *c
   unsigned long long total = 0;
   PB_CUDA(cudaMemcpyAsync(&total, lnz.p, sizeof(total), cudaMemcpyDeviceToHost, s));
   if (colcount_out) {
-    PB_CUDA(cudaMemcpyAsync(colcount_out, cc.p, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaMemcpyAsync(colcount_out, cc.p, sizeof(int) * (size_t)n, out_kind, s));
     h.stats.d2h_bytes += (long long)sizeof(int) * n;
   }
   PB_CUDA(cudaStreamSynchronize(s));

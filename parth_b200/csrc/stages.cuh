@@ -75,6 +75,8 @@ int builtin_decomposer(void *user, int M_n, const int *Mp, const int *Mi, int le
                        int *node_ptr, int *dofs, int *labels);
 
 // stage_symbolic.cu: (d) etree + column counts
-void stage_symbolic(parth_b200 &h, const int *perm_host, int *parent, int *colcount, long long *lnz);
+// on_device: perm_in / parent_out / colcount_out are device pointers (hand-off to a device solver)
+void stage_symbolic(parth_b200 &h, const int *perm_in, int *parent_out, int *colcount_out, long long *lnz_out,
+                    bool on_device = false);
 
 }  // namespace pb

@@ -84,3 +84,24 @@ def test_bad_permutation_is_rejected(gpu_api):
     bad = np.arange(64); bad[3] = 64
     with pytest.raises(gpu_api.ParthError):
         g.symbolic(bad)
+
+
+def test_device_pointer_variant_hands_off_on_the_device(gpu_api):
+    """parth_b200_symbolic_dev: permutation in, etree and column counts out, all on the device (the hand-off
+    to a device sparse Cholesky); must equal the host-pointer call"""
+    import torch
+    n = 12
+    Mp, Mi = synth.grid_graph(n)
+    N = n ** 3
+    perm = ((7919 * np.arange(N) + 13) % N).astype(np.int32)
+    g = gpu_api.ParthAPI()
+    g.setMesh(N, Mp, Mi)
+    parent, cc, lnz = g.symbolic(perm)
+    dperm = torch.from_numpy(perm).cuda()
+    dparent = torch.empty(N, dtype=torch.int32, device="cuda")
+    dcc = torch.empty(N, dtype=torch.int32, device="cuda")
+    got = g.symbolicDev(dperm.data_ptr(), dparent.data_ptr(), dcc.data_ptr())
+    torch.cuda.synchronize()
+    assert got == lnz
+    assert np.array_equal(dparent.cpu().numpy(), parent) and np.array_equal(dcc.cpu().numpy(), cc)
+    assert g.symbolicDev(dperm.data_ptr(), 0, 0) == lnz     # only nnz(L) wanted
