@@ -88,6 +88,8 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        # index: one GPU, or a comma-separated list (rank 0 samples every GPU of the job in ONE nvidia-smi
+        # process: N polling processes measurably slow the launch path of a sub-millisecond step)
         self.index, self.proc, self.path = index, None, None
 
     def start(self):
@@ -285,8 +287,9 @@ def run_ours(args):
         return dict(reuse=g.getReuse(), changes=g.getNumChanges(), dirty=[x.tolist() for x in g.dirty()])
 
     # ---- resident arm
-    sampler = ClockSampler(local)
-    sampler.start()  # samples every 50 ms from the warm-up to the end of the end-to-end arm
+    sampler = ClockSampler(",".join(str(i) for i in range(world)) if world > 1 else local)
+    if rank == 0:
+        sampler.start()  # samples every 50 ms from the warm-up to the end of the end-to-end arm
     for k in range(args.warmup):
         step_resident(g, k)
     ms, launches = timed(g, step_resident, args.warmup, args.steps)
