@@ -77,6 +77,13 @@ int parth_b200_set_assume_symmetric(parth_b200 *h, int on);
 
 /* ParthAPI::setMatrix -> computeMeshFromMatrix, ParthAPI.cpp:100-124,366-418 */
 int parth_b200_set_matrix(parth_b200 *h, int N, const int *Ap, const int *Ai, int dim);
+/* device-pointer variant: STREAM-ORDERED on the handle's stream.  In the steady state of the reuse
+ * path (same vertex set as a proven-symmetric snapshot, tree present, no DOF map) it returns with the
+ * build, the changed-row proof and the edge kernels of change detection in flight; the next call on
+ * the handle that needs their outcome waits for the flags alone.  Consequences for the caller:
+ * dAp / dAi must stay valid and unchanged until that next call has returned (normally
+ * parth_b200_compute_permutation_dev, or parth_b200_synchronize), and an input error found on the
+ * device (PARTH_B200_ERR_INPUT) is reported by that call instead of this one. */
 int parth_b200_set_matrix_dev(parth_b200 *h, int N, const int *dAp, const int *dAi, int nnz, int dim);
 /* ParthAPI::setMesh, ParthAPI.cpp:76-98 (host arrays are copied to the device) */
 int parth_b200_set_mesh(parth_b200 *h, int n, const int *Mp, const int *Mi);
@@ -165,6 +172,8 @@ typedef struct {
   int symbolic_path;                      /* 2 = per-node shared-memory kernel, 1 = wave-scheduled walk, 0 = one range */
   int build_fused_detect;                 /* 1 = the last build kernel also compared its tiles with the snapshot (stage b fused into stage a) */
   double proof_kernel_ms;                 /* dim > 1: full symmetry proof on the compacted graph (0 when the proof was incremental or in-kernel) */
+  int build_deferred;                     /* 1 = the last set_matrix_dev returned with its work in flight and was completed by the next call */
+  int expand_speculative;                 /* 1 = the last compute_permutation_dev expanded before the flags were read and the result stood */
 } parth_b200_stats;
 int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out);
 int parth_b200_synchronize(parth_b200 *h);

@@ -30,7 +30,8 @@ class Stats(C.Structure):
         ("kernels_launched", C.c_longlong), ("build_path", C.c_int),
         ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("integrate_passes", C.c_int), ("integrate_sweeps", C.c_int),
         ("symbolic_etree_ms", C.c_double), ("diff_kernel_ms", C.c_double), ("symbolic_path", C.c_int),
-        ("build_fused_detect", C.c_int), ("proof_kernel_ms", C.c_double)]
+        ("build_fused_detect", C.c_int), ("proof_kernel_ms", C.c_double), ("build_deferred", C.c_int),
+        ("expand_speculative", C.c_int)]
 
 
 DECOMPOSER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, _ip, _ip, C.c_int, C.c_int, _ip, _ip, _ip, _ip)

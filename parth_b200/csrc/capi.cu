@@ -7,10 +7,15 @@
 
 using namespace pb;
 
-#define PB_API_BEGIN  \
+// PB_API_BEGIN settles a build that parth_b200_set_matrix_dev left in flight (stage_build_settle);
+// PB_API_BEGIN_NOSETTLE is for the entry points that handle it themselves
+#define PB_API_BEGIN_NOSETTLE \
   if (!h) return PARTH_B200_ERR_ARG; \
   try {                 \
     PB_CUDA(cudaSetDevice(h->device));
+#define PB_API_BEGIN  \
+  PB_API_BEGIN_NOSETTLE \
+  stage_build_settle(*h);
 #define PB_API_END                                   \
   }                                                  \
   catch (const pb::CudaError &e) {                   \
@@ -28,6 +33,13 @@ using namespace pb;
   return PARTH_B200_OK;
 
 static thread_local std::string g_create_error;
+
+// entry points outside the PB_API_* brackets that read what a build produces settle it first
+static int settle_quiet(parth_b200 *h) {
+  if (!h->pend.active) return PARTH_B200_OK;
+  PB_API_BEGIN
+  PB_API_END
+}
 
 extern "C" {
 
@@ -59,6 +71,7 @@ int parth_b200_create(parth_b200 **out, int device) {
     PB_CUDA(cudaEventCreate(&h->ev1));
     PB_CUDA(cudaEventCreate(&h->ev2));
     PB_CUDA(cudaEventCreate(&h->ev3));
+    PB_CUDA(cudaEventCreate(&h->ev_mail));
     h->pin.reserve(1 << 16);
     {
       // keep freed work-space in the device's default pool instead of returning it to the driver
@@ -89,6 +102,7 @@ int parth_b200_destroy(parth_b200 *h) {
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev2) cudaEventDestroy(h->ev2);
   if (h->ev3) cudaEventDestroy(h->ev3);
+  if (h->ev_mail) cudaEventDestroy(h->ev_mail);
   for (auto &e : h->tev) if (e) cudaEventDestroy(e);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
@@ -170,7 +184,7 @@ int parth_b200_synchronize(parth_b200 *h) {
 
 int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out) {
   if (!h || !out) return PARTH_B200_ERR_ARG;
-  if (!h->pending_timers.empty()) {  // device-pointer calls leave their timers to be read here
+  if (!h->pending_timers.empty() || h->pend.active) {  // device-pointer calls leave their timers to be read here
     PB_API_BEGIN
     resolve_timers(*h);
     *out = h->stats;
@@ -186,7 +200,10 @@ int parth_b200_set_matrix_dev(parth_b200 *h, int N, const int *dAp, const int *d
   if (!dAp || !dAi || N <= 0 || dim <= 0 || nnz < 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: bad argument");
   h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
   h->sim_dim = dim;
-  stage_build(*h, N, dAp, dAi, nnz, dim);  // ends on its mailbox read-back: nothing is in flight
+  // steady state: returns with the build, the changed-row proof and stage (b)'s edge kernels in flight;
+  // whatever call needs their outcome next waits for the mailbox copy alone (stage_build_settle).
+  // Otherwise it ends on its mailbox read-back and nothing is in flight.
+  stage_build(*h, N, dAp, dAi, nnz, dim, /*may_defer=*/true);
   PB_API_END
 }
 
@@ -246,6 +263,7 @@ int parth_b200_set_mesh(parth_b200 *h, int n, const int *Mp, const int *Mi) {
 
 int parth_b200_mesh_dims(parth_b200 *h, int *M_n, int *nnz) {
   if (!h || !M_n || !nnz) return PARTH_B200_ERR_ARG;
+  if (int rc = settle_quiet(h)) return rc;
   *M_n = h->M_n;
   *nnz = h->nnzM;
   return PARTH_B200_OK;
@@ -263,6 +281,7 @@ int parth_b200_get_mesh(parth_b200 *h, int *Mp, int *Mi) {
 
 int parth_b200_mesh_dev(parth_b200 *h, const int **dMp, const int **dMi) {
   if (!h || !dMp || !dMi) return PARTH_B200_ERR_ARG;
+  if (int rc = settle_quiet(h)) return rc;
   *dMp = h->Mp;
   *dMi = h->Mi;
   return PARTH_B200_OK;
@@ -307,7 +326,7 @@ int parth_b200_export_tree(parth_b200 *h, int *meta, int *node_ptr, int *dofs, i
 
 int parth_b200_compute_permutation_dev(parth_b200 *h, int *dperm, int dim) {
   int rc = PARTH_B200_OK;
-  PB_API_BEGIN
+  PB_API_BEGIN_NOSETTLE
   if (!dperm || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "computePermutation: bad argument");
   h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
   // stream-ordered: dperm is valid for work enqueued on the handle's stream after this call (or
@@ -437,7 +456,7 @@ int parth_b200_get_dirty_nodes(parth_b200 *h, int *fine, int *nfine, int *coarse
 
 int parth_b200_get_timers(parth_b200 *h, double t[5]) {
   if (!h || !t) return PARTH_B200_ERR_ARG;
-  if (!h->pending_timers.empty()) {
+  if (!h->pending_timers.empty() || h->pend.active) {
     PB_API_BEGIN
     resolve_timers(*h);
     for (int i = 0; i < 5; i++) t[i] = h->timers[i];

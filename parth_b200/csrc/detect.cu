@@ -213,34 +213,44 @@ __device__ __forceinline__ bool row_contains(const int *__restrict__ Mi, int s, 
 
 // n_rows is read on the device (the host has not seen it yet); more than `cap` rows: nothing is
 // checked and the host falls back to the streaming proof
+// The two halves of a warp work on one changed row j at the same time: lanes 0-15 walk the new row
+// (condition 1, plus the problematic-edge count of stage b), lanes 16-31 the snapshot row (condition
+// 2) -- one instruction stream, so the dependent loads of both walks are in flight together.
+// zero_out / n_zero: scratch the later kernels of the chain expect cleared (node flags), done by CTA 0.
 __global__ void sym_check_rows_kernel(const int *__restrict__ rows, const int *__restrict__ n_rows_dev, int cap,
                                       const int *__restrict__ Mp, const int *__restrict__ Mi,
                                       const int *__restrict__ Mp_prev, const int *__restrict__ Mi_prev,
                                       int *__restrict__ asym, const int *__restrict__ dof2node,
-                                      int *__restrict__ counts, int spec_cap) {
-  const int lane = threadIdx.x & 31;
+                                      int *__restrict__ counts, int spec_cap, int *__restrict__ zero_out, int n_zero) {
+  const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+  if (zero_out && blockIdx.x == 0)
+    for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_out[i] = 0;
   const int n_rows = *n_rows_dev;
   if (n_rows > cap) return;
   const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int *__restrict__ P = half ? Mp_prev : Mp;
+  const int *__restrict__ I = half ? Mi_prev : Mi;
   bool bad = false;
   for (int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; k < n_rows; k += warps) {
     const int j = rows[k];
     const int s = Mp[j], e = Mp[j + 1];
+    const int s2 = P[j], e2 = P[j + 1];
     const bool want_count = counts != nullptr && k < spec_cap;  // computeTheAddedRemovedEdgesForDOF, fused in
     int c = 0;
-    for (int p = s + lane; p < e; p += 32) {
-      const int i = Mi[p];
-      if (!row_contains(Mi, Mp[i], Mp[i + 1], j)) bad = true;
-      if (want_count) c += (j < i) && problematic_d(dof2node, j, i);
+    for (int p = s2 + hl; p < e2; p += 16) {
+      const int i = I[p];
+      const bool mirrored = row_contains(Mi, Mp[i], Mp[i + 1], j);
+      if (!half) {
+        if (!mirrored) bad = true;                                    // (1) new entry without its mirror
+        if (want_count) c += (j < i) && problematic_d(dof2node, j, i);
+      } else if (mirrored && !row_contains(Mi, s, e, i)) {
+        bad = true;                                                   // (2) lost entry whose mirror stayed
+      }
     }
     if (want_count) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
       if (lane == 0) counts[k] = c;
-    }
-    for (int p = Mp_prev[j] + lane; p < Mp_prev[j + 1]; p += 32) {
-      const int i = Mi_prev[p];
-      if (!row_contains(Mi, s, e, i) && row_contains(Mi, Mp[i], Mp[i + 1], j)) bad = true;
     }
   }
   if (bad) *asym = 1;
@@ -248,9 +258,9 @@ __global__ void sym_check_rows_kernel(const int *__restrict__ rows, const int *_
 
 int launch_sym_check_rows(const int *rows, const int *n_rows_dev, int cap, const int *Mp, const int *Mi,
                           const int *Mp_prev, const int *Mi_prev, int *asym, const int *dof2node, int *counts,
-                          int spec_cap, cudaStream_t s) {
+                          int spec_cap, cudaStream_t s, int *zero_out, int n_zero) {
   sym_check_rows_kernel<<<2 * kNumSMsB200, 256, 0, s>>>(rows, n_rows_dev, cap, Mp, Mi, Mp_prev, Mi_prev, asym, dof2node,
-                                                        counts, spec_cap);
+                                                        counts, spec_cap, zero_out, n_zero);
   PB_CUDA(cudaGetLastError());
   return 1;
 }
@@ -288,79 +298,114 @@ __device__ __forceinline__ int block_excl_scan_1024(int v, int *s_warp, int *tot
   return base + incl - v;
 }
 
-// A2 (grid, one warp per tile): the changed rows of a dirty tile, ascending, at the tile's offset
-// (tile_off = device-wide exclusive scan of the tile counts; with unresolved tiles (-1) in it the
-// offsets are meaningless, the host discards the list -- only the bounds are guarded)
-__global__ void rows_from_tiles_kernel(const int *__restrict__ tile_cnt, const int *__restrict__ tile_off,
-                                       int num_tiles, int tile_cols, const unsigned *__restrict__ row_bits, int M,
-                                       int *__restrict__ rows, int cap) {
-  const int lane = threadIdx.x & 31;
-  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (t >= num_tiles || __ldg(tile_cnt + t) <= 0) return;
-  const int wpt = tile_cols >> 5, n_words = (M + 31) >> 5;
-  const int w0 = (int)(((long long)t * tile_cols) >> 5);
-  int o = __ldg(tile_off + t);
-  for (int wb = 0; wb < wpt; wb += 32) {
-    const int w = w0 + wb + lane;
-    unsigned m = (wb + lane < wpt && w < n_words) ? row_bits[w] : 0u;
-    const int c = __popc(m);
-    int incl = c;
+// Kernel A (grid, KR_TILES tiles per CTA): the changed rows of the dirty tiles, ascending.  The
+// offset of a tile is the sum of the tile counts before it: a CTA that owns a dirty tile adds up the
+// counts in front of its first tile itself (<= num_tiles ints out of L2) and scans its own -- no
+// device-wide scan kernel in front.  With unresolved tiles (-1) among the counts the offsets are
+// meaningless and the host discards the list -- only the bounds are guarded.
+constexpr int KR_TILES = 256;
+
+__global__ void __launch_bounds__(KA_THREADS)
+rows_from_tiles_kernel(const int *__restrict__ tile_cnt, int num_tiles, int tile_cols,
+                       const unsigned *__restrict__ row_bits, int M, int *__restrict__ rows, int cap) {
+  __shared__ int s_warp[32];
+  __shared__ int s_off[KR_TILES], s_list[KR_TILES];
+  __shared__ int s_n, s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int t0 = blockIdx.x * KR_TILES;
+  const int c = (tid < KR_TILES && t0 + tid < num_tiles) ? __ldg(tile_cnt + t0 + tid) : 0;
+  if (tid == 0) s_n = 0;
+  if (!__syncthreads_or(c > 0)) return;  // nothing changed in this CTA's tiles
+  int sum = 0;
+  for (int i = tid; i < t0; i += KA_THREADS) sum += __ldg(tile_cnt + i);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const int x = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += x;
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s_warp[warp] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    int w = s_warp[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) w += __shfl_xor_sync(0xffffffffu, w, o);
+    if (lane == 0) s_base = w;
+  }
+  __syncthreads();
+  int total;
+  const int excl = block_excl_scan_1024(c, s_warp, &total);
+  if (tid < KR_TILES) s_off[tid] = s_base + excl;
+  if (c > 0) s_list[atomicAdd(&s_n, 1)] = tid;
+  __syncthreads();
+  const int nd = s_n;
+  const int wpt = tile_cols >> 5, n_words = (M + 31) >> 5;
+  for (int li = warp; li < nd; li += KA_THREADS / 32) {
+    const int tl = s_list[li];
+    const int w0 = (int)(((long long)(t0 + tl) * tile_cols) >> 5);
+    int o = s_off[tl];
+    for (int wb = 0; wb < wpt; wb += 32) {
+      const int w = w0 + wb + lane;
+      unsigned m = (wb + lane < wpt && w < n_words) ? row_bits[w] : 0u;
+      const int pc = __popc(m);
+      int incl = pc;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int x = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += x;
+      }
+      int at = o + incl - pc;
+      while (m) {
+        const int b = __ffs(m) - 1;
+        m &= m - 1;
+        if (at >= 0 && at < cap) rows[at] = (w << 5) + b;
+        at++;
+      }
+      o += __shfl_sync(0xffffffffu, incl, 31);
     }
-    int at = o + incl - c;
-    while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      if (at >= 0 && at < cap) rows[at] = (w << 5) + b;
-      at++;
-    }
-    o += __shfl_sync(0xffffffffu, incl, 31);
   }
 }
 
-// Kernel C1 (one CTA): exclusive scan of the per-row edge counts -> offsets, total -> out[0]; clears
-// the node flags.  Covers up to kSpecRows changed rows; more (or unresolved tiles) -> out[0] = -1 and
-// the host uses the multi-kernel path.
-__global__ void __launch_bounds__(KA_THREADS)
-scan_counts_kernel(const DetectCounters *__restrict__ cnt, const int *__restrict__ counts, int *__restrict__ offsets,
-                   int nn, int *__restrict__ out) {
-  __shared__ int s_warp[32];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < 2 * nn; i += KA_THREADS) out[2 + i] = 0;
+// Kernel C (grid, one warp per changed row, 8 rows per CTA): ordered emission of the row's changed
+// edges (emit_row_edges_kernel's body) and, while the endpoints are in registers, the dirty-node flags
+// of Integrator::findRegionConnections (mark_dirty_nodes).  The offset of a row is the sum of the
+// per-row counts before it: every CTA adds up the counts in front of its first row itself (at most
+// kSpecRows ints out of L2) instead of waiting for a scan kernel.  out[0] = number of edges (written
+// by the warp of the last row), -1 when more than kSpecRows rows changed or tiles were left
+// unresolved (the host then uses the multi-kernel path); out[2..] were cleared by sym_check_rows_kernel.
+constexpr int KC_THREADS = 256;
+constexpr int KC_ROWS = KC_THREADS / 32;
+
+__global__ void __launch_bounds__(KC_THREADS)
+emit_mark_kernel(const int *__restrict__ rows, const DetectCounters *__restrict__ cnt,
+                 const int *__restrict__ counts, const int *__restrict__ Mp,
+                 const int *__restrict__ Mi, const int *__restrict__ dof2node,
+                 const int *__restrict__ meta, int *__restrict__ edges, int cap_edges, int nn,
+                 int *__restrict__ out) {
+  __shared__ int s_part[KC_ROWS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = cnt->changed_rows;
-  if (n > kSpecRows || cnt->pad1 > 0) {
-    if (tid == 0) out[0] = -1;
+  const bool bail = n > kSpecRows || cnt->pad1 > 0;
+  if (bail || n == 0) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[0] = bail ? -1 : 0;
     return;
   }
-  constexpr int IPT = kSpecRows / KA_THREADS;
-  int c[IPT], sum = 0;
+  const int k0 = blockIdx.x * KC_ROWS;
+  if (k0 >= n) return;
+  int sum = 0;
+  for (int i = threadIdx.x; i < k0; i += KC_THREADS) sum += counts[i];
 #pragma unroll
-  for (int u = 0; u < IPT; u++) { const int k = tid * IPT + u; c[u] = k < n ? counts[k] : 0; sum += c[u]; }
-  int total;
-  int o = block_excl_scan_1024(sum, s_warp, &total);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) s_part[warp] = sum;
+  const int own = (lane < KC_ROWS && k0 + lane < n) ? counts[k0 + lane] : 0;
+  __syncthreads();
+  int at0 = 0;
 #pragma unroll
-  for (int u = 0; u < IPT; u++) { offsets[tid * IPT + u] = o; o += c[u]; }
-  if (tid == 0) out[0] = total;
-}
-
-// Kernel C2 (grid, one warp per changed row): ordered emission of the row's changed edges
-// (emit_row_edges_kernel's body) and, while the endpoints are in registers, the dirty-node flags of
-// Integrator::findRegionConnections (mark_dirty_nodes)
-__global__ void emit_mark_kernel(const int *__restrict__ rows, const DetectCounters *__restrict__ cnt,
-                                 const int *__restrict__ offsets, const int *__restrict__ Mp,
-                                 const int *__restrict__ Mi, const int *__restrict__ dof2node,
-                                 const int *__restrict__ meta, int *__restrict__ edges, int cap_edges, int nn,
-                                 int *__restrict__ out) {
-  const int lane = threadIdx.x & 31;
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int n = cnt->changed_rows;
-  if (n > kSpecRows || cnt->pad1 > 0 || k >= n) return;
+  for (int w = 0; w < KC_ROWS; w++) {
+    at0 += s_part[w];
+    const int v = __shfl_sync(0xffffffffu, own, w);
+    if (w < warp) at0 += v;
+  }
+  const int k = k0 + warp;
+  if (k >= n) return;
   const int i = rows[k];
   const int ni = __ldg(dof2node + i);
-  int at0 = offsets[k];
   const int s = Mp[i], e = Mp[i + 1];
   for (int b = s; b < e; b += 32) {
     const int p = b + lane;
@@ -386,6 +431,7 @@ __global__ void emit_mark_kernel(const int *__restrict__ rows, const DetectCount
     }
     at0 += __popc(m);
   }
+  if (k == n - 1 && lane == 0) out[0] = at0;
 }
 
 // ------------------------------------------------------------------ host launchers
@@ -436,22 +482,19 @@ int launch_emit_row_edges(const int *rows, int n_rows, const int *n_rows_dev, co
 
 int launch_rows_from_tiles(const int *tile_cnt, int *tile_off, unsigned long long *scan_ws, int num_tiles, int tile_cols,
                            const unsigned *row_bits, int M, int *rows, int cap, cudaStream_t s) {
-  exclusive_scan<0>(tile_cnt, tile_off, num_tiles, scan_ws, s);
-  rows_from_tiles_kernel<<<(unsigned)(((long long)num_tiles * 32 + 255) / 256), 256, 0, s>>>(tile_cnt, tile_off, num_tiles,
-                                                                                            tile_cols, row_bits, M, rows, cap);
+  (void)tile_off; (void)scan_ws;  // the offsets are computed inside the kernel
+  rows_from_tiles_kernel<<<(unsigned)((num_tiles + KR_TILES - 1) / KR_TILES), KA_THREADS, 0, s>>>(tile_cnt, num_tiles, tile_cols,
+                                                                                                  row_bits, M, rows, cap);
   PB_CUDA(cudaGetLastError());
-  return 2;
+  return 1;
 }
 
 int launch_emit_mark(const int *rows, const DetectCounters *cnt, const int *counts, const int *Mp, const int *Mi,
                      const int *dof2node, const int *meta, int *edges, int cap_edges, int nn, int *out, cudaStream_t s) {
-  // counts doubles as the offsets array: the scan reads its counts into registers before it writes
-  int *offsets = const_cast<int *>(counts);
-  scan_counts_kernel<<<1, KA_THREADS, 0, s>>>(cnt, counts, offsets, nn, out);
-  emit_mark_kernel<<<(kSpecRows * 32) / 256, 256, 0, s>>>(rows, cnt, offsets, Mp, Mi, dof2node, meta, edges, cap_edges, nn,
-                                                          out);
+  emit_mark_kernel<<<kSpecRows / KC_ROWS, KC_THREADS, 0, s>>>(rows, cnt, counts, Mp, Mi, dof2node, meta, edges, cap_edges,
+                                                             nn, out);
   PB_CUDA(cudaGetLastError());
-  return 2;
+  return 1;
 }
 
 }  // namespace pb

@@ -195,7 +195,10 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
   for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, k++) {
     const int s = k & 1;
     K9Stage &B = S.st[s];
-    if (tid == 0) bulk_wait_read1();  // the store that last used out[s] has drained its smem reads
+    if (tid == 0) {
+      bulk_wait_read1();                 // the store that last used out[s] has drained its smem reads
+      if (Mp_prev) tile_state[t] = 0;    // (ordered before the tile's atomicAdds by the consumer barriers below)
+    }
     mbar_wait(&S.full[s], (k / K9_STAGES) & 1);
     const int c0 = t * TC, c1 = min(M, c0 + TC), nc = c1 - c0;
     const int q0 = S.par[s][0], q1 = S.par[s][1];
@@ -457,11 +460,15 @@ int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s) {
   PB_CUDA(cudaFuncSetAttribute(build_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K9Smem)));
   const int TC = build_pipe_tile_cols(a);
   const int num_tiles = (a.M + TC - 1) / TC;
-  PB_CUDA(cudaMemsetAsync(a.status, 0, sizeof(BuildStatus), s));
   const bool fused = a.Mp_prev && a.Mi_prev && a.tile_dirty && a.row_bits && a.dcnt;
-  if (fused) {
-    PB_CUDA(cudaMemsetAsync(a.tile_dirty, 0, sizeof(int) * (size_t)num_tiles, s));
-    PB_CUDA(cudaMemsetAsync(a.dcnt, 0, sizeof(DetectCounters), s));
+  // one memset for the whole mailbox when status and counters are its two halves (every stream
+  // operation costs ~2 us of stream time); the per-tile counts are zeroed by the kernel itself
+  char *st0 = reinterpret_cast<char *>(a.status), *dc0 = reinterpret_cast<char *>(a.dcnt);
+  if (fused && dc0 > st0 && dc0 - st0 <= 64) {
+    PB_CUDA(cudaMemsetAsync(st0, 0, (size_t)(dc0 - st0) + sizeof(DetectCounters), s));
+  } else {
+    PB_CUDA(cudaMemsetAsync(a.status, 0, sizeof(BuildStatus), s));
+    if (fused) PB_CUDA(cudaMemsetAsync(a.dcnt, 0, sizeof(DetectCounters), s));
   }
   const int grid = num_tiles < 2 * num_sms ? num_tiles : 2 * num_sms;
   if (a.ev_a) cudaEventRecord(a.ev_a, s);

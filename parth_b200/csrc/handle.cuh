@@ -21,7 +21,7 @@ struct parth_b200 {
   // final synchronisation of the API call (no intermediate cudaEventSynchronize on the hot path)
   static constexpr int kTimerPairs = 48;
   cudaEvent_t tev[2 * kTimerPairs] = {};
-  struct PendingTimer { double *dst; double *dst2; int pair; bool accumulate; };
+  struct PendingTimer { double *dst; double *dst2; int pair; bool accumulate; cudaEvent_t a, b; };
   std::vector<PendingTimer> pending_timers;  // stopped, not yet read
   std::vector<int> free_pairs;               // event pairs nobody holds (filled at creation)
   std::string err;
@@ -100,6 +100,19 @@ struct parth_b200 {
   pb::DevBuf<long long> r_wsptr;
   pb::DevBuf<int> d_out;                   // staging for host-pointer outputs
   pb::PinBuf<int> pin;                     // small pinned read-backs
+  pb::PinBuf<int> pin_mail;                // mailbox read-back of a deferred build (own buffer: nothing may move it)
+
+  // ---- deferred completion of stage (a): the stream-ordered device-pointer set_matrix enqueues the
+  // build, the changed-row proof, stage (b)'s edge kernels and the mailbox copy, records ev_mail and
+  // returns; the next call that needs the result waits for ev_mail only (stage_build_settle), so the
+  // device never idles while the host reads flags in the steady state
+  struct PendingBuild {
+    bool active = false;
+    int N = 0, nnz = 0, dim = 1, M = 0, fused_cols = 0;
+    const int *dAp = nullptr, *dAi = nullptr;
+    size_t n_spec = 0, timers_before = 0;
+  } pend;
+  cudaEvent_t ev_mail = nullptr;
   pb::PinBuf<int> pin_big;                 // pinned staging for big host transfers
 
   parth_b200_stats stats = {};

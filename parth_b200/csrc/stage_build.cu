@@ -57,7 +57,7 @@ static bool enqueue_changed_row_proof(parth_b200 &h, int M, int fused_cols, int 
     h.stats.kernels_launched += launch_sym_check_rows(h.chg_rows.p, &h.dcnt_p()->changed_rows, cap, h.Mp_own.p,
                                                       h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, &h.dcnt_p()->pad0,
                                                       spec ? h.d_dof2node.p : nullptr, spec ? h.w3.p : nullptr,
-                                                      kSpecRows, s);
+                                                      kSpecRows, s, spec ? h.w5.p : nullptr, spec ? nn * 2 + 2 : 0);
     if (spec)
       h.stats.kernels_launched += launch_emit_mark(h.chg_rows.p, h.dcnt_p(), h.w3.p, h.Mp_own.p, h.Mi_own.p,
                                                    h.d_dof2node.p, h.d_meta.p, h.d_changed.p,
@@ -106,7 +106,7 @@ static bool enqueue_speculative_detection(parth_b200 &h, int M) {
 void collect_timers(parth_b200 &h) {
   for (auto &t : h.pending_timers) {
     float ms = 0;
-    cudaEventElapsedTime(&ms, h.tev[2 * t.pair], h.tev[2 * t.pair + 1]);
+    cudaEventElapsedTime(&ms, t.a, t.b);
     if (t.accumulate) *t.dst += ms; else *t.dst = ms;
     if (t.dst2) *t.dst2 = ms;
     h.free_pairs.push_back(t.pair);
@@ -120,7 +120,71 @@ void resolve_timers(parth_b200 &h) {
   collect_timers(h);
 }
 
-void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, int dim) {
+// what a proven build leaves in the handle (shared by the synchronous path and stage_build_settle)
+static void accept_spec(parth_b200 &h, const std::vector<int> &spec_out, int changed_rows) {
+  if (h.diff_cached && changed_rows <= kSpecRows && (int)spec_out.size() == h.num_nodes * 2 + 2 && spec_out[0] >= 0 &&
+      spec_out[0] <= (int)(h.d_changed.cap / 2)) {
+    h.spec_valid = true;
+    h.spec_n_changed = spec_out[0];
+    h.spec_flags.assign(spec_out.begin() + 2, spec_out.end());
+  }
+}
+
+static void publish_graph(parth_b200 &h, int M) {
+  h.Mp = h.Mp_own.p;
+  h.Mi = h.Mi_own.p;
+  h.M_n = M;
+  h.mesh_owned = true;
+  h.map_len = 0;
+}
+
+// Completion of a build that stage_build left in flight (may_defer).  Waits for the mailbox copy
+// only -- work enqueued behind it (the speculative expansion of computePermutation) keeps running.
+// The common outcome (no flag raised, every tile compared in the build kernel, every changed row
+// mirrored) is accepted here; anything else re-runs the synchronous state machine on the same
+// arrays (they must stay valid until then, see include/parth_b200.h).
+void stage_build_settle(parth_b200 &h) {
+  if (!h.pend.active) return;
+  const parth_b200::PendingBuild p = h.pend;
+  h.pend.active = false;
+  PB_CUDA(cudaEventSynchronize(h.ev_mail));
+  BuildStatus st{};
+  DetectCounters dc{};
+  std::memcpy(&st, h.pin_mail.p, sizeof(st));
+  std::memcpy(&dc, h.pin_mail.p + 8, sizeof(dc));
+  h.stats.d2h_bytes += (long long)(sizeof(int) * (12 + p.n_spec));
+  {
+    // the timers stopped before the mailbox copy have completed with it; later ones stay pending
+    std::vector<parth_b200::PendingTimer> later(h.pending_timers.begin() + std::min(p.timers_before, h.pending_timers.size()),
+                                                h.pending_timers.end());
+    h.pending_timers.resize(std::min(p.timers_before, h.pending_timers.size()));
+    collect_timers(h);
+    h.pending_timers.swap(later);
+  }
+  const int M = p.M;
+  const bool ok = st.flags == 0 && dc.pad1 == 0 && dc.changed_rows <= changed_rows_cap(M) &&
+                  (dc.changed_rows == 0 || dc.pad0 == 0);
+  if (!ok) {
+    h.stats.build_deferred = 0;
+    stage_build(h, p.N, p.dAp, p.dAi, p.nnz, p.dim, false);
+    return;
+  }
+  float t = 0;
+  cudaEventElapsedTime(&t, h.ev2, h.ev3);
+  h.stats.build_kernel_ms = t;
+  h.n_chg_rows = dc.changed_rows;
+  h.diff_cached = true;
+  std::vector<int> spec_out(h.pin_mail.p + 16, h.pin_mail.p + 16 + p.n_spec);
+  accept_spec(h, spec_out, dc.changed_rows);
+  h.nnzM = st.nnz_out;
+  h.stats.build_path = 1;
+  h.stats.build_fused_detect = 1;
+  h.stats.build_deferred = 1;
+  h.cur_sym_proven = true;
+  publish_graph(h, M);
+}
+
+void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, int dim, bool may_defer) {
   cudaStream_t s = h.stream;
   const int M = N / dim;
   StageTimer total(h, &h.stats.build_ms);
@@ -232,6 +296,22 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
       spec_enqueued = enqueue_changed_row_proof(h, M, fused_cols, fused_cols ? build_pipe_num_tiles(a) : 0);
       if (!fused_cols) spec_enqueued = enqueue_speculative_detection(h, M);
     }
+    if (may_defer && incremental && fused_cols > 0 && spec_enqueued && h.build_mode == 0) {
+      // steady state of the device-pointer API: leave everything in flight (stage_build_settle)
+      const size_t n_spec = (size_t)h.num_nodes * 2 + 2;
+      h.pin_mail.reserve(16 + n_spec);
+      PB_CUDA(cudaMemcpyAsync(h.pin_mail.p, h.mail.p, sizeof(int) * 12, cudaMemcpyDeviceToHost, s));
+      PB_CUDA(cudaMemcpyAsync(h.pin_mail.p + 16, h.w5.p, sizeof(int) * n_spec, cudaMemcpyDeviceToHost, s));
+      total.stop(h.ev_mail);  // the mailbox event doubles as the end of the build bracket
+      PB_CUDA(cudaEventRecord(h.ev_mail, s));
+      h.pend.active = true;
+      h.pend.N = N; h.pend.nnz = nnz; h.pend.dim = dim; h.pend.M = M; h.pend.fused_cols = fused_cols;
+      h.pend.dAp = dAp; h.pend.dAi = dAi;
+      h.pend.n_spec = n_spec;
+      h.pend.timers_before = h.pending_timers.size();
+      return;
+    }
+    may_defer = false;
     read_mail();
     if (incremental && fused_cols && st.flags == 0 && dc.pad1 > 0) {
       // some tiles could not be compared inside the build kernel (over-long columns, snapshot tile
@@ -279,12 +359,8 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
       }
     }
   }
-  if (proven && incremental && spec_enqueued && h.diff_cached && dc.changed_rows <= kSpecRows &&
-      (int)spec_out.size() == h.num_nodes * 2 + 2 && spec_out[0] >= 0 && spec_out[0] <= (int)(h.d_changed.cap / 2)) {
-    h.spec_valid = true;
-    h.spec_n_changed = spec_out[0];
-    h.spec_flags.assign(spec_out.begin() + 2, spec_out.end());
-  }
+  if (proven && incremental && spec_enqueued) accept_spec(h, spec_out, dc.changed_rows);
+  h.stats.build_deferred = 0;
   if (proven) {
     h.nnzM = st.nnz_out;
     h.stats.build_path = 1;
@@ -316,11 +392,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
     h.diff_cached = false;
   }
   total.stop();
-  h.Mp = h.Mp_own.p;
-  h.Mi = h.Mi_own.p;
-  h.M_n = M;
-  h.mesh_owned = true;
-  h.map_len = 0;
+  publish_graph(h, M);
 }
 
 }  // namespace pb

@@ -121,18 +121,19 @@ void stage_export_tree(parth_b200 &h, int *meta, int *node_ptr, int *dofs, int *
 void stage_detect(parth_b200 &h) {
   cudaStream_t s = h.stream;
   const int M = h.M_n, nn = h.num_nodes;
-  StageTimer tm(h, &h.stats.detect_ms, false, &h.timer_ms[2]);
   h.n_changed = 0;
   h.node_flags_valid = false;
   if (h.spec_valid && h.diff_cached && h.map_len == 0 && h.Mp == h.Mp_own.p && (int)h.spec_flags.size() == nn * 2) {
     // stage (a) enqueued the edge kernels right behind its row diff and fetched their result with
-    // its own mailbox: nothing to launch, nothing to wait for
+    // its own mailbox: nothing to launch, nothing to wait for, nothing to time
     h.spec_valid = false;
     h.n_changed = h.spec_n_changed;
     if (h.n_chg_rows > 0) { h.node_flags.swap(h.spec_flags); h.node_flags_valid = true; }
-    tm.stop();
+    h.stats.detect_ms = 0;
+    h.timer_ms[2] = 0;
     return;
   }
+  StageTimer tm(h, &h.stats.detect_ms, false, &h.timer_ms[2]);
   h.spec_valid = false;
   const int n_words = (M + 31) / 32;
   h.scan_ws.reserve(scan_ws_words((size_t)std::max(n_words, M) + 1), s);
@@ -222,18 +223,20 @@ static long long subtree_size(const parth_b200 &h, int x) {
 void stage_dirty_sets(parth_b200 &h, const std::vector<int> &pre_fine) {
   cudaStream_t s = h.stream;
   const int nn = h.num_nodes;
-  StageTimer tm(h, &h.stats.dirty_ms);
   std::vector<int> flags;
   if (h.node_flags_valid && (int)h.node_flags.size() == nn * 2) {
     flags.swap(h.node_flags);  // fetched together with the edge list by stage_detect
     h.node_flags_valid = false;
+    h.stats.dirty_ms = 0;  // host work only: no device span to measure
   } else {
+    StageTimer tm(h, &h.stats.dirty_ms);
     // the edge list or the tree changed since detection (relocation): classify again
     h.w5.reserve((size_t)nn * 2 + 2, s);
     PB_CUDA(cudaMemsetAsync(h.w5.p, 0, sizeof(int) * (size_t)nn * 2, s));
     h.stats.kernels_launched += launch_mark_dirty_nodes(h.d_changed.p, h.n_changed, h.d_dof2node.p, h.d_meta.p,
                                                         h.w5.p, h.w5.p + nn, s);
     flags.resize((size_t)nn * 2);
+    tm.stop();
     read_ints(h, h.w5.p, flags.data(), (size_t)nn * 2);
   }
   const int *within = flags.data(), *lca = flags.data() + nn;
@@ -275,7 +278,6 @@ void stage_dirty_sets(parth_b200 &h, const std::vector<int> &pre_fine) {
   for (int x : h.dirty_coarse) nodes += (double)subtree_size(h, x);
   for (int x : h.dirty_fine) nodes += h.node_ptr[x + 1] - h.node_ptr[x];
   h.reuse = h.tree_M != 0 ? 1 - (nodes * 1.0 / h.tree_M) : 0.0;
-  tm.stop();
 }
 
 // ------------------------------------------------------------------ (e) expansion
@@ -369,6 +371,23 @@ static int global_perm(parth_b200 &h) {
 
 // ParthAPI::computePermutation (ParthAPI.cpp:191-279); dperm: device buffer of M_n*dim ints
 int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
+  // A build left in flight by the device-pointer set_matrix (steady state: tree present, same vertex
+  // set, no DOF map): expand the CURRENT mesh permutation behind it before waiting for its flags.
+  // Most reuse updates leave the permutation untouched (no change, edges inside a node or towards an
+  // ancestor, lag-dropped nodes): the expansion then already ran while the host was reading the
+  // flags; when nodes are re-ordered after all it is simply run again at the end.
+  bool spec_expanded = false;
+  cudaEvent_t spec_end = nullptr;
+  h.stats.expand_speculative = 0;
+  if (h.pend.active) {
+    if (h.tree_init && h.tree_M == h.pend.M && h.map_len == 0 && dperm) {
+      StageTimer tm(h, &h.stats.expand_ms, false, nullptr, h.ev_mail);  // bracket opens at the build's mailbox event
+      h.stats.kernels_launched += launch_expand(h.d_mesh_perm.p, h.pend.M, dim, dperm, h.stream);
+      spec_end = tm.stop();
+      spec_expanded = true;
+    }
+    stage_build_settle(h);
+  }
   for (double &t : h.timer_ms) t = 0;
   h.xchg_pending = false;
   h.xchg_nodes.clear();
@@ -390,8 +409,11 @@ int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
   } else {
     if (h.map_len > 0) stage_integrate(h);
     stage_detect(h);
-    StageTimer tc(h, &h.timer_ms[3]);
-    if (h.n_changed == 0) {
+    // compute_permutation bracket: opens at the end of the speculative expansion when there is one
+    StageTimer tc(h, &h.timer_ms[3], false, nullptr, spec_end);
+    const long long launched0 = h.stats.kernels_launched;
+    const bool no_change = h.n_changed == 0;  // (the relocation step filters the edge list later on)
+    if (no_change) {
       h.reuse = 1;
     } else {
       rc = global_perm(h);
@@ -402,8 +424,15 @@ int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
       tc.stop();
       return PARTH_B200_NEEDS_EXCHANGE;
     }
-    if (rc == PARTH_B200_OK) stage_expand(h, h.d_mesh_perm.p, h.M_n, dim, dperm);
-    tc.stop();
+    // the speculative expansion stands when nothing touched the tree or the permutation
+    const bool untouched = spec_expanded && h.tree_init && h.map_len == 0 &&
+                           (no_change || (!h.aggressive && h.dirty_fine.empty() && h.dirty_coarse.empty()));
+    if (rc == PARTH_B200_OK && untouched) {
+      h.stats.expand_speculative = 1;  // its timer (pending) fills expand_ms
+    } else if (rc == PARTH_B200_OK) {
+      stage_expand(h, h.d_mesh_perm.p, h.M_n, dim, dperm);
+    }
+    if (h.stats.kernels_launched == launched0) tc.cancel(); else tc.stop();
   }
   stage_snapshot(h);
   return rc;

@@ -21,15 +21,29 @@ struct StageTimer {
   int pair;
   double *dst, *dst2;
   bool accumulate;
-  StageTimer(parth_b200 &hh, double *d, bool acc = false, double *d2 = nullptr) : h(hh), dst(d), dst2(d2), accumulate(acc) {
+  cudaEvent_t start_ev;  // != nullptr: an event already recorded on the stream marks the start (no record of our own)
+  // Every cudaEventRecord costs 1.5-3 us of stream time on B200: brackets that share a boundary share the event.
+  StageTimer(parth_b200 &hh, double *d, bool acc = false, double *d2 = nullptr, cudaEvent_t start = nullptr)
+      : h(hh), dst(d), dst2(d2), accumulate(acc), start_ev(start) {
     pair = -1;
     if (!h.free_pairs.empty()) { pair = h.free_pairs.back(); h.free_pairs.pop_back(); }
-    if (pair >= 0) cudaEventRecord(h.tev[2 * pair], h.stream);
+    if (pair >= 0 && !start_ev) cudaEventRecord(h.tev[2 * pair], h.stream);
   }
-  void stop() {
+  // stop_with: an event the caller records right after this call (or has just recorded) marks the end.
+  // Returns the end event (nullptr when no timer pair was free).
+  cudaEvent_t stop(cudaEvent_t stop_with = nullptr) {
+    if (pair < 0) return nullptr;
+    cudaEvent_t end = stop_with ? stop_with : h.tev[2 * pair + 1];
+    if (!stop_with) cudaEventRecord(end, h.stream);
+    h.pending_timers.push_back({dst, dst2, pair, accumulate, start_ev ? start_ev : h.tev[2 * pair], end});
+    pair = -1;
+    return end;
+  }
+  // nothing was enqueued inside the bracket: the span is zero, no event needed
+  void cancel() {
     if (pair < 0) return;
-    cudaEventRecord(h.tev[2 * pair + 1], h.stream);
-    h.pending_timers.push_back({dst, dst2, pair, accumulate});
+    if (!accumulate) { *dst = 0; if (dst2) *dst2 = 0; }
+    h.free_pairs.push_back(pair);
     pair = -1;
   }
   ~StageTimer() { if (pair >= 0) h.free_pairs.push_back(pair); }  // abandoned (exception): give the pair back
@@ -41,7 +55,10 @@ void collect_timers(parth_b200 &h);  // reads the stopped timers; call only righ
 void read_ints(parth_b200 &h, const int *dsrc, int *dst, size_t n);
 
 // (a1) ParthAPI::computeMeshFromMatrix
-void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, int dim);
+// may_defer: in the steady state (fused build + detection, edge kernels enqueued speculatively) return
+// with everything in flight; stage_build_settle completes it (no-op when nothing is pending)
+void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, int dim, bool may_defer = false);
+void stage_build_settle(parth_b200 &h);
 
 // stage_perm.cu
 void upload_tree_meta(parth_b200 &h);

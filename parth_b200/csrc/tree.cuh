@@ -32,13 +32,14 @@ int launch_diff_rows_mapped(const int *Mp, const int *Mi, const int *Mp_prev, co
 // counts != nullptr: also the problematic-edge count of the first spec_cap changed rows (count_row_edges fused in)
 int launch_sym_check_rows(const int *rows, const int *n_rows_dev, int cap, const int *Mp, const int *Mi,
                           const int *Mp_prev, const int *Mi_prev, int *asym, const int *dof2node, int *counts,
-                          int spec_cap, cudaStream_t s);
+                          int spec_cap, cudaStream_t s, int *zero_out = nullptr, int n_zero = 0);
 // fused steady state (the pipeline build kernel wrote the bitmap words and per-tile counts of changed rows):
 // ascending changed-row list from the tile counts (tile_off: num_tiles + 1 ints of scratch, scan_ws: scan work-space)
 int launch_rows_from_tiles(const int *tile_cnt, int *tile_off, unsigned long long *scan_ws, int num_tiles, int tile_cols,
                            const unsigned *row_bits, int M, int *rows, int cap, cudaStream_t s);
-// scan of the per-row edge counts + ordered edge emission + dirty-node marking in one CTA; out = w5 layout
-// ([0] edge count or -1 = not computed, [2, 2+nn) within-node flags, [2+nn, 2+2nn) LCA flags)
+// ordered edge emission (row offsets summed per CTA from the per-row counts) + dirty-node marking; out = w5 layout
+// ([0] edge count or -1 = not computed, [2, 2+nn) within-node flags, [2+nn, 2+2nn) LCA flags, cleared by the
+// launch_sym_check_rows in front of it through zero_out / n_zero)
 constexpr int kSpecRows = 8192;
 int launch_emit_mark(const int *rows, const DetectCounters *cnt, const int *counts, const int *Mp, const int *Mi,
                      const int *dof2node, const int *meta, int *edges, int cap_edges, int nn, int *out, cudaStream_t s);
