@@ -84,7 +84,9 @@ int parth_b200_create(parth_b200 **out, int device) {
     }
     for (auto &e : h->tev) PB_CUDA(cudaEventCreate(&e));
     for (int i = parth_b200::kTimerPairs - 1; i >= 0; i--) h->free_pairs.push_back(i);
-    h->mail.reserve(32);
+    // [0..5] BuildStatus, [8..11] DetectCounters, [16..) stage (b)'s speculative result of the fused
+    // steady state (edge count + node flags, <= 2 + 2 * 8191 ints): one read-back fetches all of it
+    h->mail.reserve(16 + 2 + 2 * 8191 + 14);
   } catch (const std::exception &ex) {
     g_create_error = ex.what();
     delete h;

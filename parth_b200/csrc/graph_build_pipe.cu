@@ -65,12 +65,12 @@ __device__ __forceinline__ void mbar_wait(void *bar, unsigned parity) {
       "{\n"
       ".reg .pred p;\n"
       "K9_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra K9_DONE;\n"
       "bra K9_WAIT;\n"
       "K9_DONE:\n"
       "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(0x989680)  // suspend-time hint: a waiting thread sleeps instead of re-issuing the probe
       : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, void *bar) {
@@ -376,6 +376,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
           if (off + lenp <= gotp && nc + 1 <= gotpa) {
             // everything was staged (always, except next to the end of the arrays): bare compare
             const int want = shift + c0;
+#pragma unroll 1
             for (int lc = tid; lc <= nc; lc += K9_CONSUMERS) bad |= (B.ap[lc] - lc) - S.pap[lc] != want;
             const int *pv = S.pval + off;
 #pragma unroll 2

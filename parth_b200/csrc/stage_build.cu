@@ -48,20 +48,20 @@ static bool enqueue_changed_row_proof(parth_b200 &h, int M, int fused_cols, int 
     const int nn = h.num_nodes;
     if (spec) {
       h.w3.reserve((size_t)kSpecRows + 2, s);
-      h.w5.reserve((size_t)nn * 2 + 2, s);
       if (h.d_changed.cap < 2 * 65536) h.d_changed.reserve(2 * 65536, s);
     }
+    int *spec_dev = h.mail.p + 16;  // the result sits behind the mailbox and travels with it in one copy
     h.tile_off.reserve((size_t)num_tiles + 2, s);
     h.stats.kernels_launched += launch_rows_from_tiles(h.tile_dirty.p, h.tile_off.p, h.scan_ws.p, num_tiles, fused_cols, bits,
                                                        M, h.chg_rows.p, cap, s);
     h.stats.kernels_launched += launch_sym_check_rows(h.chg_rows.p, &h.dcnt_p()->changed_rows, cap, h.Mp_own.p,
                                                       h.Mi_own.p, h.Mp_prev.p, h.Mi_prev.p, &h.dcnt_p()->pad0,
                                                       spec ? h.d_dof2node.p : nullptr, spec ? h.w3.p : nullptr,
-                                                      kSpecRows, s, spec ? h.w5.p : nullptr, spec ? nn * 2 + 2 : 0);
+                                                      kSpecRows, s, spec ? spec_dev : nullptr, spec ? nn * 2 + 2 : 0);
     if (spec)
       h.stats.kernels_launched += launch_emit_mark(h.chg_rows.p, h.dcnt_p(), h.w3.p, h.Mp_own.p, h.Mi_own.p,
                                                    h.d_dof2node.p, h.d_meta.p, h.d_changed.p,
-                                                   (int)(h.d_changed.cap / 2), nn, h.w5.p, s);
+                                                   (int)(h.d_changed.cap / 2), nn, spec_dev, s);
     return spec;
   }
   {
@@ -228,13 +228,17 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   static_assert(sizeof(BuildStatus) == 24 && sizeof(DetectCounters) == 16, "mailbox layout");
   bool spec_enqueued = false;
   std::vector<int> spec_out;
+  int fused_cols = 0;  // > 0: the pipeline kernel compares each tile with the snapshot on the fly (fused change detection)
   auto read_mail = [&]() {
     // ONE synchronisation: the mailbox and, when the edge kernels ran speculatively, their result
     int m[12];
     const size_t n_spec = spec_enqueued ? (size_t)h.num_nodes * 2 + 2 : 0;
     h.pin.reserve(16 + n_spec);
     PB_CUDA(cudaMemcpyAsync(h.pin.p, h.mail.p, sizeof(int) * 12, cudaMemcpyDeviceToHost, s));
-    if (n_spec) PB_CUDA(cudaMemcpyAsync(h.pin.p + 16, h.w5.p, sizeof(int) * n_spec, cudaMemcpyDeviceToHost, s));
+    if (n_spec && fused_cols > 0)  // the fused tail wrote its result behind the mailbox: same copy, extended
+      PB_CUDA(cudaMemcpyAsync(h.pin.p + 12, h.mail.p + 12, sizeof(int) * (4 + n_spec), cudaMemcpyDeviceToHost, s));
+    else if (n_spec)
+      PB_CUDA(cudaMemcpyAsync(h.pin.p + 16, h.w5.p, sizeof(int) * n_spec, cudaMemcpyDeviceToHost, s));
     PB_CUDA(cudaStreamSynchronize(s));
     for (int i = 0; i < 12; i++) m[i] = h.pin.p[i];
     spec_out.assign(h.pin.p + 16, h.pin.p + 16 + n_spec);
@@ -243,8 +247,6 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
     std::memcpy(&st, m, sizeof(st));
     std::memcpy(&dc, m + 8, sizeof(dc));
   };
-  // fused change detection: the pipeline kernel compares each tile with the snapshot on the fly
-  int fused_cols = 0;
   auto launch_filter = [&]() {
     fused_cols = 0;
     a.Mp_prev = a.Mi_prev = nullptr;
@@ -300,8 +302,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
       // steady state of the device-pointer API: leave everything in flight (stage_build_settle)
       const size_t n_spec = (size_t)h.num_nodes * 2 + 2;
       h.pin_mail.reserve(16 + n_spec);
-      PB_CUDA(cudaMemcpyAsync(h.pin_mail.p, h.mail.p, sizeof(int) * 12, cudaMemcpyDeviceToHost, s));
-      PB_CUDA(cudaMemcpyAsync(h.pin_mail.p + 16, h.w5.p, sizeof(int) * n_spec, cudaMemcpyDeviceToHost, s));
+      PB_CUDA(cudaMemcpyAsync(h.pin_mail.p, h.mail.p, sizeof(int) * (16 + n_spec), cudaMemcpyDeviceToHost, s));
       total.stop(h.ev_mail);  // the mailbox event doubles as the end of the build bracket
       PB_CUDA(cudaEventRecord(h.ev_mail, s));
       h.pend.active = true;
