@@ -134,9 +134,11 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
   const bool producer = tid >= K9_CONSUMERS;
 
   if (tid == 0) {
-    for (int s = 0; s < K9_STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], 1); }
+    // full: one arrival (the producer's expect_tx) + the copied bytes; empty: every consumer arrives on its own
+    // after its last read of the stage -- no CTA barrier is spent on handing a stage back
+    for (int s = 0; s < K9_STAGES; s++) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], K9_CONSUMERS); }
     mbar_init(&S.pfull, 1);
-    mbar_init(&S.pempty, 1);
+    mbar_init(&S.pempty, K9_CONSUMERS);
     S.nlong = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -192,12 +194,15 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
   unsigned flags = 0;
   long long diff = 0;
   int k = 0;
+  bool order_first = false;  // something of the previous tile must be ordered before this tile's walk
   for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, k++) {
     const int s = k & 1;
     K9Stage &B = S.st[s];
     if (tid == 0) {
-      bulk_wait_read1();                 // the store that last used out[s] has drained its smem reads
-      if (Mp_prev) tile_state[t] = 0;    // (ordered before the tile's atomicAdds by the consumer barriers below)
+      // out[s] is written again in this tile: the store that last used it must have drained its smem reads.
+      // Fused mode waits for that before the OR-barrier of the previous tile instead (no barrier here).
+      if (!Mp_prev) bulk_wait_read1();
+      else tile_state[t] = 0;            // (ordered before the tile's atomicAdds by the consumer barriers below)
     }
     mbar_wait(&S.full[s], (k / K9_STAGES) & 1);
     const int c0 = t * TC, c1 = min(M, c0 + TC), nc = c1 - c0;
@@ -205,14 +210,21 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
     const bool wide = S.par[s][2] != 0;
     const int nq = q1 - q0;
     const int sbase = q0 & ~3;
+    bool by_threads = false;
     if (!wide) {
-      // elements the 16-byte granular bulk copies could not fetch without leaving the arrays
+      // elements the 16-byte granular bulk copies could not fetch without leaving the arrays (next to their end only)
       const int got = (min((q1 - sbase + 3) >> 2, (Q - sbase) >> 2)) << 2;
-      for (int j = got + tid; j < q1 - sbase; j += K9_CONSUMERS) B.val[j] = ld_stream(Ai + sbase + j);
       const int gota = (min((nc + 1 + 3) >> 2, (M + 1 - c0) >> 2)) << 2;
-      for (int j = gota + tid; j < nc + 1; j += K9_CONSUMERS) B.ap[j] = __ldg(Ap + c0 + j);
+      by_threads = got < q1 - sbase || gota < nc + 1;
+      if (by_threads) {
+        for (int j = got + tid; j < q1 - sbase; j += K9_CONSUMERS) B.val[j] = ld_stream(Ai + sbase + j);
+        for (int j = gota + tid; j < nc + 1; j += K9_CONSUMERS) B.ap[j] = __ldg(Ap + c0 + j);
+      }
     }
-    consumer_sync();
+    // every thread has seen the stage's mbarrier itself: a CTA barrier is needed only when threads staged
+    // elements for each other, or the previous tile left something to order (CTA-uniform conditions)
+    if (!Mp_prev || by_threads || order_first) consumer_sync();
+    order_first = false;
     const long long base = (long long)q0 - c0;  // Mp[c0]
     const int mis = (int)(base & 3);              // out[] is laid out with the alignment of Mi + base
     int total = 0;
@@ -350,7 +362,19 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
       fence_proxy_async();
       consumer_sync();
       if (tid == 0) S.nlong = 0;
+      order_first = true;  // the reset must be seen before the next walk appends
     }
+    // ---- the compacted tile leaves through the bulk-store path, now: the store overlaps change detection
+    if (total > 0) {
+      int *dst = Mi + base;
+      const int head = min((4 - mis) & 3, total);
+      const int n16 = (total - head) >> 2;
+      const int tail0 = head + 4 * n16;
+      if (tid == 0 && n16 > 0) bulk_s2g(dst + head, B.out + mis + head, (unsigned)n16 * 16u);
+      if (tid >= 32 && tid < 32 + head) st_stream(dst + (tid - 32), B.out[mis + tid - 32]);
+      if (tid >= 64 && tid < 64 + (total - tail0)) st_stream(dst + tail0 + (tid - 64), B.out[mis + tail0 + tid - 64]);
+    }
+    if (tid == 0) bulk_commit();  // one group per tile, even when empty: wait_group counts groups
     if (Mp_prev) {
       // ---- fused change detection (stage b): this tile against the same rows of the snapshot,
       // both sides in shared memory.  Constant row-pointer shift + identical entries <=> no row of
@@ -362,7 +386,8 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
       const int pp0 = S.ppar[0], lenp = S.ppar[2];
       const bool resolved = S.ppar[1] != 0 && nlong == 0 && !wide;
       if (!resolved) {
-        if (tid == 0) { tile_state[t] = -1; atomicAdd(&dcnt->pad1, 1); }
+        if (tid == 0) { tile_state[t] = -1; atomicAdd(&dcnt->pad1, 1); bulk_wait_read1(); }
+        consumer_sync();  // (stands in for the OR-barrier below: orders the drained store before the next tile)
       } else {
         const int pbase = pp0 & ~3, off = pp0 - pbase;
         const int gotp = lenp > 0 ? (min((pp0 + lenp - pbase + 3) >> 2, (nnz_prev - pbase) >> 2)) << 2 : 0;
@@ -386,6 +411,9 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
             for (int i = tid; i < total; i += K9_CONSUMERS) bad |= prev_val(i) != ov[i];
           }
         }
+        // the store of the PREVIOUS tile has drained (this tile's may be pending): its out[] stage is written
+        // again by the next tile, and the OR-barrier below is what orders that for every thread
+        if (tid == 0) bulk_wait_read1();
         if (consumer_any(bad)) {
           int changed_here = 0;
           for (int lb = tid & ~31; lb < nc; lb += K9_CONSUMERS) {
@@ -406,21 +434,9 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
           for (int w = tid; w < (nc + 31) >> 5; w += K9_CONSUMERS) row_bits[(c0 >> 5) + w] = 0u;
         }
       }
-      consumer_sync();
-      if (tid == 0) mbar_arrive(&S.pempty);
+      mbar_arrive(&S.pempty);  // this thread is done with the snapshot stage
     }
-    // ---- the staged input is free again; the compacted tile leaves through the bulk-store path
-    if (tid == 0) mbar_arrive(&S.empty[s]);
-    if (total > 0) {
-      int *dst = Mi + base;
-      const int head = min((4 - mis) & 3, total);
-      const int n16 = (total - head) >> 2;
-      const int tail0 = head + 4 * n16;
-      if (tid == 0 && n16 > 0) bulk_s2g(dst + head, B.out + mis + head, (unsigned)n16 * 16u);
-      if (tid >= 32 && tid < 32 + head) st_stream(dst + (tid - 32), B.out[mis + tid - 32]);
-      if (tid >= 64 && tid < 64 + (total - tail0)) st_stream(dst + tail0 + (tid - 64), B.out[mis + tail0 + tid - 64]);
-    }
-    if (tid == 0) bulk_commit();  // one group per tile, even when empty: wait_group counts groups
+    mbar_arrive(&S.empty[s]);  // ... and with the staged input
   }
   if (tid == 0) {
     bulk_wait_all();
