@@ -16,36 +16,55 @@
 // Proof obligations are unchanged and raise the same flags: strict order, range, one diagonal per
 // column (BUILD_NODIAG -> the chained-scan kernel takes over), structural symmetry by mirror
 // probes plus the global upper/lower count, over-long tiles (BUILD_WIDE -> sample-tiled kernel).
+#include <cstdlib>
+#include <string>
+
 #include "build.cuh"
 #include "tree.cuh"
 
 namespace pb {
 
-constexpr int K9_CONSUMERS = 512;
-constexpr int K9_THREADS = K9_CONSUMERS + 32;  // + producer warp
-constexpr int K9_TILE = 3584;                  // target samples per tile
-constexpr int K9_CAP = 4608;                   // staged samples per tile
-constexpr int K9_TCMAX = 1024;                 // columns per tile, upper bound
+// Tile shape as a compile-time configuration.  CONSUMERS threads walk TC <= TCMAX columns of about TILE
+// samples per tile (CAP staged at most); shared memory per CTA and the resident CTAs per SM follow.
+template <int CONSUMERS_, int TILE_, int CAP_, int TCMAX_, int CTAS_>
+struct K9Cfg {
+  static constexpr int CONSUMERS = CONSUMERS_;
+  static constexpr int THREADS = CONSUMERS_ + 32;  // + producer warp
+  static constexpr int TILE = TILE_;               // target samples per tile
+  static constexpr int CAP = CAP_;                 // staged samples per tile
+  static constexpr int TCMAX = TCMAX_;             // columns per tile, upper bound
+  static constexpr int CTAS = CTAS_;               // resident CTAs per SM
+};
+// Measured at 200^3 (8 M columns, 7 samples per column), fused with change detection, B200: the kernel is bound
+// by its instruction stream, and what a thread spends per TILE (waits, barriers, index arithmetic) weighs as much
+// as the column walk itself, so two columns per thread and tile beat one: 256 consumers 141.9 us (default),
+// 512 consumers + double tiles on one CTA per SM 143.1 us, 512 consumers (one column each) 153.8 us, 192: 151.8 us,
+// 128 (four columns each, too few warps) 163.6 us, 4 x 256-thread CTAs on small tiles 158.3 us, 3 x 384: 155.1 us.
+using K9Half = K9Cfg<256, 3584, 4608, 1024, 2>;    // 105 KB, two CTAs per SM, two columns per thread and tile (default)
+using K9Wide = K9Cfg<512, 3584, 4608, 1024, 2>;    // same tiles, one column per thread and tile
+using K9One2 = K9Cfg<512, 7168, 9216, 1024, 1>;    // 197 KB, one CTA per SM, two columns per thread and tile
+
 constexpr int K9_REG = 8;
 constexpr int K9_LONG = 64;
 constexpr int K9_STAGES = 2;
 
+template <class C>
 struct K9Stage {
-  int val[K9_CAP + 8];  // the 16-byte granular copy may fetch up to 3 samples on either side
-  int out[K9_CAP + 8];
-  int ap[K9_TCMAX + 8];
+  int val[C::CAP + 8];  // the 16-byte granular copy may fetch up to 3 samples on either side
+  int out[C::CAP + 8];
+  int ap[C::TCMAX + 8];
 };
-static_assert(sizeof(K9Stage) % 16 == 0, "bulk copies need 16-byte aligned stage buffers");
+template <class C>
 struct K9Smem {
-  K9Stage st[K9_STAGES];
+  K9Stage<C> st[K9_STAGES];
   unsigned long long full[K9_STAGES], empty[K9_STAGES];
   int par[K9_STAGES][4];  // q0, q1, wide
-  int longs[K9_CAP / K9_LONG + 2];
+  int longs[C::CAP / K9_LONG + 2];
   int nlong;
   // fused change detection: the snapshot's rows of the tile being worked on (single stage: it is
   // fetched while the tile is walked and consumed right after)
-  alignas(16) int pval[K9_CAP + 8];
-  alignas(16) int pap[K9_TCMAX + 8];
+  alignas(16) int pval[C::CAP + 8];
+  alignas(16) int pap[C::TCMAX + 8];
   alignas(8) unsigned long long pfull, pempty;
   int ppar[4];  // Mp_prev[c0], staged?, Mp_prev[c1] - Mp_prev[c0]
 };
@@ -87,9 +106,11 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(K9_CONSUMERS) : "memory"); }
+template <int N>
+__device__ __forceinline__ void consumer_sync_n() { asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory"); }
 // barrier + OR over the consumer threads
-__device__ __forceinline__ bool consumer_any(bool p) {
+template <int N>
+__device__ __forceinline__ bool consumer_any_n(bool p) {
   int r;
   asm volatile(
       "{\n"
@@ -99,7 +120,7 @@ __device__ __forceinline__ bool consumer_any(bool p) {
       "selp.s32 %0, 1, 0, o;\n"
       "}\n"
       : "=r"(r)
-      : "r"((int)p), "n"(K9_CONSUMERS)
+      : "r"((int)p), "n"(N)
       : "memory");
   return r != 0;
 }
@@ -123,13 +144,41 @@ __device__ __forceinline__ bool k9_has_mirror(const int *__restrict__ Ai, const 
   return (in_tile ? val[lo - sbase] : __ldg(Ai + lo)) == c;
 }
 
-__global__ void __launch_bounds__(K9_THREADS, 2)
+// The column walk for a column of exactly L samples without any proof obligation beyond the local
+// ones (steady state: symmetry follows from the changed rows).  No predication on the length: L loads,
+// strict order, range from the two ends, and -- the column being strictly ascending with its diagonal c
+// in it -- output slot i takes r[i] while r[i] < c and r[i + 1] from the diagonal on.  Returns false
+// (nothing written) when a check fails; the general walk then finds out which flag to raise.
+template <int L>
+__device__ __forceinline__ bool k9_walk_fixed(const int *sp, int *op, int c, int M) {
+  int r[L];
+#pragma unroll
+  for (int i = 0; i < L; i++) r[i] = sp[i];
+  bool bad = r[0] < 0 || r[L - 1] >= M;
+  bool has = false;
+#pragma unroll
+  for (int i = 0; i < L; i++) {
+    if (i + 1 < L) bad |= r[i] >= r[i + 1];
+    has |= r[i] == c;
+  }
+  if (bad || !has) return false;
+#pragma unroll
+  for (int i = 0; i + 1 < L; i++) op[i] = r[i] < c ? r[i] : r[i + 1];
+  return true;
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::CTAS)
 build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M, int Q, int TC, int num_tiles,
                   int *__restrict__ Mp, int *__restrict__ Mi, BuildStatus *__restrict__ st, int check_mirror,
                   const int *__restrict__ Mp_prev, const int *__restrict__ Mi_prev, int nnz_prev,
                   int *__restrict__ tile_state, unsigned *__restrict__ row_bits, DetectCounters *__restrict__ dcnt) {
   extern __shared__ __align__(128) unsigned char k9_raw[];
-  K9Smem &S = *reinterpret_cast<K9Smem *>(k9_raw);
+  static_assert(sizeof(K9Stage<C>) % 16 == 0, "bulk copies need 16-byte aligned stage buffers");
+  constexpr int K9_CONSUMERS = C::CONSUMERS, K9_CAP = C::CAP;
+  auto consumer_sync = [] { consumer_sync_n<C::CONSUMERS>(); };
+  auto consumer_any = [](bool p) { return consumer_any_n<C::CONSUMERS>(p); };
+  K9Smem<C> &S = *reinterpret_cast<K9Smem<C> *>(k9_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const bool producer = tid >= K9_CONSUMERS;
 
@@ -197,7 +246,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
   bool order_first = false;  // something of the previous tile must be ordered before this tile's walk
   for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, k++) {
     const int s = k & 1;
-    K9Stage &B = S.st[s];
+    K9Stage<C> &B = S.st[s];
     if (tid == 0) {
       // out[s] is written again in this tile: the store that last used it must have drained its smem reads.
       // Fused mode waits for that before the OR-barrier of the previous tile instead (no barrier here).
@@ -242,7 +291,21 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
         if (o0 < 0 || vs < q0 || ve > q1) { flags |= BUILD_NODIAG; continue; }
         const int *sp = B.val + (vs - sbase);
         int *op = B.out + mis + o0;
-        if (len <= K9_REG) {
+        bool walked = false;
+        if (!check_mirror) {
+          // threads of a warp mostly agree on the length (regular meshes): a branch per length, not a vote
+          switch (len) {
+            case 3: walked = k9_walk_fixed<3>(sp, op, c, M); break;
+            case 4: walked = k9_walk_fixed<4>(sp, op, c, M); break;
+            case 5: walked = k9_walk_fixed<5>(sp, op, c, M); break;
+            case 6: walked = k9_walk_fixed<6>(sp, op, c, M); break;
+            case 7: walked = k9_walk_fixed<7>(sp, op, c, M); break;
+            case 8: walked = k9_walk_fixed<8>(sp, op, c, M); break;
+            default: break;
+          }
+        }
+        if (walked) {
+        } else if (len <= K9_REG) {
           int r[K9_REG];
 #pragma unroll
           for (int i = 0; i < K9_REG; i++) r[i] = i < len ? sp[i] : 0x7fffffff;
@@ -404,7 +467,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
 #pragma unroll 1
             for (int lc = tid; lc <= nc; lc += K9_CONSUMERS) bad |= (B.ap[lc] - lc) - S.pap[lc] != want;
             const int *pv = S.pval + off;
-#pragma unroll 2
+#pragma unroll 4
             for (int i = tid; i < total; i += K9_CONSUMERS) bad |= pv[i] != ov[i];
           } else {
             for (int lc = tid; lc <= nc; lc += K9_CONSUMERS) bad |= (B.ap[lc] - (c0 + lc)) - prev_ptr(lc) != shift;
@@ -459,13 +522,33 @@ int build_pipe_supported(const BuildArgs &a) {
                          reinterpret_cast<uintptr_t>(a.Mi)) & 15) == 0 && a.M > 0 && a.Q > 0;
 }
 
-int build_pipe_tile_cols(const BuildArgs &a) {
+// Tile shape: PARTH_B200_PIPE = half (default) | wide | one2, read once (kept for experiments on other matrix shapes)
+static int pipe_variant() {
+  static const int v = [] {
+    const char *e = std::getenv("PARTH_B200_PIPE");
+    if (!e) return 0;
+    const std::string x(e);
+    return x == "wide" ? 1 : x == "one2" ? 2 : 0;
+  }();
+  return v;
+}
+
+template <class C>
+static int tile_cols_of(const BuildArgs &a) {
   // columns per tile from the average column length, a multiple of 32 so that Ap slices stay aligned
-  long long tc = (long long)K9_TILE * a.M / (a.Q > 0 ? a.Q : 1);
+  long long tc = (long long)C::TILE * a.M / (a.Q > 0 ? a.Q : 1);
   tc = (tc / 32) * 32;
   if (tc < 32) tc = 32;
-  if (tc > K9_TCMAX) tc = K9_TCMAX;
+  if (tc > C::TCMAX) tc = C::TCMAX;
   return (int)tc;
+}
+
+int build_pipe_tile_cols(const BuildArgs &a) {
+  switch (pipe_variant()) {
+    case 1: return tile_cols_of<K9Wide>(a);
+    case 2: return tile_cols_of<K9One2>(a);
+    default: return tile_cols_of<K9Half>(a);
+  }
 }
 
 int build_pipe_num_tiles(const BuildArgs &a) {
@@ -473,8 +556,19 @@ int build_pipe_num_tiles(const BuildArgs &a) {
   return (a.M + TC - 1) / TC;
 }
 
+template <class C>
+static void launch_cfg(const BuildArgs &a, int TC, int num_tiles, bool fused, int num_sms, cudaStream_t s) {
+  PB_CUDA(cudaFuncSetAttribute(build_pipe_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K9Smem<C>)));
+  const int grid = num_tiles < C::CTAS * num_sms ? num_tiles : C::CTAS * num_sms;
+  if (a.ev_a) cudaEventRecord(a.ev_a, s);
+  build_pipe_kernel<C><<<grid, C::THREADS, sizeof(K9Smem<C>), s>>>(a.Ap, a.Ai, a.M, a.Q, TC, num_tiles, a.Mp, a.Mi, a.status,
+                                                                  a.check_mirror, fused ? a.Mp_prev : nullptr,
+                                                                  fused ? a.Mi_prev : nullptr, a.nnz_prev,
+                                                                  fused ? a.tile_dirty : nullptr, a.row_bits, a.dcnt);
+  if (a.ev_b) cudaEventRecord(a.ev_b, s);
+}
+
 int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s) {
-  PB_CUDA(cudaFuncSetAttribute(build_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K9Smem)));
   const int TC = build_pipe_tile_cols(a);
   const int num_tiles = (a.M + TC - 1) / TC;
   const bool fused = a.Mp_prev && a.Mi_prev && a.tile_dirty && a.row_bits && a.dcnt;
@@ -487,13 +581,11 @@ int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s) {
     PB_CUDA(cudaMemsetAsync(a.status, 0, sizeof(BuildStatus), s));
     if (fused) PB_CUDA(cudaMemsetAsync(a.dcnt, 0, sizeof(DetectCounters), s));
   }
-  const int grid = num_tiles < 2 * num_sms ? num_tiles : 2 * num_sms;
-  if (a.ev_a) cudaEventRecord(a.ev_a, s);
-  build_pipe_kernel<<<grid, K9_THREADS, sizeof(K9Smem), s>>>(a.Ap, a.Ai, a.M, a.Q, TC, num_tiles, a.Mp, a.Mi, a.status,
-                                                            a.check_mirror, fused ? a.Mp_prev : nullptr,
-                                                            fused ? a.Mi_prev : nullptr, a.nnz_prev,
-                                                            fused ? a.tile_dirty : nullptr, a.row_bits, a.dcnt);
-  if (a.ev_b) cudaEventRecord(a.ev_b, s);
+  switch (pipe_variant()) {
+    case 1: launch_cfg<K9Wide>(a, TC, num_tiles, fused, num_sms, s); break;
+    case 2: launch_cfg<K9One2>(a, TC, num_tiles, fused, num_sms, s); break;
+    default: launch_cfg<K9Half>(a, TC, num_tiles, fused, num_sms, s); break;
+  }
   PB_CUDA(cudaGetLastError());
   return 1;
 }
