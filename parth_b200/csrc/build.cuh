@@ -33,6 +33,7 @@ struct BuildArgs {
   int *tile_dirty;
   unsigned *row_bits;
   struct DetectCounters *dcnt;
+  int pipe_cfg;  // pipeline kernel: tile shape (graph_build_pipe.cu)
 };
 
 int build_filter_tiles(int M, int Q);
@@ -43,6 +44,7 @@ int build_cols_launch(const BuildArgs &a, bool spec, cudaStream_t s);
 int sym_proof_csr_launch(const int *Mp, const int *Mi, int M, int nnz_cap, BuildStatus *st, cudaStream_t s);
 // graph_build_pipe.cu (dim == 1, aligned arrays): persistent bulk-copy pipeline, closed-form offsets
 int build_pipe_supported(const BuildArgs &a);
+int build_pipe_default_cfg();
 int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s);
 int build_pipe_tile_cols(const BuildArgs &a);  // columns per tile of the pipeline kernel
 int build_pipe_num_tiles(const BuildArgs &a);

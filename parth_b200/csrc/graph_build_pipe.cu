@@ -26,8 +26,9 @@ namespace pb {
 
 // Tile shape as a compile-time configuration.  CONSUMERS threads walk TC <= TCMAX columns of about TILE
 // samples per tile (CAP staged at most); shared memory per CTA and the resident CTAs per SM follow.
-template <int CONSUMERS_, int TILE_, int CAP_, int TCMAX_, int CTAS_>
+template <int CONSUMERS_, int TILE_, int CAP_, int TCMAX_, int CTAS_, int OUTS_ = 2>
 struct K9Cfg {
+  static constexpr int OUTS = OUTS_;               // output staging buffers (1: the store drains before the next walk)
   static constexpr int CONSUMERS = CONSUMERS_;
   static constexpr int THREADS = CONSUMERS_ + 32;  // + producer warp
   static constexpr int TILE = TILE_;               // target samples per tile
@@ -40,6 +41,7 @@ struct K9Cfg {
 // as the column walk itself, so two columns per thread and tile beat one: 256 consumers 141.9 us (default),
 // 512 consumers + double tiles on one CTA per SM 143.1 us, 512 consumers (one column each) 153.8 us, 192: 151.8 us,
 // 128 (four columns each, too few warps) 163.6 us, 4 x 256-thread CTAs on small tiles 158.3 us, 3 x 384: 155.1 us.
+using K9Tri = K9Cfg<256, 3584, 4096, 512, 3, 1>;   // 72.5 KB, three CTAs per SM: one output buffer, 14 % tile headroom
 using K9Half = K9Cfg<256, 3584, 4608, 1024, 2>;    // 105 KB, two CTAs per SM, two columns per thread and tile (default)
 using K9Wide = K9Cfg<512, 3584, 4608, 1024, 2>;    // same tiles, one column per thread and tile
 using K9One2 = K9Cfg<512, 7168, 9216, 1024, 1>;    // 197 KB, one CTA per SM, two columns per thread and tile
@@ -51,12 +53,12 @@ constexpr int K9_STAGES = 2;
 template <class C>
 struct K9Stage {
   int val[C::CAP + 8];  // the 16-byte granular copy may fetch up to 3 samples on either side
-  int out[C::CAP + 8];
   int ap[C::TCMAX + 8];
 };
 template <class C>
 struct K9Smem {
   K9Stage<C> st[K9_STAGES];
+  alignas(16) int out[C::OUTS][C::CAP + 8];
   unsigned long long full[K9_STAGES], empty[K9_STAGES];
   int par[K9_STAGES][4];  // q0, q1, wide
   int longs[C::CAP / K9_LONG + 2];
@@ -103,7 +105,8 @@ __device__ __forceinline__ void bulk_s2g(void *dst, const void *src, unsigned by
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 template <int N>
@@ -177,6 +180,8 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
   static_assert(sizeof(K9Stage<C>) % 16 == 0, "bulk copies need 16-byte aligned stage buffers");
   constexpr int K9_CONSUMERS = C::CONSUMERS, K9_CAP = C::CAP;
   auto consumer_sync = [] { consumer_sync_n<C::CONSUMERS>(); };
+  // the store that last used the output buffer about to be written has drained its shared-memory reads
+  auto bulk_wait_read1 = [] { bulk_wait_read<C::OUTS - 1>(); };
   auto consumer_any = [](bool p) { return consumer_any_n<C::CONSUMERS>(p); };
   K9Smem<C> &S = *reinterpret_cast<K9Smem<C> *>(k9_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -247,6 +252,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
   for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, k++) {
     const int s = k & 1;
     K9Stage<C> &B = S.st[s];
+    int *const Bout = S.out[k % C::OUTS];
     if (tid == 0) {
       // out[s] is written again in this tile: the store that last used it must have drained its smem reads.
       // Fused mode waits for that before the OR-barrier of the previous tile instead (no barrier here).
@@ -290,7 +296,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
         const int o0 = (vs - q0) - lc;
         if (o0 < 0 || vs < q0 || ve > q1) { flags |= BUILD_NODIAG; continue; }
         const int *sp = B.val + (vs - sbase);
-        int *op = B.out + mis + o0;
+        int *op = Bout + mis + o0;
         bool walked = false;
         if (!check_mirror) {
           // threads of a warp mostly agree on the length (regular meshes): a branch per length, not a vote
@@ -389,7 +395,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
         const int o0 = (vs - q0) - lc;
         if (o0 < 0 || vs < q0 || ve > q1) { flags |= BUILD_NODIAG; continue; }
         const int *sp = B.val + (vs - sbase);
-        int *op = B.out + mis + o0;
+        int *op = Bout + mis + o0;
         int dp = -1, low = 0;
         unsigned f = 0;
         for (int i0 = 0; i0 < len; i0 += 32) {
@@ -433,9 +439,9 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
       const int head = min((4 - mis) & 3, total);
       const int n16 = (total - head) >> 2;
       const int tail0 = head + 4 * n16;
-      if (tid == 0 && n16 > 0) bulk_s2g(dst + head, B.out + mis + head, (unsigned)n16 * 16u);
-      if (tid >= 32 && tid < 32 + head) st_stream(dst + (tid - 32), B.out[mis + tid - 32]);
-      if (tid >= 64 && tid < 64 + (total - tail0)) st_stream(dst + tail0 + (tid - 64), B.out[mis + tail0 + tid - 64]);
+      if (tid == 0 && n16 > 0) bulk_s2g(dst + head, Bout + mis + head, (unsigned)n16 * 16u);
+      if (tid >= 32 && tid < 32 + head) st_stream(dst + (tid - 32), Bout[mis + tid - 32]);
+      if (tid >= 64 && tid < 64 + (total - tail0)) st_stream(dst + tail0 + (tid - 64), Bout[mis + tail0 + tid - 64]);
     }
     if (tid == 0) bulk_commit();  // one group per tile, even when empty: wait_group counts groups
     if (Mp_prev) {
@@ -457,7 +463,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
         const int gotpa = (min((nc + 1 + 3) >> 2, (M + 1 - c0) >> 2)) << 2;
         auto prev_ptr = [&](int lc) { return lc < gotpa ? S.pap[lc] : __ldg(Mp_prev + c0 + lc); };
         auto prev_val = [&](int j) { return off + j < gotp ? S.pval[off + j] : __ldg(Mi_prev + pp0 + j); };
-        const int *ov = B.out + mis;
+        const int *ov = Bout + mis;
         bool bad = lenp != total;
         if (!bad) {
           const int shift = (int)base - pp0;
@@ -493,6 +499,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
           }
           if (lane == 0 && changed_here) { atomicAdd(&dcnt->changed_rows, changed_here); atomicAdd(&tile_state[t], changed_here); }
           if (tid == 0) atomicAdd(&dcnt->dirty_tiles, 1);
+          if (C::OUTS == 1) consumer_sync();  // the row compare read the one output buffer the next walk overwrites
         } else {
           for (int w = tid; w < (nc + 31) >> 5; w += K9_CONSUMERS) row_bits[(c0 >> 5) + w] = 0u;
         }
@@ -522,13 +529,15 @@ int build_pipe_supported(const BuildArgs &a) {
                          reinterpret_cast<uintptr_t>(a.Mi)) & 15) == 0 && a.M > 0 && a.Q > 0;
 }
 
-// Tile shape: PARTH_B200_PIPE = half (default) | wide | one2, read once (kept for experiments on other matrix shapes)
-static int pipe_variant() {
+// Tile shape (BuildArgs::pipe_cfg): 0 = three compact CTAs per SM (default), 1 = two CTAs with full head-room (taken
+// when a tile of the compact shape overflows), 2 / 3 = experiments.  PARTH_B200_PIPE = tri | half | wide | one2 sets
+// the starting shape of new handles.
+int build_pipe_default_cfg() {
   static const int v = [] {
     const char *e = std::getenv("PARTH_B200_PIPE");
     if (!e) return 0;
     const std::string x(e);
-    return x == "wide" ? 1 : x == "one2" ? 2 : 0;
+    return x == "half" ? 1 : x == "wide" ? 2 : x == "one2" ? 3 : 0;
   }();
   return v;
 }
@@ -544,10 +553,11 @@ static int tile_cols_of(const BuildArgs &a) {
 }
 
 int build_pipe_tile_cols(const BuildArgs &a) {
-  switch (pipe_variant()) {
-    case 1: return tile_cols_of<K9Wide>(a);
-    case 2: return tile_cols_of<K9One2>(a);
-    default: return tile_cols_of<K9Half>(a);
+  switch (a.pipe_cfg) {
+    case 1: return tile_cols_of<K9Half>(a);
+    case 2: return tile_cols_of<K9Wide>(a);
+    case 3: return tile_cols_of<K9One2>(a);
+    default: return tile_cols_of<K9Tri>(a);
   }
 }
 
@@ -581,10 +591,11 @@ int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s) {
     PB_CUDA(cudaMemsetAsync(a.status, 0, sizeof(BuildStatus), s));
     if (fused) PB_CUDA(cudaMemsetAsync(a.dcnt, 0, sizeof(DetectCounters), s));
   }
-  switch (pipe_variant()) {
-    case 1: launch_cfg<K9Wide>(a, TC, num_tiles, fused, num_sms, s); break;
-    case 2: launch_cfg<K9One2>(a, TC, num_tiles, fused, num_sms, s); break;
-    default: launch_cfg<K9Half>(a, TC, num_tiles, fused, num_sms, s); break;
+  switch (a.pipe_cfg) {
+    case 1: launch_cfg<K9Half>(a, TC, num_tiles, fused, num_sms, s); break;
+    case 2: launch_cfg<K9Wide>(a, TC, num_tiles, fused, num_sms, s); break;
+    case 3: launch_cfg<K9One2>(a, TC, num_tiles, fused, num_sms, s); break;
+    default: launch_cfg<K9Tri>(a, TC, num_tiles, fused, num_sms, s); break;
   }
   PB_CUDA(cudaGetLastError());
   return 1;

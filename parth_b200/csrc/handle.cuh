@@ -31,6 +31,7 @@ struct parth_b200 {
   int relocate_lvl = 2, lag_lvl = 5, verbose = 1, sim_dim = 1;
   int coarse_policy = PARTH_B200_COARSE_REPAIR, assume_symmetric = 0;
   int build_mode_n = 0;  // dim > 1: 0 closed-form offsets (column-aligned), 1 sample-tiled chained scan
+  int pipe_cfg = pb::build_pipe_default_cfg();  // pipeline kernel tile shape: 0 compact (3 CTAs / SM), 1 after a tile overflowed it
   int build_mode = 0;  // dim == 1 filter kernel that proved itself last time: 0 closed-form offsets, 1 chained scan, 2 sample-tiled
   int rank = 0, world = 1;
   std::vector<int> xchg_nodes, xchg_owner;  // sharded mode: plan of the last update

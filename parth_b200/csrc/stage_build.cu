@@ -202,6 +202,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
 
   BuildArgs a{};
   a.Ap = dAp; a.Ai = dAi; a.V = h.V.p; a.dim = dim; a.M = M; a.Q = Q;
+  a.pipe_cfg = h.pipe_cfg;
   // Incremental proof: when the snapshot graph is proven symmetric and has the same vertex set,
   // symmetry of the new graph follows from the rows that changed (sym_check_rows_kernel), so the
   // filter kernel skips its mirror probes; the row diff it needs is the one change detection wants
@@ -326,6 +327,10 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
       // remember the variant that works so that steady-state updates launch it directly
       const unsigned only = st.flags & ~(BUILD_NODIAG | BUILD_WIDE);
       if (h.build_mode == 0 && (st.flags & BUILD_NODIAG) && !only) { h.build_mode = 1; continue; }
+      if ((st.flags & BUILD_WIDE) && !only && h.build_mode == 0 && h.pipe_cfg == 0 && build_pipe_supported(a)) {
+        h.pipe_cfg = a.pipe_cfg = 1;  // a tile overflowed the compact shape: the roomier one takes over for this handle
+        continue;
+      }
       if ((st.flags & BUILD_WIDE) && !only) { h.build_mode = 2; continue; }
     } else if (dim > 1 && h.build_mode_n == 0) {
       const unsigned only = st.flags & ~(BUILD_NODIAG | BUILD_WIDE);
