@@ -6,16 +6,20 @@
 // one sample (the diagonal) removed per column, so Mp[c] = Ap[c] - c in closed form and tiles are
 // independent.  What changes is how the bytes move:
 //   * tiles are fixed runs of TC columns (TC chosen on the host from the average column length);
-//   * a persistent CTA (2 per SM) walks its tiles with a two-stage ring: a producer warp issues
-//     cp.async.bulk (TMA engine, SASS UBLKCP) copies of the NEXT tile's Ai window and Ap slice
-//     straight into shared memory and signals an mbarrier, while 512 consumer threads work on the
-//     current tile -- DRAM latency is overlapped instead of exposed per tile, and no register or
-//     LSU instruction is spent on staging;
+//   * a persistent CTA (3 per SM in the default shape) walks its tiles with a two-stage ring: a
+//     producer warp issues cp.async.bulk (TMA engine, SASS UBLKCP) copies of the NEXT tile's Ai
+//     window and Ap slice straight into shared memory and signals an mbarrier, while 256 consumer
+//     threads work on the current tile (two columns each) -- DRAM latency is overlapped instead of
+//     exposed per tile, and no register or LSU instruction is spent on staging;
 //   * the compacted tile leaves through one bulk shared->global store (plus <= 6 scalar stores for
-//     the unaligned head and tail), again off the LSU path.
+//     the unaligned head and tail), again off the LSU path, issued before the tile is compared with
+//     the snapshot so that the store overlaps the comparison;
+//   * stages are handed back by per-thread mbarrier arrivals; a tile costs two CTA barriers (after the
+//     walk, and the OR-reduction of the comparison).
 // Proof obligations are unchanged and raise the same flags: strict order, range, one diagonal per
 // column (BUILD_NODIAG -> the chained-scan kernel takes over), structural symmetry by mirror
-// probes plus the global upper/lower count, over-long tiles (BUILD_WIDE -> sample-tiled kernel).
+// probes plus the global upper/lower count, over-long tiles (BUILD_WIDE -> the roomier tile shape,
+// then the sample-tiled kernel).
 #include <cstdlib>
 #include <string>
 
