@@ -17,6 +17,8 @@
  *     host callback (setDecomposer) or the built-in BFS level-structure dissection builds the tree,
  *     and every node is ordered by the device AMD kernel.
  *   - dirty COARSE nodes are repaired on the device instead of re-dissected (setCoarsePolicy).
+ *   - ReorderingType::MORTON_CODE works (the reference prints "Morton code is not implemented yet",
+ *     HMD.cpp:82-83) once setCoordinates has supplied one point per DOF.
  */
 #ifndef PARTH_B200_PARTHAPI_H
 #define PARTH_B200_PARTHAPI_H
@@ -225,6 +227,20 @@ public:
   void setCoarsePolicy(int policy) { check(parth_b200_set_coarse_policy(h_, policy)); }
   void setAssumeSymmetric(bool on) { check(parth_b200_set_assume_symmetric(h_, on ? 1 : 0)); }
   void setDecomposer(parth_b200_decomposer fn, void *user) { check(parth_b200_set_decomposer(h_, fn, user)); }
+
+  /* ReorderingType::MORTON_CODE: one 3-D point per current mesh DOF (point i, axis a at
+   * xyz[i * point_stride + a * comp_stride]; an Eigen column-major V of n rows is (1, n)).  Fine nodes are then
+   * ordered by ascending (Morton key, DOF id); mortonOrder returns the global order, perm[new] = old. */
+  void setCoordinates(const double *xyz, int n, long long point_stride = 3, long long comp_stride = 1, int bits = 21) {
+    check(parth_b200_set_coordinates(h_, xyz, n, point_stride, comp_stride, bits));
+  }
+  void mortonOrder(std::vector<int> &perm) {
+    const int *d = nullptr;
+    int n = 0;
+    check(parth_b200_morton_order_dev(h_, &d, &n));
+    perm.resize((size_t)n);
+    if (n > 0) check(parth_b200_morton_order(h_, perm.data(), n));
+  }
 
   /* nnz(L) of P*A*P' for the current graph and permutation (NULL: current mesh_perm); what the
    * reference ecosystem asks CHOLMOD for (src/utils/ParthTestUtils.cpp:15-59) */

@@ -149,6 +149,22 @@ int parth_b200_stage_submesh(parth_b200 *h, int node, int coarse, int *n, int *n
 int parth_b200_amd_batch(parth_b200 *h, int count, const int *graph_ptr /*count+1, in vertices*/,
                          const int *Mp /*per graph n+1, concatenated*/, const int *Mi, int *perm);
 
+/* ReorderingType MORTON_CODE.  The reference declares the type (ParthTypes.h:11) but HMD::Permute only prints
+ * "Morton code is not implemented yet" (HMD.cpp:82-83) and ParthAPI has no coordinate input, so these entry
+ * points are an extension: set_coordinates takes one 3-D point per current DOF (point i, axis a at
+ * xyz[i * point_stride + a * comp_stride]: 3, 1 for interleaved points; 1, n for an Eigen column-major V),
+ * quantises each axis of the bounding box to `bits` (1..21) bits, interleaves (x most significant) and sorts
+ * ascending by (key, point id).  With reorder_type MORTON_CODE the fine nodes of computePermutation /
+ * stage_permute_fine are then ordered by that global rank; without coordinates the request fails with
+ * PARTH_B200_ERR_ARG.  morton_order returns the global order (perm[new] = old), morton_keys the sorted keys. */
+int parth_b200_set_coordinates(parth_b200 *h, const double *xyz, int n, long long point_stride,
+                               long long comp_stride, int bits);
+int parth_b200_set_coordinates_dev(parth_b200 *h, const double *dxyz, int n, long long point_stride,
+                                   long long comp_stride, int bits);
+int parth_b200_morton_order(parth_b200 *h, int *perm, int cap);
+int parth_b200_morton_order_dev(parth_b200 *h, const int **dperm, int *n);
+int parth_b200_morton_keys(parth_b200 *h, unsigned long long *keys_sorted, int cap);
+
 /* stage (d): elimination tree, column counts and nnz(L) of P*A*P' for the current mesh graph and
  * permutation perm[new]=old (NULL: current mesh_perm).  Replaces cholmod_analyze_p as used in
  * reference src/utils/ParthTestUtils.cpp:15-59; etree as src/utils/etree.cpp:39-115. */
@@ -174,6 +190,8 @@ typedef struct {
   double proof_kernel_ms;                 /* dim > 1: full symmetry proof on the compacted graph (0 when the proof was incremental or in-kernel) */
   int build_deferred;                     /* 1 = the last set_matrix_dev returned with its work in flight and was completed by the next call */
   int expand_speculative;                 /* 1 = the last compute_permutation_dev expanded before the flags were read and the result stood */
+  int morton_passes;                      /* radix passes the last set_coordinates ran (digits that are constant over all keys are skipped) */
+  double morton_ms;                       /* last set_coordinates: bounding box + keys + radix sort + rank */
 } parth_b200_stats;
 int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out);
 int parth_b200_synchronize(parth_b200 *h);

@@ -31,7 +31,7 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("integrate_passes", C.c_int), ("integrate_sweeps", C.c_int),
         ("symbolic_etree_ms", C.c_double), ("diff_kernel_ms", C.c_double), ("symbolic_path", C.c_int),
         ("build_fused_detect", C.c_int), ("proof_kernel_ms", C.c_double), ("build_deferred", C.c_int),
-        ("expand_speculative", C.c_int)]
+        ("expand_speculative", C.c_int), ("morton_passes", C.c_int), ("morton_ms", C.c_double)]
 
 
 DECOMPOSER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, _ip, _ip, C.c_int, C.c_int, _ip, _ip, _ip, _ip)
@@ -76,6 +76,11 @@ SYMBOLS = {
     "parth_b200_stage_permute_fine": (C.c_int, [_vp, _ip, C.c_int]),
     "parth_b200_stage_submesh": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip, _ip, _ip, _ip]),
     "parth_b200_amd_batch": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _ip]),
+    "parth_b200_set_coordinates": (C.c_int, [_vp, _vp, C.c_int, C.c_longlong, C.c_longlong, C.c_int]),
+    "parth_b200_set_coordinates_dev": (C.c_int, [_vp, _vp, C.c_int, C.c_longlong, C.c_longlong, C.c_int]),
+    "parth_b200_morton_order": (C.c_int, [_vp, _ip, C.c_int]),
+    "parth_b200_morton_order_dev": (C.c_int, [_vp, C.POINTER(_vp), _ip]),
+    "parth_b200_morton_keys": (C.c_int, [_vp, _vp, C.c_int]),
     "parth_b200_symbolic": (C.c_int, [_vp, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
     "parth_b200_symbolic_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
     "parth_b200_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
@@ -438,6 +443,46 @@ class ParthAPI:
         perm = np.empty(max(int(gp[-1]), 1), np.int32)
         self._check(self.lib.parth_b200_amd_batch(self.h, len(graphs), _p(gp), _p(Mp), _p(Mi), _p(perm)))
         return [perm[gp[i]:gp[i + 1]].copy() for i in range(len(graphs))]
+
+    # ---- ReorderingType MORTON_CODE (extension: the reference leaves it unimplemented, HMD.cpp:82-83)
+    def setCoordinates(self, xyz, bits=21):
+        """xyz: float64 array [n, 3] (C order: interleaved points; Fortran order: an Eigen column-major V)"""
+        xyz = np.asarray(xyz, dtype=np.float64)
+        if xyz.ndim != 2 or xyz.shape[1] != 3:
+            raise ValueError("setCoordinates: xyz must be [n, 3]")
+        n = xyz.shape[0]
+        if xyz.flags.f_contiguous and not xyz.flags.c_contiguous:
+            ps, cs = 1, n
+        else:
+            xyz = np.ascontiguousarray(xyz)
+            ps, cs = 3, 1
+        self._xyz_keep = xyz
+        self._check(self.lib.parth_b200_set_coordinates(self.h, C.c_void_p(xyz.ctypes.data), n, ps, cs, int(bits)))
+
+    def setCoordinatesDev(self, dxyz_ptr, n, point_stride=3, comp_stride=1, bits=21):
+        self._check(self.lib.parth_b200_set_coordinates_dev(self.h, C.c_void_p(dxyz_ptr), int(n), int(point_stride),
+                                                            int(comp_stride), int(bits)))
+
+    def mortonOrder(self):
+        """global Morton order of the points given to setCoordinates: perm[new] = old"""
+        d, n = C.c_void_p(), C.c_int()
+        self._check(self.lib.parth_b200_morton_order_dev(self.h, C.byref(d), C.byref(n)))
+        perm = np.empty(max(n.value, 1), np.int32)
+        self._check(self.lib.parth_b200_morton_order(self.h, _p(perm), len(perm)))
+        return perm[:n.value]
+
+    def mortonOrderDev(self):
+        d, n = C.c_void_p(), C.c_int()
+        self._check(self.lib.parth_b200_morton_order_dev(self.h, C.byref(d), C.byref(n)))
+        return d.value, n.value
+
+    def mortonKeys(self):
+        """the sorted keys (same order as mortonOrder)"""
+        d, n = C.c_void_p(), C.c_int()
+        self._check(self.lib.parth_b200_morton_order_dev(self.h, C.byref(d), C.byref(n)))
+        keys = np.empty(max(n.value, 1), np.uint64)
+        self._check(self.lib.parth_b200_morton_keys(self.h, C.c_void_p(keys.ctypes.data), len(keys)))
+        return keys[:n.value]
 
     def symbolicDev(self, dperm_ptr, dparent_ptr, dcolcount_ptr):
         """stage (d) with device pointers (0 = NULL): returns nnz(L); etree / column counts stay on the device"""

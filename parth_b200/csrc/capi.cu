@@ -1,4 +1,5 @@
 // parth_b200/csrc/capi.cu -- extern "C" boundary (include/parth_b200.h) and host orchestration.
+#include <algorithm>
 #include <cstring>
 #include <iostream>
 
@@ -528,6 +529,58 @@ int parth_b200_amd_batch(parth_b200 *h, int count, const int *graph_ptr, const i
   PB_API_BEGIN
   if (count < 0 || !graph_ptr || !Mp || !Mi || !perm) throw StatusError(PARTH_B200_ERR_ARG, "amd_batch: bad argument");
   stage_amd_batch(*h, count, graph_ptr, Mp, Mi, perm);
+  PB_API_END
+}
+
+// ------------------------------------------------------------------ ReorderingType MORTON_CODE (extension)
+int parth_b200_set_coordinates_dev(parth_b200 *h, const double *dxyz, int n, long long point_stride,
+                                   long long comp_stride, int bits) {
+  PB_API_BEGIN
+  stage_set_coordinates(*h, dxyz, n, point_stride, comp_stride, bits);
+  PB_API_END
+}
+
+int parth_b200_set_coordinates(parth_b200 *h, const double *xyz, int n, long long point_stride,
+                               long long comp_stride, int bits) {
+  PB_API_BEGIN
+  if (n < 0 || (n > 0 && !xyz) || point_stride < 0 || comp_stride < 0)
+    throw StatusError(PARTH_B200_ERR_ARG, "set_coordinates: bad argument");
+  // extent of the strided array in doubles
+  const size_t span = n > 0 ? (size_t)(n - 1) * (size_t)point_stride + 2 * (size_t)comp_stride + 1 : 0;
+  h->m_xyz.reserve(std::max<size_t>(span, 1), h->stream);
+  if (span) PB_CUDA(cudaMemcpyAsync(h->m_xyz.p, xyz, sizeof(double) * span, cudaMemcpyHostToDevice, h->stream));
+  h->stats.h2d_bytes = (long long)(sizeof(double) * span);
+  stage_set_coordinates(*h, h->m_xyz.p, n, point_stride, comp_stride, bits);
+  resolve_timers(*h);
+  PB_API_END
+}
+
+int parth_b200_morton_order_dev(parth_b200 *h, const int **dperm, int *n) {
+  if (!h || !dperm || !n) return PARTH_B200_ERR_ARG;
+  *dperm = h->morton_n > 0 ? (h->morton_cur ? h->m_v1.p : h->m_v0.p) : nullptr;
+  *n = h->morton_n;
+  return PARTH_B200_OK;
+}
+
+int parth_b200_morton_order(parth_b200 *h, int *perm, int cap) {
+  PB_API_BEGIN
+  if (!perm || cap < h->morton_n) throw StatusError(PARTH_B200_ERR_ARG, "morton_order: buffer too small");
+  if (h->morton_n > 0) {
+    PB_CUDA(cudaMemcpyAsync(perm, h->morton_cur ? h->m_v1.p : h->m_v0.p, sizeof(int) * (size_t)h->morton_n,
+                            cudaMemcpyDeviceToHost, h->stream));
+    PB_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  PB_API_END
+}
+
+int parth_b200_morton_keys(parth_b200 *h, unsigned long long *keys_sorted, int cap) {
+  PB_API_BEGIN
+  if (!keys_sorted || cap < h->morton_n) throw StatusError(PARTH_B200_ERR_ARG, "morton_keys: buffer too small");
+  if (h->morton_n > 0) {
+    PB_CUDA(cudaMemcpyAsync(keys_sorted, h->morton_cur ? h->m_k1.p : h->m_k0.p,
+                            sizeof(unsigned long long) * (size_t)h->morton_n, cudaMemcpyDeviceToHost, h->stream));
+    PB_CUDA(cudaStreamSynchronize(h->stream));
+  }
   PB_API_END
 }
 

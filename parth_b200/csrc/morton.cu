@@ -1,0 +1,351 @@
+// parth_b200/csrc/morton.cu -- ReorderingType MORTON_CODE (reference src/Parth/include/ParthTypes.h:11).
+//
+// The reference declares the ordering type but does not implement it: HMD::Permute prints "Morton code is
+// not implemented yet" and returns with perm unset (src/Parth/HMD.cpp:82-83), and ParthAPI has no coordinate
+// input.  BASELINE config 4 nevertheless names the path, so the device implements the textbook definition
+// (restated on the CPU in oracle/morton_oracle.py, PARITY UNPINNED: no reference implementation exists):
+//   * bounding box of the points, each axis quantised to `bits` bits (<= 21) in IEEE double arithmetic with
+//     explicitly rounded operations (no FMA contraction, so numpy reproduces the keys bit for bit);
+//   * key = bit interleave, x most significant; order = ascending (key, point id);
+//   * a fine separator-tree node is ordered by the global Morton rank of its DOFs (HMD::Permute's contract:
+//     perm[new] = old local id).
+// The sort is a hand-written stable LSD radix sort, 8 bits per pass, three launches per pass:
+//   radix_count_kernel    per-tile digit histogram (digit-major layout: one exclusive scan yields every base)
+//   exclusive_scan<0>     the device-wide single-pass scan of scan.cuh
+//   radix_scatter_kernel  ballot-ranked warps (8 votes give the peer mask of a lane's digit: match.any costs 11
+//                         cycles per distinct value on B200, 30 distinct values in a warp of random digits),
+//                         tile sorted in shared memory first so the global stores leave in digit runs
+// Passes whose digit is constant over all keys (known from the OR / AND of the keys, folded into the key
+// kernel) are skipped.  HBM bound: per pass 8n bytes (count) + 24n bytes (scatter), keys 24n + 12n.
+#include <algorithm>
+#include <cstdint>
+
+#include "reorder.cuh"
+#include "scan.cuh"
+#include "stages.cuh"
+
+namespace pb {
+
+namespace {
+
+constexpr int kRsThreads = 256;
+constexpr int kRsItems = 16;                     // keys per thread and tile
+constexpr int kRsTile = kRsThreads * kRsItems;   // 4096 keys
+constexpr int kRsWarps = kRsThreads / 32;
+constexpr int kRsChunk = kRsTile / kRsWarps;     // consecutive keys one warp ranks
+
+typedef unsigned long long u64;
+
+// order-preserving map double -> u64 (for atomicMin / atomicMax on the bounding box)
+__device__ __forceinline__ u64 ord_of(double x) {
+  const u64 u = (u64)__double_as_longlong(x);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double ord_back(u64 o) {
+  const u64 u = (o >> 63) ? (o & 0x7fffffffffffffffull) : ~o;
+  return __longlong_as_double((long long)u);
+}
+
+// box[0..2] = min, box[3..5] = max (ordered encoding); box must be initialised to {~0, ~0, ~0, 0, 0, 0}
+__global__ void morton_bbox_kernel(const double *__restrict__ xyz, int n, long long ps, long long cs,
+                                   u64 *__restrict__ box) {
+  u64 lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0, 0, 0};
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    for (int a = 0; a < 3; a++) {
+      const double x = xyz[i * ps + a * cs];
+      if (x != x) continue;  // NaN: no influence on the box, quantised to cell 0
+      const u64 o = ord_of(x);
+      lo[a] = o < lo[a] ? o : lo[a];
+      hi[a] = o > hi[a] ? o : hi[a];
+    }
+  for (int a = 0; a < 3; a++) {
+    for (int d = 16; d > 0; d >>= 1) {
+      const u64 l2 = __shfl_xor_sync(0xffffffffu, lo[a], d), h2 = __shfl_xor_sync(0xffffffffu, hi[a], d);
+      lo[a] = l2 < lo[a] ? l2 : lo[a];
+      hi[a] = h2 > hi[a] ? h2 : hi[a];
+    }
+    if ((threadIdx.x & 31) == 0) {
+      atomicMin(box + a, lo[a]);
+      atomicMax(box + 3 + a, hi[a]);
+    }
+  }
+}
+
+// spreads the low 21 bits of v: bit i -> bit 3i
+__device__ __forceinline__ u64 spread3(u64 v) {
+  v &= 0x1fffffull;
+  v = (v | (v << 32)) & 0x001f00000000ffffull;
+  v = (v | (v << 16)) & 0x001f0000ff0000ffull;
+  v = (v | (v << 8)) & 0x100f00f00f00f00full;
+  v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+  v = (v | (v << 2)) & 0x1249249249249249ull;
+  return v;
+}
+
+// keys[i] = Morton key of point i, vals[i] = i; orand[0] |= key, orand[1] &= key
+__global__ void morton_keys_kernel(const double *__restrict__ xyz, int n, long long ps, long long cs,
+                                   const u64 *__restrict__ box, int bits, u64 *__restrict__ keys,
+                                   int *__restrict__ vals, u64 *__restrict__ orand) {
+  const double scale = (double)(1ull << bits);
+  const unsigned qmax = (unsigned)((1ull << bits) - 1);
+  double lo[3], ext[3];
+  for (int a = 0; a < 3; a++) {
+    const u64 l = box[a], hgh = box[3 + a];
+    lo[a] = l <= hgh ? ord_back(l) : 0.0;
+    ext[a] = l <= hgh ? __dsub_rn(ord_back(hgh), lo[a]) : 0.0;
+  }
+  u64 o = 0, an = ~0ull;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    u64 key = 0;
+    for (int a = 0; a < 3; a++) {
+      const double x = xyz[i * ps + a * cs];
+      unsigned q = 0;
+      if (ext[a] > 0.0 && x == x) {
+        const double t = __dmul_rn(__ddiv_rn(__dsub_rn(x, lo[a]), ext[a]), scale);
+        q = t >= scale ? qmax : (unsigned)t;  // t >= 0 by construction; truncation = floor
+      }
+      key |= spread3(q) << (2 - a);
+    }
+    keys[i] = key;
+    vals[i] = (int)i;
+    o |= key;
+    an &= key;
+  }
+  for (int d = 16; d > 0; d >>= 1) {
+    o |= __shfl_xor_sync(0xffffffffu, o, d);
+    an &= __shfl_xor_sync(0xffffffffu, an, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicOr(orand, o);
+    atomicAnd(orand + 1, an);
+  }
+}
+
+// hist[d * tiles + tile] = number of keys of the tile whose digit is d
+__global__ void __launch_bounds__(kRsThreads) radix_count_kernel(const u64 *__restrict__ keys, int n, int shift,
+                                                                int *__restrict__ hist, int tiles) {
+  __shared__ int cnt[256];
+  const int tile = blockIdx.x;
+  cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const long long base = (long long)tile * kRsTile;
+#pragma unroll
+  for (int k = 0; k < kRsItems; k++) {
+    const long long i = base + k * kRsThreads + threadIdx.x;
+    if (i < n) atomicAdd(&cnt[(unsigned)(keys[i] >> shift) & 255u], 1);
+  }
+  __syncthreads();
+  hist[(size_t)threadIdx.x * tiles + tile] = cnt[threadIdx.x];
+}
+
+struct RsSmem {
+  u64 key[kRsTile];
+  int val[kRsTile];
+  int cnt[kRsWarps][256];  // per-warp digit counters, then the warp's offset inside the tile's digit run
+  int start[256];          // first slot of the digit inside the sorted tile
+  int delta[256];          // global base of (digit, tile) minus start
+  int scan[33];
+};
+
+// stable scatter of one tile by the digit at `shift`; base = exclusive scan of the digit-major histogram
+__global__ void __launch_bounds__(kRsThreads, 3) radix_scatter_kernel(const u64 *__restrict__ keys_in,
+                                                                  const int *__restrict__ vals_in,
+                                                                  u64 *__restrict__ keys_out, int *__restrict__ vals_out,
+                                                                  int n, int shift, const int *__restrict__ base, int tiles) {
+  extern __shared__ __align__(16) unsigned char rs_raw[];
+  RsSmem &sm = *reinterpret_cast<RsSmem *>(rs_raw);
+  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const long long t0 = (long long)tile * kRsTile;
+  const int valid = (int)(n - t0 < kRsTile ? n - t0 : kRsTile);
+  for (int d = lane; d < 256; d += 32) sm.cnt[w][d] = 0;
+  __syncwarp();
+
+  u64 key[kRsItems];
+  int val[kRsItems], rank[kRsItems];
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int r = 0; r < kRsItems; r++) {
+    const int loc = w * kRsChunk + r * 32 + lane;  // position inside the tile: warp chunks are contiguous
+    const bool in = loc < valid;
+    key[r] = in ? keys_in[t0 + loc] : ~0ull;  // padding sorts behind every real key of the tile (stable, last)
+    val[r] = in ? vals_in[t0 + loc] : -1;
+  }
+#pragma unroll
+  for (int r = 0; r < kRsItems; r++) {
+    const unsigned d = (unsigned)(key[r] >> shift) & 255u;
+    unsigned peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+      const unsigned vote = __ballot_sync(0xffffffffu, (d >> b) & 1u);
+      peers &= ((d >> b) & 1u) ? vote : ~vote;
+    }
+    const int leader = __ffs(peers) - 1;
+    int old = 0;
+    if (lane == leader) {
+      old = sm.cnt[w][d];
+      sm.cnt[w][d] = old + __popc(peers);
+    }
+    __syncwarp();
+    old = __shfl_sync(0xffffffffu, old, leader);
+    rank[r] = old + __popc(peers & lt);
+  }
+  __syncthreads();
+
+  // thread d: offsets of the warps inside digit d's run, the tile's count, then the tile-wide digit scan
+  {
+    const int d = tid;
+    int run = 0;
+#pragma unroll
+    for (int x = 0; x < kRsWarps; x++) {
+      const int c = sm.cnt[x][d];
+      sm.cnt[x][d] = run;
+      run += c;
+    }
+    int total = 0;
+    const int ex = block_excl_scan<kRsThreads>(run, sm.scan, &total);
+    sm.start[d] = ex;
+    sm.delta[d] = __ldg(base + (size_t)d * tiles + tile) - ex;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < kRsItems; r++) {
+    const unsigned d = (unsigned)(key[r] >> shift) & 255u;
+    const int pos = sm.start[d] + sm.cnt[w][d] + rank[r];
+    sm.key[pos] = key[r];
+    sm.val[pos] = val[r];
+  }
+  __syncthreads();
+  for (int i = tid; i < valid; i += kRsThreads) {
+    const u64 k = sm.key[i];
+    const long long out = (long long)i + sm.delta[(unsigned)(k >> shift) & 255u];
+    keys_out[out] = k;
+    vals_out[out] = sm.val[i];
+  }
+}
+
+__global__ void rank_of_order_kernel(const int *__restrict__ order, int n, int *__restrict__ rank) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i < n) rank[order[i]] = (int)i;
+}
+
+// concatenated vertex v of the batch: key = (graph << 32) | global Morton rank of its DOF, val = local id
+__global__ void node_keys_kernel(const int *__restrict__ list, const int *__restrict__ vtx_ptr, int count, int total,
+                                 const int *__restrict__ node_ptr, const int *__restrict__ dofs,
+                                 const int *__restrict__ rank, u64 *__restrict__ keys, int *__restrict__ vals) {
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= total) return;
+  int lo = 0, hi = count;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(vtx_ptr + mid) <= v) lo = mid + 1; else hi = mid;
+  }
+  const int g = lo - 1, k = v - __ldg(vtx_ptr + g);
+  const int dof = __ldg(dofs + __ldg(node_ptr + __ldg(list + g)) + k);
+  keys[v] = ((u64)(unsigned)g << 32) | (u64)(unsigned)__ldg(rank + dof);
+  vals[v] = k;
+}
+
+inline int grid_for(long long n, int threads, int cap) {
+  long long b = (n + threads - 1) / threads;
+  return (int)std::max<long long>(1, std::min<long long>(b, cap));
+}
+
+// Stable LSD radix sort of (key, val) pairs on the digits where diff_mask has a set bit.  The pairs start in
+// (k0, v0); returns 0 / 1 = the buffer pair that holds the sorted result.
+int radix_sort_pairs(parth_b200 &h, u64 *k0, int *v0, u64 *k1, int *v1, int n, u64 diff_mask) {
+  cudaStream_t s = h.stream;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
+    attr_set = true;
+  }
+  const int tiles = (n + kRsTile - 1) / kRsTile;
+  const size_t hn = (size_t)256 * tiles;
+  if (hn >= (size_t)1 << 31) throw StatusError(PARTH_B200_ERR_ARG, "radix sort: too many keys");
+  h.m_hist.reserve(hn + 1, s);
+  h.m_base.reserve(hn + 2, s);
+  h.scan_ws.reserve(scan_ws_words(hn + 1), s);
+  int cur = 0;
+  for (int shift = 0; shift < 64; shift += 8) {
+    if (((diff_mask >> shift) & 255ull) == 0) continue;
+    const u64 *ki = cur ? k1 : k0;
+    const int *vi = cur ? v1 : v0;
+    u64 *ko = cur ? k0 : k1;
+    int *vo = cur ? v0 : v1;
+    radix_count_kernel<<<tiles, kRsThreads, 0, s>>>(ki, n, shift, h.m_hist.p, tiles);
+    PB_CUDA(cudaGetLastError());
+    h.stats.kernels_launched += 1 + exclusive_scan<0>(h.m_hist.p, h.m_base.p, (int)hn, h.scan_ws.p, s);
+    radix_scatter_kernel<<<tiles, kRsThreads, sizeof(RsSmem), s>>>(ki, vi, ko, vo, n, shift, h.m_base.p, tiles);
+    PB_CUDA(cudaGetLastError());
+    h.stats.kernels_launched += 1;
+    cur ^= 1;
+  }
+  return cur;
+}
+
+}  // namespace
+
+// Coordinates of the current DOFs (device pointer, element strides): computes the Morton keys, the global
+// Morton order (perm[new] = old) and its inverse (rank).  Stream-ordered except for one 16-byte read-back.
+void stage_set_coordinates(parth_b200 &h, const double *dxyz, int n, long long ps, long long cs, int bits) {
+  if (n < 0 || (n > 0 && !dxyz) || bits < 1 || bits > 21)
+    throw StatusError(PARTH_B200_ERR_ARG, "set_coordinates: bad argument (bits must be 1..21)");
+  cudaStream_t s = h.stream;
+  StageTimer tm(h, &h.stats.morton_ms);
+  h.morton_n = 0;
+  h.morton_bits = bits;
+  h.morton_passes = 0;
+  if (n == 0) { tm.cancel(); return; }
+  h.m_k0.reserve((size_t)n, s); h.m_k1.reserve((size_t)n, s);
+  h.m_v0.reserve((size_t)n, s); h.m_v1.reserve((size_t)n, s);
+  h.m_rank.reserve((size_t)n, s);
+  h.m_box.reserve(8, s);
+  const u64 init[8] = {~0ull, ~0ull, ~0ull, 0, 0, 0, 0, ~0ull};
+  h.pin_u64.reserve(8);
+  for (int i = 0; i < 8; i++) h.pin_u64.p[i] = init[i];
+  PB_CUDA(cudaMemcpyAsync(h.m_box.p, h.pin_u64.p, sizeof(init), cudaMemcpyHostToDevice, s));
+  const int grid = grid_for(n, 256, h.num_sms * 8);
+  morton_bbox_kernel<<<grid, 256, 0, s>>>(dxyz, n, ps, cs, h.m_box.p);
+  PB_CUDA(cudaGetLastError());
+  morton_keys_kernel<<<grid, 256, 0, s>>>(dxyz, n, ps, cs, h.m_box.p, bits, h.m_k0.p, h.m_v0.p, h.m_box.p + 6);
+  PB_CUDA(cudaGetLastError());
+  h.stats.kernels_launched += 2;
+  PB_CUDA(cudaMemcpyAsync(h.pin_u64.p, h.m_box.p + 6, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+  const u64 diff = h.pin_u64.p[0] ^ h.pin_u64.p[1];  // bits that are not constant over the keys
+  for (int shift = 0; shift < 64; shift += 8) h.morton_passes += ((diff >> shift) & 255ull) != 0;
+  h.stats.morton_passes = h.morton_passes;
+  h.morton_cur = radix_sort_pairs(h, h.m_k0.p, h.m_v0.p, h.m_k1.p, h.m_v1.p, n, diff);
+  rank_of_order_kernel<<<(n + 255) / 256, 256, 0, s>>>(h.morton_cur ? h.m_v1.p : h.m_v0.p, n, h.m_rank.p);
+  PB_CUDA(cudaGetLastError());
+  h.stats.kernels_launched += 1;
+  h.morton_n = n;
+  tm.stop();
+}
+
+// HMD::Permute with ReorderingType MORTON_CODE for a batch of fine nodes: r_perm = local ids in ascending
+// (Morton key, DOF id) order, node after node.  r_list / r_vtx hold the batch (uploaded by the caller).
+void stage_morton_nodes(parth_b200 &h, int count, int total) {
+  if (h.morton_n != h.M_n)
+    throw StatusError(PARTH_B200_ERR_ARG, "MORTON_CODE: set_coordinates must supply one point per current DOF");
+  if (total <= 0) return;
+  cudaStream_t s = h.stream;
+  // the global order buffers stay untouched: the node sort has its own pairs
+  h.m_nk0.reserve((size_t)total, s); h.m_nk1.reserve((size_t)total, s);
+  h.m_nv0.reserve((size_t)total, s); h.m_nv1.reserve((size_t)total, s);
+  h.r_perm.reserve((size_t)total, s);
+  node_keys_kernel<<<(total + 255) / 256, 256, 0, s>>>(h.r_list.p, h.r_vtx.p, count, total, h.d_node_ptr.p,
+                                                       h.d_dofs.p, h.m_rank.p, h.m_nk0.p, h.m_nv0.p);
+  PB_CUDA(cudaGetLastError());
+  h.stats.kernels_launched += 1;
+  u64 mask = 0;  // digits that can differ: the rank's bits and the graph index's bits
+  for (u64 x = (u64)std::max(h.M_n - 1, 0); x; x >>= 1) mask = (mask << 1) | 1ull;
+  u64 gm = 0;
+  for (u64 x = (u64)std::max(count - 1, 0); x; x >>= 1) gm = (gm << 1) | 1ull;
+  mask |= gm << 32;
+  const int cur = radix_sort_pairs(h, h.m_nk0.p, h.m_nv0.p, h.m_nk1.p, h.m_nv1.p, total, mask);
+  PB_CUDA(cudaMemcpyAsync(h.r_perm.p, cur ? h.m_nv1.p : h.m_nv0.p, sizeof(int) * (size_t)total,
+                          cudaMemcpyDeviceToDevice, s));
+}
+
+}  // namespace pb

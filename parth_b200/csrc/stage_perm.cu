@@ -338,7 +338,8 @@ static void cold_start(parth_b200 &h) {
     // (HMD::Decompose orders leaves and separators as it goes, HMD.cpp:248-250,297-301)
     std::vector<int> all;
     for (int x = 0; x < nodes; x++) if (node_ptr[x + 1] > node_ptr[x]) all.push_back(x);
-    h.force_amd = true;
+    // (ReorderingType MORTON_CODE with coordinates for every DOF orders them along the Z curve instead)
+    h.force_amd = !(h.reorder_type == PARTH_B200_MORTON_CODE && h.morton_n == h.M_n);
     try { stage_permute_fine(h, all); } catch (...) { h.force_amd = false; throw; }
     h.force_amd = false;
   }

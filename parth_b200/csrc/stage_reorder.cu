@@ -21,8 +21,8 @@ struct Batch {
   std::vector<int> vtx;  // count + 1
 };
 
-// uploads the node list / vertex offsets and builds the concatenated sub-mesh CSR (r_G, r_sub)
-Batch extract_fine(parth_b200 &h, const std::vector<int> &nodes) {
+// uploads the node list / vertex offsets of a batch of fine nodes (r_list, r_vtx)
+Batch batch_of(parth_b200 &h, const std::vector<int> &nodes) {
   cudaStream_t s = h.stream;
   Batch b;
   b.count = (int)nodes.size();
@@ -35,12 +35,19 @@ Batch extract_fine(parth_b200 &h, const std::vector<int> &nodes) {
   b.total = b.vtx[b.count];
   h.r_list.reserve((size_t)b.count + 1, s);
   h.r_vtx.reserve((size_t)b.count + 2, s);
-  h.r_cnt.reserve((size_t)b.total + 1, s);
-  h.r_G.reserve((size_t)b.total + 2, s);
-  h.scan_ws.reserve(scan_ws_words((size_t)b.total + 1), s);
   PB_CUDA(cudaMemcpyAsync(h.r_list.p, nodes.data(), sizeof(int) * (size_t)b.count, cudaMemcpyHostToDevice, s));
   PB_CUDA(cudaMemcpyAsync(h.r_vtx.p, b.vtx.data(), sizeof(int) * ((size_t)b.count + 1), cudaMemcpyHostToDevice, s));
   PB_CUDA(cudaStreamSynchronize(s));  // pageable sources
+  return b;
+}
+
+// ... and builds the concatenated sub-mesh CSR (r_G, r_sub)
+Batch extract_fine(parth_b200 &h, const std::vector<int> &nodes) {
+  cudaStream_t s = h.stream;
+  Batch b = batch_of(h, nodes);
+  h.r_cnt.reserve((size_t)b.total + 1, s);
+  h.r_G.reserve((size_t)b.total + 2, s);
+  h.scan_ws.reserve(scan_ws_words((size_t)b.total + 1), s);
   h.stats.kernels_launched += launch_extract_count(h.r_list.p, h.r_vtx.p, b.count, b.total, h.d_node_ptr.p,
                                                    h.d_dofs.p, h.Mp, h.Mi, h.d_dof2node.p, h.r_cnt.p, s);
   h.stats.kernels_launched += exclusive_scan<0>(h.r_cnt.p, h.r_G.p, b.total, h.scan_ws.p, s);
@@ -147,21 +154,27 @@ void stage_permute_fine(parth_b200 &h, const std::vector<int> &all_nodes) {
   const bool trace = std::getenv("PARTH_B200_TRACE") != nullptr;
   auto now = [&]() { cudaStreamSynchronize(s); return std::chrono::steady_clock::now(); };
   auto t0 = trace ? now() : std::chrono::steady_clock::time_point();
-  Batch b = extract_fine(h, nodes);
-  std::vector<int> gnnz = batch_graph_nnz(h, b);
-  auto t1 = trace ? now() : t0;
-  if (!device_orders_with_amd(h))
-    for (int g = 0; g < b.count; g++)
-      if (gnnz[g] > 0) {
-        throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
-                          "permute_fine: METIS_NodeND leaf ordering is not available on the device "
-                          "(use ReorderingType AMD or the REPAIR coarse policy)");
-      }
-  if (h.reorder_type == PARTH_B200_MORTON_CODE && !h.force_amd) {
-    // the reference prints "Morton code is not implemented yet" and leaves perm unset (HMD.cpp:82-83)
-    throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "permute_fine: MORTON_CODE is not implemented in the reference");
+  Batch b;
+  const bool morton = h.reorder_type == PARTH_B200_MORTON_CODE && !h.force_amd;
+  auto t1 = t0;
+  if (morton) {
+    // The reference prints "Morton code is not implemented yet" and leaves perm unset (HMD.cpp:82-83); the
+    // device orders the node by the global Morton rank of its DOFs (morton.cu) -- no sub-mesh is needed.
+    b = batch_of(h, nodes);
+    stage_morton_nodes(h, b.count, b.total);
+  } else {
+    b = extract_fine(h, nodes);
+    std::vector<int> gnnz = batch_graph_nnz(h, b);
+    t1 = trace ? now() : t0;
+    if (!device_orders_with_amd(h))
+      for (int g = 0; g < b.count; g++)
+        if (gnnz[g] > 0) {
+          throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
+                            "permute_fine: METIS_NodeND leaf ordering is not available on the device "
+                            "(use ReorderingType AMD or the REPAIR coarse policy)");
+        }
+    order_batch(h, b, gnnz);
   }
-  order_batch(h, b, gnnz);
   auto t2 = trace ? now() : t0;
   h.stats.kernels_launched += launch_apply_order(h.r_list.p, h.r_vtx.p, b.count, b.total, h.d_node_ptr.p,
                                                  h.d_meta.p, h.d_dofs.p, h.r_perm.p, h.d_labels.p,
@@ -170,10 +183,10 @@ void stage_permute_fine(parth_b200 &h, const std::vector<int> &all_nodes) {
   if (trace) {
     auto t3 = now();
     auto ms = [](auto a, auto b2) { return std::chrono::duration<double, std::milli>(b2 - a).count(); };
-    int nmax = 0, zmax = 0;
-    for (int g = 0; g < b.count; g++) { nmax = std::max(nmax, b.vtx[g + 1] - b.vtx[g]); zmax = std::max(zmax, gnnz[g]); }
-    std::fprintf(stderr, "[parth_b200] permute_fine: %d graphs (max n %d, max nnz %d): extract %.3f ms, order %.3f ms, apply %.3f ms\n",
-                 b.count, nmax, zmax, ms(t0, t1), ms(t1, t2), ms(t2, t3));
+    int nmax = 0;
+    for (int g = 0; g < b.count; g++) nmax = std::max(nmax, b.vtx[g + 1] - b.vtx[g]);
+    std::fprintf(stderr, "[parth_b200] permute_fine: %d graphs (max n %d, %s): extract %.3f ms, order %.3f ms, apply %.3f ms\n",
+                 b.count, nmax, morton ? "Morton" : "AMD", ms(t0, t1), ms(t1, t2), ms(t2, t3));
   }
 }
 

@@ -87,6 +87,10 @@ void stage_finish_permutation(parth_b200 &h, int *dperm, int dim);
 void stage_submesh(parth_b200 &h, int node, int coarse, int *n, int *nnz, int *Mp, int *Mi, int *l2g);
 void stage_amd_batch(parth_b200 &h, int count, const int *graph_ptr, const int *Mp, const int *Mi, int *perm);
 
+// morton.cu: ReorderingType MORTON_CODE (extension: the reference leaves it unimplemented, HMD.cpp:82-83)
+void stage_set_coordinates(parth_b200 &h, const double *dxyz, int n, long long ps, long long cs, int bits);
+void stage_morton_nodes(parth_b200 &h, int count, int total);  // batch in r_list / r_vtx -> r_perm
+
 // host_decompose.cu: BFS level-structure nested dissection (host), parth_b200_decomposer signature
 int builtin_decomposer(void *user, int M_n, const int *Mp, const int *Mi, int levels, int nodes, int *meta,
                        int *node_ptr, int *dofs, int *labels);

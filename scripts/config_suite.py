@@ -113,6 +113,29 @@ def config4():
     print(json.dumps({"config": 4, "ok": ok, "M": M, "dim": dim, "expand_ms": t, "GBs": alg / t / 1e6,
                       "frac": alg / t / 1e6 / PEAK, "note": "MORTON_CODE has no reference implementation "
                       "(HMD.cpp:82-83); only the dim expansion of config 4 has an oracle"}), flush=True)
+    # the Morton ordering itself (extension, parity against oracle/morton_oracle.py only): 50 M points uniform in
+    # [0,1)^3 (SURVEY 8d asks mt19937_64(seed 7); the device generator is used here, the distribution is the same)
+    del d_out
+    gen = torch.Generator(device="cuda"); gen.manual_seed(7)
+    xyz = torch.rand((M, 3), dtype=torch.float64, device="cuda", generator=gen)
+    torch.cuda.synchronize()
+    ms = []
+    for _ in range(5):
+        g.setCoordinatesDev(xyz.data_ptr(), M)
+        ms.append(g.stats()["morton_ms"])
+    passes = g.stats()["morton_passes"]
+    perm = torch.from_numpy(g.mortonOrder()).cuda()
+    keys = torch.from_numpy(g.mortonKeys().view(np.int64)).cuda()
+    seen = torch.zeros(M, dtype=torch.int32, device="cuda")
+    seen.index_add_(0, perm.long(), torch.ones(M, dtype=torch.int32, device="cuda"))
+    tie = keys[1:] == keys[:-1]
+    ok = bool((seen == 1).all()) and bool((keys[1:] >= keys[:-1]).all()) and bool((perm[1:][tie] > perm[:-1][tie]).all())
+    # bytes: box 24n, keys 24n + 12n, per pass count 8n + scatter 24n, rank 8n
+    alg = M * (24 + 36 + passes * 32 + 8)
+    t = float(np.median(ms[1:]))
+    print(json.dumps({"config": 4, "stage": "morton_order", "ok": ok, "M": M, "bits": 21, "radix_passes": passes,
+                      "morton_ms": t, "all_ms": ms, "Mpoints_per_s": M / t / 1e3, "GBs": alg / t / 1e6,
+                      "frac": alg / t / 1e6 / PEAK}), flush=True)
 
 
 def config5(n):
