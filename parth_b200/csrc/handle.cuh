@@ -101,8 +101,9 @@ struct parth_b200 {
   pb::DevBuf<long long> r_wsptr;
   // ReorderingType MORTON_CODE (morton.cu): key / point-id pairs (double buffered), global rank, the same for a node batch
   int morton_n = 0, morton_bits = 21, morton_cur = 0, morton_passes = 0;
-  pb::DevBuf<unsigned long long> m_k0, m_k1, m_nk0, m_nk1, m_box;
-  pb::DevBuf<int> m_v0, m_v1, m_nv0, m_nv1, m_rank, m_hist, m_base;
+  bool morton_rank_valid = false;
+  pb::DevBuf<unsigned long long> m_k0, m_k1, m_nk0, m_nk1, m_box, m_desc;
+  pb::DevBuf<int> m_v0, m_v1, m_nv0, m_nv1, m_rank, m_hist;
   pb::DevBuf<double> m_xyz;                // staging of host coordinates
   pb::PinBuf<unsigned long long> pin_u64;
   pb::DevBuf<int> d_out;                   // staging for host-pointer outputs

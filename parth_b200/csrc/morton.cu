@@ -9,19 +9,19 @@
 //   * key = bit interleave, x most significant; order = ascending (key, point id);
 //   * a fine separator-tree node is ordered by the global Morton rank of its DOFs (HMD::Permute's contract:
 //     perm[new] = old local id).
-// The sort is a hand-written stable LSD radix sort, 8 bits per pass, three launches per pass:
-//   radix_count_kernel    per-tile digit histogram (digit-major layout: one exclusive scan yields every base)
-//   exclusive_scan<0>     the device-wide single-pass scan of scan.cuh
-//   radix_scatter_kernel  ballot-ranked warps (8 votes give the peer mask of a lane's digit: match.any costs 11
+// The sort is a hand-written stable LSD radix sort, 8 bits per pass:
+//   radix_hist_kernel     ONE read of the keys gives the global digit counts of all passes (+ radix_bases_kernel)
+//   radix_scatter_kernel  one launch per pass, single sweep: tile counts chained by a decoupled look-back per digit;
+//                         ballot-ranked warps (8 votes give the peer mask of a lane's digit: match.any costs 11
 //                         cycles per distinct value on B200, 30 distinct values in a warp of random digits),
 //                         tile sorted in shared memory first so the global stores leave in digit runs
 // Passes whose digit is constant over all keys (known from the OR / AND of the keys, folded into the key
-// kernel) are skipped.  HBM bound: per pass 8n bytes (count) + 24n bytes (scatter), keys 24n + 12n.
+// kernel) are skipped.  HBM bound: 8n bytes (histogram) + 24n bytes per pass (scatter); keys 24n + 12n.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "reorder.cuh"
-#include "scan.cuh"
 #include "stages.cuh"
 
 namespace pb {
@@ -29,10 +29,7 @@ namespace pb {
 namespace {
 
 constexpr int kRsThreads = 256;
-constexpr int kRsItems = 16;                     // keys per thread and tile
-constexpr int kRsTile = kRsThreads * kRsItems;   // 4096 keys
 constexpr int kRsWarps = kRsThreads / 32;
-constexpr int kRsChunk = kRsTile / kRsWarps;     // consecutive keys one warp ranks
 
 typedef unsigned long long u64;
 
@@ -121,40 +118,64 @@ __global__ void morton_keys_kernel(const double *__restrict__ xyz, int n, long l
   }
 }
 
-// hist[d * tiles + tile] = number of keys of the tile whose digit is d
-__global__ void __launch_bounds__(kRsThreads) radix_count_kernel(const u64 *__restrict__ keys, int n, int shift,
-                                                                int *__restrict__ hist, int tiles) {
-  __shared__ int cnt[256];
-  const int tile = blockIdx.x;
-  cnt[threadIdx.x] = 0;
+// ghist[p * 256 + d] += number of keys whose digit p (bits 8p .. 8p+7) is d, for every pass p of pass_mask at once:
+// the digit totals do not depend on the order of the keys, so ONE read of the keys serves all passes
+__global__ void __launch_bounds__(kRsThreads) radix_hist_kernel(const u64 *__restrict__ keys, int n, unsigned pass_mask,
+                                                               int *__restrict__ ghist) {
+  __shared__ int cnt[8][256];
+  for (int i = threadIdx.x; i < 8 * 256; i += kRsThreads) (&cnt[0][0])[i] = 0;
   __syncthreads();
-  const long long base = (long long)tile * kRsTile;
+  for (long long i = blockIdx.x * (long long)kRsThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kRsThreads) {
+    const u64 k = keys[i];
 #pragma unroll
-  for (int k = 0; k < kRsItems; k++) {
-    const long long i = base + k * kRsThreads + threadIdx.x;
-    if (i < n) atomicAdd(&cnt[(unsigned)(keys[i] >> shift) & 255u], 1);
+    for (int p = 0; p < 8; p++)
+      if (pass_mask & (1u << p)) atomicAdd(&cnt[p][(unsigned)(k >> (8 * p)) & 255u], 1);
   }
   __syncthreads();
-  hist[(size_t)threadIdx.x * tiles + tile] = cnt[threadIdx.x];
+  for (int i = threadIdx.x; i < 8 * 256; i += kRsThreads) {
+    const int c = (&cnt[0][0])[i];
+    if (c) atomicAdd(ghist + i, c);
+  }
 }
 
+// block p: gbase[p * 256 + d] = number of keys whose digit p is smaller than d
+__global__ void __launch_bounds__(256) radix_bases_kernel(const int *__restrict__ ghist, int *__restrict__ gbase) {
+  __shared__ int sc[33];
+  int total = 0;
+  const int v = ghist[blockIdx.x * 256 + threadIdx.x];
+  gbase[blockIdx.x * 256 + threadIdx.x] = block_excl_scan<256>(v, sc, &total);
+}
+
+template <int ITEMS>  // keys per thread and tile
 struct RsSmem {
-  u64 key[kRsTile];
-  int val[kRsTile];
+  static constexpr int kTile = kRsThreads * ITEMS;
+  u64 key[kTile];
+  int val[kTile];
   int cnt[kRsWarps][256];  // per-warp digit counters, then the warp's offset inside the tile's digit run
   int start[256];          // first slot of the digit inside the sorted tile
   int delta[256];          // global base of (digit, tile) minus start
   int scan[33];
+  int tile;
 };
 
-// stable scatter of one tile by the digit at `shift`; base = exclusive scan of the digit-major histogram
-__global__ void __launch_bounds__(kRsThreads, 3) radix_scatter_kernel(const u64 *__restrict__ keys_in,
+// Stable scatter of one tile by the digit at `shift`, single pass over the keys ("onesweep"): the tile's digit
+// counts are chained through desc[tile * 256 + digit] by a decoupled look-back, one thread per digit (status in
+// bits 63..62 as in common.cuh: aggregate / inclusive prefix), so no count kernel and no device-wide scan run per
+// pass.  gbase = the digit's global base (radix_bases_kernel).  desc[256 * tiles] is the dynamic tile counter; tile
+// ids are handed out in launch order, so every predecessor is resident or finished.  All of desc must be zero.
+template <int ITEMS, int CTAS>
+__global__ void __launch_bounds__(kRsThreads, CTAS) radix_scatter_kernel(const u64 *__restrict__ keys_in,
                                                                   const int *__restrict__ vals_in,
                                                                   u64 *__restrict__ keys_out, int *__restrict__ vals_out,
-                                                                  int n, int shift, const int *__restrict__ base, int tiles) {
+                                                                  int n, int shift, const int *__restrict__ gbase,
+                                                                  u64 *__restrict__ desc, int tiles) {
   extern __shared__ __align__(16) unsigned char rs_raw[];
-  RsSmem &sm = *reinterpret_cast<RsSmem *>(rs_raw);
-  const int tile = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  constexpr int kRsItems = ITEMS, kRsTile = kRsThreads * ITEMS, kRsChunk = kRsTile / kRsWarps;  // a warp ranks kRsChunk consecutive keys
+  RsSmem<ITEMS> &sm = *reinterpret_cast<RsSmem<ITEMS> *>(rs_raw);
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid == 0) sm.tile = (int)atomicAdd(desc + (size_t)256 * tiles, 1ull);
+  __syncthreads();
+  const int tile = sm.tile;
   const long long t0 = (long long)tile * kRsTile;
   const int valid = (int)(n - t0 < kRsTile ? n - t0 : kRsTile);
   for (int d = lane; d < 256; d += 32) sm.cnt[w][d] = 0;
@@ -191,28 +212,66 @@ __global__ void __launch_bounds__(kRsThreads, 3) radix_scatter_kernel(const u64 
   }
   __syncthreads();
 
-  // thread d: offsets of the warps inside digit d's run, the tile's count, then the tile-wide digit scan
-  {
-    const int d = tid;
-    int run = 0;
+  // thread d: offsets of the warps inside digit d's run and the tile's count of digit d, published at once as the
+  // tile's aggregate; the four nearest predecessors' descriptors are requested now and read after the tile has
+  // been sorted in shared memory, so their latency (a third of the kernel's stall samples when the walk was done
+  // on the spot) hides behind that work and the predecessors have had time to publish their prefixes
+  constexpr int kAhead = 4;
+  const int d = tid;
+  int run = 0;
 #pragma unroll
-    for (int x = 0; x < kRsWarps; x++) {
-      const int c = sm.cnt[x][d];
-      sm.cnt[x][d] = run;
-      run += c;
-    }
+  for (int x = 0; x < kRsWarps; x++) {
+    const int c = sm.cnt[x][d];
+    sm.cnt[x][d] = run;
+    run += c;
+  }
+  u64 *mine = desc + (size_t)tile * 256 + d;
+  u64 ahead[kAhead];
+  if (tile > 0) st_relaxed_u64(mine, kTileAgg | (u64)run);
+#pragma unroll
+  for (int j = 0; j < kAhead; j++)
+    ahead[j] = tile - 1 - j >= 0 ? ld_relaxed_u64(desc + (size_t)(tile - 1 - j) * 256 + d) : kTilePre;
+  {
     int total = 0;
-    const int ex = block_excl_scan<kRsThreads>(run, sm.scan, &total);
-    sm.start[d] = ex;
-    sm.delta[d] = __ldg(base + (size_t)d * tiles + tile) - ex;
+    sm.start[d] = block_excl_scan<kRsThreads>(run, sm.scan, &total);
   }
   __syncthreads();
 #pragma unroll
   for (int r = 0; r < kRsItems; r++) {
-    const unsigned d = (unsigned)(key[r] >> shift) & 255u;
-    const int pos = sm.start[d] + sm.cnt[w][d] + rank[r];
+    const unsigned dg = (unsigned)(key[r] >> shift) & 255u;
+    const int pos = sm.start[dg] + sm.cnt[w][dg] + rank[r];
     sm.key[pos] = key[r];
     sm.val[pos] = val[r];
+  }
+  {
+    // sum the predecessors' counts back to the nearest inclusive prefix (decoupled look-back, one digit per thread)
+    long long before = 0;
+    bool done = tile == 0;
+#pragma unroll
+    for (int j = 0; j < kAhead; j++) {
+      if (done) break;
+      u64 x = ahead[j];
+      const u64 *theirs = desc + (size_t)(tile - 1 - j) * 256 + d;
+      while ((x & ~kTileVal) == 0) x = ld_relaxed_u64(theirs);
+      before += (long long)(x & kTileVal);
+      done = (x & ~kTileVal) == kTilePre;
+    }
+    for (int t = tile - 1 - kAhead; !done; t -= kAhead) {  // rare: a longer walk, again four requests at a time
+      u64 y[kAhead];
+#pragma unroll
+      for (int j = 0; j < kAhead; j++) y[j] = t - j >= 0 ? ld_relaxed_u64(desc + (size_t)(t - j) * 256 + d) : kTilePre;
+#pragma unroll
+      for (int j = 0; j < kAhead; j++) {
+        if (done) break;
+        u64 x = y[j];
+        const u64 *theirs = desc + (size_t)(t - j) * 256 + d;
+        while ((x & ~kTileVal) == 0) x = ld_relaxed_u64(theirs);
+        before += (long long)(x & kTileVal);
+        done = (x & ~kTileVal) == kTilePre;
+      }
+    }
+    st_relaxed_u64(mine, kTilePre | (u64)(before + run));
+    sm.delta[d] = (int)(__ldg(gbase + d) + before) - sm.start[d];
   }
   __syncthreads();
   for (int i = tid; i < valid; i += kRsThreads) {
@@ -254,28 +313,36 @@ inline int grid_for(long long n, int threads, int cap) {
 // (k0, v0); returns 0 / 1 = the buffer pair that holds the sorted result.
 int radix_sort_pairs(parth_b200 &h, u64 *k0, int *v0, u64 *k1, int *v1, int n, u64 diff_mask) {
   cudaStream_t s = h.stream;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PB_CUDA(cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RsSmem)));
-    attr_set = true;
-  }
-  const int tiles = (n + kRsTile - 1) / kRsTile;
-  const size_t hn = (size_t)256 * tiles;
-  if (hn >= (size_t)1 << 31) throw StatusError(PARTH_B200_ERR_ARG, "radix sort: too many keys");
-  h.m_hist.reserve(hn + 1, s);
-  h.m_base.reserve(hn + 2, s);
-  h.scan_ws.reserve(scan_ws_words(hn + 1), s);
+  // tile shape: 16 keys per thread (3 CTAs / SM) or 8 keys per thread (5 CTAs / SM, twice the look-back chains)
+  static const int items = [] { const char *e = std::getenv("PARTH_B200_RADIX_ITEMS"); return e ? std::atoi(e) : 16; }();
+  const bool small = items == 8;
+  auto kern = small ? radix_scatter_kernel<8, 5> : radix_scatter_kernel<16, 3>;
+  const size_t smem = small ? sizeof(RsSmem<8>) : sizeof(RsSmem<16>);
+  const int tile_keys = kRsThreads * (small ? 8 : 16);
+  PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int tiles = (n + tile_keys - 1) / tile_keys;
+  unsigned pass_mask = 0;
+  for (int p = 0; p < 8; p++) pass_mask |= (((diff_mask >> (8 * p)) & 255ull) != 0) << p;
+  if (!pass_mask) return 0;
+  const size_t dn = (size_t)256 * tiles + 1;
+  h.m_hist.reserve(2 * 8 * 256, s);  // global digit counts, then their exclusive scans
+  h.m_desc.reserve(dn, s);
+  int *ghist = h.m_hist.p, *gbase = h.m_hist.p + 8 * 256;
+  PB_CUDA(cudaMemsetAsync(ghist, 0, sizeof(int) * 8 * 256, s));
+  radix_hist_kernel<<<grid_for(n, kRsThreads * 8, h.num_sms * 8), kRsThreads, 0, s>>>(k0, n, pass_mask, ghist);
+  PB_CUDA(cudaGetLastError());
+  radix_bases_kernel<<<8, 256, 0, s>>>(ghist, gbase);
+  PB_CUDA(cudaGetLastError());
+  h.stats.kernels_launched += 2;
   int cur = 0;
-  for (int shift = 0; shift < 64; shift += 8) {
-    if (((diff_mask >> shift) & 255ull) == 0) continue;
+  for (int p = 0; p < 8; p++) {
+    if (!(pass_mask & (1u << p))) continue;
     const u64 *ki = cur ? k1 : k0;
     const int *vi = cur ? v1 : v0;
     u64 *ko = cur ? k0 : k1;
     int *vo = cur ? v0 : v1;
-    radix_count_kernel<<<tiles, kRsThreads, 0, s>>>(ki, n, shift, h.m_hist.p, tiles);
-    PB_CUDA(cudaGetLastError());
-    h.stats.kernels_launched += 1 + exclusive_scan<0>(h.m_hist.p, h.m_base.p, (int)hn, h.scan_ws.p, s);
-    radix_scatter_kernel<<<tiles, kRsThreads, sizeof(RsSmem), s>>>(ki, vi, ko, vo, n, shift, h.m_base.p, tiles);
+    PB_CUDA(cudaMemsetAsync(h.m_desc.p, 0, sizeof(u64) * dn, s));
+    kern<<<tiles, kRsThreads, smem, s>>>(ki, vi, ko, vo, n, 8 * p, gbase + 256 * p, h.m_desc.p, tiles);
     PB_CUDA(cudaGetLastError());
     h.stats.kernels_launched += 1;
     cur ^= 1;
@@ -316,9 +383,7 @@ void stage_set_coordinates(parth_b200 &h, const double *dxyz, int n, long long p
   for (int shift = 0; shift < 64; shift += 8) h.morton_passes += ((diff >> shift) & 255ull) != 0;
   h.stats.morton_passes = h.morton_passes;
   h.morton_cur = radix_sort_pairs(h, h.m_k0.p, h.m_v0.p, h.m_k1.p, h.m_v1.p, n, diff);
-  rank_of_order_kernel<<<(n + 255) / 256, 256, 0, s>>>(h.morton_cur ? h.m_v1.p : h.m_v0.p, n, h.m_rank.p);
-  PB_CUDA(cudaGetLastError());
-  h.stats.kernels_launched += 1;
+  h.morton_rank_valid = false;  // the inverse is a random scatter (1.5 ms at 50 M points): built when a node is ordered
   h.morton_n = n;
   tm.stop();
 }
@@ -330,6 +395,12 @@ void stage_morton_nodes(parth_b200 &h, int count, int total) {
     throw StatusError(PARTH_B200_ERR_ARG, "MORTON_CODE: set_coordinates must supply one point per current DOF");
   if (total <= 0) return;
   cudaStream_t s = h.stream;
+  if (!h.morton_rank_valid) {
+    rank_of_order_kernel<<<(h.morton_n + 255) / 256, 256, 0, s>>>(h.morton_cur ? h.m_v1.p : h.m_v0.p, h.morton_n, h.m_rank.p);
+    PB_CUDA(cudaGetLastError());
+    h.stats.kernels_launched += 1;
+    h.morton_rank_valid = true;
+  }
   // the global order buffers stay untouched: the node sort has its own pairs
   h.m_nk0.reserve((size_t)total, s); h.m_nk1.reserve((size_t)total, s);
   h.m_nv0.reserve((size_t)total, s); h.m_nv1.reserve((size_t)total, s);

@@ -130,8 +130,8 @@ def config4():
     seen.index_add_(0, perm.long(), torch.ones(M, dtype=torch.int32, device="cuda"))
     tie = keys[1:] == keys[:-1]
     ok = bool((seen == 1).all()) and bool((keys[1:] >= keys[:-1]).all()) and bool((perm[1:][tie] > perm[:-1][tie]).all())
-    # bytes: box 24n, keys 24n + 12n, per pass count 8n + scatter 24n, rank 8n
-    alg = M * (24 + 36 + passes * 32 + 8)
+    # bytes: box 24n, keys 24n + 12n, histogram 8n, scatter 24n per pass
+    alg = M * (24 + 36 + 8 + passes * 24)
     t = float(np.median(ms[1:]))
     print(json.dumps({"config": 4, "stage": "morton_order", "ok": ok, "M": M, "bits": 21, "radix_passes": passes,
                       "morton_ms": t, "all_ms": ms, "Mpoints_per_s": M / t / 1e3, "GBs": alg / t / 1e6,
