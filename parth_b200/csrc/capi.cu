@@ -119,6 +119,7 @@ int parth_b200_clear(parth_b200 *h) {
   h->M_n = h->nnzM = 0;
   h->M_n_prev = h->nnz_prev = 0;
   h->map_len = 0;
+  h->morton_n = 0;
   h->tree_init = false;
   h->cur_sym_proven = h->prev_sym_proven = false;
   h->diff_cached = false;

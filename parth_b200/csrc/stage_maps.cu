@@ -491,6 +491,7 @@ void stage_set_map(parth_b200 &h, const int *map, int len) {
   h.n_added = h.n_removed = 0;
   if (len == 0 || h.M_n_prev == 0) return;  // ParthAPI.cpp:138-142: no previous mesh -> the map is dropped
   if (len != h.M_n) throw StatusError(PARTH_B200_ERR_ARG, "setNewToOldDOFMap: map length must equal M_n");
+  h.morton_n = 0;  // the DOF set changes: coordinates (MORTON_CODE) must be supplied again, after this call
   const int M = h.M_n, Mp = h.M_n_prev;
   h.new_to_old.reserve((size_t)M, s);
   h.old_to_new.reserve((size_t)Mp, s);

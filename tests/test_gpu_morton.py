@@ -151,3 +151,19 @@ def test_compute_permutation_with_morton_cold_and_warm(gpu_api):
     assert np.array_equal(t2["mesh_perm"], perm)
     every = [x for x in range(t2["nodes"]) if t2["node_ptr"][x + 1] > t2["node_ptr"][x]]
     _slices_follow_rank(t2, rank, every)   # untouched nodes kept their (Morton) order, touched ones were re-sorted
+
+
+def test_dof_map_invalidates_coordinates(gpu_api):
+    """a new-to-old DOF map changes the DOF set: stale coordinates must not be used silently"""
+    tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 16, 5)))
+    M = tree.M_n
+    g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 5; g.reorder_type = gpu_api.MORTON_CODE
+    g.setCoarsePolicy(gpu_api.COARSE_REPORT)
+    g.import_tree(tree, Mp, Mi)
+    xyz = np.random.default_rng(2).random((M, 3))
+    g.setCoordinates(xyz)
+    g.setMesh(M, Mp, Mi, np.arange(M, dtype=np.int32))     # identity map, same size: still a new DOF set
+    with pytest.raises(gpu_api.ParthError):
+        g.stage_permute_fine([31])
+    g.setCoordinates(xyz)
+    g.stage_permute_fine([31])
