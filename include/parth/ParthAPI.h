@@ -24,6 +24,7 @@
 #define PARTH_B200_PARTHAPI_H
 
 #include <cstdint>
+#include <cstdio>
 #include <iostream>
 #include <stdexcept>
 #include <string>
@@ -274,6 +275,52 @@ public:
       t.permuted_new_label.assign(labels.begin() + node_ptr[x], labels.begin() + node_ptr[x + 1]);
     }
   }
+  /* Separator-tree fixture on disk (the on-disk format either side of the path; the reference keeps
+   * its tree only in memory, HMD.h:94-104).  Layout, all little-endian int32: "PB2T", version 1, M_n, levels,
+   * nodes, nnz, meta[nodes*7], node_ptr[nodes+1], dofs[M_n], labels[M_n], then the graph the tree belongs to --
+   * Mp[M_n+1], Mi[nnz] (the snapshot the next update is compared with).  parth_b200.api.load_tree_file reads the
+   * same file, so a tool written against this class and the Python tests update an identical tree. */
+  bool saveTree(const std::string &path) {
+    int tm = 0, lv = 0, nodes = 0, mn = 0, nnz = 0;
+    if (parth_b200_tree_dims(h_, &tm, &lv, &nodes) != PARTH_B200_OK || tm <= 0) return false;
+    check(parth_b200_mesh_dims(h_, &mn, &nnz));
+    if (mn != tm) return false; /* the tree must describe the current graph */
+    std::vector<int> meta((size_t)nodes * 7), node_ptr((size_t)nodes + 1), dofs((size_t)tm), labels((size_t)tm),
+        d2n((size_t)tm), mp((size_t)tm), gp((size_t)tm + 1), gi((size_t)(nnz > 0 ? nnz : 1));
+    check(parth_b200_export_tree(h_, meta.data(), node_ptr.data(), dofs.data(), labels.data(), d2n.data(), mp.data()));
+    check(parth_b200_get_mesh(h_, gp.data(), gi.data()));
+    std::FILE *f = std::fopen(path.c_str(), "wb");
+    if (!f) return false;
+    const int hdr[6] = {0x54324250 /* "PB2T" */, 1, tm, lv, nodes, nnz};
+    bool ok = std::fwrite(hdr, sizeof(int), 6, f) == 6;
+    auto put = [&](const std::vector<int> &v, size_t n) { ok = ok && std::fwrite(v.data(), sizeof(int), n, f) == n; };
+    put(meta, meta.size()); put(node_ptr, node_ptr.size()); put(dofs, dofs.size()); put(labels, labels.size());
+    put(gp, gp.size()); put(gi, (size_t)nnz);
+    return std::fclose(f) == 0 && ok;
+  }
+  bool loadTree(const std::string &path) {
+    std::FILE *f = std::fopen(path.c_str(), "rb");
+    if (!f) return false;
+    int hdr[6] = {0, 0, 0, 0, 0, 0};
+    bool ok = std::fread(hdr, sizeof(int), 6, f) == 6 && hdr[0] == 0x54324250 && hdr[1] == 1 && hdr[2] > 0 &&
+              hdr[4] > 0 && hdr[5] >= 0;
+    const int tm = hdr[2], lv = hdr[3], nodes = hdr[4], nnz = hdr[5];
+    std::vector<int> meta, node_ptr, dofs, labels, gp, gi;
+    auto get = [&](std::vector<int> &v, size_t n) { v.resize(n > 0 ? n : 1); ok = ok && std::fread(v.data(), sizeof(int), n, f) == n; };
+    if (ok) {
+      get(meta, (size_t)nodes * 7); get(node_ptr, (size_t)nodes + 1); get(dofs, (size_t)tm); get(labels, (size_t)tm);
+      get(gp, (size_t)tm + 1); get(gi, (size_t)nnz);
+    }
+    std::fclose(f);
+    if (!ok) return false;
+    ND_levels = lv;
+    pushOptions();
+    check(parth_b200_import_tree(h_, tm, lv, nodes, meta.data(), node_ptr.data(), dofs.data(), labels.data(), gp.data(),
+                                 gi.data()));
+    M_n_prev = tm;
+    return true;
+  }
+
   /* copy the mesh graph back (Mp_vec / Mi_vec, ParthAPI.h:63-67) and point Mp / Mi at it */
   void syncMeshMirror() {
     int nnz = 0;

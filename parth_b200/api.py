@@ -95,6 +95,39 @@ SYMBOLS = {
 }
 
 
+TREE_MAGIC = 0x54324250  # "PB2T"
+
+
+def save_tree_file(path, M_n, levels, nodes, meta, node_ptr, dofs, labels, Mp, Mi):
+    """the separator-tree fixture format of PARTH::ParthAPI::saveTree (include/parth/ParthAPI.h): int32 little-endian
+    "PB2T", 1, M_n, levels, nodes, nnz, meta[nodes*7], node_ptr[nodes+1], dofs[M_n], labels[M_n], Mp[M_n+1], Mi[nnz]"""
+    Mp, Mi = _i32(Mp), _i32(Mi)
+    nnz = int(Mp[-1])
+    with open(path, "wb") as f:
+        np.array([TREE_MAGIC, 1, M_n, levels, nodes, nnz], "<i4").tofile(f)
+        for a, n in ((meta, nodes * 7), (node_ptr, nodes + 1), (dofs, M_n), (labels, M_n), (Mp, M_n + 1), (Mi, nnz)):
+            a = np.ascontiguousarray(np.asarray(a).reshape(-1)[:n], "<i4")
+            if len(a) != n:
+                raise ValueError("save_tree_file: array shorter than the header says")
+            a.tofile(f)
+
+
+def load_tree_file(path):
+    with open(path, "rb") as f:
+        hdr = np.fromfile(f, "<i4", 6)
+        if len(hdr) != 6 or hdr[0] != TREE_MAGIC or hdr[1] != 1:
+            raise ValueError("not a parth_b200 tree fixture: " + path)
+        M_n, levels, nodes, nnz = (int(x) for x in hdr[2:])
+        out = dict(M_n=M_n, levels=levels, nodes=nodes)
+        for k, n in (("meta", nodes * 7), ("node_ptr", nodes + 1), ("dofs", M_n), ("labels", M_n), ("Mp", M_n + 1), ("Mi", nnz)):
+            a = np.fromfile(f, "<i4", n)
+            if len(a) != n:
+                raise ValueError("truncated tree fixture: " + path)
+            out[k] = a.astype(np.int32)
+        out["meta"] = out["meta"].reshape(nodes, 7)
+    return out
+
+
 class ParthError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"parth_b200 status {code}: {msg}")

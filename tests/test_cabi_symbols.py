@@ -60,6 +60,27 @@ def test_cpp_drop_in_example_compiles_and_links():
     reference (examples/api_demos/quick_start.cpp:72-118) build against the library with g++ alone"""
     from parth_b200 import build
     build.build()
-    exe = build.build_example("quick_start")
     import os
-    assert os.path.exists(exe)
+    for name in ("quick_start", "example_creator"):   # example_creator: reference tests/example_creator.cpp:61-164
+        exe = build.build_example(name)
+        assert os.path.exists(exe)
+
+
+def test_tree_fixture_file_round_trip(tmp_path):
+    """the on-disk tree fixture format shared by PARTH::ParthAPI::saveTree / loadTree and the Python side"""
+    import numpy as np
+    from parth_b200 import api, synth
+    n, L = 8, 3
+    meta, node_ptr, dofs, labels = synth.geometric_tree(n, L)
+    Mp, Mi = synth.grid_graph(n)
+    path = str(tmp_path / "tree.bin")
+    api.save_tree_file(path, n ** 3, L, len(meta), meta, node_ptr, dofs, labels, Mp, Mi)
+    t = api.load_tree_file(path)
+    assert (t["M_n"], t["levels"], t["nodes"]) == (n ** 3, L, len(meta))
+    for k, v in (("meta", meta), ("node_ptr", node_ptr), ("dofs", dofs), ("labels", labels), ("Mp", Mp), ("Mi", Mi)):
+        assert np.array_equal(np.asarray(t[k]).reshape(-1), np.asarray(v).reshape(-1)), k
+    with open(path, "r+b") as f:
+        f.truncate(100)
+    import pytest as _pt
+    with _pt.raises(ValueError):
+        api.load_tree_file(path)
