@@ -207,6 +207,8 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        # stdout carries ONE JSON line: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
