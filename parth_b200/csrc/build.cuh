@@ -34,6 +34,7 @@ struct BuildArgs {
   unsigned *row_bits;
   struct DetectCounters *dcnt;
   int pipe_cfg;  // pipeline kernel: tile shape (graph_build_pipe.cu)
+  int mail_prezeroed;  // pipeline kernel, fused: status + counters were zeroed behind the previous update's mailbox copy
 };
 
 int build_filter_tiles(int M, int Q);

@@ -572,7 +572,14 @@ int build_pipe_num_tiles(const BuildArgs &a) {
 
 template <class C>
 static void launch_cfg(const BuildArgs &a, int TC, int num_tiles, bool fused, int num_sms, cudaStream_t s) {
-  PB_CUDA(cudaFuncSetAttribute(build_pipe_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K9Smem<C>)));
+  // once per device: the call is a driver round trip on the critical path between two updates
+  static bool attr_done[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+    PB_CUDA(cudaFuncSetAttribute(build_pipe_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K9Smem<C>)));
+    if (dev >= 0 && dev < 64) attr_done[dev] = true;
+  }
   const int grid = num_tiles < C::CTAS * num_sms ? num_tiles : C::CTAS * num_sms;
   if (a.ev_a) cudaEventRecord(a.ev_a, s);
   build_pipe_kernel<C><<<grid, C::THREADS, sizeof(K9Smem<C>), s>>>(a.Ap, a.Ai, a.M, a.Q, TC, num_tiles, a.Mp, a.Mi, a.status,
@@ -589,7 +596,9 @@ int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s) {
   // one memset for the whole mailbox when status and counters are its two halves (every stream
   // operation costs ~2 us of stream time); the per-tile counts are zeroed by the kernel itself
   char *st0 = reinterpret_cast<char *>(a.status), *dc0 = reinterpret_cast<char *>(a.dcnt);
-  if (fused && dc0 > st0 && dc0 - st0 <= 64) {
+  if (fused && a.mail_prezeroed) {
+    // zeroed behind the previous update's mailbox copy (stage_build): nothing to do on the critical path
+  } else if (fused && dc0 > st0 && dc0 - st0 <= 64) {
     PB_CUDA(cudaMemsetAsync(st0, 0, (size_t)(dc0 - st0) + sizeof(DetectCounters), s));
   } else {
     PB_CUDA(cudaMemsetAsync(a.status, 0, sizeof(BuildStatus), s));

@@ -88,6 +88,10 @@ struct parth_b200 {
   pb::DevBuf<int> mail;
   pb::BuildStatus *bstatus_p() { return reinterpret_cast<pb::BuildStatus *>(mail.p); }
   pb::DetectCounters *dcnt_p() { return reinterpret_cast<pb::DetectCounters *>(mail.p + 8); }
+  // the first 12 ints of the mailbox were zeroed on the stream right behind the last deferred build's mailbox copy and
+  // nothing has been enqueued since that writes them: the next fused build skips its memset (one stream operation
+  // less between two updates, where the device is idle)
+  bool mail_clean = false;
   // node flags fetched together with the changed-edge count (stage b)
   bool node_flags_valid = false;
   std::vector<int> node_flags;

@@ -250,6 +250,8 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
   };
   auto launch_filter = [&]() {
     fused_cols = 0;
+    const bool was_clean = h.mail_clean;
+    h.mail_clean = false;
     a.Mp_prev = a.Mi_prev = nullptr;
     a.tile_dirty = nullptr;
     a.row_bits = nullptr;
@@ -264,6 +266,7 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
           a.dcnt = h.dcnt_p();
           fused_cols = build_pipe_tile_cols(a);
         }
+        a.mail_prezeroed = (fused_cols > 0 && was_clean) ? 1 : 0;
         h.stats.kernels_launched += build_pipe_launch(a, h.num_sms, s);
       }
       else h.stats.kernels_launched += build_cols_launch(a, h.build_mode == 0, s);
@@ -306,6 +309,9 @@ void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, 
       PB_CUDA(cudaMemcpyAsync(h.pin_mail.p, h.mail.p, sizeof(int) * (16 + n_spec), cudaMemcpyDeviceToHost, s));
       total.stop(h.ev_mail);  // the mailbox event doubles as the end of the build bracket
       PB_CUDA(cudaEventRecord(h.ev_mail, s));
+      // status + counters for the NEXT build, zeroed here where the stream is busy anyway
+      PB_CUDA(cudaMemsetAsync(h.mail.p, 0, sizeof(int) * 12, s));
+      h.mail_clean = true;
       h.pend.active = true;
       h.pend.N = N; h.pend.nnz = nnz; h.pend.dim = dim; h.pend.M = M; h.pend.fused_cols = fused_cols;
       h.pend.dAp = dAp; h.pend.dAi = dAi;

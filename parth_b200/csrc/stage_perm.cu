@@ -147,6 +147,7 @@ void stage_detect(parth_b200 &h) {
     h.w0.reserve((size_t)n_words + 1, s);  // row bitmap
     h.w1.reserve((size_t)n_words + 2, s);  // popc prefix
     unsigned *bits = reinterpret_cast<unsigned *>(h.w0.p);
+    h.mail_clean = false;  // the diff kernels count into the mailbox
     if (h.map_len > 0)
       h.stats.kernels_launched += launch_diff_rows_mapped(h.Mp, h.Mi, h.Mp_prev.p, h.Mi_prev.p, h.new_to_old.p,
                                                           h.old_to_new.p, M, bits, h.dcnt_p(), s);
