@@ -78,6 +78,27 @@ struct PinBuf {
 // ------------------------------------------------------------------ device helpers
 #ifdef __CUDACC__
 
+// Programmatic dependent launch: the grid may be set up and its CTAs scheduled while the previous kernel of the
+// stream is still draining; the kernel must call pdl_wait() before it touches anything that kernel wrote (the
+// wait returns once the previous grid has completed and its writes are visible).  Hides the 2-3 us of launch
+// latency between the small dependent kernels that follow the build kernel.  pdl_wait() is a no-op under a
+// plain launch.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  PB_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+}
+
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p) {
   unsigned long long v;
   asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

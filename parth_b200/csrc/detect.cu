@@ -222,6 +222,7 @@ __global__ void sym_check_rows_kernel(const int *__restrict__ rows, const int *_
                                       const int *__restrict__ Mp_prev, const int *__restrict__ Mi_prev,
                                       int *__restrict__ asym, const int *__restrict__ dof2node,
                                       int *__restrict__ counts, int spec_cap, int *__restrict__ zero_out, int n_zero) {
+  pdl_wait();
   const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
   if (zero_out && blockIdx.x == 0)
     for (int i = threadIdx.x; i < n_zero; i += blockDim.x) zero_out[i] = 0;
@@ -259,8 +260,8 @@ __global__ void sym_check_rows_kernel(const int *__restrict__ rows, const int *_
 int launch_sym_check_rows(const int *rows, const int *n_rows_dev, int cap, const int *Mp, const int *Mi,
                           const int *Mp_prev, const int *Mi_prev, int *asym, const int *dof2node, int *counts,
                           int spec_cap, cudaStream_t s, int *zero_out, int n_zero) {
-  sym_check_rows_kernel<<<2 * kNumSMsB200, 256, 0, s>>>(rows, n_rows_dev, cap, Mp, Mi, Mp_prev, Mi_prev, asym, dof2node,
-                                                        counts, spec_cap, zero_out, n_zero);
+  launch_pdl(sym_check_rows_kernel, dim3(2 * kNumSMsB200), dim3(256), 0, s, rows, n_rows_dev, cap, Mp, Mi, Mp_prev, Mi_prev,
+             asym, dof2node, counts, spec_cap, zero_out, n_zero);
   PB_CUDA(cudaGetLastError());
   return 1;
 }
@@ -311,6 +312,7 @@ rows_from_tiles_kernel(const int *__restrict__ tile_cnt, int num_tiles, int tile
   __shared__ int s_warp[32];
   __shared__ int s_off[KR_TILES], s_list[KR_TILES];
   __shared__ int s_n, s_base;
+  pdl_wait();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int t0 = blockIdx.x * KR_TILES;
   const int c = (tid < KR_TILES && t0 + tid < num_tiles) ? __ldg(tile_cnt + t0 + tid) : 0;
@@ -378,6 +380,7 @@ emit_mark_kernel(const int *__restrict__ rows, const DetectCounters *__restrict_
                  const int *__restrict__ Mi, const int *__restrict__ dof2node,
                  const int *__restrict__ meta, int *__restrict__ edges, int cap_edges, int nn,
                  int *__restrict__ out) {
+  pdl_wait();
   __shared__ int s_part[KC_ROWS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n = cnt->changed_rows;
@@ -483,16 +486,16 @@ int launch_emit_row_edges(const int *rows, int n_rows, const int *n_rows_dev, co
 int launch_rows_from_tiles(const int *tile_cnt, int *tile_off, unsigned long long *scan_ws, int num_tiles, int tile_cols,
                            const unsigned *row_bits, int M, int *rows, int cap, cudaStream_t s) {
   (void)tile_off; (void)scan_ws;  // the offsets are computed inside the kernel
-  rows_from_tiles_kernel<<<(unsigned)((num_tiles + KR_TILES - 1) / KR_TILES), KA_THREADS, 0, s>>>(tile_cnt, num_tiles, tile_cols,
-                                                                                                  row_bits, M, rows, cap);
+  launch_pdl(rows_from_tiles_kernel, dim3((unsigned)((num_tiles + KR_TILES - 1) / KR_TILES)), dim3(KA_THREADS), 0, s, tile_cnt,
+             num_tiles, tile_cols, row_bits, M, rows, cap);
   PB_CUDA(cudaGetLastError());
   return 1;
 }
 
 int launch_emit_mark(const int *rows, const DetectCounters *cnt, const int *counts, const int *Mp, const int *Mi,
                      const int *dof2node, const int *meta, int *edges, int cap_edges, int nn, int *out, cudaStream_t s) {
-  emit_mark_kernel<<<kSpecRows / KC_ROWS, KC_THREADS, 0, s>>>(rows, cnt, counts, Mp, Mi, dof2node, meta, edges, cap_edges,
-                                                             nn, out);
+  launch_pdl(emit_mark_kernel, dim3(kSpecRows / KC_ROWS), dim3(KC_THREADS), 0, s, rows, cnt, counts, Mp, Mi, dof2node, meta,
+             edges, cap_edges, nn, out);
   PB_CUDA(cudaGetLastError());
   return 1;
 }
