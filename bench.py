@@ -207,8 +207,6 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        # stdout carries ONE JSON line: NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION on some boxes) goes to stderr
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
@@ -397,8 +395,19 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def _own_stdout():
+    """stdout carries ONE JSON line.  Native libraries write to file descriptor 1 behind Python's back (NCCL prints its
+    "NCCL version ..." banner there on some boxes): descriptor 1 is pointed at stderr for the whole run and the JSON
+    line goes to a private duplicate of the original stdout."""
+    sys.stdout.flush()
+    keep = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(keep, "w", buffering=1)
+
+
 if __name__ == "__main__":
     a = parse()
+    _own_stdout()
     if a.impl == "reference":
         run_reference(a)
     else:
