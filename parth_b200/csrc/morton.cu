@@ -16,7 +16,9 @@
 //                         cycles per distinct value on B200, 30 distinct values in a warp of random digits),
 //                         tile sorted in shared memory first so the global stores leave in digit runs
 // Passes whose digit is constant over all keys (known from the OR / AND of the keys, folded into the key
-// kernel) are skipped.  HBM bound: 8n bytes (histogram) + 24n bytes per pass (scatter); keys 24n + 12n.
+// kernel) are skipped.  Hybrid: when the lower 32 bits hold two or more live digits only the upper 32 bits are
+// radix-sorted and morton_fix_runs_kernel sorts the short runs of equal upper halves in place (one thread per run);
+// clustered points whose runs exceed 16 fall back to all passes.  HBM bound: 8n bytes (histogram) + 24n bytes per pass (scatter); keys 24n + 12n.
 #include <algorithm>
 #include <cstdint>
 #include <cstdlib>
@@ -282,6 +284,39 @@ __global__ void __launch_bounds__(kRsThreads, CTAS) radix_scatter_kernel(const u
   }
 }
 
+// Hybrid sort, second half: the pairs are sorted by the upper 32 key bits with ties in ascending point id.  The thread
+// of a run's first element sorts the run by the full key (stable insertion sort: equal keys keep ascending ids).  With
+// keys that spread over the box the runs are pairs and triples; a run longer than kFixRun raises *overflow and the
+// caller falls back to the full radix sort (whatever was already fixed stays a valid input for it).
+constexpr int kFixRun = 16;
+__global__ void morton_fix_runs_kernel(u64 *__restrict__ keys, int *__restrict__ vals, int n, int *__restrict__ overflow) {
+  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned hi = (unsigned)(keys[i] >> 32);
+  if (i > 0 && (unsigned)(keys[i - 1] >> 32) == hi) return;       // not the head of a run
+  if (i + 1 >= n || (unsigned)(keys[i + 1] >> 32) != hi) return;  // a run of one
+  u64 rk[kFixRun];
+  int rv[kFixRun];
+  int len = 0;
+  for (long long j = i; j < n; j++) {
+    const u64 k = keys[j];
+    if ((unsigned)(k >> 32) != hi) break;
+    if (len == kFixRun) { atomicOr(overflow, 1); return; }
+    rk[len] = k;
+    rv[len] = vals[j];
+    len++;
+  }
+  for (int a = 1; a < len; a++) {
+    const u64 x = rk[a];
+    const int y = rv[a];
+    int b = a - 1;
+    while (b >= 0 && rk[b] > x) { rk[b + 1] = rk[b]; rv[b + 1] = rv[b]; b--; }
+    rk[b + 1] = x;
+    rv[b + 1] = y;
+  }
+  for (int a = 0; a < len; a++) { keys[i + a] = rk[a]; vals[i + a] = rv[a]; }
+}
+
 __global__ void rank_of_order_kernel(const int *__restrict__ order, int n, int *__restrict__ rank) {
   const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i < n) rank[order[i]] = (int)i;
@@ -380,9 +415,32 @@ void stage_set_coordinates(parth_b200 &h, const double *dxyz, int n, long long p
   PB_CUDA(cudaMemcpyAsync(h.pin_u64.p, h.m_box.p + 6, 2 * sizeof(u64), cudaMemcpyDeviceToHost, s));
   PB_CUDA(cudaStreamSynchronize(s));
   const u64 diff = h.pin_u64.p[0] ^ h.pin_u64.p[1];  // bits that are not constant over the keys
-  for (int shift = 0; shift < 64; shift += 8) h.morton_passes += ((diff >> shift) & 255ull) != 0;
+  auto passes_of = [](u64 m) { int c = 0; for (int sh = 0; sh < 64; sh += 8) c += ((m >> sh) & 255ull) != 0; return c; };
+  auto sort_from = [&](int from, u64 mask) {  // the pairs sit in buffer pair `from`; returns the pair holding the result
+    h.morton_passes += passes_of(mask);
+    return from == 0 ? radix_sort_pairs(h, h.m_k0.p, h.m_v0.p, h.m_k1.p, h.m_v1.p, n, mask)
+                     : 1 - radix_sort_pairs(h, h.m_k1.p, h.m_v1.p, h.m_k0.p, h.m_v0.p, n, mask);
+  };
+  const u64 hi_mask = diff & 0xffffffff00000000ull, lo_mask = diff & 0x00000000ffffffffull;
+  static const bool no_hybrid = std::getenv("PARTH_B200_MORTON_NO_HYBRID") != nullptr;
+  if (passes_of(lo_mask) >= 2 && hi_mask != 0 && !no_hybrid) {
+    // Hybrid: radix passes over the upper 32 bits only, then the (short) runs of equal upper halves are sorted in place
+    // by one thread each.  Keys that spread over the box share their upper half with one or two others at most, so the
+    // passes over the lower digits are saved; clustered points overflow the run limit and take all passes below.
+    int cur = sort_from(0, hi_mask);
+    int *d_over = reinterpret_cast<int *>(h.m_box.p + 6);
+    PB_CUDA(cudaMemsetAsync(d_over, 0, sizeof(int), s));
+    morton_fix_runs_kernel<<<(n + 255) / 256, 256, 0, s>>>(cur ? h.m_k1.p : h.m_k0.p, cur ? h.m_v1.p : h.m_v0.p, n, d_over);
+    PB_CUDA(cudaGetLastError());
+    h.stats.kernels_launched += 1;
+    PB_CUDA(cudaMemcpyAsync(h.pin_u64.p, d_over, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PB_CUDA(cudaStreamSynchronize(s));
+    if (*reinterpret_cast<int *>(h.pin_u64.p) != 0) cur = sort_from(cur, diff);  // stable: ties are still in ascending id
+    h.morton_cur = cur;
+  } else {
+    h.morton_cur = sort_from(0, diff);
+  }
   h.stats.morton_passes = h.morton_passes;
-  h.morton_cur = radix_sort_pairs(h, h.m_k0.p, h.m_v0.p, h.m_k1.p, h.m_v1.p, n, diff);
   h.morton_rank_valid = false;  // the inverse is a random scatter (1.5 ms at 50 M points): built when a node is ordered
   h.morton_n = n;
   tm.stop();
