@@ -289,12 +289,8 @@ __global__ void __launch_bounds__(kRsThreads, CTAS) radix_scatter_kernel(const u
 // keys that spread over the box the runs are pairs and triples; a run longer than kFixRun raises *overflow and the
 // caller falls back to the full radix sort (whatever was already fixed stays a valid input for it).
 constexpr int kFixRun = 16;
-__global__ void morton_fix_runs_kernel(u64 *__restrict__ keys, int *__restrict__ vals, int n, int *__restrict__ overflow) {
-  const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const unsigned hi = (unsigned)(keys[i] >> 32);
-  if (i > 0 && (unsigned)(keys[i - 1] >> 32) == hi) return;       // not the head of a run
-  if (i + 1 >= n || (unsigned)(keys[i + 1] >> 32) != hi) return;  // a run of one
+__device__ __noinline__ void morton_fix_one_run(u64 *__restrict__ keys, int *__restrict__ vals, int n, long long i,
+                                                unsigned hi, int *__restrict__ overflow) {
   u64 rk[kFixRun];
   int rv[kFixRun];
   int len = 0;
@@ -315,6 +311,32 @@ __global__ void morton_fix_runs_kernel(u64 *__restrict__ keys, int *__restrict__
     rv[b + 1] = y;
   }
   for (int a = 0; a < len; a++) { keys[i + a] = rk[a]; vals[i + a] = rv[a]; }
+}
+
+// a thread looks at four consecutive keys (two 16-byte loads) and their two neighbours; run heads are rare
+__global__ void morton_fix_runs_kernel(u64 *__restrict__ keys, int *__restrict__ vals, int n, int *__restrict__ overflow) {
+  const long long i0 = 4 * (blockIdx.x * (long long)blockDim.x + threadIdx.x);
+  if (i0 >= n) return;
+  unsigned hi[6];  // upper halves of keys[i0 - 1 .. i0 + 4]; positions outside the array never equal a neighbour
+  u64 k[4];
+  if (i0 + 4 <= n) {
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(keys + i0), b = *reinterpret_cast<const ulonglong2 *>(keys + i0 + 2);
+    k[0] = a.x; k[1] = a.y; k[2] = b.x; k[3] = b.y;
+  } else {
+    for (int j = 0; j < 4; j++) k[j] = i0 + j < n ? keys[i0 + j] : 0;
+  }
+  for (int j = 0; j < 4; j++) hi[j + 1] = (unsigned)(k[j] >> 32);
+  const bool has_prev = i0 > 0, has_next = i0 + 4 < n;
+  hi[0] = has_prev ? (unsigned)(keys[i0 - 1] >> 32) : 0;
+  hi[5] = has_next ? (unsigned)(keys[i0 + 4] >> 32) : 0;
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    const long long i = i0 + j;
+    if (i >= n) break;
+    const bool same_prev = (j > 0 || has_prev) && hi[j] == hi[j + 1];
+    const bool same_next = i + 1 < n && (j < 3 || has_next) && hi[j + 2] == hi[j + 1];
+    if (!same_prev && same_next) morton_fix_one_run(keys, vals, n, i, hi[j + 1], overflow);
+  }
 }
 
 __global__ void rank_of_order_kernel(const int *__restrict__ order, int n, int *__restrict__ rank) {
@@ -430,7 +452,7 @@ void stage_set_coordinates(parth_b200 &h, const double *dxyz, int n, long long p
     int cur = sort_from(0, hi_mask);
     int *d_over = reinterpret_cast<int *>(h.m_box.p + 6);
     PB_CUDA(cudaMemsetAsync(d_over, 0, sizeof(int), s));
-    morton_fix_runs_kernel<<<(n + 255) / 256, 256, 0, s>>>(cur ? h.m_k1.p : h.m_k0.p, cur ? h.m_v1.p : h.m_v0.p, n, d_over);
+    morton_fix_runs_kernel<<<(int)(((long long)n + 1023) / 1024), 256, 0, s>>>(cur ? h.m_k1.p : h.m_k0.p, cur ? h.m_v1.p : h.m_v0.p, n, d_over);
     PB_CUDA(cudaGetLastError());
     h.stats.kernels_launched += 1;
     PB_CUDA(cudaMemcpyAsync(h.pin_u64.p, d_over, sizeof(int), cudaMemcpyDeviceToHost, s));
