@@ -44,10 +44,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=200, help="grid edge (200 -> 8 M DOF)")
-    ap.add_argument("--variant", default="lag", choices=["lag", "nolag", "aggr"],
-                    help="lag: reference defaults (lagging on: the dirty level-7 node is dropped, reuse 1); "
+    ap.add_argument("--variant", default="nolag", choices=["lag", "nolag", "aggr"],
+                    help="nolag (headline, SURVEY 8d variant 2a): lagging off, the dirty level-7 node is really re-ordered "
+                         "(device: REPAIR = relocation + AMD; reference: METIS re-dissection); "
                          "aggr: aggressive reuse on (relocation into the separator + AMD of the touched nodes, "
-                         "bit-exact with the reference); nolag: lagging off, the dirty coarse node is REPAIRed")
+                         "bit-exact with the reference); lag: reference defaults (the dirty node is lag-dropped, reuse 1)")
     ap.add_argument("--no-variants", action="store_true", help="skip the secondary variants (reported under 'variants')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -158,7 +159,19 @@ def cpu_kind():
     return "reference" if cpu_parth.available("reference") else "port"
 
 
+def config_dict(n, variant, world):
+    """identical on both arms (the driver compares the two config objects)"""
+    return {"workload": workload_name(n, variant), "variant": variant,
+            "l2": "inputs larger than L2: 701 MB touched by the build + detect pass per step, a different matrix every step",
+            "parallelism": f"{world} GPU(s)" if world == 1 else PARALLELISM_TEXT.format(world=world)}
+
+
+PARALLELISM_TEXT = "{world} independent meshes (one per GPU), no data-path collective"
+
+
 def run_reference(args):
+    """the reference's own CPU implementation (oracle/_ref, else the port) on the SAME config: every step is one
+    full update of the named 200^3 workload (no shrinking, no extrapolation)"""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -169,24 +182,18 @@ def run_reference(args):
         cpu_parth.build("port")
     cores = os.cpu_count() or 1
     os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    # bounded sample: the full 200^3 update costs ~8 s on the CPU; shrink the grid for long runs
-    total = args.steps + args.warmup
-    n = args.n if total <= 24 else min(args.n, 128)
-    stream = workloads.PoissonUpdateStream(n=n, levels=8)
-    full_nnz = 7 * args.n ** 3 - 6 * args.n ** 2
+    stream = workloads.PoissonUpdateStream(n=args.n, levels=8)
     nnz = int(stream.Ap[-1])
     times, info = cpu_update_stream(kind, stream, args.variant, args.steps, args.warmup)
     per = float(np.mean(times))
-    scale = nnz / full_nnz  # updates/s of the named workload, extrapolated linearly in nnz when sampled
-    value = (1.0 / per) * scale
-    sample = (f"{args.steps} full updates (setMatrix + computePermutation) at {n}^3"
-              + ("" if n == args.n else f", scaled by nnz ratio {scale:.4f} to {args.n}^3"))
+    value = 1.0 / per
+    sample = f"{args.steps} full updates (setMatrix + computePermutation) at {args.n}^3 after {args.warmup} warm-up updates"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * per / scale, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * per, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": workload_name(args.n, args.variant), "variant": args.variant},
-        "gnnz_per_s": value * full_nnz / 1e9,
+        "config": config_dict(args.n, args.variant, args.gpus),
+        "gnnz_per_s": value * nnz / 1e9,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "last_update": info,
@@ -352,14 +359,13 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": workload_name(args.n, args.variant), "variant": args.variant,
-                   "l2": "inputs larger than L2: 701 MB touched by the build + detect kernel per step, a different matrix every step",
-                   "parallelism": f"{world} independent meshes (one per GPU), no data-path collective"},
+        "config": config_dict(args.n, args.variant, world),
         "gnnz_per_s": value * nnzA / 1e9,
         "roofline": {"bound": "hbm", "kernel": "build_pipe_kernel" + (" (stage a + fused stage b)" if fused else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/)
-                     "traffic": TRAFFIC.get((args.n, fused)), "algorithmic_bytes": alg,
+                     "traffic": TRAFFIC.get((args.n, fused)), "traffic_source": "profiles/r05_bench_ncu_summary.md (ncu --set full of "
+                     "the same kernel and workload; not re-measured by this run)", "algorithmic_bytes": alg,
                      "algorithmic_bytes_stage_a": alg_build, "algorithmic_bytes_snapshot_read": alg_detect // 2 if fused else 0,
                      "algorithmic_bytes_unfused": alg_build + (alg_detect if fused else 0),
                      "kernel_ms": kms,

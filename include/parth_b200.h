@@ -91,6 +91,14 @@ int parth_b200_set_mesh_dev(parth_b200 *h, int n, const int *dMp, const int *dMi
 /* ParthAPI::setNewToOldDOFMap -> computeOldToNewDOFMap, ParthAPI.cpp:126-189; len 0 clears */
 int parth_b200_set_new_to_old_map(parth_b200 *h, const int *map, int len);
 
+/* ParthAPI::old_to_new_map / added_dofs / removed_dofs (ParthAPI.h:79-84) as computeOldToNewDOFMap
+ * (ParthAPI.cpp:131-189) left them; two-call protocol: array pointers may be NULL to get the sizes.  All sizes are 0
+ * when no map is active (none set, dropped for lack of a previous mesh, or cleared by the 0.4*M_n cold-start rule). */
+int parth_b200_get_dof_maps(parth_b200 *h, int *len_old, int *old_to_new, int *n_added, int *added, int *n_removed,
+                            int *removed);
+/* ParthAPI::Mp_prev / Mi_prev / M_n_prev (ParthAPI.h:71-73): the snapshot graph; array pointers may be NULL */
+int parth_b200_get_snapshot(parth_b200 *h, int *M_n_prev, int *nnz_prev, int *Mp_prev, int *Mi_prev);
+
 /* current mesh graph (ParthAPI::Mp / Mi / M_n, ParthAPI.h:66-71) */
 int parth_b200_mesh_dims(parth_b200 *h, int *M_n, int *nnz);
 int parth_b200_get_mesh(parth_b200 *h, int *Mp, int *Mi);
@@ -120,6 +128,12 @@ int parth_b200_compute_permutation(parth_b200 *h, int *perm, int dim);
  * (parth_b200_stream); it is valid for later work on that stream, or on the host after
  * parth_b200_synchronize.  No synchronisation is done just to return. */
 int parth_b200_compute_permutation_dev(parth_b200 *h, int *dperm, int dim);
+/* After PARTH_B200_NEEDS_REDISSECT (COARSE_REPORT policy) perm holds the tree's CURRENT permutation (valid, but
+ * nothing was re-ordered) and the snapshot has NOT advanced: the next update reports the unresolved edges again.
+ * A caller that has dealt with the report -- it re-dissected and imported a new tree, or it accepts the tree as it
+ * is -- advances the snapshot to the current graph with this call (the copy at the end of ParthAPI::computePermutation,
+ * ParthAPI.cpp:270-278). */
+int parth_b200_accept_snapshot(parth_b200 *h);
 /* ParthAPI::mapMeshPermToMatrixPerm, ParthAPI.cpp:285-337 (dim == -1: sim_dim) */
 int parth_b200_map_mesh_perm_to_matrix_perm(parth_b200 *h, const int *mesh_perm, int n, int *out,
                                             int dim);

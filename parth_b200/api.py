@@ -62,6 +62,9 @@ SYMBOLS = {
     "parth_b200_use_builtin_decomposer": (C.c_int, [_vp, C.c_int]),
     "parth_b200_compute_permutation": (C.c_int, [_vp, _ip, C.c_int]),
     "parth_b200_compute_permutation_dev": (C.c_int, [_vp, _vp, C.c_int]),
+    "parth_b200_accept_snapshot": (C.c_int, [_vp]),
+    "parth_b200_get_dof_maps": (C.c_int, [_vp, _ip, _ip, _ip, _ip, _ip, _ip]),
+    "parth_b200_get_snapshot": (C.c_int, [_vp, _ip, _ip, _ip, _ip]),
     "parth_b200_map_mesh_perm_to_matrix_perm": (C.c_int, [_vp, _ip, C.c_int, _ip, C.c_int]),
     "parth_b200_map_mesh_perm_to_matrix_perm_dev": (C.c_int, [_vp, _vp, C.c_int, _vp, C.c_int]),
     "parth_b200_get_reuse": (C.c_double, [_vp]),
@@ -179,6 +182,10 @@ class ParthAPI:
         self.relocate_lvl = 2
         self.lag_lvl = 5
         self._decomposer_ref = None
+        # COARSE_REPORT: the C ABI leaves the snapshot where it was after PARTH_B200_NEEDS_REDISSECT.  The parity
+        # tests compare multi-update sequences with the oracle port, which snapshots after reporting (the reference
+        # always finishes the update), so this mirror accepts the snapshot on the caller's behalf by default.
+        self.report_advances_snapshot = True
         self._push_options()
 
     def __del__(self):
@@ -352,12 +359,37 @@ class ParthAPI:
         else:
             perm = np.empty(max(n * dim, 1), np.int32)
         rc = self._check(self.lib.parth_b200_compute_permutation(self.h, _p(perm), int(dim)), allow=(NEEDS_REDISSECT, NEEDS_EXCHANGE))
+        if rc == NEEDS_REDISSECT and self.report_advances_snapshot:
+            self.acceptSnapshot()
         return rc, perm[:n * dim]
 
     def computePermutationDev(self, dperm_ptr, dim=3):
         self._push_options()
-        return self._check(self.lib.parth_b200_compute_permutation_dev(self.h, C.c_void_p(dperm_ptr), int(dim)),
-                           allow=(NEEDS_REDISSECT, NEEDS_EXCHANGE))
+        rc = self._check(self.lib.parth_b200_compute_permutation_dev(self.h, C.c_void_p(dperm_ptr), int(dim)),
+                         allow=(NEEDS_REDISSECT, NEEDS_EXCHANGE))
+        if rc == NEEDS_REDISSECT and self.report_advances_snapshot:
+            self.acceptSnapshot()
+        return rc
+
+    def dof_maps(self):
+        """(old_to_new_map, added_dofs, removed_dofs) as ParthAPI::computeOldToNewDOFMap leaves them"""
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self._check(self.lib.parth_b200_get_dof_maps(self.h, C.byref(a), None, C.byref(b), None, C.byref(c), None))
+        o2n, add, rem = (np.empty(max(x.value, 1), np.int32) for x in (a, b, c))
+        self._check(self.lib.parth_b200_get_dof_maps(self.h, C.byref(a), _p(o2n), C.byref(b), _p(add), C.byref(c), _p(rem)))
+        return o2n[:a.value], add[:b.value], rem[:c.value]
+
+    def snapshot(self):
+        """(Mp_prev, Mi_prev) of the handle"""
+        m, z = C.c_int(), C.c_int()
+        self._check(self.lib.parth_b200_get_snapshot(self.h, C.byref(m), C.byref(z), None, None))
+        Mp, Mi = np.zeros(m.value + 1, np.int32), np.empty(max(z.value, 1), np.int32)
+        self._check(self.lib.parth_b200_get_snapshot(self.h, C.byref(m), C.byref(z), _p(Mp), _p(Mi)))
+        return Mp, Mi[:z.value]
+
+    def acceptSnapshot(self):
+        """after NEEDS_REDISSECT: advance the snapshot to the current graph (parth_b200_accept_snapshot)"""
+        self._check(self.lib.parth_b200_accept_snapshot(self.h))
 
     # ---- multi-GPU exchange (see parth_b200/sharded.py)
     def exchange_plan(self):

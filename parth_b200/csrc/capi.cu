@@ -202,6 +202,7 @@ int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out) {
 int parth_b200_set_matrix_dev(parth_b200 *h, int N, const int *dAp, const int *dAi, int nnz, int dim) {
   PB_API_BEGIN
   if (!dAp || !dAi || N <= 0 || dim <= 0 || nnz < 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: bad argument");
+  if (N % dim != 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: N is not a multiple of dim (ParthAPI.cpp:371 asserts it)");
   h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
   h->sim_dim = dim;
   // steady state: returns with the build, the changed-row proof and stage (b)'s edge kernels in flight;
@@ -214,6 +215,7 @@ int parth_b200_set_matrix_dev(parth_b200 *h, int N, const int *dAp, const int *d
 int parth_b200_set_matrix(parth_b200 *h, int N, const int *Ap, const int *Ai, int dim) {
   PB_API_BEGIN
   if (!Ap || !Ai || N <= 0 || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: bad argument");
+  if (N % dim != 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: N is not a multiple of dim (ParthAPI.cpp:371 asserts it)");
   const int nnz = Ap[N];
   if (Ap[0] != 0 || nnz < 0) throw StatusError(PARTH_B200_ERR_INPUT, "set_matrix: Ap[0] != 0 or Ap[N] < 0");
   h->dAp.reserve((size_t)N + 1, h->stream);
@@ -247,6 +249,7 @@ int parth_b200_set_mesh(parth_b200 *h, int n, const int *Mp, const int *Mi) {
   PB_API_BEGIN
   if (!Mp || !Mi || n <= 0) throw StatusError(PARTH_B200_ERR_ARG, "set_mesh: bad argument");
   const int nnz = Mp[n];
+  if (Mp[0] != 0 || nnz < 0) throw StatusError(PARTH_B200_ERR_ARG, "set_mesh: Mp[0] != 0 or Mp[n] < 0");
   h->Mp_own.reserve((size_t)n + 1, h->stream);
   h->Mi_own.reserve((size_t)(nnz > 0 ? nnz : 1), h->stream);
   PB_CUDA(cudaMemcpyAsync(h->Mp_own.p, Mp, sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, h->stream));
@@ -348,12 +351,50 @@ int parth_b200_compute_permutation(parth_b200 *h, int *perm, int dim) {
   const size_t n_out = (size_t)h->M_n * dim;
   h->d_out.reserve(n_out > 0 ? n_out : 1, h->stream);
   rc = stage_compute_permutation(*h, h->d_out.p, dim);
-  if (rc == PARTH_B200_OK) {
+  if (rc == PARTH_B200_OK || rc == PARTH_B200_NEEDS_REDISSECT) {  // REPORT: the tree's current permutation
     PB_CUDA(cudaMemcpyAsync(perm, h->d_out.p, sizeof(int) * n_out, cudaMemcpyDeviceToHost, h->stream));
     h->stats.d2h_bytes += (long long)(sizeof(int) * n_out);
   }
   resolve_timers(*h);
   if (rc != PARTH_B200_OK) return rc;
+  PB_API_END
+}
+
+int parth_b200_get_snapshot(parth_b200 *h, int *M_n_prev, int *nnz_prev, int *Mp_prev, int *Mi_prev) {
+  PB_API_BEGIN
+  if (!M_n_prev || !nnz_prev) throw StatusError(PARTH_B200_ERR_ARG, "get_snapshot: null size pointer");
+  *M_n_prev = h->M_n_prev;
+  *nnz_prev = h->M_n_prev > 0 ? h->nnz_prev : 0;
+  if (h->M_n_prev > 0 && Mp_prev)
+    PB_CUDA(cudaMemcpyAsync(Mp_prev, h->Mp_prev.p, sizeof(int) * ((size_t)h->M_n_prev + 1), cudaMemcpyDeviceToHost, h->stream));
+  if (h->M_n_prev > 0 && Mi_prev && h->nnz_prev > 0)
+    PB_CUDA(cudaMemcpyAsync(Mi_prev, h->Mi_prev.p, sizeof(int) * (size_t)h->nnz_prev, cudaMemcpyDeviceToHost, h->stream));
+  PB_CUDA(cudaStreamSynchronize(h->stream));
+  PB_API_END
+}
+
+int parth_b200_get_dof_maps(parth_b200 *h, int *len_old, int *old_to_new, int *n_added, int *added, int *n_removed,
+                            int *removed) {
+  PB_API_BEGIN
+  if (!len_old || !n_added || !n_removed) throw StatusError(PARTH_B200_ERR_ARG, "get_dof_maps: null size pointer");
+  const bool have = h->map_len > 0;
+  *len_old = have ? h->M_n_prev : 0;
+  *n_added = have ? h->n_added : 0;
+  *n_removed = have ? h->n_removed : 0;
+  if (have && old_to_new)
+    PB_CUDA(cudaMemcpyAsync(old_to_new, h->old_to_new.p, sizeof(int) * (size_t)h->M_n_prev, cudaMemcpyDeviceToHost, h->stream));
+  if (have && added && h->n_added > 0)
+    PB_CUDA(cudaMemcpyAsync(added, h->added.p, sizeof(int) * (size_t)h->n_added, cudaMemcpyDeviceToHost, h->stream));
+  if (have && removed && h->n_removed > 0)
+    PB_CUDA(cudaMemcpyAsync(removed, h->removed.p, sizeof(int) * (size_t)h->n_removed, cudaMemcpyDeviceToHost, h->stream));
+  PB_CUDA(cudaStreamSynchronize(h->stream));
+  PB_API_END
+}
+
+int parth_b200_accept_snapshot(parth_b200 *h) {
+  PB_API_BEGIN
+  if (!h->Mp || h->M_n <= 0) throw StatusError(PARTH_B200_ERR_ARG, "accept_snapshot: no mesh set");
+  stage_snapshot(*h);
   PB_API_END
 }
 
@@ -409,6 +450,7 @@ int parth_b200_map_mesh_perm_to_matrix_perm_dev(parth_b200 *h, const int *dmesh_
   PB_API_BEGIN
   if (!dmesh_perm || !dout || n <= 0) throw StatusError(PARTH_B200_ERR_ARG, "mapMeshPermToMatrixPerm: bad argument");
   if (dim == -1) dim = h->sim_dim;
+  if (dim < 1) throw StatusError(PARTH_B200_ERR_ARG, "mapMeshPermToMatrixPerm: dim must be >= 1 (or -1 for sim_dim)");
   stage_expand(*h, dmesh_perm, n, dim, dout);
   resolve_timers(*h);
   PB_API_END
@@ -419,6 +461,7 @@ int parth_b200_map_mesh_perm_to_matrix_perm(parth_b200 *h, const int *mesh_perm,
   PB_API_BEGIN
   if (!mesh_perm || !out || n <= 0) throw StatusError(PARTH_B200_ERR_ARG, "mapMeshPermToMatrixPerm: bad argument");
   if (dim == -1) dim = h->sim_dim;
+  if (dim < 1) throw StatusError(PARTH_B200_ERR_ARG, "mapMeshPermToMatrixPerm: dim must be >= 1 (or -1 for sim_dim)");
   h->w0.reserve((size_t)n, h->stream);
   h->d_out.reserve((size_t)n * dim, h->stream);
   PB_CUDA(cudaMemcpyAsync(h->w0.p, mesh_perm, sizeof(int) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
@@ -537,6 +580,8 @@ int parth_b200_amd_batch(parth_b200 *h, int count, const int *graph_ptr, const i
 int parth_b200_set_coordinates_dev(parth_b200 *h, const double *dxyz, int n, long long point_stride,
                                    long long comp_stride, int bits) {
   PB_API_BEGIN
+  if (n < 0 || (n > 0 && !dxyz) || point_stride < 0 || comp_stride < 0)
+    throw StatusError(PARTH_B200_ERR_ARG, "set_coordinates: bad argument");
   stage_set_coordinates(*h, dxyz, n, point_stride, comp_stride, bits);
   PB_API_END
 }

@@ -62,8 +62,26 @@ void stage_import_tree(parth_b200 &h, int M_n, int levels, int nodes, const int 
                        const int *node_ptr, const int *dofs, const int *labels, const int *Mp_prev,
                        const int *Mi_prev) {
   cudaStream_t s = h.stream;
-  if (nodes <= 0 || M_n <= 0 || node_ptr[nodes] > M_n)
-    throw StatusError(PARTH_B200_ERR_ARG, "import_tree: inconsistent sizes");
+  // the mailbox, the node flags and the host-side dirty-set code are sized for <= 8191 nodes (12 levels, what
+  // HMD::initHMD clamps to, HMD.cpp:98-100)
+  if (nodes <= 0 || nodes > 8191 || M_n <= 0 || node_ptr[0] != 0 || node_ptr[nodes] > M_n)
+    throw StatusError(PARTH_B200_ERR_ARG, "import_tree: inconsistent sizes (1 <= nodes <= 8191, node_ptr[nodes] <= M_n)");
+  for (int x = 0; x < nodes; x++) {
+    if (node_ptr[x + 1] < node_ptr[x]) throw StatusError(PARTH_B200_ERR_ARG, "import_tree: node_ptr is not monotone");
+    for (int k = 0; k < 2; k++) {  // left / right links
+      const int c = meta[(size_t)x * 7 + k];
+      if (c < -1 || c >= nodes) throw StatusError(PARTH_B200_ERR_ARG, "import_tree: child link out of range");
+    }
+    const int par = meta[(size_t)x * 7 + 3];
+    if (par < -1 || par >= nodes) throw StatusError(PARTH_B200_ERR_ARG, "import_tree: parent link out of range");
+  }
+  {
+    const int total_in = node_ptr[nodes];
+    for (int k = 0; k < total_in; k++)
+      if (dofs[k] < 0 || dofs[k] >= M_n) throw StatusError(PARTH_B200_ERR_ARG, "import_tree: DOF id out of range");
+  }
+  if (Mp_prev && Mi_prev && (Mp_prev[0] != 0 || Mp_prev[M_n] < 0))
+    throw StatusError(PARTH_B200_ERR_ARG, "import_tree: snapshot row pointers are inconsistent");
   h.num_levels = levels;
   h.nd_levels = levels;
   h.num_nodes = nodes;
@@ -85,6 +103,13 @@ void stage_import_tree(parth_b200 &h, int M_n, int levels, int nodes, const int 
   h.tree_init = true;
   if (Mp_prev && Mi_prev) {
     const int nnz = Mp_prev[M_n];
+    if (h.Mp && (h.Mp == h.Mp_prev.p || h.Mi == h.Mi_prev.p)) {
+      // the current graph aliases the snapshot buffers (right after a computePermutation): they are about to
+      // hold the imported snapshot, so there is no current graph until the next setMatrix / setMesh
+      h.Mp = h.Mi = nullptr;
+      h.M_n = h.nnzM = 0;
+      h.cur_sym_proven = false;
+    }
     h.Mp_prev.reserve((size_t)M_n + 1, s);
     h.Mi_prev.reserve((size_t)std::max(nnz, 1), s);
     PB_CUDA(cudaMemcpyAsync(h.Mp_prev.p, Mp_prev, sizeof(int) * ((size_t)M_n + 1), cudaMemcpyHostToDevice, s));
@@ -94,6 +119,7 @@ void stage_import_tree(parth_b200 &h, int M_n, int levels, int nodes, const int 
     h.nnz_prev = nnz;
     h.prev_sym_proven = false;  // caller-provided snapshot: nothing is known about it
     h.diff_cached = false;
+    h.spec_valid = false;
   }
   PB_CUDA(cudaStreamSynchronize(s));
 }
@@ -433,6 +459,15 @@ int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
       h.stats.expand_speculative = 1;  // its timer (pending) fills expand_ms
     } else if (rc == PARTH_B200_OK) {
       stage_expand(h, h.d_mesh_perm.p, h.M_n, dim, dperm);
+    } else if (rc == PARTH_B200_NEEDS_REDISSECT) {
+      // REPORT policy: nothing was re-ordered.  The caller still gets a valid permutation (the tree's current one)
+      // and the snapshot does NOT advance: the unresolved edges are reported again by the next update, like a
+      // reference update that never finished (the reference snapshots only after getGlobalPerm, ParthAPI.cpp:244-278).
+      if (!spec_expanded && dperm) stage_expand(h, h.d_mesh_perm.p, h.M_n, dim, dperm);
+      if (h.stats.kernels_launched == launched0) tc.cancel(); else tc.stop();
+      h.diff_cached = false;  // the row diff was taken against a snapshot that stays; recompute next time
+      h.spec_valid = false;
+      return rc;
     }
     if (h.stats.kernels_launched == launched0) tc.cancel(); else tc.stop();
   }

@@ -57,3 +57,62 @@ def test_repair_restores_the_separator_property(gpu_api, port, k, rt):
     g.setMesh(M, P, I)
     st2, perm2 = g.computePermutation(1)
     assert st2 == 0 and g.getNumChanges() == 0 and g.getReuse() == 1.0 and np.array_equal(perm, perm2)
+
+
+def test_report_status_keeps_the_snapshot_and_returns_a_valid_permutation(gpu_api, port):
+    """COARSE_REPORT: PARTH_B200_NEEDS_REDISSECT hands back the tree's current (valid) permutation and does not
+    advance the snapshot -- the same edges are reported again until the caller accepts the snapshot
+    (the reference snapshots only after a finished update, ParthAPI.cpp:244-278)."""
+    tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 16, 5)))
+    M = 16 ** 3
+    rng = np.random.default_rng(3)
+    P, I = synth.add_edges(Mp, Mi, rng.integers(0, M, size=(60, 2)))
+    g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 5; g.reorder_type = 1; g.lagging = False
+    g.setCoarsePolicy(gpu_api.COARSE_REPORT)
+    g.report_advances_snapshot = False
+    g.import_tree(tree, Mp, Mi)
+    g.setMesh(M, P, I)
+    st, perm = g.computePermutation(1)
+    assert st == gpu_api.NEEDS_REDISSECT
+    assert sorted(perm.tolist()) == list(range(M))
+    n1, e1 = g.getNumChanges(), g.changed_edges().copy()
+    assert n1 > 0
+    sp, si = g.snapshot()
+    assert np.array_equal(sp, Mp) and np.array_equal(si, Mi)
+    # second update on the same graph: the unresolved edges come back
+    g.setMesh(M, P, I)
+    st2, perm2 = g.computePermutation(1)
+    assert st2 == gpu_api.NEEDS_REDISSECT and g.getNumChanges() == n1
+    assert np.array_equal(g.changed_edges(), e1) and np.array_equal(perm, perm2)
+    # the caller accepts: snapshot advances, the next identical update is clean
+    g.acceptSnapshot()
+    sp, si = g.snapshot()
+    assert np.array_equal(sp, P) and np.array_equal(si, I)
+    g.setMesh(M, P, I)
+    st3, perm3 = g.computePermutation(1)
+    assert st3 == 0 and g.getNumChanges() == 0 and np.array_equal(perm3, perm)
+
+
+def test_dof_map_getters_match_the_oracle(gpu_api, port):
+    """ParthAPI::old_to_new_map / added_dofs / removed_dofs (ParthAPI.h:79-84) after computeOldToNewDOFMap"""
+    tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 12, 4)))
+    M = 12 ** 3
+    rng = np.random.default_rng(5)
+    keep = np.sort(rng.choice(M, M - 40, replace=False)).astype(np.int32)
+    n2o = np.concatenate([keep, -np.ones(25, np.int32)]).astype(np.int32)
+    g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 4; g.reorder_type = 1
+    g.import_tree(tree, Mp, Mi)
+    Mn = len(n2o)
+    # any graph over Mn vertices will do: a path
+    P = np.zeros(Mn + 1, np.int32); deg = np.full(Mn, 2, np.int32); deg[0] = deg[-1] = 1
+    P[1:] = np.cumsum(deg)
+    I = np.empty(P[-1], np.int32)
+    for v in range(Mn):
+        nb = [u for u in (v - 1, v + 1) if 0 <= u < Mn]
+        I[P[v]:P[v + 1]] = nb
+    g.setMesh(Mn, P, I, n2o)
+    o2n, added, removed = g.dof_maps()
+    want = -np.ones(M, np.int32); want[keep] = np.arange(len(keep), dtype=np.int32)
+    assert np.array_equal(o2n, want)
+    assert added.tolist() == list(range(len(keep), Mn))
+    assert removed.tolist() == sorted(set(range(M)) - set(keep.tolist()))
