@@ -23,6 +23,7 @@
 #ifndef PARTH_B200_PARTHAPI_H
 #define PARTH_B200_PARTHAPI_H
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <iostream>
@@ -88,8 +89,17 @@ public:
   int *Mi = nullptr;
   int M_n = 0;
   int M_n_prev = 0;
+  std::vector<int> Mp_prev, Mi_prev; /* ParthAPI.h:72-73; filled on demand by syncSnapshotMirror() */
   std::vector<int> mesh_perm;
   std::vector<std::pair<int, int>> changed_dof_edges;
+
+  /* ParthAPI.h:77-84: new_to_old_map is the caller's map as passed in; the other three are what
+   * computeOldToNewDOFMap (ParthAPI.cpp:131-189) derived from it, copied back from the device by
+   * setNewToOldDOFMap / computeOldToNewDOFMap */
+  std::vector<int> new_to_old_map;
+  std::vector<int> old_to_new_map;
+  std::vector<int> added_dofs;
+  std::vector<int> removed_dofs;
 
   double dof_change_integrator_time = 0.0;
   double change_computation_time = 0.0;
@@ -115,9 +125,16 @@ public:
     check(parth_b200_clear(h_));
     mesh_perm.clear();
     changed_dof_edges.clear();
+    new_to_old_map.clear();
+    old_to_new_map.clear();
+    added_dofs.clear();
+    removed_dofs.clear();
+    Mp_prev.clear();
+    Mi_prev.clear();
     hmd = HMDMirror();
     M_n = M_n_prev = 0;
     Mp = Mi = nullptr;
+    results_stale_ = false;
   }
 
   /* ParthAPI.cpp:76-98: the arrays are copied to the device during the call */
@@ -131,6 +148,7 @@ public:
     Mp = Mp_in;
     Mi = Mi_in;
     M_n = n;
+    new_to_old_map.clear(); /* ParthAPI.cpp:97 */
   }
 
   /* ParthAPI.cpp:100-124, 366-418 */
@@ -146,11 +164,38 @@ public:
     setMatrix(N, Ap, Ai, dim);
     setNewToOldDOFMap(map);
   }
+  /* ParthAPI.cpp:366-418 (public in the reference): the graph is built on the device and, as in the reference,
+   * left in Mp_vec / Mi_vec with Mp / Mi / M_n pointing at it; sim_dim is not touched */
+  void computeMeshFromMatrix(int *Ap, int *Ai, int N, int dim) {
+    const int keep = sim_dim;
+    setMatrix(N, Ap, Ai, dim);
+    sim_dim = keep;
+    syncMeshMirror();
+  }
 
   /* ParthAPI.cpp:126-189 */
   void setNewToOldDOFMap(std::vector<int> &map) {
-    check(parth_b200_set_new_to_old_map(h_, map.empty() ? nullptr : map.data(), (int)map.size()));
-    map_set_ = !map.empty();
+    if (&map != &new_to_old_map) new_to_old_map = map;
+    computeOldToNewDOFMap();
+  }
+  /* ParthAPI.cpp:131-189: inverts new_to_old_map on the device (cold-start rule for > 0.4 M_n added DOFs
+   * included) and mirrors old_to_new_map / added_dofs / removed_dofs; set mirror_dof_maps = false to skip the copy */
+  bool mirror_dof_maps = true;
+  void computeOldToNewDOFMap() {
+    check(parth_b200_set_new_to_old_map(h_, new_to_old_map.empty() ? nullptr : new_to_old_map.data(),
+                                        (int)new_to_old_map.size()));
+    map_set_ = !new_to_old_map.empty();
+    old_to_new_map.clear();
+    added_dofs.clear();
+    removed_dofs.clear();
+    if (!mirror_dof_maps || new_to_old_map.empty()) return;
+    int a = 0, b = 0, c = 0;
+    check(parth_b200_get_dof_maps(h_, &a, nullptr, &b, nullptr, &c, nullptr));
+    old_to_new_map.resize((size_t)a);
+    added_dofs.resize((size_t)b);
+    removed_dofs.resize((size_t)c);
+    check(parth_b200_get_dof_maps(h_, &a, old_to_new_map.data(), &b, added_dofs.data(), &c, removed_dofs.data()));
+    if (a == 0) new_to_old_map.clear(); /* the map was dropped (no previous mesh / cold-start rule) */
   }
 
   /* ParthAPI.cpp:191-279; default dim is 3 as in the reference (ParthAPI.h:135) */
@@ -172,10 +217,6 @@ public:
     map_mesh_to_matrix_computation_time = t[4];
     integrator.reuse_ratio = parth_b200_get_reuse(h_);
     const int nc = parth_b200_get_num_changes(h_);
-    std::vector<int> flat((size_t)(nc > 0 ? nc : 0) * 2);
-    if (nc > 0) parth_b200_get_changed_edges(h_, flat.data(), nc);
-    changed_dof_edges.resize((size_t)(nc > 0 ? nc : 0));
-    for (int e = 0; e < nc; e++) changed_dof_edges[e] = {flat[2 * e], flat[2 * e + 1]};
     /* the reference prints this line on every warm update, even with verbose == false (ParthAPI.cpp:254) */
     if (warm) std::cout << "+++ PARTH: number of bad edges are " << nc << std::endl;
     int nf = 0, ncs = 0, tm = 0, lv = 0, nodes = 0;
@@ -186,12 +227,41 @@ public:
                                integrator.dirty_coarse_HMD_nodes_saved.data(), &ncs);
     integrator.dirty_fine_HMD_nodes_saved.resize((size_t)nf);
     integrator.dirty_coarse_HMD_nodes_saved.resize((size_t)ncs);
-    mesh_perm.resize((size_t)M_n);
-    parth_b200_get_mesh_perm(h_, mesh_perm.data(), M_n);
     M_n_prev = M_n;
     hmd.HMD_init = true;
     hmd.num_levels = lv;
     hmd.num_HMD_nodes = nodes;
+    results_stale_ = true;
+    if (!lazy_result_mirrors) syncResultMirror();
+  }
+
+  /* mesh_perm (M_n ints) and changed_dof_edges are public vectors in the reference (ParthAPI.h:75-76), so by
+   * default they are copied back after every computePermutation.  Most callers read neither (the solver wrappers
+   * only take `perm`): with lazy_result_mirrors = true the 4*M_n-byte device-to-host copy is skipped and
+   * syncResultMirror() fetches both when somebody wants them. */
+  bool lazy_result_mirrors = false;
+  void syncResultMirror() {
+    if (!results_stale_) return;
+    const int nc = parth_b200_get_num_changes(h_);
+    std::vector<int> flat((size_t)(nc > 0 ? nc : 0) * 2);
+    if (nc > 0) check(parth_b200_get_changed_edges(h_, flat.data(), nc));
+    changed_dof_edges.resize((size_t)(nc > 0 ? nc : 0));
+    for (int e = 0; e < nc; e++) changed_dof_edges[e] = {flat[2 * e], flat[2 * e + 1]};
+    mesh_perm.resize((size_t)M_n);
+    if (M_n > 0) check(parth_b200_get_mesh_perm(h_, mesh_perm.data(), M_n));
+    results_stale_ = false;
+  }
+  /* Mp_prev / Mi_prev (ParthAPI.h:72-73): the snapshot the next update is compared with */
+  void syncSnapshotMirror() {
+    int mn = 0, nnz = 0;
+    check(parth_b200_get_snapshot(h_, &mn, &nnz, nullptr, nullptr));
+    Mp_prev.assign((size_t)(mn > 0 ? mn + 1 : 0), 0);
+    Mi_prev.resize((size_t)(nnz > 0 ? nnz : 0));
+    if (mn > 0) {
+      std::vector<int> tmp((size_t)(nnz > 0 ? nnz : 1));
+      check(parth_b200_get_snapshot(h_, &mn, &nnz, Mp_prev.data(), tmp.data()));
+      std::copy(tmp.begin(), tmp.begin() + nnz, Mi_prev.begin());
+    }
   }
 
   /* ParthAPI.cpp:285-337; dim == -1 means sim_dim */
@@ -335,7 +405,7 @@ public:
 
 private:
   parth_b200 *h_ = nullptr;
-  bool map_set_ = false;
+  bool map_set_ = false, results_stale_ = false;
   void pushOptions() {
     check(parth_b200_set_options(h_, (int)reorder_type, ND_levels, lagging ? 1 : 0, activate_aggressive_reuse ? 1 : 0,
                                  integrator.relocate_lvl, integrator.lag_lvl, verbose ? 1 : 0));

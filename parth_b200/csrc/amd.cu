@@ -45,8 +45,8 @@ template <bool STAGED>
 __global__ void __launch_bounds__(kAmdThreads)
 amd_batch_kernel(int count, const int *__restrict__ vtx_ptr, const int *__restrict__ G,
                  const int *__restrict__ sub_Mi, const long long *__restrict__ ws_ptr,
-                 int *__restrict__ ws, int *__restrict__ perm_out, int smem_ints) {
-  const int g = blockIdx.x;
+                 int *__restrict__ ws, int *__restrict__ perm_out, int smem_ints, const int *__restrict__ glist) {
+  const int g = glist ? glist[blockIdx.x] : blockIdx.x;
   if (g >= count) return;
   const int v0 = vtx_ptr[g], n = vtx_ptr[g + 1] - v0;
   if (n <= 0) return;
@@ -77,8 +77,10 @@ amd_batch_kernel(int count, const int *__restrict__ vtx_ptr, const int *__restri
 // shared memory (0 = none fits / unknown -> stage with the device maximum)
 int launch_amd_batch(int count, const int *vtx_ptr, const int *G, const int *sub_Mi,
                      const long long *ws_ptr, int *ws, int *perm_out, long long max_stage_ints, bool any_unstaged,
-                     cudaStream_t s) {
+                     cudaStream_t s, const int *glist, int n_list) {
   if (count <= 0) return 0;
+  const int grid = glist ? n_list : count;
+  if (grid <= 0) return 0;
   int launches = 0;
   const int cap_bytes = amd_stage_capacity_ints() * 4;
   // the smaller the staging area, the more CTAs share an SM
@@ -88,14 +90,14 @@ int launch_amd_batch(int count, const int *vtx_ptr, const int *G, const int *sub
   const int smem_bytes = (int)(want > cap_bytes ? cap_bytes : want);
   if (max_stage_ints != 0) {
     PB_CUDA(cudaFuncSetAttribute(amd_batch_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
-    amd_batch_kernel<true><<<count, kAmdThreads, smem_bytes, s>>>(count, vtx_ptr, G, sub_Mi, ws_ptr, ws, perm_out,
-                                                                  smem_bytes / 4);
+    amd_batch_kernel<true><<<grid, kAmdThreads, smem_bytes, s>>>(count, vtx_ptr, G, sub_Mi, ws_ptr, ws, perm_out,
+                                                                 smem_bytes / 4, glist);
     PB_CUDA(cudaGetLastError());
     launches++;
   }
   if (any_unstaged) {
-    amd_batch_kernel<false><<<count, kAmdThreads, 0, s>>>(count, vtx_ptr, G, sub_Mi, ws_ptr, ws, perm_out,
-                                                          smem_bytes / 4);
+    amd_batch_kernel<false><<<grid, kAmdThreads, 0, s>>>(count, vtx_ptr, G, sub_Mi, ws_ptr, ws, perm_out,
+                                                         smem_bytes / 4, glist);
     PB_CUDA(cudaGetLastError());
     launches++;
   }

@@ -35,6 +35,10 @@ struct BuildArgs {
   struct DetectCounters *dcnt;
   int pipe_cfg;  // pipeline kernel: tile shape (graph_build_pipe.cu)
   int mail_prezeroed;  // pipeline kernel, fused: status + counters were zeroed behind the previous update's mailbox copy
+  // pipeline kernel, row-block mode (stage_sharded.cu): blk_TC > 0 fixes the tile shape of the whole matrix
+  // (M_rows columns); this launch owns tiles [blk_t0, blk_t1), M / Q / nnz_prev are the ends of the block's slices
+  // and every pointer is biased so that global ids index it
+  int blk_TC, blk_t0, blk_t1, M_rows;
 };
 
 int build_filter_tiles(int M, int Q);

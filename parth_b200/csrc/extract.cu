@@ -26,12 +26,14 @@ __global__ void extract_count_kernel(const int *__restrict__ list, const int *__
                                      int count, int total, const int *__restrict__ node_ptr,
                                      const int *__restrict__ dofs, const int *__restrict__ Mp,
                                      const int *__restrict__ Mi, const int *__restrict__ dof2node,
-                                     int *__restrict__ cnt) {
+                                     int *__restrict__ cnt, int row0, int row1) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= total) return;
   const int g = graph_of_vertex(vtx_ptr, count, v);
   const int nd = __ldg(list + g);
   const int d = __ldg(dofs + __ldg(node_ptr + nd) + (v - __ldg(vtx_ptr + g)));
+  // row-block mode: rows outside [row0, row1) live on another rank (their counts arrive by all-reduce)
+  if (d < row0 || d >= row1) { cnt[v] = 0; return; }
   int c = 0;
   for (int p = __ldg(Mp + d); p < __ldg(Mp + d + 1); p++) c += __ldg(dof2node + __ldg(Mi + p)) == nd;
   cnt[v] = c;
@@ -41,7 +43,7 @@ __global__ void extract_fill_kernel(const int *__restrict__ list, const int *__r
                                     int count, int total, const int *__restrict__ node_ptr,
                                     const int *__restrict__ dofs, const int *__restrict__ Mp,
                                     const int *__restrict__ Mi, const int *__restrict__ dof2node,
-                                    const int *__restrict__ G, int *__restrict__ sub_Mi) {
+                                    const int *__restrict__ G, int *__restrict__ sub_Mi, int row0, int row1) {
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= total) return;
   const int g = graph_of_vertex(vtx_ptr, count, v);
@@ -49,6 +51,7 @@ __global__ void extract_fill_kernel(const int *__restrict__ list, const int *__r
   const int a = __ldg(node_ptr + nd), n = __ldg(node_ptr + nd + 1) - a;
   const int *slice = dofs + a;
   const int d = __ldg(slice + (v - __ldg(vtx_ptr + g)));
+  if (d < row0 || d >= row1) return;
   int o = G[v];
   for (int p = __ldg(Mp + d); p < __ldg(Mp + d + 1); p++) {
     const int nb = __ldg(Mi + p);
@@ -144,20 +147,20 @@ static inline unsigned blocks_for(long long n) { return (unsigned)((n + 255) / 2
 
 int launch_extract_count(const int *list, const int *vtx_ptr, int count, int total,
                          const int *node_ptr, const int *dofs, const int *Mp, const int *Mi,
-                         const int *dof2node, int *cnt, cudaStream_t s) {
+                         const int *dof2node, int *cnt, cudaStream_t s, int row0, int row1) {
   if (total <= 0) return 0;
   extract_count_kernel<<<blocks_for(total), 256, 0, s>>>(list, vtx_ptr, count, total, node_ptr, dofs, Mp,
-                                                        Mi, dof2node, cnt);
+                                                        Mi, dof2node, cnt, row0, row1);
   PB_CUDA(cudaGetLastError());
   return 1;
 }
 
 int launch_extract_fill(const int *list, const int *vtx_ptr, int count, int total,
                         const int *node_ptr, const int *dofs, const int *Mp, const int *Mi,
-                        const int *dof2node, const int *G, int *sub_Mi, cudaStream_t s) {
+                        const int *dof2node, const int *G, int *sub_Mi, cudaStream_t s, int row0, int row1) {
   if (total <= 0) return 0;
   extract_fill_kernel<<<blocks_for(total), 256, 0, s>>>(list, vtx_ptr, count, total, node_ptr, dofs, Mp,
-                                                       Mi, dof2node, G, sub_Mi);
+                                                       Mi, dof2node, G, sub_Mi, row0, row1);
   PB_CUDA(cudaGetLastError());
   return 1;
 }

@@ -179,7 +179,12 @@ __global__ void __launch_bounds__(C::THREADS, C::CTAS)
 build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M, int Q, int TC, int num_tiles,
                   int *__restrict__ Mp, int *__restrict__ Mi, BuildStatus *__restrict__ st, int check_mirror,
                   const int *__restrict__ Mp_prev, const int *__restrict__ Mi_prev, int nnz_prev,
-                  int *__restrict__ tile_state, unsigned *__restrict__ row_bits, DetectCounters *__restrict__ dcnt) {
+                  int *__restrict__ tile_state, unsigned *__restrict__ row_bits, DetectCounters *__restrict__ dcnt,
+                  int tile_begin, int M_rows) {
+  // Row-block mode (one mesh over several GPUs, stage_sharded.cu): this launch owns tiles [tile_begin, num_tiles)
+  // = columns [tile_begin * TC, M) of a matrix with M_rows columns.  Every array pointer is biased so that GLOBAL
+  // column ids / entry offsets index it (only the block's own range is ever touched); M and Q are the ends of the
+  // block's slices of Ap / Ai, nnz_prev the end of the snapshot's slice.  Whole matrix: tile_begin 0, M_rows == M.
   extern __shared__ __align__(128) unsigned char k9_raw[];
   static_assert(sizeof(K9Stage<C>) % 16 == 0, "bulk copies need 16-byte aligned stage buffers");
   constexpr int K9_CONSUMERS = C::CONSUMERS, K9_CAP = C::CAP;
@@ -205,7 +210,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
   if (producer) {
     if (lane != 0) return;
     int k = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, k++) {
+    for (int t = tile_begin + blockIdx.x; t < num_tiles; t += gridDim.x, k++) {
       const int s = k & 1;
       const int c0 = t * TC, c1 = min(M, c0 + TC), nc = c1 - c0;
       const int q0 = __ldg(Ap + c0), q1 = __ldg(Ap + c1);
@@ -253,7 +258,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
   long long diff = 0;
   int k = 0;
   bool order_first = false;  // something of the previous tile must be ordered before this tile's walk
-  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, k++) {
+  for (int t = tile_begin + blockIdx.x; t < num_tiles; t += gridDim.x, k++) {
     const int s = k & 1;
     K9Stage<C> &B = S.st[s];
     int *const Bout = S.out[k % C::OUTS];
@@ -305,12 +310,12 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
         if (!check_mirror) {
           // threads of a warp mostly agree on the length (regular meshes): a branch per length, not a vote
           switch (len) {
-            case 3: walked = k9_walk_fixed<3>(sp, op, c, M); break;
-            case 4: walked = k9_walk_fixed<4>(sp, op, c, M); break;
-            case 5: walked = k9_walk_fixed<5>(sp, op, c, M); break;
-            case 6: walked = k9_walk_fixed<6>(sp, op, c, M); break;
-            case 7: walked = k9_walk_fixed<7>(sp, op, c, M); break;
-            case 8: walked = k9_walk_fixed<8>(sp, op, c, M); break;
+            case 3: walked = k9_walk_fixed<3>(sp, op, c, M_rows); break;
+            case 4: walked = k9_walk_fixed<4>(sp, op, c, M_rows); break;
+            case 5: walked = k9_walk_fixed<5>(sp, op, c, M_rows); break;
+            case 6: walked = k9_walk_fixed<6>(sp, op, c, M_rows); break;
+            case 7: walked = k9_walk_fixed<7>(sp, op, c, M_rows); break;
+            case 8: walked = k9_walk_fixed<8>(sp, op, c, M_rows); break;
             default: break;
           }
         }
@@ -338,7 +343,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
               prev = sp[i];
             }
           }
-          if (lastv >= M) flags |= BUILD_RANGE;
+          if (lastv >= M_rows) flags |= BUILD_RANGE;
           const int has = di < K9_REG;
           if (!has) flags |= BUILD_NODIAG;
           if (check_mirror) diff += (len - has - low) - low;
@@ -348,7 +353,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
             const int v = (i >= di && i + 1 < K9_REG) ? r[i + 1] : r[i];
             if (i < len - has) op[i] = v;
           }
-          if (check_mirror && !bad && lastv < M) {
+          if (check_mirror && !bad && lastv < M_rows) {
             for (int i = low + has; i < len; i += 4) {
               int a[4], b[4];
 #pragma unroll
@@ -372,7 +377,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
             low += r < c;
             prev = r;
           }
-          if (prev >= M) flags |= BUILD_RANGE;
+          if (prev >= M_rows) flags |= BUILD_RANGE;
           if (dpos < 0) flags |= BUILD_NODIAG;
           const int has = dpos >= 0;
           diff += (len - has - low) - low;
@@ -409,7 +414,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
           if (lane == 0) prev = i0 > 0 ? sp[i0 - 1] : -1;
           if (i < len) {
             if (r <= prev) f |= (r < 0) ? BUILD_RANGE : (r == prev ? BUILD_DUP : BUILD_UNSORTED);
-            if (r >= M) f |= BUILD_RANGE;
+            if (r >= M_rows) f |= BUILD_RANGE;
             if (r == c) dp = i;
             low += r < c;
           }
@@ -514,7 +519,7 @@ build_pipe_kernel(const int *__restrict__ Ap, const int *__restrict__ Ai, int M,
   }
   if (tid == 0) {
     bulk_wait_all();
-    if (blockIdx.x == (num_tiles - 1) % gridDim.x) {
+    if (blockIdx.x == (num_tiles - 1 - tile_begin) % gridDim.x) {
       Mp[M] = Q - M;
       st->nnz_out = Q - M;
     }
@@ -557,6 +562,7 @@ static int tile_cols_of(const BuildArgs &a) {
 }
 
 int build_pipe_tile_cols(const BuildArgs &a) {
+  if (a.blk_TC > 0) return a.blk_TC;  // row-block mode: the tile shape of the WHOLE matrix, fixed by the caller
   switch (a.pipe_cfg) {
     case 1: return tile_cols_of<K9Half>(a);
     case 2: return tile_cols_of<K9Wide>(a);
@@ -567,7 +573,7 @@ int build_pipe_tile_cols(const BuildArgs &a) {
 
 int build_pipe_num_tiles(const BuildArgs &a) {
   const int TC = build_pipe_tile_cols(a);
-  return (a.M + TC - 1) / TC;
+  return ((a.blk_TC > 0 ? a.M_rows : a.M) + TC - 1) / TC;
 }
 
 template <class C>
@@ -580,18 +586,22 @@ static void launch_cfg(const BuildArgs &a, int TC, int num_tiles, bool fused, in
     PB_CUDA(cudaFuncSetAttribute(build_pipe_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K9Smem<C>)));
     if (dev >= 0 && dev < 64) attr_done[dev] = true;
   }
-  const int grid = num_tiles < C::CTAS * num_sms ? num_tiles : C::CTAS * num_sms;
+  const int t0 = a.blk_TC > 0 ? a.blk_t0 : 0;
+  const int own = num_tiles - t0;
+  const int grid = own < C::CTAS * num_sms ? own : C::CTAS * num_sms;
   if (a.ev_a) cudaEventRecord(a.ev_a, s);
   build_pipe_kernel<C><<<grid, C::THREADS, sizeof(K9Smem<C>), s>>>(a.Ap, a.Ai, a.M, a.Q, TC, num_tiles, a.Mp, a.Mi, a.status,
                                                                   a.check_mirror, fused ? a.Mp_prev : nullptr,
                                                                   fused ? a.Mi_prev : nullptr, a.nnz_prev,
-                                                                  fused ? a.tile_dirty : nullptr, a.row_bits, a.dcnt);
+                                                                  fused ? a.tile_dirty : nullptr, a.row_bits, a.dcnt, t0,
+                                                                  a.blk_TC > 0 ? a.M_rows : a.M);
   if (a.ev_b) cudaEventRecord(a.ev_b, s);
 }
 
 int build_pipe_launch(const BuildArgs &a, int num_sms, cudaStream_t s) {
   const int TC = build_pipe_tile_cols(a);
-  const int num_tiles = (a.M + TC - 1) / TC;
+  const int num_tiles = a.blk_TC > 0 ? a.blk_t1 : (a.M + TC - 1) / TC;
+  if (num_tiles - (a.blk_TC > 0 ? a.blk_t0 : 0) <= 0) return 0;
   const bool fused = a.Mp_prev && a.Mi_prev && a.tile_dirty && a.row_bits && a.dcnt;
   // one memset for the whole mailbox when status and counters are its two halves (every stream
   // operation costs ~2 us of stream time); the per-tile counts are zeroed by the kernel itself

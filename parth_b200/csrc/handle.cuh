@@ -10,6 +10,7 @@
 
 #include "../../include/parth_b200.h"
 #include "build.cuh"
+#include "comm.cuh"
 #include "common.cuh"
 #include "tree.cuh"
 
@@ -50,6 +51,23 @@ struct parth_b200 {
   pb::DevBuf<int> Mp_own, Mi_own;
   int M_n_prev = 0, nnz_prev = 0;
   pb::DevBuf<int> Mp_prev, Mi_prev;
+
+  // ---- row-block mode: ONE mesh over the ranks of a communicator (stage_sharded.cu).  Mp_own / Mi_own / Mp_prev /
+  // Mi_prev then hold only the rows [blk_c0, blk_c1) of the two graphs; h.Mp / h.Mi and the pointers handed to the
+  // kernels are BIASED (Mp_own.p - blk_c0, Mi_own.p + own_off - own_q0) so that global row ids and global entry
+  // offsets index them; own_q0 / own_q1 = global Mp[blk_c0] / Mp[blk_c1], own_off = own_q0 & 3 keeps the biased
+  // Mi pointer 16-byte aligned for the bulk copies.  The separator tree and every per-DOF array stay replicated.
+  pb::Comm *comm = nullptr;
+  bool block_mode = false;
+  int blk_TC = 0, blk_t0 = 0, blk_t1 = 0, blk_tiles = 0, blk_c0 = 0, blk_c1 = 0;
+  int own_off = 0, prev_off = 0, own_q0 = 0, own_q1 = 0, prev_q0 = 0, prev_q1 = 0;
+  const int *Mp_own_b() const { return Mp_own.p - blk_c0; }
+  const int *Mi_own_b() const { return Mi_own.p + own_off - own_q0; }
+  const int *Mp_prev_b() const { return Mp_prev.p - blk_c0; }
+  const int *Mi_prev_b() const { return Mi_prev.p + prev_off - prev_q0; }
+  pb::DevBuf<int> x_hdr, x_buf, x_len, x_off, x_glist;  // exchange: headers of all ranks, payload, row lengths / offsets
+  pb::PinBuf<int> pin_x;
+  int n_chg_rows_total = 0;
 
   // ---- symmetry bookkeeping (stage a): a proven-symmetric snapshot lets the next build prove its
   // graph by checking only the rows that changed; the row diff is then reused by change detection
