@@ -244,7 +244,10 @@ public:
     if (!results_stale_) return;
     const int nc = parth_b200_get_num_changes(h_);
     std::vector<int> flat((size_t)(nc > 0 ? nc : 0) * 2);
-    if (nc > 0) check(parth_b200_get_changed_edges(h_, flat.data(), nc));
+    if (nc > 0) {
+      const int got = parth_b200_get_changed_edges(h_, flat.data(), nc); /* returns the count, negative = error */
+      if (got < 0) check(got);
+    }
     changed_dof_edges.resize((size_t)(nc > 0 ? nc : 0));
     for (int e = 0; e < nc; e++) changed_dof_edges[e] = {flat[2 * e], flat[2 * e + 1]};
     mesh_perm.resize((size_t)M_n);

@@ -233,6 +233,40 @@ int parth_b200_unpack_labels_dev(parth_b200 *h, const int *nodes, int n, const i
 int parth_b200_finish_permutation(parth_b200 *h, int *perm, int dim);
 int parth_b200_finish_permutation_dev(parth_b200 *h, int *dperm, int dim);
 
+/* ONE mesh over several GPUs: row blocks of the graph build and of change detection (SURVEY.md section 8e rows 1-2;
+ * reference sites ParthAPI.cpp:366-418, Integrator.cpp:259-338), one process per GPU, the collectives inside the
+ * library (NCCL, loaded with dlopen when a communicator is created -- a single-GPU caller never needs it).
+ *
+ *   rank 0: parth_b200_comm_unique_id(id)  -> send the 128 bytes to every rank (file, MPI, a socket ...)
+ *   all   : parth_b200_comm_init(h, id, rank, world)
+ *           parth_b200_import_tree(h, ..., NULL, NULL)      the replicated separator tree (a fixture)
+ *           parth_b200_set_matrix*(h, ...)                  first matrix: builds this rank's rows, proves symmetry
+ *           parth_b200_accept_snapshot(h)                   ... which the tree belongs to
+ *   per update, all ranks: parth_b200_set_matrix*(h, ...); parth_b200_compute_permutation*(h, perm, dim)
+ *
+ * With a communicator set, set_matrix / set_matrix_dev / set_matrix_block* read ONLY this rank's block of the
+ * arrays -- Ap[c0 .. c1] and Ai[Ap[c0] .. Ap[c1]), global indexing, [c0, c1) from parth_b200_block_range -- so a
+ * host caller uploads 1/world of the matrix over its own PCIe link and a caller that holds only its block passes
+ * pointers biased by -c0 / -Ap[c0].  Detection exchanges one small slot per rank (header, dirty-node flags, changed
+ * edges, directed row diffs: one all-gather); dirty sub-meshes are assembled by all-reduce, the graphs of an update
+ * are dealt to the ranks and their permutations all-reduced.  Every rank returns the same full permutation.
+ * Restrictions of the block path: dim == 1, matrices the pipeline build kernel accepts (sorted symmetric columns
+ * with their diagonal), no DOF map, at most 16384 changed rows per rank and update; the stage-wise entry points,
+ * get_mesh, symbolic and the coarse sub-mesh extraction need the whole graph and are refused.
+ * parth_b200_comm_init_local: the ranks are `world` handles of ONE process, each driven by its own host thread
+ * (test plumbing for the sharded logic on a single GPU, or several GPUs of one process). */
+int parth_b200_comm_unique_id(void *id128);
+int parth_b200_comm_init(parth_b200 *h, const void *id128, int rank, int world);
+int parth_b200_comm_init_local(parth_b200 **handles, int world);
+int parth_b200_comm_info(parth_b200 *h, int *rank, int *world, const char **kind);
+/* columns [c0, c1) this rank owns of an N x N matrix with nnz entries (fixes the partition of the handle) */
+int parth_b200_block_range(parth_b200 *h, int N, int nnz, int *c0, int *c1);
+/* host arrays, global indexing, only the block is dereferenced; nnz = Ap[N] of the whole matrix */
+int parth_b200_set_matrix_block(parth_b200 *h, int N, int nnz, const int *Ap, const int *Ai, int dim);
+/* device arrays, global indexing, only the block is dereferenced; q0 = Ap[c0], q1 = Ap[c1] (no read-back) */
+int parth_b200_set_matrix_block_dev(parth_b200 *h, int N, int nnz, const int *dAp, const int *dAi, int dim, int q0,
+                                    int q1);
+
 #ifdef __cplusplus
 }
 #endif

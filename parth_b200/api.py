@@ -95,6 +95,13 @@ SYMBOLS = {
     "parth_b200_unpack_labels_dev": (C.c_int, [_vp, _ip, C.c_int, _vp]),
     "parth_b200_finish_permutation": (C.c_int, [_vp, _ip, C.c_int]),
     "parth_b200_finish_permutation_dev": (C.c_int, [_vp, _vp, C.c_int]),
+    "parth_b200_comm_unique_id": (C.c_int, [_vp]),
+    "parth_b200_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "parth_b200_comm_init_local": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "parth_b200_comm_info": (C.c_int, [_vp, _ip, _ip, C.POINTER(C.c_char_p)]),
+    "parth_b200_block_range": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _ip]),
+    "parth_b200_set_matrix_block": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int]),
+    "parth_b200_set_matrix_block_dev": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, C.c_int, C.c_int]),
 }
 
 
@@ -262,6 +269,52 @@ class ParthAPI:
     def clearParth(self):
         self._check(self.lib.parth_b200_clear(self.h))
 
+    # ---- one mesh over several GPUs: row blocks (include/parth_b200.h, stage_sharded.cu)
+    @staticmethod
+    def commUniqueId():
+        """128 bytes from rank 0 (NCCL unique id) to hand to every rank's commInit"""
+        lib = load_library()
+        buf = C.create_string_buffer(128)
+        rc = lib.parth_b200_comm_unique_id(buf)
+        if rc != 0:
+            raise ParthError(rc, lib.parth_b200_last_error(None).decode())
+        return buf.raw
+
+    def commInit(self, unique_id, rank, world):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.lib.parth_b200_comm_init(self.h, buf, int(rank), int(world)))
+
+    @staticmethod
+    def commInitLocal(apis):
+        """the ranks are the given ParthAPI objects of this process, one host thread each (test plumbing)"""
+        lib = load_library()
+        arr = (C.c_void_p * len(apis))(*[a.h for a in apis])
+        rc = lib.parth_b200_comm_init_local(arr, len(apis))
+        if rc != 0:
+            raise ParthError(rc, "comm_init_local failed")
+
+    def commInfo(self):
+        r, w, k = C.c_int(), C.c_int(), C.c_char_p()
+        self._check(self.lib.parth_b200_comm_info(self.h, C.byref(r), C.byref(w), C.byref(k)))
+        return r.value, w.value, (k.value or b"").decode()
+
+    def blockRange(self, N, nnz):
+        a, b = C.c_int(), C.c_int()
+        self._check(self.lib.parth_b200_block_range(self.h, int(N), int(nnz), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def setMatrixBlock(self, N, nnz, Ap, Ai, dim=1):
+        """Ap / Ai: whole host arrays (int32, contiguous) of which only this rank's block is read"""
+        self._push_options()
+        Ap, Ai = _i32(Ap), _i32(Ai)
+        self._check(self.lib.parth_b200_set_matrix_block(self.h, int(N), int(nnz), C.c_void_p(Ap.ctypes.data),
+                                                         C.c_void_p(Ai.ctypes.data), int(dim)))
+
+    def setMatrixBlockDev(self, N, nnz, dAp_ptr, dAi_ptr, q0, q1, dim=1):
+        self._push_options()
+        self._check(self.lib.parth_b200_set_matrix_block_dev(self.h, int(N), int(nnz), C.c_void_p(dAp_ptr),
+                                                             C.c_void_p(dAi_ptr), int(dim), int(q0), int(q1)))
+
     # ---- inputs
     def setMatrix(self, N, Ap, Ai, dim=1, new_to_old=None):
         self._push_options()
@@ -304,8 +357,9 @@ class ParthAPI:
         self._check(self.lib.parth_b200_get_mesh(self.h, _p(Mp), _p(Mi)))
         return Mp, Mi[:nnz]
 
-    def import_tree(self, tree, Mp_prev, Mi_prev):
-        Mp_prev, Mi_prev = _i32(Mp_prev), _i32(Mi_prev)
+    def import_tree(self, tree, Mp_prev=None, Mi_prev=None):
+        Mp_prev = None if Mp_prev is None else _i32(Mp_prev)
+        Mi_prev = None if Mi_prev is None else _i32(Mi_prev)
         meta, node_ptr, dofs, labels = _i32(tree.meta), _i32(tree.node_ptr), _i32(tree.dofs), _i32(tree.labels)
         self._check(self.lib.parth_b200_import_tree(self.h, tree.M_n, tree.levels, tree.nodes, _p(meta), _p(node_ptr),
                                                     _p(dofs), _p(labels), _p(Mp_prev), _p(Mi_prev)))

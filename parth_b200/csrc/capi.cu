@@ -42,6 +42,29 @@ static int settle_quiet(parth_b200 *h) {
   PB_API_END
 }
 
+
+// Row-block mode, host arrays in GLOBAL indexing: uploads Ap[c0..c1] and Ai[Ap[c0]..Ap[c1]) -- 1/world of the matrix --
+// and builds this rank's rows.  The staging buffers are placed so that the biased pointers the kernels index with
+// global ids keep the 16-byte alignment of the bulk copies (graph_build_pipe.cu).
+static void set_matrix_block_host(parth_b200 &h, int N, int nnz, const int *Ap, const int *Ai, int dim) {
+  if (dim != 1) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "row-block mode: dim must be 1");
+  if (nnz < 0) throw StatusError(PARTH_B200_ERR_INPUT, "set_matrix: nnz < 0");
+  block_plan(h, N, nnz);
+  const int c0 = h.blk_c0, c1 = h.blk_c1;
+  const int q0 = Ap[c0], q1 = Ap[c1];
+  if (q0 < 0 || q1 < q0 || q1 > nnz) throw StatusError(PARTH_B200_ERR_INPUT, "set_matrix: Ap is not monotone over the block");
+  cudaStream_t s = h.stream;
+  const int off = q0 & 3;
+  h.dAp.reserve((size_t)(c1 - c0) + 8, s);
+  h.dAi.reserve((size_t)(q1 - q0) + 16, s);
+  PB_CUDA(cudaMemcpyAsync(h.dAp.p, Ap + c0, sizeof(int) * ((size_t)(c1 - c0) + 1), cudaMemcpyHostToDevice, s));
+  if (q1 > q0) PB_CUDA(cudaMemcpyAsync(h.dAi.p + off, Ai + q0, sizeof(int) * (size_t)(q1 - q0), cudaMemcpyHostToDevice, s));
+  h.stats.h2d_bytes = (long long)sizeof(int) * ((long long)(c1 - c0) + 1 + (q1 - q0));
+  h.stats.d2h_bytes = 0;
+  stage_build_block(h, N, nnz, h.dAp.p - c0, h.dAi.p + off - q0, q0, q1);
+  resolve_timers(h);
+}
+
 extern "C" {
 
 const char *parth_b200_version(void) { return "parth_b200 0.1 (sm_100a)"; }
@@ -107,6 +130,8 @@ int parth_b200_destroy(parth_b200 *h) {
   if (h->ev3) cudaEventDestroy(h->ev3);
   if (h->ev_mail) cudaEventDestroy(h->ev_mail);
   for (auto &e : h->tev) if (e) cudaEventDestroy(e);
+  delete h->comm;
+  h->comm = nullptr;
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return PARTH_B200_OK;
@@ -130,6 +155,11 @@ int parth_b200_clear(parth_b200 *h) {
   h->dirty_fine.clear(); h->dirty_coarse.clear();
   h->dirty_fine_saved.clear(); h->dirty_coarse_saved.clear();
   h->reuse = 1;
+  // row-block mode: the partition is chosen again by the next matrix (the communicator stays)
+  h->block_mode = false;
+  h->blk_TC = h->blk_tiles = h->blk_t0 = h->blk_t1 = h->blk_c0 = h->blk_c1 = 0;
+  h->blk_tiles_zeroed = false;
+  h->pipe_cfg = pb::build_pipe_default_cfg();
   PB_API_END
 }
 
@@ -205,6 +235,16 @@ int parth_b200_set_matrix_dev(parth_b200 *h, int N, const int *dAp, const int *d
   if (N % dim != 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: N is not a multiple of dim (ParthAPI.cpp:371 asserts it)");
   h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
   h->sim_dim = dim;
+  if (h->comm) {
+    // one mesh over the ranks of the communicator: only this rank's block of the arrays is read
+    if (dim != 1) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "row-block mode: dim must be 1");
+    block_plan(*h, N, nnz);
+    int q[2] = {0, 0};
+    read_ints(*h, dAp + h->blk_c0, &q[0], 1);
+    read_ints(*h, dAp + h->blk_c1, &q[1], 1);
+    stage_build_block(*h, N, nnz, dAp, dAi, q[0], q[1]);
+    return PARTH_B200_OK;
+  }
   // steady state: returns with the build, the changed-row proof and stage (b)'s edge kernels in flight;
   // whatever call needs their outcome next waits for the mailbox copy alone (stage_build_settle).
   // Otherwise it ends on its mailbox read-back and nothing is in flight.
@@ -218,6 +258,11 @@ int parth_b200_set_matrix(parth_b200 *h, int N, const int *Ap, const int *Ai, in
   if (N % dim != 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: N is not a multiple of dim (ParthAPI.cpp:371 asserts it)");
   const int nnz = Ap[N];
   if (Ap[0] != 0 || nnz < 0) throw StatusError(PARTH_B200_ERR_INPUT, "set_matrix: Ap[0] != 0 or Ap[N] < 0");
+  if (h->comm) {
+    h->sim_dim = dim;
+    set_matrix_block_host(*h, N, nnz, Ap, Ai, dim);
+    return PARTH_B200_OK;
+  }
   h->dAp.reserve((size_t)N + 1, h->stream);
   h->dAi.reserve((size_t)(nnz > 0 ? nnz : 1), h->stream);
   PB_CUDA(cudaMemcpyAsync(h->dAp.p, Ap, sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, h->stream));
@@ -279,6 +324,7 @@ int parth_b200_mesh_dims(parth_b200 *h, int *M_n, int *nnz) {
 int parth_b200_get_mesh(parth_b200 *h, int *Mp, int *Mi) {
   PB_API_BEGIN
   if (!h->Mp || !Mp || !Mi) throw StatusError(PARTH_B200_ERR_ARG, "get_mesh: no mesh");
+  if (h->block_mode) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "get_mesh: the handle holds one row block of a sharded mesh");
   PB_CUDA(cudaMemcpyAsync(Mp, h->Mp, sizeof(int) * ((size_t)h->M_n + 1), cudaMemcpyDeviceToHost, h->stream));
   if (h->nnzM > 0)
     PB_CUDA(cudaMemcpyAsync(Mi, h->Mi, sizeof(int) * (size_t)h->nnzM, cudaMemcpyDeviceToHost, h->stream));
@@ -302,6 +348,7 @@ extern "C" {
 int parth_b200_set_new_to_old_map(parth_b200 *h, const int *map, int len) {
   PB_API_BEGIN
   if (len < 0 || (len > 0 && !map)) throw StatusError(PARTH_B200_ERR_ARG, "set_new_to_old_map: bad argument");
+  if (len > 0 && h->block_mode) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "set_new_to_old_map: DOF maps are not sharded (row-block mode)");
   stage_set_map(*h, map, len);
   PB_API_END
 }
@@ -363,6 +410,7 @@ int parth_b200_compute_permutation(parth_b200 *h, int *perm, int dim) {
 int parth_b200_get_snapshot(parth_b200 *h, int *M_n_prev, int *nnz_prev, int *Mp_prev, int *Mi_prev) {
   PB_API_BEGIN
   if (!M_n_prev || !nnz_prev) throw StatusError(PARTH_B200_ERR_ARG, "get_snapshot: null size pointer");
+  if (h->block_mode) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "get_snapshot: the handle holds one row block of a sharded mesh");
   *M_n_prev = h->M_n_prev;
   *nnz_prev = h->M_n_prev > 0 ? h->nnz_prev : 0;
   if (h->M_n_prev > 0 && Mp_prev)
@@ -564,6 +612,7 @@ int parth_b200_stage_submesh(parth_b200 *h, int node, int coarse, int *n, int *n
   PB_API_BEGIN
   if (!h->tree_init || !h->Mp || !n || !nnz || node < 0 || node >= h->num_nodes)
     throw StatusError(PARTH_B200_ERR_ARG, "stage_submesh: bad argument");
+  if (h->block_mode && coarse) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "stage_submesh(coarse): needs the whole graph (row-block mode)");
   stage_submesh(*h, node, coarse, n, nnz, Mp, Mi, local_to_global);
   PB_API_END
 }
@@ -633,6 +682,7 @@ int parth_b200_morton_keys(parth_b200 *h, unsigned long long *keys_sorted, int c
 int parth_b200_symbolic(parth_b200 *h, const int *perm, int *parent, int *colcount, int64_t *lnz) {
   PB_API_BEGIN
   if (!h->Mp || !lnz) throw StatusError(PARTH_B200_ERR_ARG, "symbolic: needs a mesh");
+  if (h->block_mode) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "symbolic: the handle holds one row block of a sharded mesh");
   long long v = 0;
   stage_symbolic(*h, perm, parent, colcount, &v);
   resolve_timers(*h);
@@ -645,10 +695,82 @@ int parth_b200_symbolic(parth_b200 *h, const int *perm, int *parent, int *colcou
 int parth_b200_symbolic_dev(parth_b200 *h, const int *dperm, int *dparent, int *dcolcount, int64_t *lnz) {
   PB_API_BEGIN
   if (!h->Mp || !lnz) throw StatusError(PARTH_B200_ERR_ARG, "symbolic: needs a mesh");
+  if (h->block_mode) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "symbolic: the handle holds one row block of a sharded mesh");
   long long v = 0;
   stage_symbolic(*h, dperm, dparent, dcolcount, &v, /*on_device=*/true);
   resolve_timers(*h);
   *lnz = v;
+  PB_API_END
+}
+
+
+// ------------------------------------------------------------------ one mesh over several GPUs (row blocks)
+int parth_b200_comm_unique_id(void *id128) {
+  if (!id128) return PARTH_B200_ERR_ARG;
+  try {
+    nccl_unique_id(id128);
+  } catch (const pb::StatusError &e) {
+    g_create_error = e.what();
+    return e.code;
+  } catch (const std::exception &e) {
+    g_create_error = e.what();
+    return PARTH_B200_ERR_INTERNAL;
+  }
+  return PARTH_B200_OK;
+}
+
+int parth_b200_comm_init(parth_b200 *h, const void *id128, int rank, int world) {
+  PB_API_BEGIN
+  if (!id128 || world < 1 || rank < 0 || rank >= world) throw StatusError(PARTH_B200_ERR_ARG, "comm_init: bad argument");
+  if (h->comm) throw StatusError(PARTH_B200_ERR_ARG, "comm_init: the handle already has a communicator");
+  h->comm = nccl_comm_create(id128, rank, world);
+  PB_API_END
+}
+
+int parth_b200_comm_init_local(parth_b200 **handles, int world) {
+  if (!handles || world < 1) return PARTH_B200_ERR_ARG;
+  for (int r = 0; r < world; r++)
+    if (!handles[r] || handles[r]->comm) return PARTH_B200_ERR_ARG;
+  LocalGroup *g = local_group_create(world);
+  for (int r = 0; r < world; r++) handles[r]->comm = local_comm_create(g, r);
+  return PARTH_B200_OK;
+}
+
+int parth_b200_comm_info(parth_b200 *h, int *rank, int *world, const char **kind) {
+  if (!h) return PARTH_B200_ERR_ARG;
+  if (rank) *rank = h->comm ? h->comm->rank : 0;
+  if (world) *world = h->comm ? h->comm->world : 1;
+  if (kind) *kind = h->comm ? h->comm->kind() : "none";
+  return PARTH_B200_OK;
+}
+
+int parth_b200_block_range(parth_b200 *h, int N, int nnz, int *c0, int *c1) {
+  PB_API_BEGIN
+  if (N <= 0 || nnz < 0 || !c0 || !c1) throw StatusError(PARTH_B200_ERR_ARG, "block_range: bad argument");
+  block_plan(*h, N, nnz);
+  *c0 = h->blk_c0;
+  *c1 = h->blk_c1;
+  PB_API_END
+}
+
+int parth_b200_set_matrix_block(parth_b200 *h, int N, int nnz, const int *Ap, const int *Ai, int dim) {
+  PB_API_BEGIN
+  if (!Ap || !Ai || N <= 0 || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix_block: bad argument");
+  if (!h->comm) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix_block: no communicator (parth_b200_comm_init*)");
+  h->sim_dim = dim;
+  set_matrix_block_host(*h, N, nnz, Ap, Ai, dim);
+  PB_API_END
+}
+
+int parth_b200_set_matrix_block_dev(parth_b200 *h, int N, int nnz, const int *dAp, const int *dAi, int dim, int q0,
+                                    int q1) {
+  PB_API_BEGIN
+  if (!dAp || !dAi || N <= 0 || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix_block: bad argument");
+  if (!h->comm) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix_block: no communicator (parth_b200_comm_init*)");
+  if (dim != 1) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "row-block mode: dim must be 1");
+  h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
+  h->sim_dim = dim;
+  stage_build_block(*h, N, nnz, dAp, dAi, q0, q1);
   PB_API_END
 }
 

@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 #include <nccl.h>  // types and prototypes only: the symbols are resolved with dlsym, nothing is linked
 
+#include <chrono>
 #include <condition_variable>
 #include <cstdlib>
 #include <mutex>
@@ -100,6 +101,7 @@ __global__ void sum_slices_kernel(const int *__restrict__ all, size_t n, int wor
 
 struct LocalGroup {
   int world = 1;
+  int refs = 0;  // communicators alive; the last one frees the group
   std::mutex mu;
   std::condition_variable cv;
   int waiting = 0;
@@ -112,8 +114,9 @@ struct LocalGroup {
       waiting = 0;
       generation++;
       cv.notify_all();
-    } else {
-      cv.wait(lk, [&] { return generation != gen; });
+    } else if (!cv.wait_for(lk, std::chrono::seconds(60), [&] { return generation != gen; })) {
+      waiting--;  // a rank failed before it got here: give up instead of hanging the process
+      throw StatusError(PARTH_B200_ERR_INTERNAL, "local communicator: a rank did not reach the collective within 60 s");
     }
   }
 };
@@ -122,6 +125,14 @@ namespace {
 
 struct LocalComm final : Comm {
   LocalGroup *g = nullptr;
+  ~LocalComm() override {
+    bool last;
+    {
+      std::lock_guard<std::mutex> lk(g->mu);
+      last = --g->refs == 0;
+    }
+    if (last) delete g;
+  }
   void publish(const int *p, cudaStream_t s) {
     PB_CUDA(cudaStreamSynchronize(s));  // what this rank contributes is complete
     g->slot[rank] = p;
@@ -190,6 +201,10 @@ Comm *local_comm_create(LocalGroup *g, int rank) {
   c->g = g;
   c->rank = rank;
   c->world = g->world;
+  {
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->refs++;
+  }
   return c;
 }
 

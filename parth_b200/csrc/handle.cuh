@@ -65,8 +65,9 @@ struct parth_b200 {
   const int *Mi_own_b() const { return Mi_own.p + own_off - own_q0; }
   const int *Mp_prev_b() const { return Mp_prev.p - blk_c0; }
   const int *Mi_prev_b() const { return Mi_prev.p + prev_off - prev_q0; }
-  pb::DevBuf<int> x_hdr, x_buf, x_len, x_off, x_glist;  // exchange: headers of all ranks, payload, row lengths / offsets
-  pb::PinBuf<int> pin_x;
+  pb::DevBuf<int> x_hdr, x_buf, x_off, x_glist;  // exchange: own slot, gathered slots, reduced mailbox, graph share
+  int x_cap = 4096;            // edge / diff pairs a slot holds (grown when a rank overflows it)
+  bool blk_tiles_zeroed = false;
   int n_chg_rows_total = 0;
 
   // ---- symmetry bookkeeping (stage a): a proven-symmetric snapshot lets the next build prove its

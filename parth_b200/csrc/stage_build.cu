@@ -189,6 +189,8 @@ void stage_build_settle(parth_b200 &h) {
 
 void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, int dim, bool may_defer) {
   cudaStream_t s = h.stream;
+  if (h.block_mode)
+    throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "the handle holds a row block of a sharded mesh (parth_b200_clear resets it)");
   const int M = N / dim;
   // dim == 1: nothing is enqueued before the filter kernel, so the event recorded right in front of it (ev2) opens
   // the build bracket as well -- one stream operation less while the device is idle between two updates

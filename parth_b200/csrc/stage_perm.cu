@@ -149,7 +149,8 @@ void stage_detect(parth_b200 &h) {
   const int M = h.M_n, nn = h.num_nodes;
   h.n_changed = 0;
   h.node_flags_valid = false;
-  if (h.spec_valid && h.diff_cached && h.map_len == 0 && h.Mp == h.Mp_own.p && (int)h.spec_flags.size() == nn * 2) {
+  if (h.spec_valid && h.diff_cached && h.map_len == 0 && (h.Mp == h.Mp_own.p || h.block_mode) &&
+      (int)h.spec_flags.size() == nn * 2) {
     // stage (a) enqueued the edge kernels right behind its row diff and fetched their result with
     // its own mailbox: nothing to launch, nothing to wait for, nothing to time
     h.spec_valid = false;
@@ -159,6 +160,10 @@ void stage_detect(parth_b200 &h) {
     h.timer_ms[2] = 0;
     return;
   }
+  if (h.block_mode)
+    throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
+                      "row-block mode: change detection runs with the build (set_matrix); there is no snapshot of this graph "
+                      "to compare with (call parth_b200_accept_snapshot after the first matrix)");
   StageTimer tm(h, &h.stats.detect_ms, false, &h.timer_ms[2]);
   h.spec_valid = false;
   const int n_words = (M + 31) / 32;
@@ -317,6 +322,26 @@ void stage_expand(parth_b200 &h, const int *dmesh_perm, int n, int dim, int *dou
 // (a19) snapshot, ParthAPI.cpp:270-278: a buffer swap when the graph is ours, a copy when borrowed
 void stage_snapshot(parth_b200 &h) {
   cudaStream_t s = h.stream;
+  if (h.block_mode) {
+    // row-block mode: the rank's rows of the two graphs trade places, with the offsets that bias their pointers
+    if (h.Mp == h.Mp_own_b()) {
+      h.Mp_own.swap(h.Mp_prev);
+      h.Mi_own.swap(h.Mi_prev);
+      std::swap(h.own_off, h.prev_off);
+      std::swap(h.own_q0, h.prev_q0);
+      std::swap(h.own_q1, h.prev_q1);
+    }
+    h.prev_sym_proven = h.cur_sym_proven;
+    h.diff_cached = false;
+    h.spec_valid = false;
+    h.Mp = h.Mp_prev_b();
+    h.Mi = h.Mi_prev_b();
+    h.M_n_prev = h.M_n;
+    h.nnz_prev = h.nnzM;
+    h.map_len = 0;
+    h.n_added = h.n_removed = 0;
+    return;
+  }
   if (h.mesh_owned && h.Mp == h.Mp_own.p) {
     h.Mp_own.swap(h.Mp_prev);
     h.Mi_own.swap(h.Mi_prev);
@@ -426,6 +451,10 @@ int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
   h.stats.detect_ms = h.stats.integrate_ms = h.stats.dirty_ms = h.stats.reorder_ms = 0;
   h.stats.assemble_ms = h.stats.expand_ms = 0;
   if (!h.Mp || h.M_n <= 0) throw StatusError(PARTH_B200_ERR_ARG, "computePermutation: no mesh set");
+  if (h.block_mode && (!h.tree_init || h.M_n != h.M_n_prev || h.tree_M != h.M_n))
+    throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
+                      "computePermutation (row-block mode): the cold start needs the whole graph on one rank; import the "
+                      "separator tree and call parth_b200_accept_snapshot after the first matrix");
   if (h.M_n != h.M_n_prev && h.map_len == 0) h.tree_init = false;
   int rc = PARTH_B200_OK;
   if (!h.tree_init) {

@@ -48,13 +48,20 @@ Batch extract_fine(parth_b200 &h, const std::vector<int> &nodes) {
   h.r_cnt.reserve((size_t)b.total + 1, s);
   h.r_G.reserve((size_t)b.total + 2, s);
   h.scan_ws.reserve(scan_ws_words((size_t)b.total + 1), s);
+  // row-block mode (stage_sharded.cu): the rows of the batch are spread over the ranks; each rank counts / fills the
+  // rows it owns and two all-reduces give every rank the whole sub-mesh CSR
+  const bool blk = h.block_mode && h.comm;
+  const int row0 = blk ? h.blk_c0 : 0, row1 = blk ? h.blk_c1 : 0x7fffffff;
   h.stats.kernels_launched += launch_extract_count(h.r_list.p, h.r_vtx.p, b.count, b.total, h.d_node_ptr.p,
-                                                   h.d_dofs.p, h.Mp, h.Mi, h.d_dof2node.p, h.r_cnt.p, s);
+                                                   h.d_dofs.p, h.Mp, h.Mi, h.d_dof2node.p, h.r_cnt.p, s, row0, row1);
+  if (blk && h.comm->world > 1 && b.total > 0) h.comm->all_reduce_sum(h.r_cnt.p, (size_t)b.total, s);
   h.stats.kernels_launched += exclusive_scan<0>(h.r_cnt.p, h.r_G.p, b.total, h.scan_ws.p, s);
   read_ints(h, h.r_G.p + b.total, &b.nnz, 1);
   h.r_sub.reserve((size_t)std::max(b.nnz, 1), s);
+  if (blk && h.comm->world > 1 && b.nnz > 0) PB_CUDA(cudaMemsetAsync(h.r_sub.p, 0, sizeof(int) * (size_t)b.nnz, s));
   h.stats.kernels_launched += launch_extract_fill(h.r_list.p, h.r_vtx.p, b.count, b.total, h.d_node_ptr.p,
-                                                  h.d_dofs.p, h.Mp, h.Mi, h.d_dof2node.p, h.r_G.p, h.r_sub.p, s);
+                                                  h.d_dofs.p, h.Mp, h.Mi, h.d_dof2node.p, h.r_G.p, h.r_sub.p, s, row0, row1);
+  if (blk && h.comm->world > 1 && b.nnz > 0) h.comm->all_reduce_sum(h.r_sub.p, (size_t)b.nnz, s);
   return b;
 }
 
@@ -84,6 +91,34 @@ void order_batch(parth_b200 &h, const Batch &b, const std::vector<int> &graph_nn
   PB_CUDA(cudaMemcpyAsync(h.r_wsptr.p, wsptr.data(), sizeof(long long) * ((size_t)b.count + 1), cudaMemcpyHostToDevice, s));
   PB_CUDA(cudaStreamSynchronize(s));
   const auto tb = tick();
+  if (h.block_mode && h.comm && h.comm->world > 1 && b.count > 1) {
+    // row-block mode: every rank holds every graph of the batch; they are dealt to the ranks largest first onto the
+    // least loaded rank (same plan everywhere), ordered there, and the local permutations all-reduced (the other
+    // ranks' segments are zero).  A single graph is ordered redundantly by every rank instead: no collective.
+    const int world = h.comm->world;
+    std::vector<int> order((size_t)b.count), mine;
+    for (int g = 0; g < b.count; g++) order[g] = g;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+      return b.vtx[x + 1] - b.vtx[x] > b.vtx[y + 1] - b.vtx[y];
+    });
+    std::vector<long long> load((size_t)world, 0);
+    for (int g : order) {
+      int best = 0;
+      for (int r = 1; r < world; r++) if (load[r] < load[best]) best = r;
+      const long long n = b.vtx[g + 1] - b.vtx[g];
+      load[best] += n * n / 64 + n;  // ordering cost grows faster than the size
+      if (best == h.comm->rank) mine.push_back(g);
+    }
+    std::sort(mine.begin(), mine.end());
+    h.x_glist.reserve(mine.size() + 1, s);
+    if (!mine.empty())
+      PB_CUDA(cudaMemcpyAsync(h.x_glist.p, mine.data(), sizeof(int) * mine.size(), cudaMemcpyHostToDevice, s));
+    PB_CUDA(cudaMemsetAsync(h.r_perm.p, 0, sizeof(int) * (size_t)std::max(b.total, 1), s));
+    PB_CUDA(cudaStreamSynchronize(s));  // pageable source
+    h.stats.kernels_launched += launch_amd_batch(b.count, h.r_vtx.p, h.r_G.p, h.r_sub.p, h.r_wsptr.p, h.r_ws.p,
+                                                 h.r_perm.p, max_stage, any_unstaged, s, h.x_glist.p, (int)mine.size());
+    h.comm->all_reduce_sum(h.r_perm.p, (size_t)b.total, s);
+  } else
   h.stats.kernels_launched += launch_amd_batch(b.count, h.r_vtx.p, h.r_G.p, h.r_sub.p, h.r_wsptr.p, h.r_ws.p,
                                                h.r_perm.p, max_stage, any_unstaged, s);
   if (trace) {

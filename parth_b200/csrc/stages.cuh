@@ -60,6 +60,10 @@ void read_ints(parth_b200 &h, const int *dsrc, int *dst, size_t n);
 void stage_build(parth_b200 &h, int N, const int *dAp, const int *dAi, int nnz, int dim, bool may_defer = false);
 void stage_build_settle(parth_b200 &h);
 
+// stage_sharded.cu: one mesh over the ranks of h.comm, row blocks
+void block_plan(parth_b200 &h, int M, int nnz);
+void stage_build_block(parth_b200 &h, int N, int nnz, const int *dAp, const int *dAi, int q0, int q1);
+
 // stage_perm.cu
 void upload_tree_meta(parth_b200 &h);
 void assemble_all(parth_b200 &h);
