@@ -13,7 +13,10 @@ the DOFs dirtied per update (workloads.PoissonUpdateStream; SURVEY.md section 8d
 `e2e`   : updates/s through the host-pointer C ABI (pinned host CSC in, host permutation out)
 `roofline`: dominant kernel (build_pipe_kernel) algorithmic bytes / its CUDA-event time
 `cpu_baseline`: the reference CPU implementation timed on this box's host cores (rank 0, N = 1)
-N > 1: every rank updates its own mesh (independent objects, no data-path collective): weak scaling.
+N > 1: ONE mesh over the N GPUs: row blocks of the graph build and of change detection, one NCCL
+all-gather of {flags, changed edges, row diffs} per update, dirty sub-meshes by all-reduce -- total work is fixed
+("scaling": "strong"); every rank uploads 1/N of the matrix and returns the whole permutation.  The N independent
+meshes of round 1 (no collective, weak scaling) are reported beside it under "replicas".
 """
 import argparse
 import json
@@ -52,6 +55,8 @@ def parse():
     ap.add_argument("--no-variants", action="store_true", help="skip the secondary variants (reported under 'variants')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--replicas-only", action="store_true",
+                    help="N > 1: only the N independent meshes of round 1 (no collective)")
     return ap.parse_args()
 
 
@@ -166,7 +171,8 @@ def config_dict(n, variant, world):
             "parallelism": f"{world} GPU(s)" if world == 1 else PARALLELISM_TEXT.format(world=world)}
 
 
-PARALLELISM_TEXT = "{world} independent meshes (one per GPU), no data-path collective"
+PARALLELISM_TEXT = ("one mesh over {world} GPUs: row blocks of build + change detection, 1 NCCL all-gather of "
+                    "{{flags, changed edges, row diffs}} per update, dirty sub-meshes by all-reduce")
 
 
 def run_reference(args):
@@ -202,19 +208,27 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------ our arm (CUDA)
-def run_ours(args):
+def _init_dist():
     import torch
     import torch.distributed as dist
-    from parth_b200 import api, workloads
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
     torch.cuda.set_device(local)
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def run_ours(args, emit=True):
+    """N independent meshes, one per GPU (N = 1: the single-GPU line)"""
+    import torch
+    import torch.distributed as dist
+    from parth_b200 import api, workloads
+
+    world, rank, local = _init_dist()
     dev = torch.device("cuda", local)
 
     stream = workloads.PoissonUpdateStream(n=args.n, levels=8)
@@ -359,7 +373,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": config_dict(args.n, args.variant, world),
+        "config": config_dict(args.n, args.variant, world) if world == 1 else
+        dict(config_dict(args.n, args.variant, 1), parallelism=f"{world} independent meshes (one per GPU), no data-path collective"),
         "gnnz_per_s": value * nnzA / 1e9,
         "roofline": {"bound": "hbm", "kernel": "build_pipe_kernel" + (" (stage a + fused stage b)" if fused else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -395,10 +410,164 @@ def run_ours(args):
                                     "last_update": cinfo}
         except Exception as e:  # the checker must never take the product number down
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+    if not emit:
+        return line
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------ our arm, N > 1: one mesh over the N GPUs
+def run_sharded(args):
+    import torch
+    import torch.distributed as dist
+    from parth_b200 import api, workloads
+
+    world, rank, local = _init_dist()
+    dev = torch.device("cuda", local)
+    stream = workloads.PoissonUpdateStream(n=args.n, levels=8)
+    N = M = stream.N
+
+    g = api.ParthAPI(local)
+    g.verbose = False
+    g.ND_levels = stream.levels
+    apply_variant(g, args.variant, api)
+    uid = [api.ParthAPI.commUniqueId() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    g.commInit(uid[0], rank, world)  # the library's own NCCL communicator (C++ host, csrc/comm.cu)
+    g.import_tree(stream.tree())
+    c0, c1 = g.blockRange(N, int(stream.Ap[-1]))
+
+    def block_of(Ap, Ai):
+        """this rank's block of a matrix: pinned host slices + device copies, addressed in GLOBAL indexing (the
+        pointers are biased by -c0 / -Ap[c0]; the Ai slices are placed so that the biased pointer is 16-byte aligned)"""
+        q0, q1, nnz = int(Ap[c0]), int(Ap[c1]), int(Ap[-1])
+        pad = q0 & 3
+        hAp = torch.from_numpy(np.ascontiguousarray(Ap[c0:c1 + 1])).pin_memory()
+        hAi = torch.zeros(pad + (q1 - q0) + 8, dtype=torch.int32).pin_memory()
+        hAi[pad:pad + q1 - q0] = torch.from_numpy(np.ascontiguousarray(Ai[q0:q1]))
+        dAp, dAi = hAp.to(dev), hAi.to(dev)
+        return dict(nnz=nnz, q0=q0, q1=q1, keep=(hAp, hAi, dAp, dAi),
+                    h=(hAp.data_ptr() - 4 * c0, hAi.data_ptr() + 4 * pad - 4 * q0),
+                    d=(dAp.data_ptr() - 4 * c0, dAi.data_ptr() + 4 * pad - 4 * q0))
+
+    base = block_of(stream.Ap, stream.Ai)
+    g.setMatrixBlockPtr(N, base["nnz"], base["h"][0], base["h"][1], 1)
+    g.acceptSnapshot()  # the tree fixture belongs to the base matrix
+
+    need = args.warmup + args.steps + min(args.steps, 8) + (0 if args.no_e2e else 2 + args.steps)
+    D = min(args.steps + args.warmup, 12) if args.variant == "lag" else min(need, 64)
+    mats = [block_of(*stream.matrix(k)) for k in range(D)]  # the same update stream on every rank
+    dperm = torch.empty(M, dtype=torch.int32, device=dev)
+    hperm = torch.empty(M, dtype=torch.int32).pin_memory()
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(k):
+        b = mats[k % D]
+        g.setMatrixBlockDev(N, b["nnz"], b["d"][0], b["d"][1], b["q0"], b["q1"], 1)
+        g.computePermutationDev(dperm.data_ptr(), 1)
+
+    def step_e2e(k):
+        b = mats[k % D]
+        g.setMatrixBlockPtr(N, b["nnz"], b["h"][0], b["h"][1], 1)
+        g.computePermutation(1, out=hperm.numpy())
+
+    def timed(fn, k0, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = g.stats()["kernels_launched"]
+        with torch.cuda.stream(torch.cuda.ExternalStream(g.stream(), device=dev)):
+            e0.record()
+            for k in range(k0, k0 + steps):
+                fn(k)
+            e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), g.stats()["kernels_launched"] - launches0
+
+    sampler = ClockSampler(",".join(str(i) for i in range(world)))
+    if rank == 0:
+        sampler.start()
+    for k in range(args.warmup):
+        step_resident(k)
+    ms, launches = timed(step_resident, args.warmup, args.steps)
+    kernel_ms, stages = [], []
+    for k in range(args.warmup + args.steps, args.warmup + args.steps + min(args.steps, 8)):
+        b = mats[k % D]
+        g.setMatrixBlockDev(N, b["nnz"], b["d"][0], b["d"][1], b["q0"], b["q1"], 1)
+        s0 = g.stats()
+        g.computePermutationDev(dperm.data_ptr(), 1)
+        s1 = g.stats()
+        kernel_ms.append(s0["build_kernel_ms"])
+        stages.append((s0["build_ms"], s1["detect_ms"], s1["dirty_ms"], s1["reorder_ms"], s1["expand_ms"]))
+    info = dict(reuse=g.getReuse(), changes=g.getNumChanges(), dirty=[x.tolist() for x in g.dirty()])
+    value = args.steps / (ms * 1e-3)  # ONE mesh: the job's updates per second
+
+    e2e = None
+    if not args.no_e2e:
+        k0 = args.warmup + args.steps + 8
+        for k in range(2):
+            step_e2e(k0 + k)
+        ms_e, _ = timed(step_e2e, k0 + 2, args.steps)
+        b = mats[0]
+        mine = 4 * ((c1 - c0 + 1) + (b["q1"] - b["q0"]))
+        t = torch.tensor([mine], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e = {"value": args.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(t.item()),
+               "d2h_bytes_per_step": 4 * M * world, "ms_per_step": ms_e / args.steps,
+               "note": f"bytes are totals over the {world} ranks: every rank uploads its block ({mine} bytes on rank 0) and "
+                       f"downloads the whole permutation ({4 * M} bytes)"}
+    clocks = sampler.stop()
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    b = mats[0]
+    cols, qa = c1 - c0, b["q1"] - b["q0"]
+    # this rank's launch: its block of Ap / Ai in, its rows of the graph out, its rows of the snapshot in (every array once)
+    alg = 4 * ((cols + 1) + qa + (cols + 1) + (qa - cols) + (cols + 1) + (qa - cols))
+    kms = float(np.mean(kernel_ms)) if kernel_ms else float("nan")
+    achieved = alg / (kms * 1e-3) / 1e9
+    st = np.mean(np.array(stages), axis=0) if stages else np.zeros(5)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "int32", "data": "synthetic", "config": config_dict(args.n, args.variant, world),
+        "gnnz_per_s": value * mats[0]["nnz"] / 1e9,
+        "roofline": {"bound": "hbm", "kernel": "build_pipe_kernel (stage a + fused stage b), rank 0's row block",
+                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "algorithmic_bytes": alg, "kernel_ms": kms, "columns": [c0, c1],
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured copy)" if peaks else "fallback 6650 GB/s"},
+        "stage_ms": {"build": float(st[0]), "detect": float(st[1]), "dirty_sets": float(st[2]),
+                     "reorder": float(st[3]), "expand": float(st[4])},
+        "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "last_update": info,
+        "collectives": {"library": "NCCL through the C++ host (parth_b200/csrc/comm.cu), communicator " + g.commInfo()[2],
+                        "per_update": "1 all-gather of one slot per rank (header, node flags, changed edges, row diffs); "
+                                      "a re-ordering update adds 2 all-reduces for the dirty sub-mesh (counts, entries) and, "
+                                      "with more than one dirty graph, 1 for the local permutations"},
+    }
+    del g, mats
+    torch.cuda.empty_cache()
+    if not args.no_variants:
+        # the N independent meshes of round 1 (weak scaling, no collective), a few steps
+        import copy
+        a2 = copy.copy(args)
+        a2.steps, a2.warmup, a2.no_variants, a2.no_cpu_baseline = max(2, min(args.steps, 5)), 3, True, True
+        rep = run_ours(a2, emit=False)
+        line["replicas"] = {"what": f"{world} independent meshes, one per GPU, no collective (weak scaling)",
+                            "value": rep["value"], "unit": UNIT, "ms_per_step": rep["ms_per_step"], "steps": a2.steps,
+                            "e2e": rep["e2e"]}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    dist.destroy_process_group()
 
 
 def _own_stdout():
@@ -416,5 +585,7 @@ if __name__ == "__main__":
     _own_stdout()
     if a.impl == "reference":
         run_reference(a)
+    elif int(os.environ.get("WORLD_SIZE", "1")) > 1 and not a.replicas_only:
+        run_sharded(a)
     else:
         run_ours(a)

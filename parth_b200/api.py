@@ -310,6 +310,12 @@ class ParthAPI:
         self._check(self.lib.parth_b200_set_matrix_block(self.h, int(N), int(nnz), C.c_void_p(Ap.ctypes.data),
                                                          C.c_void_p(Ai.ctypes.data), int(dim)))
 
+    def setMatrixBlockPtr(self, N, nnz, Ap_addr, Ai_addr, dim=1):
+        """host addresses in GLOBAL indexing (a caller that holds only its block passes them biased by -c0 / -Ap[c0])"""
+        self._push_options()
+        self._check(self.lib.parth_b200_set_matrix_block(self.h, int(N), int(nnz), C.c_void_p(Ap_addr),
+                                                         C.c_void_p(Ai_addr), int(dim)))
+
     def setMatrixBlockDev(self, N, nnz, dAp_ptr, dAi_ptr, q0, q1, dim=1):
         self._push_options()
         self._check(self.lib.parth_b200_set_matrix_block_dev(self.h, int(N), int(nnz), C.c_void_p(dAp_ptr),

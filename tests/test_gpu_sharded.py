@@ -23,3 +23,16 @@ def test_sharded_update_equals_single_gpu():
     last = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
     out = json.loads(last)
     assert out["ok"] and out["world"] == 2 and out["exchanged_bytes"] > 0
+
+
+def test_row_block_update_over_nccl_equals_single_gpu():
+    """one mesh over 2 processes / GPUs, the library's own NCCL communicator (scripts/rowblock_check.py)"""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2); tests/test_gpu_rowblock.py covers the same logic on one")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "scripts", "rowblock_check.py"), "24", "6"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["ok"] and out["world"] == 2
