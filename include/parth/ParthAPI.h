@@ -251,7 +251,10 @@ public:
     changed_dof_edges.resize((size_t)(nc > 0 ? nc : 0));
     for (int e = 0; e < nc; e++) changed_dof_edges[e] = {flat[2 * e], flat[2 * e + 1]};
     mesh_perm.resize((size_t)M_n);
-    if (M_n > 0) check(parth_b200_get_mesh_perm(h_, mesh_perm.data(), M_n));
+    if (M_n > 0) {
+      const int got = parth_b200_get_mesh_perm(h_, mesh_perm.data(), M_n); /* returns the length, negative = error */
+      if (got < 0) check(got);
+    }
     results_stale_ = false;
   }
   /* Mp_prev / Mi_prev (ParthAPI.h:72-73): the snapshot the next update is compared with */
@@ -301,6 +304,56 @@ public:
   void setCoarsePolicy(int policy) { check(parth_b200_set_coarse_policy(h_, policy)); }
   void setAssumeSymmetric(bool on) { check(parth_b200_set_assume_symmetric(h_, on ? 1 : 0)); }
   void setDecomposer(parth_b200_decomposer fn, void *user) { check(parth_b200_set_decomposer(h_, fn, user)); }
+
+  /* ---- ONE mesh over several GPUs (row blocks; include/parth_b200.h "ONE mesh over several GPUs").
+   * One process (or thread) per GPU, each with its own ParthAPI object:
+   *   rank 0: id = ParthAPI::commUniqueId(); hand the 128 bytes to every rank
+   *   all   : p.commInit(id.data(), rank, world); p.importTree(tree); p.setMatrix(N, Ap, Ai, 1); p.acceptSnapshot();
+   *   update: p.setMatrix(N, Ap, Ai, 1); p.computePermutation(perm, 1);   -- the collectives (NCCL) run inside
+   * setMatrix then uploads only this rank's block of Ap / Ai; every rank gets the same full permutation. */
+  static std::vector<unsigned char> commUniqueId() {
+    std::vector<unsigned char> id(128);
+    const int rc = parth_b200_comm_unique_id(id.data());
+    if (rc != PARTH_B200_OK)
+      throw std::runtime_error(std::string("PARTH (B200) status ") + std::to_string(rc) + ": " + parth_b200_last_error(nullptr));
+    return id;
+  }
+  void commInit(const void *id128, int rank, int world) { check(parth_b200_comm_init(h_, id128, rank, world)); }
+  /* the ranks are objects of THIS process, one host thread each (tests on one GPU) */
+  static void commInitLocal(const std::vector<ParthAPI *> &ranks) {
+    std::vector<parth_b200 *> hs;
+    for (ParthAPI *p : ranks) hs.push_back(p->h_);
+    if (parth_b200_comm_init_local(hs.data(), (int)hs.size()) != PARTH_B200_OK)
+      throw std::runtime_error("PARTH (B200): comm_init_local failed");
+  }
+  void blockRange(int N, int nnz, int &c0, int &c1) { check(parth_b200_block_range(h_, N, nnz, &c0, &c1)); }
+  /* the snapshot advances to the current graph (after the first matrix of a sharded handle, or after a REPORT) */
+  void acceptSnapshot() {
+    check(parth_b200_accept_snapshot(h_));
+    M_n_prev = M_n;
+  }
+  /* a separator tree held in a host mirror (another object's `hmd` after syncTreeMirror, or one built by hand)
+   * becomes this object's tree; no snapshot graph comes with it */
+  void importTree(const HMDMirror &t) {
+    const int nodes = (int)t.HMD_tree.size();
+    std::vector<int> meta((size_t)nodes * 7), node_ptr((size_t)nodes + 1, 0), dofs, labels;
+    for (int x = 0; x < nodes; x++) {
+      const HMDNodeMirror &nd = t.HMD_tree[(size_t)x];
+      int *m = &meta[(size_t)x * 7];
+      m[0] = nd.left_node_idx; m[1] = nd.right_node_idx; m[2] = nd.node_id; m[3] = nd.parent_idx;
+      m[4] = nd.offset; m[5] = nd.level; m[6] = nd.org_size;
+      dofs.insert(dofs.end(), nd.DOFs.begin(), nd.DOFs.end());
+      labels.insert(labels.end(), nd.permuted_new_label.begin(), nd.permuted_new_label.end());
+      node_ptr[(size_t)x + 1] = (int)dofs.size();
+    }
+    ND_levels = t.num_levels;
+    pushOptions();
+    check(parth_b200_import_tree(h_, (int)dofs.size(), t.num_levels, nodes, meta.data(), node_ptr.data(), dofs.data(),
+                                 labels.data(), nullptr, nullptr));
+    hmd.HMD_init = true;
+    hmd.num_levels = t.num_levels;
+    hmd.num_HMD_nodes = nodes;
+  }
 
   /* ReorderingType::MORTON_CODE: one 3-D point per current mesh DOF (point i, axis a at
    * xyz[i * point_stride + a * comp_stride]; an Eigen column-major V of n rows is (1, n)).  Fine nodes are then

@@ -85,7 +85,7 @@ def build_example(name="quick_start"):
     src = os.path.join(ROOT, "examples", name + ".cpp")
     out = os.path.join(ROOT, "examples", name)
     cmd = ["/usr/bin/g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), src, "-o", out,
-           "-L" + HERE, "-lparth_b200", "-Wl,-rpath," + HERE]
+           "-L" + HERE, "-lparth_b200", "-Wl,-rpath," + HERE, "-pthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
