@@ -47,9 +47,11 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=200, help="grid edge (200 -> 8 M DOF)")
-    ap.add_argument("--variant", default="nolag", choices=["lag", "nolag", "aggr"],
-                    help="nolag (headline, SURVEY 8d variant 2a): lagging off, the dirty level-7 node is really re-ordered "
-                         "(device: REPAIR = relocation + AMD; reference: METIS re-dissection); "
+    ap.add_argument("--variant", default="nolag", choices=["lag", "nolag", "nolag_amd", "aggr"],
+                    help="nolag (headline, SURVEY 8d variant 2a): lagging off, the dirty level-7 sub-tree is repaired "
+                         "(device: RELOCATE policy = broken edges relocated into the common separator, joiners at its end; "
+                         "reference: METIS re-dissection); nolag_amd: the same with the REPAIR policy (relocation + AMD "
+                         "of the receiving separators: stage c runs, same fill, 5x the time -- profiles/r07_repair_drift.md); "
                          "aggr: aggressive reuse on (relocation into the separator + AMD of the touched nodes, "
                          "bit-exact with the reference); lag: reference defaults (the dirty node is lag-dropped, reuse 1)")
     ap.add_argument("--no-variants", action="store_true", help="skip the secondary variants (reported under 'variants')")
@@ -64,8 +66,11 @@ VARIANT_TEXT = {
     "lag": "lagging=true (reference defaults: the dirty level-7 node is lag-dropped, reuse 1)",
     "aggr": "reference defaults + aggressive reuse (relocate level 8), ReorderingType AMD: broken edges are relocated "
             "into the common separator and the touched nodes are re-ordered with AMD",
-    "nolag": "lagging=false: the dirty coarse node is repaired on the device (relocation + AMD) where the reference "
-             "re-dissects it with METIS",
+    "nolag": "lagging=false: the dirty coarse node is repaired on the device (RELOCATE policy: one endpoint of every "
+             "broken edge moves into the common separator, which keeps its order and takes the joiners at its end) where "
+             "the reference re-dissects it with METIS",
+    "nolag_amd": "lagging=false, REPAIR policy: the relocation of nolag + AMD re-ordering of the separators that received "
+                 "DOFs (stage c runs; fill within 0.1-0.5 % of RELOCATE, profiles/r07_repair_drift.md)",
 }
 
 
@@ -77,13 +82,13 @@ def workload_name(n, variant):
 def apply_variant(h, variant, api=None):
     """the option set of a variant on either implementation (our ParthAPI mirror or oracle.CpuParth)"""
     if api is not None:  # our arm
-        h.lagging = variant != "nolag"
+        h.lagging = not variant.startswith("nolag")
         h.activate_aggressive_reuse = variant == "aggr"
         h.relocate_lvl = 8 if variant == "aggr" else 2
         h.reorder_type = api.AMD if variant == "aggr" else api.METIS
-        h.setCoarsePolicy(api.COARSE_REPAIR)
+        h.setCoarsePolicy(api.COARSE_RELOCATE if variant == "nolag" else api.COARSE_REPAIR)
     else:
-        h.set_options(reorder_type=1 if variant == "aggr" else 0, nd_levels=8, lagging=variant != "nolag",
+        h.set_options(reorder_type=1 if variant == "aggr" else 0, nd_levels=8, lagging=not variant.startswith("nolag"),
                       aggressive=variant == "aggr", relocate_lvl=8 if variant == "aggr" else 2)
 
 
@@ -333,7 +338,7 @@ def run_ours(args, emit=True):
     # costs when the dirty nodes really are re-ordered (stage c: extraction + batched AMD)
     variants = {}
     if not args.no_variants:
-        for v in ("lag", "aggr", "nolag"):
+        for v in ("lag", "aggr", "nolag", "nolag_amd"):
             if v == args.variant:
                 continue
             gv = make_handle(v)

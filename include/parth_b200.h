@@ -51,7 +51,13 @@ enum {
   PARTH_B200_COARSE_REPAIR = 0,   /* device: relocate one endpoint of every broken edge into the
                                      common separator, re-order the touched nodes (default) */
   PARTH_B200_COARSE_CALLBACK = 1, /* host callback re-dissects the extracted sub-mesh */
-  PARTH_B200_COARSE_REPORT = 2    /* leave the permutation, report PARTH_B200_NEEDS_REDISSECT */
+  PARTH_B200_COARSE_REPORT = 2,   /* leave the permutation, report PARTH_B200_NEEDS_REDISSECT */
+  PARTH_B200_COARSE_RELOCATE = 3  /* device: the relocation of REPAIR without its re-ordering -- a separator that
+                                     receives DOFs keeps the order of the DOFs it had and takes the new ones at its
+                                     end (ascending id), a node that loses DOFs keeps the order of the rest.  The
+                                     columns of a separator form a nearly dense block of L whatever their order, so
+                                     fill stays within a fraction of a percent of REPAIR (profiles/) at none of the
+                                     ordering cost */
 };
 #define PARTH_B200_NEEDS_REDISSECT 100 /* positive, non-error status of compute_permutation */
 #define PARTH_B200_NEEDS_EXCHANGE 101  /* sharded mode: gather the re-ordered nodes, then call finish */

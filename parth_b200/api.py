@@ -18,7 +18,7 @@ OK = 0
 NEEDS_REDISSECT = 100
 NEEDS_EXCHANGE = 101
 METIS, AMD, MORTON_CODE = 0, 1, 2
-COARSE_REPAIR, COARSE_CALLBACK, COARSE_REPORT = 0, 1, 2
+COARSE_REPAIR, COARSE_CALLBACK, COARSE_REPORT, COARSE_RELOCATE = 0, 1, 2, 3
 
 _ip = C.POINTER(C.c_int)
 _lib = None

@@ -177,7 +177,7 @@ int parth_b200_set_options(parth_b200 *h, int reorder_type, int nd_levels, int l
 }
 
 int parth_b200_set_coarse_policy(parth_b200 *h, int policy) {
-  if (!h || policy < 0 || policy > 2) return PARTH_B200_ERR_ARG;
+  if (!h || policy < 0 || policy > 3) return PARTH_B200_ERR_ARG;
   h->coarse_policy = policy;
   return PARTH_B200_OK;
 }

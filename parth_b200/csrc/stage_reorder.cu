@@ -149,7 +149,8 @@ bool device_orders_with_amd(const parth_b200 &h) {
   // the device has one ordering kernel (AMD).  METIS_NodeND leaf ordering (ReorderingType METIS,
   // HMD.cpp:34-56) is third-party and not reproduced; under the REPAIR policy AMD stands in for
   // it, otherwise the request is refused so that parity runs never silently diverge.
-  return h.force_amd || h.reorder_type == PARTH_B200_AMD || h.coarse_policy == PARTH_B200_COARSE_REPAIR;
+  return h.force_amd || h.reorder_type == PARTH_B200_AMD || h.coarse_policy == PARTH_B200_COARSE_REPAIR ||
+         h.coarse_policy == PARTH_B200_COARSE_RELOCATE;
 }
 
 }  // namespace
@@ -310,7 +311,9 @@ int stage_coarse(parth_b200 &h) {
   std::vector<int> touched;
   stage_relocate(h, 1 << 29, touched, /*filter_edges=*/false);
   std::vector<int> nodes = h.dirty_fine;
-  nodes.insert(nodes.end(), touched.begin(), touched.end());
+  // RELOCATE: the labels the relocation left (survivors in their old order, joiners appended) stand; stage_relocate
+  // has already re-assembled mesh_perm from them
+  if (h.coarse_policy != PARTH_B200_COARSE_RELOCATE) nodes.insert(nodes.end(), touched.begin(), touched.end());
   std::sort(nodes.begin(), nodes.end());
   nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
   stage_permute_fine(h, nodes);

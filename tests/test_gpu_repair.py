@@ -26,13 +26,14 @@ def problematic_edges(Mp, Mi, dof2node):
 
 @pytest.mark.parametrize("k", [1, 7, 60, 400])
 @pytest.mark.parametrize("rt", [0, 1])
-def test_repair_restores_the_separator_property(gpu_api, port, k, rt):
+@pytest.mark.parametrize("policy", ["REPAIR", "RELOCATE"])
+def test_repair_restores_the_separator_property(gpu_api, port, k, rt, policy):
     tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 16, 5)))
     M = 16 ** 3
     rng = np.random.default_rng(k)
     P, I = synth.add_edges(Mp, Mi, rng.integers(0, M, size=(k, 2)))
     g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 5; g.reorder_type = rt; g.lagging = False
-    g.setCoarsePolicy(gpu_api.COARSE_REPAIR)
+    g.setCoarsePolicy(getattr(gpu_api, "COARSE_" + policy))
     o = port.CpuParth("port"); o.set_options(reorder_type=rt, nd_levels=5, lagging=False)
     g.import_tree(tree, Mp, Mi); o.import_tree(tree, Mp, Mi)
     g.setMesh(M, P, I); o.setMesh(M, P, I)
