@@ -18,6 +18,7 @@
 // passes, and ignores later-queue neighbours even if they were placed in the same pass.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "scan.cuh"
 #include "stages.cuh"
@@ -367,6 +368,173 @@ __global__ void list_moved_kernel(const int *__restrict__ flag, const int *__res
 
 inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
 
+// ---------------------------------------------------------------- (f2) relocation, sparse formulation
+// A reuse update moves a few hundred DOFs; the dense formulation above spends a dozen passes over M ints on them.
+// Here the per-DOF scratch (occurrence counts, relocation targets) lives in two PERSISTENT arrays that are clean
+// between calls and are reset entry by entry afterwards, the moved DOFs are collected from the edge endpoints and
+// sorted by one CTA, and only the nodes that lose or receive DOFs are regrouped (one CTA each); the slices of all
+// other nodes are copied to their new place in one streaming pass.  Same arrays as regroup_finish<1>, bit for bit.
+constexpr int kSparseEdges = 8192;            // changed edges the sparse path takes (2 * kSparseEdges candidates)
+constexpr int kSparseCand = 2 * kSparseEdges;
+
+__global__ void reloc_collect_kernel(const int *__restrict__ edges, int n_edges, const int *__restrict__ target,
+                                     int *__restrict__ occ, int *__restrict__ moved, int *__restrict__ n_moved) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= 2 * n_edges) return;
+  const int d = edges[q];
+  if (target[d] == kNoInit) return;
+  if (atomicExch(occ + d, (int)0x80000000) >= 0) moved[atomicAdd(n_moved, 1)] = d;  // first visitor lists it
+}
+
+// ascending sort of n <= kSparseCand ints by one CTA (bitonic network in shared memory)
+__global__ void __launch_bounds__(1024) reloc_sort_kernel(int *__restrict__ a, const int *__restrict__ n_dev) {
+  extern __shared__ int s[];  // kSparseCand ints
+  const int n = *n_dev;
+  int P = 1;
+  while (P < n) P <<= 1;
+  for (int i = threadIdx.x; i < P; i += 1024) s[i] = i < n ? a[i] : 0x7fffffff;
+  __syncthreads();
+  for (int k = 2; k <= P; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < P; i += 1024) {
+        const int l = i ^ j;
+        if (l > i) {
+          const int x = s[i], y = s[l];
+          const bool up = (i & k) == 0;
+          if ((x > y) == up) { s[i] = y; s[l] = x; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += 1024) a[i] = s[i];
+}
+
+// per moved DOF: its target node, the per-node counts of leavers / joiners, and the redirect of dof2node
+__global__ void reloc_info_kernel(const int *__restrict__ moved, const int *__restrict__ n_dev,
+                                  const int *__restrict__ target, int *__restrict__ dof2node,
+                                  int *__restrict__ moved_node, int *__restrict__ cnt_out, int *__restrict__ cnt_in) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *n_dev) return;
+  const int d = moved[i];
+  const int t = target[d];
+  atomicAdd(cnt_out + dof2node[d], 1);
+  atomicAdd(cnt_in + t, 1);
+  moved_node[i] = t;
+  dof2node[d] = t;
+}
+
+// the slices of the nodes nothing happens to move to their new offsets
+__global__ void regroup_copy_kernel(const int *__restrict__ optr, const int *__restrict__ nptr,
+                                    const int *__restrict__ changed, int nodes, int new_total,
+                                    const int *__restrict__ dofs, const int *__restrict__ labels,
+                                    int *__restrict__ dofs2, int *__restrict__ labels2) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= new_total) return;
+  const int nd = node_of_entry_d(nptr, nodes, p);
+  if (__ldg(changed + nd)) return;
+  const int src = __ldg(optr + nd) + (p - __ldg(nptr + nd));
+  dofs2[p] = dofs[src];
+  labels2[p] = labels[src];
+}
+
+// one CTA per node that loses or receives DOFs.  Shared memory: bitmap of the deleted labels + its word prefix
+// (label compaction), histogram of the survivors over "number of joiners below" (joiner positions), scan scratch.
+constexpr int RG_THREADS = 512;
+__global__ void __launch_bounds__(RG_THREADS)
+regroup_changed_kernel(const int *__restrict__ list, const int *__restrict__ optr, const int *__restrict__ nptr,
+                       const int *__restrict__ aptr, const int *__restrict__ target, const int *__restrict__ joinS,
+                       const int *__restrict__ dofs, const int *__restrict__ labels, int *__restrict__ dofs2,
+                       int *__restrict__ labels2, int *__restrict__ flags /*[0] unsorted, [1] size mismatch*/) {
+  extern __shared__ int rg_smem[];
+  __shared__ int s_scan[33];
+  __shared__ int s_last;
+  const int x = list[blockIdx.x];
+  const int o0 = optr[x], size = optr[x + 1] - o0;
+  const int base = nptr[x], new_size = nptr[x + 1] - base;
+  const int a0 = aptr[x], na = aptr[x + 1] - a0;
+  const int words = (size + 31) >> 5;
+  int *bits = rg_smem, *wpre = rg_smem + words, *hist = rg_smem + 2 * words;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * words + na + 1; i += RG_THREADS) rg_smem[i] = 0;
+  if (tid == 0) s_last = -1;
+  __syncthreads();
+  for (int k = tid; k < size; k += RG_THREADS)
+    if (__ldg(target + dofs[o0 + k]) != kNoInit) {
+      const int lab = labels[o0 + k];
+      atomicOr(bits + (lab >> 5), 1 << (lab & 31));
+    }
+  __syncthreads();
+  int running = 0;
+  for (int w0 = 0; w0 < words; w0 += RG_THREADS) {
+    const int w = w0 + tid;
+    const int c = w < words ? __popc((unsigned)bits[w]) : 0;
+    int total;
+    const int ex = block_excl_scan<RG_THREADS>(c, s_scan, &total);
+    if (w < words) wpre[w] = running + ex;
+    running += total;
+  }
+  __syncthreads();
+  // survivors, in entry order
+  int ns = 0;
+  for (int k0 = 0; k0 < size; k0 += RG_THREADS) {
+    const int k = k0 + tid;
+    int v = 0, lab = 0;
+    bool keep = false;
+    if (k < size) {
+      v = dofs[o0 + k];
+      keep = __ldg(target + v) == kNoInit;
+      lab = labels[o0 + k];
+    }
+    int total;
+    const int ex = block_excl_scan<RG_THREADS>(keep ? 1 : 0, s_scan, &total);
+    // ascending survivors (the merge with the joiners needs it): compare with the previous survivor
+    __shared__ int s_val[RG_THREADS];
+    if (keep) s_val[ex] = v;
+    __syncthreads();
+    if (keep) {
+      const int j = ns + ex;
+      const int prev = ex > 0 ? s_val[ex - 1] : s_last;
+      int shift = 0;
+      if (na > 0) {
+        shift = lower_bound_d(joinS + a0, na, v);
+        if (prev > v) flags[0] = 1;
+        atomicAdd(hist + shift, 1);
+      }
+      dofs2[base + j + shift] = v;
+      labels2[base + j] = lab - (wpre[lab >> 5] + __popc((unsigned)bits[lab >> 5] & ((1u << (lab & 31)) - 1u)));
+    }
+    __syncthreads();
+    if (tid == 0 && total > 0) s_last = s_val[total - 1];
+    ns += total;
+    __syncthreads();
+  }
+  if (ns + na != new_size && tid == 0) flags[1] = 1;
+  // joiner r sits behind the survivors with at most r joiners below them
+  running = 0;
+  for (int r0 = 0; r0 < na; r0 += RG_THREADS) {
+    const int r = r0 + tid;
+    const int c = r < na ? hist[r] : 0;
+    int total;
+    const int ex = block_excl_scan<RG_THREADS>(c, s_scan, &total);
+    if (r < na) {
+      const int below = running + ex + c;  // survivors with shift <= r
+      dofs2[base + r + below] = joinS[a0 + r];
+      labels2[base + ns + r] = ns + r;
+    }
+    running += total;
+  }
+}
+
+// the persistent scratch goes back to its clean state, entry by entry
+__global__ void reloc_reset_occ_kernel(const int *__restrict__ edges, int n_edges, int *__restrict__ occ) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < 2 * n_edges) occ[edges[q]] = 0;
+}
+__global__ void reloc_reset_target_kernel(const int *__restrict__ moved, int n_moved, int *__restrict__ target) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < n_moved) target[moved[q]] = kNoInit;
+}
+
 // HMD::getCoarseHMDNodeOffset (HMD.cpp:525-536) on the host mirror
 int coarse_offset(const parth_b200 &h, int node) {
   int cur = h.meta[node * 7 + 2];
@@ -614,6 +782,132 @@ void stage_integrate(parth_b200 &h) {
   tm.stop();
 }
 
+
+// Sparse relocation (kernels: "relocation, sparse formulation" above).  Same result as the dense path below.
+static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> &dirty_fine_out, bool filter_edges) {
+  cudaStream_t s = h.stream;
+  const int nn = h.num_nodes, M = h.tree_M, ne = h.n_changed;
+  if (h.rel_M != M) {
+    h.rel_occ.reserve((size_t)M + 1, s);
+    h.rel_target.reserve((size_t)M + 1, s);
+    PB_CUDA(cudaMemsetAsync(h.rel_occ.p, 0, sizeof(int) * (size_t)M, s));
+    fill_kernel<<<nblk(M), 256, 0, s>>>(h.rel_target.p, M, kNoInit);
+    h.stats.kernels_launched++;
+    h.rel_M = M;
+  }
+  h.w0.reserve((size_t)ne + 2, s);               // keep_edge
+  h.w1.reserve((size_t)ne + 2, s);               // its prefix
+  h.w2.reserve((size_t)std::max(ne, 1) * 2, s);  // kept edges
+  h.w4.reserve((size_t)nn * 2 + 8, s);           // cnt_out | cnt_in
+  h.r_perm.reserve((size_t)kSparseCand, s);      // moved ids, ascending
+  h.r_ws.reserve((size_t)kSparseCand, s);        // their target nodes
+  h.scan_ws.reserve(scan_ws_words((size_t)ne + 1), s);
+  int *d_cnt = h.mail.p + 16;  // [0] n_moved, [1] unsorted survivors, [2] size mismatch
+  PB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * 4, s));
+  PB_CUDA(cudaMemsetAsync(h.w4.p, 0, sizeof(int) * (size_t)nn * 2, s));
+  occ_kernel<<<nblk(ne), 256, 0, s>>>(h.d_changed.p, ne, h.rel_occ.p);
+  relocate_targets_kernel<<<nblk(ne), 256, 0, s>>>(h.d_changed.p, ne, h.d_dof2node.p, h.d_meta.p, h.rel_occ.p,
+                                                  threshold_node, h.rel_target.p, h.w0.p);
+  h.stats.kernels_launched += 2 + exclusive_scan<0>(h.w0.p, h.w1.p, ne, h.scan_ws.p, s);
+  compact_edges_kernel<<<nblk(ne), 256, 0, s>>>(h.d_changed.p, ne, h.w0.p, h.w1.p, h.w2.p);
+  reloc_collect_kernel<<<nblk(2 * ne), 256, 0, s>>>(h.d_changed.p, ne, h.rel_target.p, h.rel_occ.p, h.r_perm.p, d_cnt);
+  {
+    static bool attr[64] = {};  // 64 KB of dynamic shared memory: opt in once per device
+    const int dev = h.device;
+    if (dev < 0 || dev >= 64 || !attr[dev]) {
+      PB_CUDA(cudaFuncSetAttribute(reloc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(int) * kSparseCand));
+      if (dev >= 0 && dev < 64) attr[dev] = true;
+    }
+  }
+  reloc_sort_kernel<<<1, 1024, sizeof(int) * kSparseCand, s>>>(h.r_perm.p, d_cnt);
+  // (before dof2node is redirected: the nodes that lose DOFs are the old ones)
+  reloc_info_kernel<<<nblk(2 * ne), 256, 0, s>>>(h.r_perm.p, d_cnt, h.rel_target.p, h.d_dof2node.p, h.r_ws.p, h.w4.p,
+                                                h.w4.p + nn);
+  reloc_reset_occ_kernel<<<nblk(2 * ne), 256, 0, s>>>(h.d_changed.p, ne, h.rel_occ.p);
+  h.stats.kernels_launched += 5;
+  // ONE read-back: kept edges, moved DOFs, leavers / joiners per node
+  h.pin.reserve((size_t)2 * nn + 8);
+  PB_CUDA(cudaMemcpyAsync(h.pin.p, h.w1.p + ne, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PB_CUDA(cudaMemcpyAsync(h.pin.p + 1, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
+  PB_CUDA(cudaMemcpyAsync(h.pin.p + 2, h.w4.p, sizeof(int) * (size_t)nn * 2, cudaMemcpyDeviceToHost, s));
+  PB_CUDA(cudaStreamSynchronize(s));
+  h.stats.d2h_bytes += (long long)sizeof(int) * (2 * nn + 2);
+  collect_timers(h);
+  const int kept = h.pin.p[0], n_moved = h.pin.p[1];
+  const std::vector<int> cnt_out(h.pin.p + 2, h.pin.p + 2 + nn), cnt_in(h.pin.p + 2 + nn, h.pin.p + 2 + 2 * nn);
+  if (filter_edges) {
+    if (kept > 0)
+      PB_CUDA(cudaMemcpyAsync(h.d_changed.p, h.w2.p, sizeof(int) * 2 * (size_t)kept, cudaMemcpyDeviceToDevice, s));
+    h.n_changed = kept;
+  }
+  if (n_moved == 0) return;
+  // new layout on the host (<= 8191 nodes)
+  std::vector<int> aptr((size_t)nn + 1, 0), nptr((size_t)nn + 1, 0), changed_flag((size_t)nn, 0), changed, touched;
+  int max_words = 0, max_in = 0;
+  for (int x = 0; x < nn; x++) {
+    const int size = h.node_ptr[x + 1] - h.node_ptr[x];
+    aptr[x + 1] = aptr[x] + cnt_in[x];
+    nptr[x + 1] = nptr[x] + size - cnt_out[x] + cnt_in[x];
+    if (cnt_in[x]) touched.push_back(x);
+    if (cnt_in[x] || cnt_out[x]) {
+      changed.push_back(x);
+      changed_flag[x] = 1;
+      max_words = std::max(max_words, (size + 31) / 32);
+      max_in = std::max(max_in, cnt_in[x]);
+    }
+  }
+  const int new_total = nptr[nn];
+  if (new_total != h.node_ptr[nn]) throw StatusError(PARTH_B200_ERR_INTERNAL, "relocate: entry count mismatch");
+  // one upload: aptr | nptr | changed flags | changed list | touched list  (pinned: no wait)
+  const size_t up = (size_t)3 * nn + 2 + changed.size() + touched.size();
+  h.pin_rel.reserve(up + 8);
+  h.w5.reserve(up + 8, s);
+  {
+    int *q = h.pin_rel.p;
+    std::copy(aptr.begin(), aptr.end(), q); q += nn + 1;
+    std::copy(nptr.begin(), nptr.end(), q); q += nn + 1;
+    std::copy(changed_flag.begin(), changed_flag.end(), q); q += nn;
+    std::copy(changed.begin(), changed.end(), q); q += changed.size();
+    std::copy(touched.begin(), touched.end(), q);
+  }
+  PB_CUDA(cudaMemcpyAsync(h.w5.p, h.pin_rel.p, sizeof(int) * up, cudaMemcpyHostToDevice, s));
+  const int *d_aptr = h.w5.p, *d_nptr = h.w5.p + (nn + 1), *d_flag = h.w5.p + 2 * (nn + 1);
+  const int *d_changed_list = d_flag + nn, *d_touched = d_changed_list + changed.size();
+  h.r_sub.reserve((size_t)std::max(n_moved, 1), s);  // joiners grouped by node
+  if (!touched.empty()) {
+    rank_joiners_kernel<<<(unsigned)touched.size(), 256, 0, s>>>(d_touched, h.r_perm.p, h.r_ws.p, n_moved, d_aptr, h.r_sub.p);
+    h.stats.kernels_launched++;
+  }
+  h.d_dofs2.reserve((size_t)std::max(new_total, 1), s);
+  h.d_labels2.reserve((size_t)std::max(new_total, 1), s);
+  regroup_copy_kernel<<<nblk(new_total), 256, 0, s>>>(h.d_node_ptr.p, d_nptr, d_flag, nn, new_total, h.d_dofs.p, h.d_labels.p,
+                                                     h.d_dofs2.p, h.d_labels2.p);
+  const size_t smem = sizeof(int) * ((size_t)2 * max_words + max_in + 2);
+  if (smem > 200 * 1024) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "relocate: a node is too large for the regroup kernel");
+  if (smem > 48 * 1024)
+    PB_CUDA(cudaFuncSetAttribute(regroup_changed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  regroup_changed_kernel<<<(unsigned)changed.size(), RG_THREADS, smem, s>>>(d_changed_list, h.d_node_ptr.p, d_nptr, d_aptr,
+                                                                          h.rel_target.p, h.r_sub.p, h.d_dofs.p, h.d_labels.p,
+                                                                          h.d_dofs2.p, h.d_labels2.p, d_cnt + 1);
+  reloc_reset_target_kernel<<<nblk(n_moved), 256, 0, s>>>(h.r_perm.p, n_moved, h.rel_target.p);
+  PB_CUDA(cudaGetLastError());
+  h.stats.kernels_launched += 3;
+  h.d_dofs.swap(h.d_dofs2);
+  h.d_labels.swap(h.d_labels2);
+  h.node_ptr = nptr;
+  update_offsets(h);
+  upload_tree_meta(h);  // synchronises: the flags below have arrived as well
+  int fl[2] = {0, 0};
+  read_ints(h, d_cnt + 1, fl, 2);
+  if (fl[1]) throw StatusError(PARTH_B200_ERR_INTERNAL, "relocate: regrouped node size mismatch");
+  if (fl[0])
+    throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
+                      "DOF map: surviving DOFs of a node that receives DOFs are not in ascending order "
+                      "(the reference expects survivors to keep their order, remeshPatch.cpp:160-176)");
+  dirty_fine_out.insert(dirty_fine_out.end(), touched.begin(), touched.end());
+  assemble_all(h);
+}
+
 // ------------------------------------------------------------------ (f2)
 // Moves one endpoint of every changed edge whose common separator lies above `threshold_node`
 // into that separator; the edge list keeps only the edges that still need a repair.
@@ -622,6 +916,10 @@ void stage_relocate(parth_b200 &h, int threshold_node, std::vector<int> &dirty_f
   const int nn = h.num_nodes, M = h.tree_M, ne = h.n_changed;
   if (ne <= 0) return;
   const int total = h.node_ptr[nn];
+  if (ne <= kSparseEdges && total == M && !std::getenv("PARTH_B200_DENSE_RELOCATE")) {
+    relocate_sparse(h, threshold_node, dirty_fine_out, filter_edges);
+    return;
+  }
   h.r_chosen.reserve((size_t)M + 1, s);  // occ
   h.r_g2l.reserve((size_t)M + 2, s);     // target
   h.r_l2g.reserve((size_t)std::max(M, ne) + 2, s);  // moved flag / its prefix lives in w1

@@ -117,3 +117,42 @@ def test_dof_map_getters_match_the_oracle(gpu_api, port):
     assert np.array_equal(o2n, want)
     assert added.tolist() == list(range(len(keep), Mn))
     assert removed.tolist() == sorted(set(range(M)) - set(keep.tolist()))
+
+
+@pytest.mark.parametrize("variant", ["aggr", "nolag", "relocate"])
+def test_sparse_relocation_equals_the_dense_formulation(gpu_api, variant):
+    """stage_maps.cu has two formulations of relocateDOFsForAggressiveReuse (Integrator.cpp:377-544): passes over all
+    M DOFs, and a sparse one over the moved DOFs and the nodes they touch (taken for <= 8192 changed edges).  They must
+    leave the same tree, update after update (PARTH_B200_DENSE_RELOCATE forces the dense one)."""
+    import os
+    tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 20, 5)))
+    M = 20 ** 3
+    hs = []
+    for _ in range(2):
+        g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 5; g.reorder_type = gpu_api.AMD
+        g.lagging = variant == "aggr"
+        g.activate_aggressive_reuse = variant == "aggr"
+        g.relocate_lvl = 5
+        g.setCoarsePolicy(gpu_api.COARSE_RELOCATE if variant == "relocate" else gpu_api.COARSE_REPAIR)
+        g.import_tree(tree, Mp, Mi)
+        hs.append(g)
+    rng = np.random.default_rng(5)
+    cur = (Mp, Mi)
+    for step in range(6):
+        k = [3, 40, 400, 1, 2000, 25][step]
+        cur = synth.add_edges(cur[0], cur[1], rng.integers(0, M, size=(k, 2)))
+        outs = []
+        for which, g in enumerate(hs):
+            if which == 0:
+                os.environ["PARTH_B200_DENSE_RELOCATE"] = "1"
+            else:
+                os.environ.pop("PARTH_B200_DENSE_RELOCATE", None)
+            g.setMesh(M, cur[0], cur[1])
+            st, perm = g.computePermutation(1)
+            assert st == 0
+            outs.append((perm.copy(), g.export_tree(), g.changed_edges().copy(), g.getReuse()))
+        os.environ.pop("PARTH_B200_DENSE_RELOCATE", None)
+        assert np.array_equal(outs[0][0], outs[1][0])
+        assert np.array_equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
+        for key in ("labels", "dofs", "mesh_perm", "dof2node", "node_ptr", "meta"):
+            assert np.array_equal(outs[0][1][key], outs[1][1][key]), (step, key)
