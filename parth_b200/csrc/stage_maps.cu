@@ -17,6 +17,7 @@
 // neighbours with a smaller id (they precede it in the queue), sees the placements of earlier
 // passes, and ignores later-queue neighbours even if they were placed in the same pass.
 #include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdlib>
 
@@ -423,23 +424,77 @@ __global__ void reloc_info_kernel(const int *__restrict__ moved, const int *__re
   dof2node[d] = t;
 }
 
-// the slices of the nodes nothing happens to move to their new offsets
+// the slices of the nodes nothing happens to move to their new offsets (8 consecutive entries per thread: one node
+// look-up for the run unless it crosses a node boundary)
+constexpr int RC_RUN = 8;
 __global__ void regroup_copy_kernel(const int *__restrict__ optr, const int *__restrict__ nptr,
                                     const int *__restrict__ changed, int nodes, int new_total,
                                     const int *__restrict__ dofs, const int *__restrict__ labels,
                                     int *__restrict__ dofs2, int *__restrict__ labels2) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= new_total) return;
-  const int nd = node_of_entry_d(nptr, nodes, p);
-  if (__ldg(changed + nd)) return;
-  const int src = __ldg(optr + nd) + (p - __ldg(nptr + nd));
-  dofs2[p] = dofs[src];
-  labels2[p] = labels[src];
+  const long long p0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * RC_RUN;
+  if (p0 >= new_total) return;
+  int nd = node_of_entry_d(nptr, nodes, (int)p0);
+  int end = __ldg(nptr + nd + 1), delta = __ldg(optr + nd) - __ldg(nptr + nd), skip = __ldg(changed + nd);
+  const int p1 = (int)min((long long)new_total, p0 + RC_RUN);
+  if (p1 <= end && !skip && ((p0 | (long long)delta) & 3) == 0 && p1 - p0 == RC_RUN) {
+    // the whole run lies in one unchanged node and source and destination are 16-byte aligned
+    const int4 *sd = reinterpret_cast<const int4 *>(dofs + p0 + delta), *sl = reinterpret_cast<const int4 *>(labels + p0 + delta);
+    int4 *dd = reinterpret_cast<int4 *>(dofs2 + p0), *dl = reinterpret_cast<int4 *>(labels2 + p0);
+    const int4 a0 = sd[0], a1 = sd[1], b0 = sl[0], b1 = sl[1];
+    dd[0] = a0; dd[1] = a1; dl[0] = b0; dl[1] = b1;
+    return;
+  }
+  for (int p = (int)p0; p < p1; p++) {
+    while (p >= end) {  // next non-empty node
+      nd++;
+      end = __ldg(nptr + nd + 1);
+      delta = __ldg(optr + nd) - __ldg(nptr + nd);
+      skip = __ldg(changed + nd);
+    }
+    if (skip) continue;
+    dofs2[p] = dofs[p + delta];
+    labels2[p] = labels[p + delta];
+  }
+}
+
+// exclusive prefix MAXIMUM over the threads of a 512-thread block (smem: int[17]); *total = block maximum
+__device__ __forceinline__ int block_excl_max_scan_512(int v, int *smem, int *total) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc = max(inc, t);
+  }
+  int ex = __shfl_up_sync(0xffffffffu, inc, 1);
+  if (lane == 0) ex = INT_MIN;
+  if (lane == 31) smem[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = lane < 16 ? smem[lane] : INT_MIN;
+    int wi = w;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, wi, d);
+      if (lane >= d) wi = max(wi, t);
+    }
+    int wex = __shfl_up_sync(0xffffffffu, wi, 1);
+    if (lane == 0) wex = INT_MIN;
+    if (lane < 16) smem[lane] = wex;
+    if (lane == 15) smem[16] = wi;
+  }
+  __syncthreads();
+  const int res = max(ex, smem[warp]);
+  *total = smem[16];
+  __syncthreads();
+  return res;
 }
 
 // one CTA per node that loses or receives DOFs.  Shared memory: bitmap of the deleted labels + its word prefix
 // (label compaction), histogram of the survivors over "number of joiners below" (joiner positions), scan scratch.
+// A thread owns RG_ITEMS consecutive entries of a chunk, so the entry order is the thread order.
 constexpr int RG_THREADS = 512;
+constexpr int RG_ITEMS = 8;
 __global__ void __launch_bounds__(RG_THREADS)
 regroup_changed_kernel(const int *__restrict__ list, const int *__restrict__ optr, const int *__restrict__ nptr,
                        const int *__restrict__ aptr, const int *__restrict__ target, const int *__restrict__ joinS,
@@ -447,7 +502,6 @@ regroup_changed_kernel(const int *__restrict__ list, const int *__restrict__ opt
                        int *__restrict__ labels2, int *__restrict__ flags /*[0] unsorted, [1] size mismatch*/) {
   extern __shared__ int rg_smem[];
   __shared__ int s_scan[33];
-  __shared__ int s_last;
   const int x = list[blockIdx.x];
   const int o0 = optr[x], size = optr[x + 1] - o0;
   const int base = nptr[x], new_size = nptr[x + 1] - base;
@@ -456,7 +510,6 @@ regroup_changed_kernel(const int *__restrict__ list, const int *__restrict__ opt
   int *bits = rg_smem, *wpre = rg_smem + words, *hist = rg_smem + 2 * words;
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * words + na + 1; i += RG_THREADS) rg_smem[i] = 0;
-  if (tid == 0) s_last = -1;
   __syncthreads();
   for (int k = tid; k < size; k += RG_THREADS)
     if (__ldg(target + dofs[o0 + k]) != kNoInit) {
@@ -475,40 +528,47 @@ regroup_changed_kernel(const int *__restrict__ list, const int *__restrict__ opt
   }
   __syncthreads();
   // survivors, in entry order
-  int ns = 0;
-  for (int k0 = 0; k0 < size; k0 += RG_THREADS) {
-    const int k = k0 + tid;
-    int v = 0, lab = 0;
-    bool keep = false;
-    if (k < size) {
-      v = dofs[o0 + k];
-      keep = __ldg(target + v) == kNoInit;
-      lab = labels[o0 + k];
+  int ns = 0, last = INT_MIN;  // survivors so far, largest survivor so far (ascending <=> each exceeds it)
+  bool unsorted = false;
+  for (int k0 = 0; k0 < size; k0 += RG_THREADS * RG_ITEMS) {
+    int v[RG_ITEMS], lab[RG_ITEMS];
+    unsigned keep = 0;
+    int lmax = INT_MIN;
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; i++) {
+      const int k = k0 + tid * RG_ITEMS + i;
+      v[i] = 0; lab[i] = 0;
+      if (k < size) {
+        v[i] = dofs[o0 + k];
+        lab[i] = labels[o0 + k];
+        if (__ldg(target + v[i]) == kNoInit) { keep |= 1u << i; lmax = max(lmax, v[i]); }
+      }
     }
-    int total;
-    const int ex = block_excl_scan<RG_THREADS>(keep ? 1 : 0, s_scan, &total);
-    // ascending survivors (the merge with the joiners needs it): compare with the previous survivor
-    __shared__ int s_val[RG_THREADS];
-    if (keep) s_val[ex] = v;
-    __syncthreads();
-    if (keep) {
-      const int j = ns + ex;
-      const int prev = ex > 0 ? s_val[ex - 1] : s_last;
+    int total, tmax;
+    const int ex = block_excl_scan<RG_THREADS>(__popc(keep), s_scan, &total);
+    int prev = max(last, block_excl_max_scan_512(lmax, s_scan, &tmax));
+    int j = ns + ex;
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; i++) {
+      if (!((keep >> i) & 1u)) continue;
       int shift = 0;
       if (na > 0) {
-        shift = lower_bound_d(joinS + a0, na, v);
-        if (prev > v) flags[0] = 1;
+        shift = lower_bound_d(joinS + a0, na, v[i]);
+        unsorted |= prev > v[i];  // the merge with the joiners needs ascending survivors
+        prev = max(prev, v[i]);
         atomicAdd(hist + shift, 1);
       }
-      dofs2[base + j + shift] = v;
-      labels2[base + j] = lab - (wpre[lab >> 5] + __popc((unsigned)bits[lab >> 5] & ((1u << (lab & 31)) - 1u)));
+      dofs2[base + j + shift] = v[i];
+      labels2[base + j] =
+          lab[i] - (wpre[lab[i] >> 5] + __popc((unsigned)bits[lab[i] >> 5] & ((1u << (lab[i] & 31)) - 1u)));
+      j++;
     }
-    __syncthreads();
-    if (tid == 0 && total > 0) s_last = s_val[total - 1];
     ns += total;
-    __syncthreads();
+    last = max(last, tmax);
   }
+  if (unsorted) flags[0] = 1;
   if (ns + na != new_size && tid == 0) flags[1] = 1;
+  __syncthreads();  // the histogram is complete
   // joiner r sits behind the survivors with at most r joiners below them
   running = 0;
   for (int r0 = 0; r0 < na; r0 += RG_THREADS) {
@@ -523,6 +583,16 @@ regroup_changed_kernel(const int *__restrict__ list, const int *__restrict__ opt
     }
     running += total;
   }
+}
+
+// mesh_perm of the listed nodes (HMD::assignCoarseLocalPermToGlobal restricted to the nodes whose slice or offset changed)
+__global__ void assemble_listed_kernel(const int *__restrict__ list, const int *__restrict__ node_ptr,
+                                       const int *__restrict__ offs, const int *__restrict__ dofs,
+                                       const int *__restrict__ labels, int *__restrict__ mesh_perm) {
+  const int nd = list[blockIdx.y];
+  const int a = node_ptr[nd], b = node_ptr[nd + 1], off = offs[blockIdx.y];
+  for (int k = a + blockIdx.x * blockDim.x + threadIdx.x; k < b; k += gridDim.x * blockDim.x)
+    mesh_perm[labels[k] + off] = dofs[k];
 }
 
 // the persistent scratch goes back to its clean state, entry by entry
@@ -858,8 +928,20 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
   }
   const int new_total = nptr[nn];
   if (new_total != h.node_ptr[nn]) throw StatusError(PARTH_B200_ERR_INTERNAL, "relocate: entry count mismatch");
-  // one upload: aptr | nptr | changed flags | changed list | touched list  (pinned: no wait)
-  const size_t up = (size_t)3 * nn + 2 + changed.size() + touched.size();
+  // offsets of the new layout (host, <= 8191 nodes); mesh_perm is re-assembled only for the nodes whose slice or
+  // offset changed (DOFs move inside the sub-tree of the receiving separator: nothing outside it shifts)
+  std::vector<int> old_off((size_t)nn);
+  for (int x = 0; x < nn; x++) old_off[x] = h.meta[(size_t)x * 7 + 4];
+  h.node_ptr = nptr;
+  update_offsets(h);
+  std::vector<int> asm_list, asm_off;
+  for (int x = 0; x < nn; x++)
+    if (nptr[x + 1] > nptr[x] && (changed_flag[x] || h.meta[(size_t)x * 7 + 4] != old_off[x])) {
+      asm_list.push_back(x);
+      asm_off.push_back(h.meta[(size_t)x * 7 + 4]);
+    }
+  // one upload: aptr | nptr | changed flags | changed list | touched list | assemble list | its offsets  (pinned: no wait)
+  const size_t up = (size_t)3 * nn + 2 + changed.size() + touched.size() + 2 * asm_list.size();
   h.pin_rel.reserve(up + 8);
   h.w5.reserve(up + 8, s);
   {
@@ -868,11 +950,14 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
     std::copy(nptr.begin(), nptr.end(), q); q += nn + 1;
     std::copy(changed_flag.begin(), changed_flag.end(), q); q += nn;
     std::copy(changed.begin(), changed.end(), q); q += changed.size();
-    std::copy(touched.begin(), touched.end(), q);
+    std::copy(touched.begin(), touched.end(), q); q += touched.size();
+    std::copy(asm_list.begin(), asm_list.end(), q); q += asm_list.size();
+    std::copy(asm_off.begin(), asm_off.end(), q);
   }
   PB_CUDA(cudaMemcpyAsync(h.w5.p, h.pin_rel.p, sizeof(int) * up, cudaMemcpyHostToDevice, s));
   const int *d_aptr = h.w5.p, *d_nptr = h.w5.p + (nn + 1), *d_flag = h.w5.p + 2 * (nn + 1);
   const int *d_changed_list = d_flag + nn, *d_touched = d_changed_list + changed.size();
+  const int *d_asm = d_touched + touched.size(), *d_asm_off = d_asm + asm_list.size();
   h.r_sub.reserve((size_t)std::max(n_moved, 1), s);  // joiners grouped by node
   if (!touched.empty()) {
     rank_joiners_kernel<<<(unsigned)touched.size(), 256, 0, s>>>(d_touched, h.r_perm.p, h.r_ws.p, n_moved, d_aptr, h.r_sub.p);
@@ -880,8 +965,8 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
   }
   h.d_dofs2.reserve((size_t)std::max(new_total, 1), s);
   h.d_labels2.reserve((size_t)std::max(new_total, 1), s);
-  regroup_copy_kernel<<<nblk(new_total), 256, 0, s>>>(h.d_node_ptr.p, d_nptr, d_flag, nn, new_total, h.d_dofs.p, h.d_labels.p,
-                                                     h.d_dofs2.p, h.d_labels2.p);
+  regroup_copy_kernel<<<nblk((new_total + RC_RUN - 1) / RC_RUN), 256, 0, s>>>(h.d_node_ptr.p, d_nptr, d_flag, nn, new_total,
+                                                                            h.d_dofs.p, h.d_labels.p, h.d_dofs2.p, h.d_labels2.p);
   const size_t smem = sizeof(int) * ((size_t)2 * max_words + max_in + 2);
   if (smem > 200 * 1024) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "relocate: a node is too large for the regroup kernel");
   if (smem > 48 * 1024)
@@ -894,8 +979,13 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
   h.stats.kernels_launched += 3;
   h.d_dofs.swap(h.d_dofs2);
   h.d_labels.swap(h.d_labels2);
-  h.node_ptr = nptr;
-  update_offsets(h);
+  if (!asm_list.empty()) {
+    // (d_nptr: the new node_ptr, already on the device; upload_tree_meta below refreshes the handle's own copy)
+    assemble_listed_kernel<<<dim3(32, (unsigned)asm_list.size()), 256, 0, s>>>(d_asm, d_nptr, d_asm_off, h.d_dofs.p,
+                                                                              h.d_labels.p, h.d_mesh_perm.p);
+    PB_CUDA(cudaGetLastError());
+    h.stats.kernels_launched++;
+  }
   upload_tree_meta(h);  // synchronises: the flags below have arrived as well
   int fl[2] = {0, 0};
   read_ints(h, d_cnt + 1, fl, 2);
@@ -905,7 +995,6 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
                       "DOF map: surviving DOFs of a node that receives DOFs are not in ascending order "
                       "(the reference expects survivors to keep their order, remeshPatch.cpp:160-176)");
   dirty_fine_out.insert(dirty_fine_out.end(), touched.begin(), touched.end());
-  assemble_all(h);
 }
 
 // ------------------------------------------------------------------ (f2)
