@@ -13,6 +13,10 @@ the DOFs dirtied per update (workloads.PoissonUpdateStream; SURVEY.md section 8d
 `e2e`   : updates/s through the host-pointer C ABI (pinned host CSC in, host permutation out)
 `roofline`: dominant kernel (build_pipe_kernel) algorithmic bytes / its CUDA-event time
 `cpu_baseline`: the reference CPU implementation timed on this box's host cores (rank 0, N = 1)
+`nnz_L*`: the metric's second half -- nnz(L) of our permutation from the device symbolic stage, from the CPU oracle,
+and of the reference's permutation (nnz_l_block)
+`configs`: configs 1, 3, 4 and 5 of BASELINE.json, one bounded measurement each with its own parity verdict, roofline
+and CPU reference time (bench_configs.py; N = 1)
 N > 1: ONE mesh over the N GPUs: row blocks of the graph build and of change detection, one NCCL
 all-gather of {flags, changed edges, row diffs} per update, dirty sub-meshes by all-reduce -- total work is fixed
 ("scaling": "strong"); every rank uploads 1/N of the matrix and returns the whole permutation.  The N independent
@@ -57,6 +61,10 @@ def parse():
     ap.add_argument("--no-variants", action="store_true", help="skip the secondary variants (reported under 'variants')")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--configs", default="1,3,4,5",
+                    help="the other BASELINE.json configs measured under the key 'configs' (N = 1 only; bench_configs.py)")
+    ap.add_argument("--no-configs", action="store_true")
+    ap.add_argument("--no-nnzl", action="store_true", help="skip the nnz(L) comparison of config 2")
     ap.add_argument("--replicas-only", action="store_true",
                     help="N > 1: only the N independent meshes of round 1 (no collective)")
     return ap.parse_args()
@@ -161,6 +169,7 @@ def cpu_update_stream(kind, stream, variant, steps, warmup, first=0):
         if k >= warmup:
             times.append(t1 - t0)
         info = dict(status=int(st), reuse=h.getReuse(), changes=h.getNumChanges())
+    info["_perm"] = perm
     return times, info
 
 
@@ -196,6 +205,7 @@ def run_reference(args):
     stream = workloads.PoissonUpdateStream(n=args.n, levels=8)
     nnz = int(stream.Ap[-1])
     times, info = cpu_update_stream(kind, stream, args.variant, args.steps, args.warmup)
+    info.pop("_perm", None)
     per = float(np.mean(times))
     value = 1.0 / per
     sample = f"{args.steps} full updates (setMatrix + computePermutation) at {args.n}^3 after {args.warmup} warm-up updates"
@@ -210,6 +220,45 @@ def run_reference(args):
         "last_update": info,
     }
     print(json.dumps(line), flush=True)
+
+
+def nnz_l_block(make_handle, stream, variant, ref_perm, kind):
+    """the metric's second half ("nnz(L) bit-exact vs ref"): the same two updates the cpu_baseline leg has just run,
+    on a fresh handle; nnz(L) of OUR permutation from the device symbolic stage (stage d), the same number from the CPU
+    oracle (etree as reference src/utils/etree.cpp:39-115 + column counts), and nnz(L) of the REFERENCE's permutation.
+    aggr: the permutations are identical, so all three agree; nolag: the reference re-dissects the dirty sub-tree with
+    METIS where the device relocates, so nnz_L_reference is a fill-quality comparison, not a parity value."""
+    from oracle import cpu_parth
+    cpu_parth.build("port")
+    g = make_handle(variant)
+    for k in range(2):
+        Ap, Ai = stream.matrix(k)
+        g.setMatrix(stream.N, Ap, Ai, 1)
+        st, perm = g.computePermutation(1)
+    Mp, Mi = g.mesh()
+    g.symbolic()  # first call: the stage's scratch buffers are carved out of the memory pool
+    parent, cc, lnz = g.symbolic()
+    sym_ms = g.stats()["symbolic_ms"]
+    lnz_given = g.symbolic(perm)[2]
+    sn = g.supernodes(parent, cc)  # (f4) the consumer's first step, on the device
+    sn_ms = g.stats()["supernodes_ms"]
+    par = cpu_parth.etree(Mp, Mi, perm)
+    lnz_o, _ = cpu_parth.colcount(Mp, Mi, perm, par)
+    par_r = cpu_parth.etree(Mp, Mi, ref_perm)
+    lnz_r, _ = cpu_parth.colcount(Mp, Mi, ref_perm, par_r)
+    return {"nnz_L": int(lnz), "nnz_L_oracle": int(lnz_o), "nnz_L_reference": int(lnz_r),
+            "nnz_L_detail": {"what": "nnz(L) = sum of the column counts of P A P^T (lower triangle with diagonal) after 2 updates "
+                                     "from the tree fixture; nnz_L: device stage (d) on our permutation (tree-aware path); "
+                                     "nnz_L_oracle: CPU oracle on the same permutation; nnz_L_reference: CPU oracle on the "
+                                     f"permutation of the reference's CPU path ({kind}) after the same 2 updates",
+                             "device_equals_oracle": bool(lnz == lnz_o and lnz_given == lnz_o),
+                             "permutation_equals_reference": bool(np.array_equal(perm, ref_perm)),
+                             "fill_vs_reference": float(lnz) / float(lnz_r),
+                             "cholmod_L_NNZ": int(2 * lnz - stream.N),
+                             "device_symbolic_ms": sym_ms, "status": int(st),
+                             "supernodes": {"nsuper": sn["nsuper"], "ssize": sn["ssize"], "xsize": sn["xsize"],
+                                            "device_ms": sn_ms,
+                                            "equals_oracle": bool(np.array_equal(sn["super"], cpu_parth.supernodes(parent, cc)["super"]))}}}
 
 
 # ------------------------------------------------------------------ our arm (CUDA)
@@ -410,11 +459,21 @@ def run_ours(args, emit=True):
                 cpu_parth.build("port")
             cores = os.cpu_count() or 1
             times, cinfo = cpu_update_stream(kind, stream, args.variant, 2, 0)
+            ref_perm = cinfo.pop("_perm")
             line["cpu_baseline"] = {"value": 1.0 / float(np.mean(times)), "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"2 full updates at {args.n}^3 on a freshly injected tree",
                                     "last_update": cinfo}
+            if not args.no_nnzl:
+                line.update(nnz_l_block(make_handle, stream, args.variant, ref_perm, kind))
         except Exception as e:  # the checker must never take the product number down
-            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)}
+            line.setdefault("cpu_baseline", {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)})
+            line.setdefault("nnz_L", None)
+            line["checker_error"] = repr(e)
+    if rank == 0 and world == 1 and not args.no_configs and emit:
+        import bench_configs
+        del dev_mats, host_mats, g
+        torch.cuda.empty_cache()
+        line["configs"] = bench_configs.run_all(api, cpu_kind(), peak, tuple(args.configs.split(",")))
     if not emit:
         return line
     if rank == 0:

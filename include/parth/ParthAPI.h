@@ -379,6 +379,24 @@ public:
     return lnz;
   }
 
+  /* fundamental supernodes of L from the arrays symbolic() returned (the first step of the supernodal analysis
+   * behind reference src/LinSysSolver/CHOLMODSolver.cpp:108-151): super[s] = first column of supernode s
+   * (super[nsuper] = n), sparent = supernodal elimination tree; returns the number of supernodes */
+  int supernodes(const std::vector<int> &parent, const std::vector<int> &colcount, std::vector<int> &super,
+                 std::vector<int> &supermap, std::vector<int> &sparent, int64_t *ssize = nullptr,
+                 int64_t *xsize = nullptr) {
+    const int n = (int)parent.size();
+    int ns = 0;
+    super.resize((size_t)n + 1);
+    supermap.resize((size_t)n);
+    sparent.resize((size_t)n);
+    check(parth_b200_supernodes(h_, n, parent.data(), colcount.data(), super.data(), supermap.data(), sparent.data(),
+                                &ns, ssize, xsize));
+    super.resize((size_t)ns + 1);
+    sparent.resize((size_t)ns);
+    return ns;
+  }
+
   /* copy the separator tree back into `hmd` (HMD.h:94-104 layout) */
   void syncTreeMirror() {
     int tm = 0, lv = 0, nodes = 0;

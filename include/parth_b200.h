@@ -193,6 +193,19 @@ int parth_b200_symbolic(parth_b200 *h, const int *perm, int *parent, int *colcou
  * ordering (the symbolic phase of a device sparse Cholesky: reference src/LinSysSolver/LinSysSolver.hpp:92-113,
  * CHOLMODSolver.cpp:108-151 recompute them on the host).  dperm NULL: current mesh_perm. */
 int parth_b200_symbolic_dev(parth_b200 *h, const int *dperm, int *dparent, int *dcolcount, int64_t *lnz);
+/* the step after stage (d): fundamental supernodes of L from the elimination tree and the column
+ * counts, on the device -- what the supernodal analysis behind reference src/LinSysSolver/CHOLMODSolver.cpp:108-151
+ * (cholmod_analyze_p, cm.supernodal = CHOLMOD_SUPERNODAL) derives first, after recomputing both arrays on the host.
+ * Column j > 0 continues the supernode of j-1 iff parent[j-1] == j, colcount[j-1] == colcount[j] + 1 and j has
+ * exactly one child.  Outputs (each may be NULL): super[0..nsuper] first column of every supernode (super[nsuper] = n;
+ * capacity n + 1), supermap[n] supernode of every column, sparent[nsuper] supernodal elimination tree (-1 = root;
+ * capacity n); *nsuper, *ssize = sum of colcount[first column] (row indices of the supernodal structure),
+ * *xsize = sum of ncols * colcount[first column] (numerical entries).  Relaxed amalgamation is not applied. */
+int parth_b200_supernodes(parth_b200 *h, int n, const int *parent, const int *colcount, int *super, int *supermap,
+                          int *sparent, int *nsuper, int64_t *ssize, int64_t *xsize);
+/* same with device pointers for the five arrays (stream-ordered behind parth_b200_symbolic_dev) */
+int parth_b200_supernodes_dev(parth_b200 *h, int n, const int *dparent, const int *dcolcount, int *dsuper,
+                              int *dsupermap, int *dsparent, int *nsuper, int64_t *ssize, int64_t *xsize);
 
 /* instrumentation: device time of the last call's stages (CUDA events on the handle's stream)
  * and the number of kernels launched by the library since creation */
@@ -212,6 +225,7 @@ typedef struct {
   int expand_speculative;                 /* 1 = the last compute_permutation_dev expanded before the flags were read and the result stood */
   int morton_passes;                      /* radix passes the last set_coordinates ran (digits that are constant over all keys are skipped) */
   double morton_ms;                       /* last set_coordinates: bounding box + keys + radix sort + rank */
+  double supernodes_ms;                   /* last parth_b200_supernodes* call */
 } parth_b200_stats;
 int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out);
 int parth_b200_synchronize(parth_b200 *h);

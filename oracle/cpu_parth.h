@@ -78,6 +78,9 @@ int cpu_parth_etree(int n, const int *Ap, const int *Ai, const int *perm, int *p
 /* column counts of L (diagonal included); returns nnz(L) or -1 if unsupported */
 int64_t cpu_parth_colcount(int n, const int *Ap, const int *Ai, const int *perm,
                            const int *parent, int *colcount);
+/* fundamental supernodes from (parent, colcount): port only (see symbolic_oracle.c); returns nsuper */
+int cpu_parth_supernodes(int n, const int *parent, const int *colcount, int *super, int *supermap,
+                         int *sparent, int64_t *sizes);
 
 #ifdef __cplusplus
 }

@@ -82,6 +82,8 @@ def load(kind="port"):
     lib.cpu_parth_etree.argtypes = [C.c_int, _ip, _ip, _ip, _ip]
     lib.cpu_parth_colcount.argtypes = [C.c_int, _ip, _ip, _ip, _ip, _ip]
     lib.cpu_parth_colcount.restype = C.c_int64
+    if hasattr(lib, "cpu_parth_supernodes"):  # port only
+        lib.cpu_parth_supernodes.argtypes = [C.c_int, _ip, _ip, _ip, _ip, _ip, C.POINTER(C.c_int64)]
     _libs[kind] = lib
     return lib
 
@@ -267,3 +269,13 @@ def colcount(Ap, Ai, perm, parent, kind="port"):
     cc = np.empty(max(n, 1), np.int32)
     lnz = load(kind).cpu_parth_colcount(n, _p(Ap), _p(Ai), _p(perm), _p(parent), _p(cc))
     return int(lnz), cc[:n]
+
+
+def supernodes(parent, colcount):
+    """(f4) fundamental supernodes (port restatement): dict(super, supermap, sparent, nsuper, ssize, xsize)"""
+    parent, colcount = _i32(parent), _i32(colcount)
+    n = len(parent)
+    sup, smap, spar = np.empty(n + 1, np.int32), np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.int32)
+    sizes = (C.c_int64 * 2)()
+    k = load("port").cpu_parth_supernodes(n, _p(parent), _p(colcount), _p(sup), _p(smap), _p(spar), sizes)
+    return dict(super=sup[:k + 1], supermap=smap[:n], sparent=spar[:k], nsuper=k, ssize=int(sizes[0]), xsize=int(sizes[1]))

@@ -116,3 +116,33 @@ int64_t cpu_parth_colcount(int n, const int *Ap, const int *Ai, const int *perm,
   free(inv); free(post); free(w);
   return lnz;
 }
+
+/* (f4) fundamental supernodes of L from (parent, colcount), sequentially: the definition CHOLMOD's supernodal
+ * analysis starts from (the step behind reference src/LinSysSolver/CHOLMODSolver.cpp:108-151; SuiteSparse itself is
+ * absent from the reference tree -- PARITY UNPINNED against CHOLMOD, pinned by the brute-force symbolic
+ * factorisation in tests/test_oracle_symbolic.py).  Column j > 0 continues the supernode of j-1 iff
+ * parent[j-1] == j, colcount[j-1] == colcount[j] + 1 and j has exactly one child.  super has n+1 entries,
+ * supermap n, sparent n (first nsuper used); sizes[0] = sum colcount[first], sizes[1] = sum ncols*colcount[first].
+ * Returns nsuper. */
+int cpu_parth_supernodes(int n, const int *parent, const int *colcount, int *super, int *supermap,
+                         int *sparent, int64_t *sizes) {
+  sizes[0] = sizes[1] = 0;
+  if (n == 0) { super[0] = 0; return 0; }
+  int *nchild = (int *)calloc((size_t)n, sizeof(int));
+  for (int j = 0; j < n; j++)
+    if (parent[j] >= 0 && parent[j] < n) nchild[parent[j]]++;
+  int ns = 0;
+  for (int j = 0; j < n; j++) {
+    if (j == 0 || parent[j - 1] != j || colcount[j - 1] != colcount[j] + 1 || nchild[j] > 1) super[ns++] = j;
+    supermap[j] = ns - 1;
+  }
+  super[ns] = n;
+  for (int s = 0; s < ns; s++) {
+    int last = super[s + 1] - 1, p = parent[last];
+    sparent[s] = (p < 0 || p >= n) ? -1 : supermap[p];
+    sizes[0] += colcount[super[s]];
+    sizes[1] += (int64_t)colcount[super[s]] * (super[s + 1] - super[s]);
+  }
+  free(nchild);
+  return ns;
+}

@@ -31,7 +31,8 @@ class Stats(C.Structure):
         ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("integrate_passes", C.c_int), ("integrate_sweeps", C.c_int),
         ("symbolic_etree_ms", C.c_double), ("diff_kernel_ms", C.c_double), ("symbolic_path", C.c_int),
         ("build_fused_detect", C.c_int), ("proof_kernel_ms", C.c_double), ("build_deferred", C.c_int),
-        ("expand_speculative", C.c_int), ("morton_passes", C.c_int), ("morton_ms", C.c_double)]
+        ("expand_speculative", C.c_int), ("morton_passes", C.c_int), ("morton_ms", C.c_double),
+        ("supernodes_ms", C.c_double)]
 
 
 DECOMPOSER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, _ip, _ip, C.c_int, C.c_int, _ip, _ip, _ip, _ip)
@@ -86,6 +87,10 @@ SYMBOLS = {
     "parth_b200_morton_keys": (C.c_int, [_vp, _vp, C.c_int]),
     "parth_b200_symbolic": (C.c_int, [_vp, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
     "parth_b200_symbolic_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
+    "parth_b200_supernodes": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _ip, _ip, C.POINTER(C.c_int), C.POINTER(C.c_int64),
+                                        C.POINTER(C.c_int64)]),
+    "parth_b200_supernodes_dev": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, _vp, C.POINTER(C.c_int), C.POINTER(C.c_int64),
+                                            C.POINTER(C.c_int64)]),
     "parth_b200_get_stats": (C.c_int, [_vp, C.POINTER(Stats)]),
     "parth_b200_synchronize": (C.c_int, [_vp]),
     "parth_b200_stream": (_vp, [_vp]),
@@ -615,6 +620,28 @@ class ParthAPI:
         self._check(self.lib.parth_b200_symbolic_dev(self.h, C.c_void_p(dperm_ptr or None), C.c_void_p(dparent_ptr or None),
                                                      C.c_void_p(dcolcount_ptr or None), C.byref(lnz)))
         return int(lnz.value)
+
+    def supernodes(self, parent, colcount):
+        """(f4) fundamental supernodes of L from etree + column counts (host arrays in and out):
+        returns dict(super, supermap, sparent, nsuper, ssize, xsize)"""
+        parent, colcount = _i32(parent), _i32(colcount)
+        n = len(parent)
+        sup = np.empty(n + 1, np.int32)
+        smap = np.empty(max(n, 1), np.int32)
+        spar = np.empty(max(n, 1), np.int32)
+        ns, a, b = C.c_int(), C.c_int64(), C.c_int64()
+        self._check(self.lib.parth_b200_supernodes(self.h, n, _p(parent), _p(colcount), _p(sup), _p(smap), _p(spar),
+                                                   C.byref(ns), C.byref(a), C.byref(b)))
+        k = ns.value
+        return dict(super=sup[:k + 1], supermap=smap[:n], sparent=spar[:k], nsuper=k, ssize=int(a.value), xsize=int(b.value))
+
+    def supernodesDev(self, n, dparent_ptr, dcolcount_ptr, dsuper_ptr=0, dsupermap_ptr=0, dsparent_ptr=0):
+        """device pointers (0 = NULL for the outputs): returns (nsuper, ssize, xsize)"""
+        ns, a, b = C.c_int(), C.c_int64(), C.c_int64()
+        self._check(self.lib.parth_b200_supernodes_dev(self.h, int(n), C.c_void_p(dparent_ptr), C.c_void_p(dcolcount_ptr),
+                                                       C.c_void_p(dsuper_ptr or None), C.c_void_p(dsupermap_ptr or None),
+                                                       C.c_void_p(dsparent_ptr or None), C.byref(ns), C.byref(a), C.byref(b)))
+        return ns.value, int(a.value), int(b.value)
 
     def symbolic(self, perm=None):
         n, _ = self.mesh_dims()

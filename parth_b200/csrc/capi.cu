@@ -703,6 +703,33 @@ int parth_b200_symbolic_dev(parth_b200 *h, const int *dperm, int *dparent, int *
   PB_API_END
 }
 
+int parth_b200_supernodes(parth_b200 *h, int n, const int *parent, const int *colcount, int *super, int *supermap,
+                          int *sparent, int *nsuper, int64_t *ssize, int64_t *xsize) {
+  PB_API_BEGIN
+  if (n < 0 || (n > 0 && (!parent || !colcount))) throw StatusError(PARTH_B200_ERR_ARG, "supernodes: parent / colcount missing");
+  long long a = 0, b = 0;
+  int ns = 0;
+  stage_supernodes(*h, n, parent, colcount, super, supermap, sparent, &ns, &a, &b, /*on_device=*/false);
+  resolve_timers(*h);
+  if (nsuper) *nsuper = ns;
+  if (ssize) *ssize = a;
+  if (xsize) *xsize = b;
+  PB_API_END
+}
+
+int parth_b200_supernodes_dev(parth_b200 *h, int n, const int *dparent, const int *dcolcount, int *dsuper,
+                              int *dsupermap, int *dsparent, int *nsuper, int64_t *ssize, int64_t *xsize) {
+  PB_API_BEGIN
+  if (n < 0 || (n > 0 && (!dparent || !dcolcount))) throw StatusError(PARTH_B200_ERR_ARG, "supernodes: parent / colcount missing");
+  long long a = 0, b = 0;
+  int ns = 0;
+  stage_supernodes(*h, n, dparent, dcolcount, dsuper, dsupermap, dsparent, &ns, &a, &b, /*on_device=*/true);
+  resolve_timers(*h);
+  if (nsuper) *nsuper = ns;
+  if (ssize) *ssize = a;
+  if (xsize) *xsize = b;
+  PB_API_END
+}
 
 // ------------------------------------------------------------------ one mesh over several GPUs (row blocks)
 int parth_b200_comm_unique_id(void *id128) {

@@ -104,4 +104,10 @@ int builtin_decomposer(void *user, int M_n, const int *Mp, const int *Mi, int le
 void stage_symbolic(parth_b200 &h, const int *perm_in, int *parent_out, int *colcount_out, long long *lnz_out,
                     bool on_device = false);
 
+
+// supernodes.cu: (f4) fundamental supernodes + supernodal etree from parent / colcount
+void stage_supernodes(parth_b200 &h, int n, const int *parent_in, const int *colcount_in, int *super_out,
+                      int *supermap_out, int *sparent_out, int *nsuper, long long *ssize, long long *xsize,
+                      bool on_device);
+
 }  // namespace pb

@@ -105,3 +105,60 @@ def test_device_pointer_variant_hands_off_on_the_device(gpu_api):
     assert got == lnz
     assert np.array_equal(dparent.cpu().numpy(), parent) and np.array_equal(dcc.cpu().numpy(), cc)
     assert g.symbolicDev(dperm.data_ptr(), 0, 0) == lnz     # only nnz(L) wanted
+
+
+@pytest.mark.parametrize("key", [("geo", 16, 5), ("fish",), ("g12",), ("rand", 7), ("rand", 8), ("clique",)])
+def test_supernodes_match_oracle(gpu_api, port, key):
+    """(f4) fundamental supernodes + supernodal etree on the device against oracle/symbolic_oracle.c
+    (itself checked against a brute-force symbolic factorisation, tests/test_oracle_symbolic.py)"""
+    g = gpu_api.ParthAPI()
+    if key[0] == "rand":
+        rng = np.random.default_rng(key[1])
+        n = 3000
+        r, c = rng.integers(0, n, 4 * n), rng.integers(0, n, 4 * n)
+        keep = r != c
+        _, Mp, Mi = synth.coo_to_csc(n, np.concatenate([r[keep], c[keep]]), np.concatenate([c[keep], r[keep]]))
+        perm = rng.permutation(n)
+    elif key[0] == "clique":
+        n = 5000  # one supernode, longer than a scan tile
+        Mp = (np.arange(n + 1, dtype=np.int64) * (n - 1)).astype(np.int32)
+        full = np.tile(np.arange(n, dtype=np.int32), n).reshape(n, n)
+        Mi = full[~np.eye(n, dtype=bool)]
+        perm = np.arange(n)
+    else:
+        tree, Mp, Mi = sd.tree_of({"tree": key})
+        perm = synth.assemble_mesh_perm(tree.meta, tree.node_ptr, tree.dofs, tree.labels)
+    n = len(Mp) - 1
+    g.setMesh(n, Mp, Mi)
+    parent, cc, lnz = g.symbolic(perm)
+    got = g.supernodes(parent, cc)
+    want = port.supernodes(parent, cc)
+    for k in ("super", "supermap", "sparent"):
+        assert np.array_equal(got[k], want[k]), k
+    assert (got["nsuper"], got["ssize"], got["xsize"]) == (want["nsuper"], want["ssize"], want["xsize"])
+    if key[0] == "clique":
+        assert got["nsuper"] == 1 and got["xsize"] == n * n
+
+
+def test_supernodes_device_pointers(gpu_api, port):
+    """hand-off without leaving the device: symbolic_dev -> supernodes_dev"""
+    import torch
+    tree, Mp, Mi = sd.tree_of({"tree": ("geo", 16, 5)})
+    n = len(Mp) - 1
+    g = gpu_api.ParthAPI()
+    g.import_tree(tree, Mp, Mi)
+    g.setMesh(n, Mp, Mi)
+    dpar = torch.empty(n, dtype=torch.int32, device="cuda")
+    dcc = torch.empty(n, dtype=torch.int32, device="cuda")
+    dsup = torch.empty(n + 1, dtype=torch.int32, device="cuda")
+    dmap = torch.empty(n, dtype=torch.int32, device="cuda")
+    dsp = torch.empty(n, dtype=torch.int32, device="cuda")
+    lnz = g.symbolicDev(0, dpar.data_ptr(), dcc.data_ptr())
+    ns, ssize, xsize = g.supernodesDev(n, dpar.data_ptr(), dcc.data_ptr(), dsup.data_ptr(), dmap.data_ptr(), dsp.data_ptr())
+    g.synchronize()
+    want = port.supernodes(dpar.cpu().numpy(), dcc.cpu().numpy())
+    assert ns == want["nsuper"] and ssize == want["ssize"] and xsize == want["xsize"] and xsize >= lnz
+    assert np.array_equal(dsup[:ns + 1].cpu().numpy(), want["super"])
+    assert np.array_equal(dmap.cpu().numpy(), want["supermap"]) and np.array_equal(dsp[:ns].cpu().numpy(), want["sparent"])
+    # outputs are optional
+    assert g.supernodesDev(n, dpar.data_ptr(), dcc.data_ptr()) == (ns, ssize, xsize)
