@@ -244,7 +244,7 @@ def config1(api, kind, peak):
 
 
 # ------------------------------------------------------------------ config 3: tet mesh, dim = 3, remesh with a DOF map
-def config3(api, kind, peak, n=126):
+def config3(api, kind, peak, n=126, frac=0.05):
     import torch
     from parth_b200 import synth, workloads
     cpu = _cpu(kind)
@@ -254,7 +254,7 @@ def config3(api, kind, peak, n=126):
     Mp_d, Mi_d = lattice_pattern_dev(n, KUHN_DIRS, False, dev)
     Nv = n ** 3
     lo = 40 * n // 126
-    hi = lo + int(round((0.05 * Nv) ** (1 / 3)))
+    hi = lo + int(round((frac * Nv) ** (1 / 3)))
     P, I, n2o = remesh_box_dev(n, Mp_d, Mi_d, lo, hi)
     Apm, Aim = graph_to_matrix_dev(P, I)
     N3, Ap3, Ai3 = kron_blocks_dev(Apm, Aim, dim)

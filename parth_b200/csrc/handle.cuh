@@ -92,7 +92,7 @@ struct parth_b200 {
   pb::DevBuf<int> d_meta, d_node_ptr, d_visit, d_dofs, d_labels, d_dof2node, d_mesh_perm;
   pb::DevBuf<int> d_dofs2, d_labels2;  // double buffers for integration / relocation
   // sparse relocation (stage_maps.cu): per-DOF occurrence counts / relocation targets, clean between calls
-  pb::DevBuf<int> rel_occ, rel_target;
+  pb::DevBuf<int> rel_occ, rel_target, rank_seg;
   int rel_M = 0;
   pb::PinBuf<int> pin_rel;
 

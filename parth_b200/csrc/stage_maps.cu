@@ -136,18 +136,51 @@ __global__ void regroup_compact_kernel(const int *__restrict__ node_ptr, int nod
 }
 
 // ---------------------------------------------------------------- joiners: per-node rank
-// one CTA per touched node walks the (ascending) joiner list: rank = position among the joiners of
-// the same node; joinS[aptr[node] + rank] = dof
+// rank = position among the joiners of the same node in the (ascending) joiner list; joinS[aptr[node] + rank] = dof.
+// The list is cut into segments: CTA (t, g) counts the joiners of touched node t in segment g, a tiny scan turns the
+// counts into segment bases, and the same grid walks its segments again with a block scan per 256 entries.  (One CTA
+// per node over the whole list took 0.27 ms for the 97 000 joiners of config 3.)
+__global__ void __launch_bounds__(256)
+rank_joiners_count_kernel(const int *__restrict__ touched, const int *__restrict__ join_node, int n_join, int seg,
+                          int *__restrict__ segcnt) {
+  const int node = touched[blockIdx.x];
+  const int lo = blockIdx.y * seg, hi = min(n_join, lo + seg);
+  int c = 0;
+  for (int i = lo + threadIdx.x; i < hi; i += 256) c += __ldg(join_node + i) == node;
+  c = __reduce_add_sync(0xffffffffu, c);
+  __shared__ int s_w[8];
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = 0;
+    for (int k = 0; k < 8; k++) t += s_w[k];
+    segcnt[blockIdx.x * gridDim.y + blockIdx.y] = t;
+  }
+}
+
+__global__ void rank_joiners_scan_kernel(int *__restrict__ segcnt, int n_touched, int n_seg) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_touched) return;
+  int run = 0;
+  for (int g = 0; g < n_seg; g++) {
+    const int c = segcnt[t * n_seg + g];
+    segcnt[t * n_seg + g] = run;
+    run += c;
+  }
+}
+
 __global__ void __launch_bounds__(256)
 rank_joiners_kernel(const int *__restrict__ touched, const int *__restrict__ join, const int *__restrict__ join_node,
-                    int n_join, const int *__restrict__ aptr, int *__restrict__ joinS) {
+                    int n_join, int seg, const int *__restrict__ segbase, const int *__restrict__ aptr,
+                    int *__restrict__ joinS) {
   __shared__ int s_scan[33];
   const int node = touched[blockIdx.x];
-  const int base = aptr[node];
+  const int base = aptr[node] + segbase[blockIdx.x * gridDim.y + blockIdx.y];
+  const int lo = blockIdx.y * seg, hi = min(n_join, lo + seg);
   int running = 0;
-  for (int i0 = 0; i0 < n_join; i0 += 256) {
+  for (int i0 = lo; i0 < hi; i0 += 256) {
     const int i = i0 + threadIdx.x;
-    const int f = i < n_join && __ldg(join_node + i) == node;
+    const int f = i < hi && __ldg(join_node + i) == node;
     int total;
     const int ex = block_excl_scan<256>(f, s_scan, &total);
     if (f) joinS[base + running + ex] = join[i];
@@ -236,6 +269,76 @@ __global__ void place_pass_init_kernel(const int *__restrict__ added, int n_adde
   if (deg == 0) frontier[atomicAdd(fcnt, 1)] = d;
 }
 
+// Decision of ONE ready DOF d by ONE thread: the node it joins, or -2 when it has no visible neighbour (it stays
+// unplaced: next ring).  The arrays other CTAs write during the pass (nd2n, placed_pass) are read through L2
+// (ld.global.cg): the dataflow kernel keeps running while they change, so a line cached in L1 earlier must not be
+// served again.
+__device__ __forceinline__ int place_decide_one(int d, const int *__restrict__ Mp, const int *__restrict__ Mi,
+                                                const int *__restrict__ n2o, const int *__restrict__ meta,
+                                                const int *nd2n, const int *placed_pass, int pass) {
+  const int s = Mp[d], e = Mp[d + 1];
+  // visible node of a neighbour, -1 if none: survivors always; added DOFs placed in an earlier
+  // pass, or in this pass if they precede d in the queue (then they were decided before d became ready)
+  auto visible = [&](int nb) -> int {
+    if (__ldg(n2o + nb) != -1) return __ldcg(nd2n + nb);
+    const int pp = __ldcg(placed_pass + nb);
+    if (pp != 0 && (pp < pass || nb < d)) return __ldcg(nd2n + nb);
+    return -1;
+  };
+  // distinct visible neighbour nodes (a mesh vertex touches a handful of nodes at most)
+  constexpr int kMaxDistinct = 16;
+  int uniq[kMaxDistinct];
+  int nu = 0;
+  bool overflow = false;
+  for (int p = s; p < e; p++) {
+    const int r = visible(Mi[p]);
+    if (r == -1) continue;
+    bool seen = false;
+    for (int u = 0; u < nu; u++) seen |= uniq[u] == r;
+    if (seen) continue;
+    if (nu < kMaxDistinct) uniq[nu++] = r; else overflow = true;
+  }
+  if (nu == 0) return -2;
+  if (nu == 1 && !overflow) return uniq[0];
+  // minimum over all pairs of distinct neighbour nodes of {descendant if ancestor-related, else LCA}
+  int mn = 1 << 30;
+  auto pair_node = [&](int ra, int rb) {
+    const int big = ra > rb ? ra : rb, small = ra > rb ? rb : ra;
+    const int c = is_sep_d(small, big) ? big : lca_d(meta, small, big);
+    mn = c < mn ? c : mn;
+  };
+  if (!overflow) {
+    for (int a = 0; a < nu; a++)
+      for (int b2 = a + 1; b2 < nu; b2++) pair_node(uniq[a], uniq[b2]);
+  } else {
+    for (int p = s; p < e; p++) {
+      const int ra = visible(Mi[p]);
+      if (ra == -1) continue;
+      for (int p2 = p + 1; p2 < e; p2++) {
+        const int rb = visible(Mi[p2]);
+        if (rb != -1 && rb != ra) pair_node(ra, rb);
+      }
+    }
+  }
+  return mn;
+}
+
+// the successors of d (added neighbours with a larger id that were unplaced at pass start) lose one predecessor;
+// the ones that became ready are appended to the next frontier (launch-per-sweep path)
+__device__ __forceinline__ void place_release_one(int d, int *__restrict__ next, int *__restrict__ fcnt_out,
+                                                  const int *__restrict__ Mp, const int *__restrict__ Mi,
+                                                  const int *__restrict__ n2o, const int *placed_pass, int *indeg,
+                                                  int pass) {
+  for (int p = Mp[d]; p < Mp[d + 1]; p++) {
+    const int nb = Mi[p];
+    if (nb <= d || __ldg(n2o + nb) != -1) continue;
+    const int pp = __ldcg(placed_pass + nb);
+    if (pp != 0 && pp != pass) continue;            // placed in an earlier pass: not in this DAG
+    if (atomicSub(indeg + nb, 1) == 1) next[atomicAdd(fcnt_out, 1)] = nb;
+  }
+}
+
+// launch-per-sweep path (kept for wavefronts of millions of DOFs and as the cross-check of the dataflow kernel)
 __global__ void place_sweep_kernel(const int *__restrict__ frontier, const int *__restrict__ fcnt_in,
                                    int *__restrict__ next, int *__restrict__ fcnt_out, const int *__restrict__ Mp,
                                    const int *__restrict__ Mi, const int *__restrict__ n2o,
@@ -244,69 +347,207 @@ __global__ void place_sweep_kernel(const int *__restrict__ frontier, const int *
   const int nf = *fcnt_in;
   for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < nf; q += gridDim.x * blockDim.x) {
     const int d = frontier[q];
-    const int s = Mp[d], e = Mp[d + 1];
-    // visible node of a neighbour, -1 if none: survivors always; added DOFs placed in an earlier
-    // pass, or in this pass if they precede d in the queue (then they were decided in an earlier sweep)
-    auto visible = [&](int nb) -> int {
-      if (__ldg(n2o + nb) != -1) return nd2n[nb];
-      const int pp = placed_pass[nb];
-      if (pp != 0 && (pp < pass || nb < d)) return nd2n[nb];
-      return -1;
-    };
-    // distinct visible neighbour nodes (a mesh vertex touches a handful of nodes at most)
-    constexpr int kMaxDistinct = 16;
-    int uniq[kMaxDistinct];
-    int nu = 0;
-    bool overflow = false;
-    for (int p = s; p < e; p++) {
-      const int r = visible(Mi[p]);
-      if (r == -1) continue;
-      bool seen = false;
-      for (int u = 0; u < nu; u++) seen |= uniq[u] == r;
-      if (seen) continue;
-      if (nu < kMaxDistinct) uniq[nu++] = r; else overflow = true;
-    }
-    const int first = nu > 0 ? uniq[0] : -1;
-    int result = -1;
-    if (nu == 1 && !overflow) result = first;
-    else if (nu > 1) {
-      // minimum over all pairs of distinct neighbour nodes of {descendant if ancestor-related, else LCA}
-      int mn = 1 << 30;
-      auto pair_node = [&](int ra, int rb) {
-        const int big = ra > rb ? ra : rb, small = ra > rb ? rb : ra;
-        const int c = is_sep_d(small, big) ? big : lca_d(meta, small, big);
-        mn = c < mn ? c : mn;
-      };
-      if (!overflow) {
-        for (int a = 0; a < nu; a++)
-          for (int b2 = a + 1; b2 < nu; b2++) pair_node(uniq[a], uniq[b2]);
-      } else {
-        for (int p = s; p < e; p++) {
-          const int ra = visible(Mi[p]);
-          if (ra == -1) continue;
-          for (int p2 = p + 1; p2 < e; p2++) {
-            const int rb = visible(Mi[p2]);
-            if (rb != -1 && rb != ra) pair_node(ra, rb);
-          }
-        }
-      }
-      result = mn;
-    }
-    // release the successors first: their test "unplaced at pass start" must still see d as unplaced
-    // or placed in THIS pass, both of which hold before and after the write below
-    for (int p = s; p < e; p++) {
-      const int nb = Mi[p];
-      if (nb <= d || __ldg(n2o + nb) != -1) continue;
-      const int pp = placed_pass[nb];
-      if (pp != 0 && pp != pass) continue;            // placed in an earlier pass: not in this DAG
-      if (atomicSub(indeg + nb, 1) == 1) next[atomicAdd(fcnt_out, 1)] = nb;
-    }
-    if (first != -1) {  // no placed neighbour: stays unplaced, next ring
-      nd2n[d] = result;
-      placed_pass[d] = pass;
+    const int r = place_decide_one(d, Mp, Mi, n2o, meta, nd2n, placed_pass, pass);
+    // the successors' test "unplaced at pass start" sees d as unplaced or placed in THIS pass: both pass it
+    place_release_one(d, next, fcnt_out, Mp, Mi, n2o, placed_pass, indeg, pass);
+    if (r != -2) {
+      __stcg(nd2n + d, r);
+      __stcg(placed_pass + d, pass);
       atomicAdd(&cnt->placed_in_pass, 1);
     }
   }
+}
+
+// ---- pull placement: ONE launch per pass, no barrier between wavefronts, no fences.
+// The wavefront schedule is a DAG (a DOF waits for its unplaced added neighbours with a smaller id).  Walking it sweep
+// by sweep costs a barrier (or a launch) per wavefront and leaves the GPU idle: a remeshed patch has ~3 x patch-edge
+// wavefronts of a few hundred DOFs (config 3: 136 sweeps).  History on that config (profiles/r08_placement.md): launch
+// per sweep 4.6 ms; thread-block cluster + hardware barrier per sweep 1.6 ms; push queue with fenced hand-over 1.7 ms
+// (three device-scope fences per hop); this kernel 0.3 ms.
+//
+// The whole state of a DOF during placement lives in ONE 32-bit word,
+//   st[v] = pass << 16 | (node + 1)   placed in `pass` (survivors: pass 0);   pass << 16   decided in `pass`: stays
+//   unplaced;   0   added, never decided,
+// so a reader needs no ordering between locations: it polls the words of the predecessors it waits for and the value it
+// finally reads IS the decision (relaxed device-scope loads and stores, measured 430 ns store -> visible on B200,
+// scripts/gmem_latency_probe.cu).  One warp per DOF, one lane per neighbour (the neighbours' words are fetched by one
+// load instruction: a dependent load costs 155 ns at L2).  The ORDER in which the warps take the DOFs comes from a
+// ready queue: a DOF is pushed when its last predecessor has STARTED (relaxed atomic countdown), tickets are dealt
+// statically (warp w takes slots w, w + W, ...), so the warps follow the wavefronts whatever the numbering of the mesh
+// (owning the DOFs in id order serialises the walk plane by plane: 3.4 ms) and a successor has its adjacency and its
+// other predecessors' words in registers by the time the last decision it waits for lands.  The queue is only a
+// schedule -- correctness rests on the polled words alone.  Progress: a popped DOF always has a warp; among the popped,
+// undecided DOFs the one with the smallest id waits for nobody that is not decided or being decided, and the smallest
+// unfilled slot gets filled (DAG) -- provided every warp is resident, hence grid <= SM count.  One warp per DOF, not
+// two half-warps: two groups in one warp time-share its issue slot while either of them spins (measured 2x slower).
+constexpr int kPullThreads = 512;
+
+// relaxed device-scope accesses for the words other CTAs poll (volatile would make them system-scope)
+__device__ __forceinline__ int ld_poll(const int *p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_poll(int *p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// visible node of neighbour nb for the DOF d being decided in `pass` (-1: none), given a first read v of its word;
+// waits for an undecided predecessor
+__device__ __forceinline__ int pull_visible(int v, int nb, int d, const int *st, int pass) {
+  for (;;) {
+    const int code = v & 0xffff, p = v >> 16;
+    if (code) return (p < pass || nb < d) ? code - 1 : -1;
+    if (p == pass || nb > d) return -1;  // decided "stays unplaced" in this pass / later in the queue: invisible
+    v = ld_poll(st + nb);
+  }
+}
+
+__device__ __forceinline__ int pair_node_d(const int *__restrict__ meta, int ra, int rb) {
+  const int big = ra > rb ? ra : rb, small = ra > rb ? rb : ra;
+  return is_sep_d(small, big) ? big : lca_d(meta, small, big);
+}
+
+// kPullQueues ready queues (a DOF goes to queue id % kPullQueues; its segment of the slot array starts at qoff[q] and
+// holds qoff[q + 1] - qoff[q] = the number of unplaced DOFs of that residue, known at pass start): the push counter
+// is the one same-address atomic on the path of every DOF, and same-address atomics serialise at L2.
+constexpr int kPullQueues = 16, kTailStride = 32;  // one tail per 128-byte line
+
+__device__ __forceinline__ void pull_push(int *queue, int *tails, const int *qoff, int x) {
+  const int q = x & (kPullQueues - 1);
+  st_poll(queue + __ldg(qoff + q) + atomicAdd(tails + q * kTailStride, 1), x);
+}
+
+__global__ void __launch_bounds__(kPullThreads)
+place_pass_pull_kernel(int *queue, int *tails, const int *__restrict__ qoff, const int *__restrict__ Mp,
+                       const int *__restrict__ Mi, const int *__restrict__ meta, int *st, int *indeg, int pass,
+                       PlaceCounters *cnt) {
+  const int lane = threadIdx.x & 31;
+  // warp w serves queue w % kPullQueues, slots w / kPullQueues, + (warps per queue), ... (CTA-interleaved: consecutive
+  // slots of a queue go to different SMs)
+  const int w = (threadIdx.x >> 5) * gridDim.x + blockIdx.x, nwarps = gridDim.x * (kPullThreads / 32);
+  const int q = w & (kPullQueues - 1), per_q = nwarps / kPullQueues;
+  const int q0 = __ldg(qoff + q), total = __ldg(qoff + q + 1) - q0;
+  int placed = 0;
+  for (int t = w / kPullQueues; t < total && w < per_q * kPullQueues; t += per_q) {
+    int d = 0;
+    if (lane == 0)
+      while ((d = ld_poll(queue + q0 + t)) < 0) {}
+    d = __shfl_sync(0xffffffffu, d, 0);
+    const int s = __ldg(Mp + d), deg = __ldg(Mp + d + 1) - s;
+    int code = 0;
+    if (deg > 32) {  // wide row: one thread walks it, neighbour by neighbour (same rule)
+      if (lane == 0) {
+        for (int p = s; p < s + deg; p++) {  // successors first: they fetch their rows while this one is decided
+          const int x = __ldg(Mi + p);
+          if (x > d && (ld_poll(st + x) & 0xffff) == 0 && atomicSub(indeg + x, 1) == 1) pull_push(queue, tails, qoff, x);
+        }
+        int mn = 1 << 30, first = -1;
+        bool two = false;
+        for (int p = s; p < s + deg; p++) {
+          const int a = __ldg(Mi + p), ra = pull_visible(ld_poll(st + a), a, d, st, pass);
+          if (ra == -1) continue;
+          if (first == -1) first = ra;
+          for (int p2 = p + 1; p2 < s + deg; p2++) {
+            const int b2 = __ldg(Mi + p2), rb = pull_visible(ld_poll(st + b2), b2, d, st, pass);
+            if (rb == -1 || rb == ra) continue;
+            const int c = pair_node_d(meta, ra, rb);
+            mn = c < mn ? c : mn;
+            two = true;
+          }
+        }
+        code = first == -1 ? 0 : (two ? mn : first) + 1;
+      }
+    } else {
+      const int nb = lane < deg ? __ldg(Mi + s + lane) : -1;
+      const int v = nb >= 0 ? ld_poll(st + nb) : (1 << 16);
+      // release the successors (added neighbours with a larger id, unplaced at pass start) BEFORE deciding
+      const bool ready = nb > d && (v & 0xffff) == 0 && atomicSub(indeg + nb, 1) == 1;
+      if (ready) pull_push(queue, tails, qoff, nb);
+      const int r = nb >= 0 ? pull_visible(v, nb, d, st, pass) : -1;
+      // distinct visible nodes by match_any; minimum over all pairs of distinct nodes by a shuffle loop over the leaders
+      const unsigned peers = __match_any_sync(0xffffffffu, r);
+      const bool leader = r != -1 && (__ffs(peers) - 1) == lane;
+      const unsigned um = __ballot_sync(0xffffffffu, leader);
+      const int nu = __popc(um);
+      if (nu == 1) code = __shfl_sync(0xffffffffu, r, __ffs(um) - 1) + 1;
+      else if (nu > 1) {
+        int mn = 1 << 30;
+        for (unsigned m = um; m; m &= m - 1) {
+          const int k = __ffs(m) - 1;
+          const int rk = __shfl_sync(0xffffffffu, r, k);
+          if (leader && k > lane) {
+            const int c = pair_node_d(meta, r, rk);
+            mn = c < mn ? c : mn;
+          }
+        }
+        code = __reduce_min_sync(0xffffffffu, mn) + 1;
+      }
+    }
+    if (lane == 0) {  // code 0: no visible neighbour, stays unplaced (next ring)
+      st_poll(st + d, (pass << 16) | code);
+      placed += code != 0;
+    }
+    __syncwarp();
+  }
+  placed = __reduce_add_sync(0xffffffffu, placed);
+  if (lane == 0 && placed) atomicAdd(&cnt->placed_in_pass, placed);
+}
+
+// st = node + 1 for the survivors (pass 0), 0 for the added DOFs (nd2n holds -1 for them)
+__global__ void place_state_init_kernel(const int *__restrict__ nd2n, int n, int *__restrict__ st) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) st[i] = nd2n[i] + 1;
+}
+
+// pass start of the pull path, three small launches: (1) predecessor counts + unplaced DOFs per queue, (2) queue
+// segment offsets, (3) the DOFs without predecessor enter their queues
+__global__ void place_pull_count_kernel(const int *__restrict__ added, int n_added, const int *__restrict__ Mp,
+                                        const int *__restrict__ Mi, const int *__restrict__ st, int *__restrict__ indeg,
+                                        int *__restrict__ qcount) {
+  __shared__ int hist[kPullQueues];
+  if (threadIdx.x < kPullQueues) hist[threadIdx.x] = 0;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_added && (st[added[i]] & 0xffff) == 0) {
+    const int d = added[i];
+    int deg = 0;
+    for (int p = Mp[d]; p < Mp[d + 1]; p++) {
+      const int nb = Mi[p];
+      deg += nb < d && (st[nb] & 0xffff) == 0;
+    }
+    indeg[d] = deg;
+    atomicAdd(hist + (d & (kPullQueues - 1)), 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < kPullQueues && hist[threadIdx.x]) atomicAdd(qcount + threadIdx.x, hist[threadIdx.x]);
+}
+
+__global__ void place_pull_offsets_kernel(const int *__restrict__ qcount, int *__restrict__ qoff, PlaceCounters *cnt) {
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int q = 0; q < kPullQueues; q++) { qoff[q] = run; run += qcount[q]; }
+    qoff[kPullQueues] = run;
+    cnt->unplaced = run;
+  }
+}
+
+__global__ void place_pull_roots_kernel(const int *__restrict__ added, int n_added, const int *__restrict__ st,
+                                        const int *__restrict__ indeg, int *__restrict__ queue, int *__restrict__ tails,
+                                        const int *__restrict__ qoff) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_added) return;
+  const int d = added[i];
+  if ((st[d] & 0xffff) == 0 && indeg[d] == 0) pull_push(queue, tails, qoff, d);
+}
+
+// pull path epilogue: the node of every added DOF out of its state word
+__global__ void place_decode_kernel(const int *__restrict__ added, int n_added, const int *__restrict__ st,
+                                    int *__restrict__ nd2n) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= n_added) return;
+  const int d = added[q], code = st[d] & 0xffff;
+  nd2n[d] = code ? code - 1 : -1;
 }
 
 __global__ void finish_added_kernel(const int *__restrict__ added, int n_added, int spare, int *__restrict__ nd2n,
@@ -639,6 +880,20 @@ void update_offsets(parth_b200 &h) {
 // Shared tail of integrate / relocate.  On entry: keep[] (w0) and del[] (w1) are filled for the
 // `total` old entries; join (ascending ids) / join_node hold the n_join DOFs that enter nodes.
 // Rebuilds dofs/labels (double buffered), node_ptr, offsets.  Returns the touched-node list.
+void rank_joiners(parth_b200 &h, int n_touched, const int *d_touched, const int *d_join, const int *d_join_node, int n_join,
+                  const int *d_aptr, int *d_out) {
+  if (n_touched == 0 || n_join == 0) return;
+  cudaStream_t s = h.stream;
+  const int n_seg = std::max(1, std::min(128, n_join / 2048));
+  const int seg = ((n_join + n_seg - 1) / n_seg + 255) / 256 * 256;
+  h.rank_seg.reserve((size_t)n_touched * n_seg + 1, s);
+  const dim3 grid((unsigned)n_touched, (unsigned)n_seg);
+  rank_joiners_count_kernel<<<grid, 256, 0, s>>>(d_touched, d_join_node, n_join, seg, h.rank_seg.p);
+  rank_joiners_scan_kernel<<<nblk(n_touched), 256, 0, s>>>(h.rank_seg.p, n_touched, n_seg);
+  rank_joiners_kernel<<<grid, 256, 0, s>>>(d_touched, d_join, d_join_node, n_join, seg, h.rank_seg.p, d_aptr, d_out);
+  h.stats.kernels_launched += 3;
+}
+
 template <int MODE>
 std::vector<int> regroup_finish(parth_b200 &h, int total, const int *key, const int *d_join, const int *d_join_node,
                                 int n_join, int new_total) {
@@ -688,10 +943,7 @@ std::vector<int> regroup_finish(parth_b200 &h, int total, const int *key, const 
                                                             h.w2.p, h.w3.p, h.r_cnt.p, h.r_G.p);
     h.stats.kernels_launched++;
   }
-  if (!touched.empty()) {
-    rank_joiners_kernel<<<(unsigned)touched.size(), 256, 0, s>>>(d_touched, d_join, d_join_node, n_join, d_aptr, h.r_sub.p);
-    h.stats.kernels_launched++;
-  }
+  rank_joiners(h, (int)touched.size(), d_touched, d_join, d_join_node, n_join, d_aptr, h.r_sub.p);
   h.d_dofs2.reserve((size_t)std::max(new_total, 1), s);
   h.d_labels2.reserve((size_t)std::max(new_total, 1), s);
   int *d_flag = h.mail.p + 16;
@@ -787,13 +1039,16 @@ void stage_integrate(parth_b200 &h) {
     // ---- ring placement (Integrator.cpp:118-202)
     h.r_g2l.reserve((size_t)M + 1, s);  // placed_pass
     h.r_l2g.reserve((size_t)M + 1, s);  // indeg
-    PB_CUDA(cudaMemsetAsync(h.r_g2l.p, 0, sizeof(int) * (size_t)M, s));
-    constexpr int kBatch = 16;          // sweeps enqueued per read-back
+    // one launch per pass (place_pass_pull_kernel: r_g2l holds the state words); PARTH_B200_PLACE_PER_SWEEP forces
+    // the launch-per-sweep path (cross-check in tests/test_gpu_scenarios.py; r_g2l = placed_pass, r_l2g = indeg)
+    const bool pull_path = !std::getenv("PARTH_B200_PLACE_PER_SWEEP") && nn < 65535;
+    if (!pull_path) PB_CUDA(cudaMemsetAsync(h.r_g2l.p, 0, sizeof(int) * (size_t)M, s));
+    constexpr int kBatch = 16;          // launch-per-sweep path: sweeps enqueued per read-back
     const int max_sweeps = n_added + kBatch + 2;
     pb::DevBuf<int> cbuf, fr, fcnt;
     cbuf.reserve(8, s);
     fr.reserve((size_t)2 * n_added + 2, s);
-    fcnt.reserve((size_t)max_sweeps + kBatch + 4, s);
+    fcnt.reserve(pull_path ? 1024 : (size_t)max_sweeps + kBatch + 4, s);
     PlaceCounters *d_cnt = reinterpret_cast<PlaceCounters *>(cbuf.p);
     int *F[2] = {fr.p, fr.p + n_added};
     std::vector<int> fc((size_t)kBatch);
@@ -802,29 +1057,55 @@ void stage_integrate(parth_b200 &h) {
     for (int pass = 1;; pass++) {
       h.stats.integrate_passes = pass;
       PB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(PlaceCounters), s));
-      PB_CUDA(cudaMemsetAsync(fcnt.p, 0, sizeof(int) * ((size_t)max_sweeps + kBatch + 4), s));
-      place_pass_init_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.Mp, h.Mi, h.new_to_old.p, h.r_g2l.p,
-                                                          h.r_l2g.p, F[0], fcnt.p, d_cnt);
-      h.stats.kernels_launched++;
-      int sweep = 0;
-      bool done = false;
-      while (!done) {
-        for (int rep = 0; rep < kBatch; rep++, sweep++) {
-          place_sweep_kernel<<<grid, 256, 0, s>>>(F[sweep & 1], fcnt.p + sweep, F[(sweep + 1) & 1], fcnt.p + sweep + 1,
-                                                  h.Mp, h.Mi, h.new_to_old.p, h.meta_heap ? nullptr : h.d_meta.p, nd2n,
-                                                  h.r_g2l.p, h.r_l2g.p, pass, d_cnt);
+      int c[4] = {0, 0, 0, 0};
+      if (pull_path) {
+        if (pass > 30000) throw StatusError(PARTH_B200_ERR_INTERNAL, "integrate: more than 30000 placement passes");
+        if (pass == 1) {
+          place_state_init_kernel<<<nblk(M), 256, 0, s>>>(nd2n, M, h.r_g2l.p);
           h.stats.kernels_launched++;
         }
-        // an empty frontier ends the pass (the dependency graph is acyclic)
-        read_ints(h, fcnt.p + sweep - kBatch + 1, fc.data(), (size_t)kBatch);
-        for (int v : fc) if (v == 0) done = true;
-        if (sweep > max_sweeps) throw StatusError(PARTH_B200_ERR_INTERNAL, "integrate: placement did not terminate");
+        // fcnt: [0, Q*32) queue tails (one per 128-byte line), then Q counts, then Q + 1 segment offsets
+        int *tails = fcnt.p, *qcount = fcnt.p + kPullQueues * kTailStride, *qoff = qcount + kPullQueues;
+        PB_CUDA(cudaMemsetAsync(fcnt.p, 0, sizeof(int) * (kPullQueues * kTailStride + 2 * kPullQueues + 1), s));
+        PB_CUDA(cudaMemsetAsync(fr.p, 0xff, sizeof(int) * (size_t)n_added, s));        // queue slots: -1 = empty
+        place_pull_count_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.Mp, h.Mi, h.r_g2l.p, h.r_l2g.p, qcount);
+        place_pull_offsets_kernel<<<1, 32, 0, s>>>(qcount, qoff, d_cnt);
+        place_pull_roots_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.r_g2l.p, h.r_l2g.p, fr.p, tails, qoff);
+        place_pass_pull_kernel<<<h.num_sms, kPullThreads, 0, s>>>(fr.p, tails, qoff, h.Mp, h.Mi,
+                                                                 h.meta_heap ? nullptr : h.d_meta.p, h.r_g2l.p, h.r_l2g.p,
+                                                                 pass, d_cnt);
+        h.stats.kernels_launched += 2;
+        PB_CUDA(cudaGetLastError());
+        h.stats.kernels_launched += 2;
+        read_ints(h, reinterpret_cast<const int *>(d_cnt), c, 4);
+      } else {
+        PB_CUDA(cudaMemsetAsync(fcnt.p, 0, sizeof(int) * ((size_t)max_sweeps + kBatch + 4), s));
+        place_pass_init_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.Mp, h.Mi, h.new_to_old.p, h.r_g2l.p,
+                                                            h.r_l2g.p, F[0], fcnt.p, d_cnt);
+        h.stats.kernels_launched++;
+        int sweep = 0;
+        bool done = false;
+        while (!done) {
+          for (int rep = 0; rep < kBatch; rep++, sweep++) {
+            place_sweep_kernel<<<grid, 256, 0, s>>>(F[sweep & 1], fcnt.p + sweep, F[(sweep + 1) & 1], fcnt.p + sweep + 1,
+                                                    h.Mp, h.Mi, h.new_to_old.p, h.meta_heap ? nullptr : h.d_meta.p, nd2n,
+                                                    h.r_g2l.p, h.r_l2g.p, pass, d_cnt);
+            h.stats.kernels_launched++;
+          }
+          // an empty frontier ends the pass (the dependency graph is acyclic)
+          read_ints(h, fcnt.p + sweep - kBatch + 1, fc.data(), (size_t)kBatch);
+          for (int v : fc) if (v == 0) done = true;
+          if (sweep > max_sweeps) throw StatusError(PARTH_B200_ERR_INTERNAL, "integrate: placement did not terminate");
+        }
+        h.stats.integrate_sweeps += sweep;
+        read_ints(h, reinterpret_cast<const int *>(d_cnt), c, 4);
       }
-      h.stats.integrate_sweeps += sweep;
-      int c[4] = {0, 0, 0, 0};
-      read_ints(h, reinterpret_cast<const int *>(d_cnt), c, 4);
       if (c[0] == 0 || c[1] == 0) break;  // nothing left, or a pass that placed nothing ends the loop
       if (c[1] == c[0]) break;            // everything that was left has been placed
+    }
+    if (pull_path) {
+      place_decode_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.r_g2l.p, nd2n);
+      h.stats.kernels_launched++;
     }
     // ---- leftovers: last empty leaf, else the last node (Integrator.cpp:204-217)
     h.w2.reserve((size_t)total + 2, s);
@@ -959,10 +1240,7 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
   const int *d_changed_list = d_flag + nn, *d_touched = d_changed_list + changed.size();
   const int *d_asm = d_touched + touched.size(), *d_asm_off = d_asm + asm_list.size();
   h.r_sub.reserve((size_t)std::max(n_moved, 1), s);  // joiners grouped by node
-  if (!touched.empty()) {
-    rank_joiners_kernel<<<(unsigned)touched.size(), 256, 0, s>>>(d_touched, h.r_perm.p, h.r_ws.p, n_moved, d_aptr, h.r_sub.p);
-    h.stats.kernels_launched++;
-  }
+  rank_joiners(h, (int)touched.size(), d_touched, h.r_perm.p, h.r_ws.p, n_moved, d_aptr, h.r_sub.p);
   h.d_dofs2.reserve((size_t)std::max(new_total, 1), s);
   h.d_labels2.reserve((size_t)std::max(new_total, 1), s);
   regroup_copy_kernel<<<nblk((new_total + RC_RUN - 1) / RC_RUN), 256, 0, s>>>(h.d_node_ptr.p, d_nptr, d_flag, nn, new_total,

@@ -200,3 +200,19 @@ def test_random_update_sequences_match_oracle(gpu_api, port, seed, lagging):
         else:
             # the oracle stops at a dirty coarse node (METIS); keep both sides on the same tree
             g.import_tree(tree, *cur); o.import_tree(tree, *cur)
+
+
+@pytest.mark.parametrize("name", sorted(n for n in SCEN if "remesh" in n or "delete" in n))
+def test_placement_dataflow_kernel_equals_launch_per_sweep(gpu_api, name, monkeypatch):
+    """(a6) added-DOF placement: the one-launch-per-pass dataflow kernel (ticket queue, no barrier between
+    wavefronts) and the launch-per-sweep path (PARTH_B200_PLACE_PER_SWEEP) leave the same tree; both equal the
+    oracle (tests above)"""
+    res_c, g_c = sd.run_scenario_gpu(gpu_api, SCEN[name])
+    assert g_c.stats()["integrate_sweeps"] == 0  # no sweeps on the dataflow path
+    monkeypatch.setenv("PARTH_B200_PLACE_PER_SWEEP", "1")
+    res_s, g_s = sd.run_scenario_gpu(gpu_api, SCEN[name])
+    for k in res_c:
+        if k.endswith("_hash") or k in ("num_changes", "reuse", "status"):
+            assert str(res_c[k]) == str(res_s[k]), k
+    assert g_s.stats()["integrate_passes"] == g_c.stats()["integrate_passes"]
+    assert g_s.stats()["integrate_sweeps"] > 0 or g_s.stats()["integrate_passes"] == 0
