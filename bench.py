@@ -520,7 +520,7 @@ def run_sharded(args):
     g.setMatrixBlockPtr(N, base["nnz"], base["h"][0], base["h"][1], 1)
     g.acceptSnapshot()  # the tree fixture belongs to the base matrix
 
-    need = args.warmup + args.steps + min(args.steps, 8) + (0 if args.no_e2e else 2 + args.steps)
+    need = args.warmup + args.steps + min(args.steps, 8) + (0 if args.no_e2e else 2 + args.steps + max(2, args.steps // 2))
     D = min(args.steps + args.warmup, 12) if args.variant == "lag" else min(need, 64)
     mats = [block_of(*stream.matrix(k)) for k in range(D)]  # the same update stream on every rank
     dperm = torch.empty(M, dtype=torch.int32, device=dev)
@@ -536,6 +536,14 @@ def run_sharded(args):
         g.computePermutationDev(dperm.data_ptr(), 1)
 
     def step_e2e(k):
+        """distributed in, distributed out: this rank uploads its block of the matrix and downloads its block of the
+        permutation (parth_b200_compute_permutation_block)"""
+        b = mats[k % D]
+        g.setMatrixBlockPtr(N, b["nnz"], b["h"][0], b["h"][1], 1)
+        g.computePermutationBlock(1, out=hperm.numpy())
+
+    def step_e2e_full(k):
+        """the whole permutation on EVERY rank's host"""
         b = mats[k % D]
         g.setMatrixBlockPtr(N, b["nnz"], b["h"][0], b["h"][1], 1)
         g.computePermutation(1, out=hperm.numpy())
@@ -578,14 +586,21 @@ def run_sharded(args):
         for k in range(2):
             step_e2e(k0 + k)
         ms_e, _ = timed(step_e2e, k0 + 2, args.steps)
+        half = max(2, args.steps // 2)
+        ms_f, _ = timed(step_e2e_full, k0 + 2 + args.steps, half)
         b = mats[0]
         mine = 4 * ((c1 - c0 + 1) + (b["q1"] - b["q0"]))
-        t = torch.tensor([mine], dtype=torch.float64, device=dev)
+        t = torch.tensor([mine, 4 * (c1 - c0)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        e2e = {"value": args.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(t.item()),
-               "d2h_bytes_per_step": 4 * M * world, "ms_per_step": ms_e / args.steps,
-               "note": f"bytes are totals over the {world} ranks: every rank uploads its block ({mine} bytes on rank 0) and "
-                       f"downloads the whole permutation ({4 * M} bytes)"}
+        e2e = {"value": args.steps / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(t[0].item()),
+               "d2h_bytes_per_step": int(t[1].item()), "ms_per_step": ms_e / args.steps,
+               "note": f"bytes are totals over the {world} ranks: every rank uploads its block of the matrix ({mine} bytes on "
+                       f"rank 0) and downloads its block of the permutation ({4 * (c1 - c0)} bytes on rank 0); "
+                       "parth_b200_compute_permutation_block",
+               "full_result_on_every_rank": {"value": half / (ms_f * 1e-3), "ms_per_step": ms_f / half, "steps": half,
+                                             "d2h_bytes_per_step": 4 * M * world,
+                                             "note": "parth_b200_compute_permutation: every rank also downloads the whole "
+                                                     "permutation"}}
     clocks = sampler.stop()
 
     peaks = {}

@@ -379,6 +379,20 @@ public:
     return lnz;
   }
 
+  /* one mesh over the ranks of a communicator (commInit*): the update of computePermutation with a DISTRIBUTED result --
+   * this rank receives entries [first, first + perm_block.size()) of the expanded permutation (its row block times dim);
+   * returns `first` */
+  int computePermutationBlock(std::vector<int> &perm_block, int dim = 3) {
+    int c0 = 0, c1 = 0;
+    check(parth_b200_block_range(h_, M_n * sim_dim, 0, &c0, &c1));
+    perm_block.resize((size_t)(c1 - c0) * (size_t)dim);
+    int first = 0, count = 0;
+    pushOptions();
+    check(parth_b200_compute_permutation_block(h_, perm_block.data(), dim, &first, &count));
+    perm_block.resize((size_t)count);
+    return first;
+  }
+
   /* fundamental supernodes of L from the arrays symbolic() returned (the first step of the supernodal analysis
    * behind reference src/LinSysSolver/CHOLMODSolver.cpp:108-151): super[s] = first column of supernode s
    * (super[nsuper] = n), sparent = supernodal elimination tree; returns the number of supernodes */

@@ -85,6 +85,7 @@ SYMBOLS = {
     "parth_b200_morton_order": (C.c_int, [_vp, _ip, C.c_int]),
     "parth_b200_morton_order_dev": (C.c_int, [_vp, C.POINTER(_vp), _ip]),
     "parth_b200_morton_keys": (C.c_int, [_vp, _vp, C.c_int]),
+    "parth_b200_compute_permutation_block": (C.c_int, [_vp, _ip, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "parth_b200_symbolic": (C.c_int, [_vp, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
     "parth_b200_symbolic_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
     "parth_b200_supernodes": (C.c_int, [_vp, C.c_int, _ip, _ip, _ip, _ip, _ip, C.POINTER(C.c_int), C.POINTER(C.c_int64),
@@ -427,6 +428,17 @@ class ParthAPI:
         if rc == NEEDS_REDISSECT and self.report_advances_snapshot:
             self.acceptSnapshot()
         return rc, perm[:n * dim]
+
+    def computePermutationBlock(self, dim=3, out=None):
+        """sharded mesh: this rank's block of the expanded permutation -> (status, first, block)"""
+        self._push_options()
+        n, _ = self.mesh_dims()
+        if out is None:
+            out = np.empty(max(n * dim, 1), np.int32)
+        first, count = C.c_int(), C.c_int()
+        rc = self._check(self.lib.parth_b200_compute_permutation_block(self.h, _p(out), int(dim), C.byref(first),
+                                                                       C.byref(count)), allow=(NEEDS_REDISSECT,))
+        return rc, first.value, out[:count.value]
 
     def computePermutationDev(self, dperm_ptr, dim=3):
         self._push_options()

@@ -407,6 +407,29 @@ int parth_b200_compute_permutation(parth_b200 *h, int *perm, int dim) {
   PB_API_END
 }
 
+// one mesh over the ranks of a communicator: the whole update runs as in compute_permutation, but this rank's host
+// receives only ITS block of the expanded permutation, entries [c0 * dim, c1 * dim) with [c0, c1) its row block
+int parth_b200_compute_permutation_block(parth_b200 *h, int *perm_block, int dim, int *first, int *count) {
+  int rc = PARTH_B200_OK;
+  PB_API_BEGIN
+  if (!perm_block || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "computePermutationBlock: bad argument");
+  if (!h->block_mode) throw StatusError(PARTH_B200_ERR_ARG, "computePermutationBlock: the handle holds no row block (set_matrix_block*)");
+  h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
+  const size_t n_out = (size_t)h->M_n * dim;
+  h->d_out.reserve(n_out > 0 ? n_out : 1, h->stream);
+  rc = stage_compute_permutation(*h, h->d_out.p, dim);
+  const size_t b0 = (size_t)h->blk_c0 * dim, nb = (size_t)(h->blk_c1 - h->blk_c0) * dim;
+  if (first) *first = (int)b0;
+  if (count) *count = (int)nb;
+  if ((rc == PARTH_B200_OK || rc == PARTH_B200_NEEDS_REDISSECT) && nb > 0) {
+    PB_CUDA(cudaMemcpyAsync(perm_block, h->d_out.p + b0, sizeof(int) * nb, cudaMemcpyDeviceToHost, h->stream));
+    h->stats.d2h_bytes += (long long)(sizeof(int) * nb);
+  }
+  resolve_timers(*h);
+  if (rc != PARTH_B200_OK) return rc;
+  PB_API_END
+}
+
 int parth_b200_get_snapshot(parth_b200 *h, int *M_n_prev, int *nnz_prev, int *Mp_prev, int *Mi_prev) {
   PB_API_BEGIN
   if (!M_n_prev || !nnz_prev) throw StatusError(PARTH_B200_ERR_ARG, "get_snapshot: null size pointer");

@@ -21,9 +21,13 @@
 #include <cmath>
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "scan.cuh"
 #include "stages.cuh"
 #include "tree.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace pb {
 
@@ -826,6 +830,147 @@ regroup_changed_kernel(const int *__restrict__ list, const int *__restrict__ opt
   }
 }
 
+// The same regrouping by a thread-block CLUSTER per node (RGC CTAs, one GPC): a leaf that loses a handful of DOFs
+// still has ~30 000 entries to walk (two random 4-byte gathers each), which one CTA did in 85 us at 200^3.  Every CTA
+// takes one chunk of the node's entries; the leaving-label bitmap and its word prefix are spread over the CTAs'
+// shared memory by label-word range (remote atomicOr / loads through distributed shared memory), the survivor counts
+// and the per-range totals are exchanged the same way, and four cluster barriers separate the phases.  The joiner
+// histogram lives in rank 0's shared memory.
+constexpr int RGC = 8;
+
+__global__ void __cluster_dims__(RGC, 1, 1) __launch_bounds__(RG_THREADS)
+regroup_changed_cluster_kernel(const int *__restrict__ list, const int *__restrict__ optr,
+                               const int *__restrict__ nptr, const int *__restrict__ aptr,
+                               const int *__restrict__ target, const int *__restrict__ joinS,
+                               const int *__restrict__ dofs, const int *__restrict__ labels, int *__restrict__ dofs2,
+                               int *__restrict__ labels2, int *__restrict__ flags /*[0] unsorted, [1] size mismatch*/,
+                               int wper_cap, int hist_cap) {
+  extern __shared__ int rg_smem[];
+  __shared__ int s_scan[33];
+  __shared__ int s_meta[4];   // [0] survivors of my chunk, [1] leaving labels in my word range, [2] largest survivor of my chunk
+  __shared__ int s_pre[2 * RGC];  // survivors before rank r | leaving labels in the word ranges before rank r
+  cg::cluster_group cl = cg::this_cluster();
+  const int rank = (int)cl.block_rank(), tid = threadIdx.x;
+  const int x = list[blockIdx.x / RGC];
+  const int o0 = optr[x], size = optr[x + 1] - o0;
+  const int base = nptr[x], new_size = nptr[x + 1] - base;
+  const int a0 = aptr[x], na = aptr[x + 1] - a0;
+  const int words = (size + 31) >> 5, wper = max(1, (words + RGC - 1) / RGC);  // label words owned per CTA (<= wper_cap)
+  int *bits = rg_smem, *wpre = rg_smem + wper_cap, *hist = rg_smem + 2 * wper_cap;  // hist: rank 0 only
+  for (int i = tid; i < 2 * wper_cap + (rank == 0 ? hist_cap : 0); i += RG_THREADS) rg_smem[i] = 0;
+  cl.sync();
+  // my chunk of the entries: whole 4096-entry tiles, so that the tile loop below is the original one
+  constexpr int TILE = RG_THREADS * RG_ITEMS;
+  const int tiles = (size + TILE - 1) / TILE, tper = (tiles + RGC - 1) / RGC;
+  const int k_lo = min(size, rank * tper * TILE), k_hi = min(size, (rank + 1) * tper * TILE);
+  // ---- phase 1: leaving labels into the distributed bitmap, survivors of my chunk counted
+  int mine = 0, mymax = INT_MIN;
+  for (int k = k_lo + tid; k < k_hi; k += RG_THREADS) {
+    const int v = dofs[o0 + k];
+    if (__ldg(target + v) != kNoInit) {
+      const int lab = labels[o0 + k], w = lab >> 5, owner = w / wper;
+      atomicOr(cl.map_shared_rank(bits, owner) + (w - owner * wper), 1 << (lab & 31));
+    } else {
+      mine++;
+      mymax = max(mymax, v);
+    }
+  }
+  {
+    int total, tmax;
+    block_excl_scan<RG_THREADS>(mine, s_scan, &total);
+    block_excl_max_scan_512(mymax, s_scan, &tmax);
+    if (tid == 0) { s_meta[0] = total; s_meta[2] = tmax; }
+  }
+  cl.sync();
+  // ---- phase 2: word prefix inside my range
+  {
+    int running = 0;
+    for (int w0 = 0; w0 < wper; w0 += RG_THREADS) {
+      const int w = w0 + tid;
+      const int c = w < wper ? __popc((unsigned)bits[w]) : 0;
+      int total;
+      const int ex = block_excl_scan<RG_THREADS>(c, s_scan, &total);
+      if (w < wper) wpre[w] = running + ex;
+      running += total;
+    }
+    if (tid == 0) s_meta[1] = running;
+  }
+  cl.sync();
+  if (tid == 0) {
+    int sv = 0, lv = 0;
+    for (int r = 0; r < RGC; r++) {
+      const int *m = cl.map_shared_rank(s_meta, r);
+      s_pre[r] = sv; s_pre[RGC + r] = lv;
+      sv += m[0]; lv += m[1];
+    }
+  }
+  __syncthreads();
+  // ---- phase 3: survivors of my chunk, in entry order
+  int ns = s_pre[rank], last = INT_MIN;
+  for (int r = 0; r < rank; r++) last = max(last, cl.map_shared_rank(s_meta, r)[2]);
+  bool unsorted = false;
+  int *hist0 = cl.map_shared_rank(hist, 0);
+  for (int k0 = k_lo; k0 < k_hi; k0 += TILE) {
+    int v[RG_ITEMS], lab[RG_ITEMS];
+    unsigned keep = 0;
+    int lmax = INT_MIN;
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; i++) {
+      const int k = k0 + tid * RG_ITEMS + i;
+      v[i] = 0; lab[i] = 0;
+      if (k < k_hi) {
+        v[i] = dofs[o0 + k];
+        lab[i] = labels[o0 + k];
+        if (__ldg(target + v[i]) == kNoInit) { keep |= 1u << i; lmax = max(lmax, v[i]); }
+      }
+    }
+    int total, tmax;
+    const int ex = block_excl_scan<RG_THREADS>(__popc(keep), s_scan, &total);
+    int prev = max(last, block_excl_max_scan_512(lmax, s_scan, &tmax));
+    int j = ns + ex;
+#pragma unroll
+    for (int i = 0; i < RG_ITEMS; i++) {
+      if (!((keep >> i) & 1u)) continue;
+      int shift = 0;
+      if (na > 0) {
+        shift = lower_bound_d(joinS + a0, na, v[i]);
+        unsorted |= prev > v[i];  // the merge with the joiners needs ascending survivors
+        prev = max(prev, v[i]);
+        atomicAdd(hist0 + shift, 1);
+      }
+      dofs2[base + j + shift] = v[i];
+      const int w = lab[i] >> 5, owner = w / wper, wl = w - owner * wper;
+      const int below = s_pre[RGC + owner] + cl.map_shared_rank(wpre, owner)[wl] +
+                        __popc((unsigned)cl.map_shared_rank(bits, owner)[wl] & ((1u << (lab[i] & 31)) - 1u));
+      labels2[base + j] = lab[i] - below;
+      j++;
+    }
+    ns += total;
+    last = max(last, tmax);
+  }
+  if (unsorted) flags[0] = 1;
+  if (rank == RGC - 1 && tid == 0 && ns + na != new_size) flags[1] = 1;
+  cl.sync();  // the histogram is complete; nobody reads remote shared memory after this point except rank 0 its own
+  // ---- phase 4 (rank 0): joiner r sits behind the survivors with at most r joiners below them
+  if (rank == 0) {
+    const int ns_all = s_pre[RGC - 1] + cl.map_shared_rank(s_meta, RGC - 1)[0];
+    int running = 0;
+    for (int r0 = 0; r0 < na; r0 += RG_THREADS) {
+      const int r = r0 + tid;
+      const int c = r < na ? hist[r] : 0;
+      int total;
+      const int ex = block_excl_scan<RG_THREADS>(c, s_scan, &total);
+      if (r < na) {
+        const int below = running + ex + c;  // survivors with shift <= r
+        dofs2[base + r + below] = joinS[a0 + r];
+        labels2[base + ns_all + r] = ns_all + r;
+      }
+      running += total;
+    }
+  }
+  cl.sync();  // remote shared memory (s_meta of the last rank) stays alive until rank 0 is done
+}
+
 // mesh_perm of the listed nodes (HMD::assignCoarseLocalPermToGlobal restricted to the nodes whose slice or offset changed)
 __global__ void assemble_listed_kernel(const int *__restrict__ list, const int *__restrict__ node_ptr,
                                        const int *__restrict__ offs, const int *__restrict__ dofs,
@@ -1245,13 +1390,25 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
   h.d_labels2.reserve((size_t)std::max(new_total, 1), s);
   regroup_copy_kernel<<<nblk((new_total + RC_RUN - 1) / RC_RUN), 256, 0, s>>>(h.d_node_ptr.p, d_nptr, d_flag, nn, new_total,
                                                                             h.d_dofs.p, h.d_labels.p, h.d_dofs2.p, h.d_labels2.p);
-  const size_t smem = sizeof(int) * ((size_t)2 * max_words + max_in + 2);
-  if (smem > 200 * 1024) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "relocate: a node is too large for the regroup kernel");
-  if (smem > 48 * 1024)
-    PB_CUDA(cudaFuncSetAttribute(regroup_changed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  regroup_changed_kernel<<<(unsigned)changed.size(), RG_THREADS, smem, s>>>(d_changed_list, h.d_node_ptr.p, d_nptr, d_aptr,
-                                                                          h.rel_target.p, h.r_sub.p, h.d_dofs.p, h.d_labels.p,
-                                                                          h.d_dofs2.p, h.d_labels2.p, d_cnt + 1);
+  // one cluster of RGC CTAs per changed node; shared memory: its slice of the label bitmap + word prefix, and (rank 0)
+  // the joiner histogram.  PARTH_B200_REGROUP_ONE_CTA keeps the one-CTA-per-node kernel (cross-check in tests)
+  const int wper_cap = ((max_words + RGC - 1) / RGC + 3) & ~3, hist_cap = max_in + 2;
+  const size_t smem_c = sizeof(int) * ((size_t)2 * wper_cap + hist_cap);
+  if (smem_c <= 200 * 1024 && !std::getenv("PARTH_B200_REGROUP_ONE_CTA")) {
+    if (smem_c > 48 * 1024)
+      PB_CUDA(cudaFuncSetAttribute(regroup_changed_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
+    regroup_changed_cluster_kernel<<<(unsigned)changed.size() * RGC, RG_THREADS, smem_c, s>>>(
+        d_changed_list, h.d_node_ptr.p, d_nptr, d_aptr, h.rel_target.p, h.r_sub.p, h.d_dofs.p, h.d_labels.p, h.d_dofs2.p,
+        h.d_labels2.p, d_cnt + 1, wper_cap, hist_cap);
+  } else {
+    const size_t smem = sizeof(int) * ((size_t)2 * max_words + max_in + 2);
+    if (smem > 200 * 1024) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "relocate: a node is too large for the regroup kernel");
+    if (smem > 48 * 1024)
+      PB_CUDA(cudaFuncSetAttribute(regroup_changed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    regroup_changed_kernel<<<(unsigned)changed.size(), RG_THREADS, smem, s>>>(d_changed_list, h.d_node_ptr.p, d_nptr, d_aptr,
+                                                                            h.rel_target.p, h.r_sub.p, h.d_dofs.p, h.d_labels.p,
+                                                                            h.d_dofs2.p, h.d_labels2.p, d_cnt + 1);
+  }
   reloc_reset_target_kernel<<<nblk(n_moved), 256, 0, s>>>(h.r_perm.p, n_moved, h.rel_target.p);
   PB_CUDA(cudaGetLastError());
   h.stats.kernels_launched += 3;

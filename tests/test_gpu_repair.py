@@ -128,7 +128,7 @@ def test_sparse_relocation_equals_the_dense_formulation(gpu_api, variant):
     tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 20, 5)))
     M = 20 ** 3
     hs = []
-    for _ in range(2):
+    for _ in range(3):  # dense | sparse with the cluster regroup kernel | sparse with one CTA per node
         g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 5; g.reorder_type = gpu_api.AMD
         g.lagging = variant == "aggr"
         g.activate_aggressive_reuse = variant == "aggr"
@@ -143,16 +143,20 @@ def test_sparse_relocation_equals_the_dense_formulation(gpu_api, variant):
         cur = synth.add_edges(cur[0], cur[1], rng.integers(0, M, size=(k, 2)))
         outs = []
         for which, g in enumerate(hs):
+            os.environ.pop("PARTH_B200_DENSE_RELOCATE", None)
+            os.environ.pop("PARTH_B200_REGROUP_ONE_CTA", None)
             if which == 0:
                 os.environ["PARTH_B200_DENSE_RELOCATE"] = "1"
-            else:
-                os.environ.pop("PARTH_B200_DENSE_RELOCATE", None)
+            elif which == 2:
+                os.environ["PARTH_B200_REGROUP_ONE_CTA"] = "1"
             g.setMesh(M, cur[0], cur[1])
             st, perm = g.computePermutation(1)
             assert st == 0
             outs.append((perm.copy(), g.export_tree(), g.changed_edges().copy(), g.getReuse()))
         os.environ.pop("PARTH_B200_DENSE_RELOCATE", None)
-        assert np.array_equal(outs[0][0], outs[1][0])
-        assert np.array_equal(outs[0][2], outs[1][2]) and outs[0][3] == outs[1][3]
-        for key in ("labels", "dofs", "mesh_perm", "dof2node", "node_ptr", "meta"):
-            assert np.array_equal(outs[0][1][key], outs[1][1][key]), (step, key)
+        os.environ.pop("PARTH_B200_REGROUP_ONE_CTA", None)
+        for other in (1, 2):
+            assert np.array_equal(outs[0][0], outs[other][0])
+            assert np.array_equal(outs[0][2], outs[other][2]) and outs[0][3] == outs[other][3]
+            for key in ("labels", "dofs", "mesh_perm", "dof2node", "node_ptr", "meta"):
+                assert np.array_equal(outs[0][1][key], outs[other][1][key]), (step, other, key)

@@ -157,6 +157,48 @@ def test_row_blocks_device_arrays_and_no_change_update():
     assert len(want[-1]["edges"]) == 0 and want[-1]["reuse"] == 1.0
 
 
+def test_block_result_is_the_ranks_slice_of_the_permutation():
+    """computePermutationBlock: every rank's host receives entries [c0 * dim, c1 * dim) of the expanded permutation;
+    the blocks tile it"""
+    n, L, world, dim = 20, 5, 3, 3
+    tree = _tree(n, L)
+    base, mats = _matrices(n, steps=2, edges=30, seed=5)
+    want = _run_single(tree, base, mats, L, "nolag")
+    ref_full = np.repeat(want[-1]["perm"].astype(np.int64) * dim, dim) + np.tile(np.arange(dim), n ** 3)
+    apis = [api.ParthAPI() for _ in range(world)]
+    for g in apis:
+        _configure(g, L, "nolag")
+    api.ParthAPI.commInitLocal(apis)
+    out, errors = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            g = apis[r]
+            g.import_tree(tree)
+            N, Ap, Ai = mats[0]
+            g.setMatrixBlock(N, int(Ap[N]), Ap, Ai, 1)
+            g.acceptSnapshot()
+            for N, Ap, Ai in mats[1:]:
+                g.setMatrix(N, Ap, Ai, 1)
+                rc, first, blk = g.computePermutationBlock(dim)
+            c0, c1 = g.blockRange(N, int(Ap[N]))
+            assert rc == 0 and first == c0 * dim and len(blk) == (c1 - c0) * dim
+            # the block plus the update's own small read-backs, not the whole permutation
+            assert 4 * (c1 - c0) * dim <= g.stats()["d2h_bytes"] < 4 * (c1 - c0) * dim + 4 * n ** 3
+            out[r] = (first, blk.copy())
+        except Exception as e:  # noqa: BLE001
+            errors[r] = e
+
+    ts = [threading.Thread(target=work, args=(r,), daemon=True) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=300) for t in ts]
+    for e in errors:
+        if e is not None:
+            raise e
+    got = np.concatenate([b for _, b in sorted(out, key=lambda x: x[0])])
+    assert np.array_equal(got, ref_full)
+
+
 def test_row_blocks_reject_asymmetric_update():
     n, L = 16, 4
     tree = _tree(n, L)
