@@ -282,15 +282,15 @@ int parth_b200_comm_info(parth_b200 *h, int *rank, int *world, const char **kind
 /* columns [c0, c1) this rank owns of an N x N matrix with nnz entries (fixes the partition of the handle) */
 int parth_b200_block_range(parth_b200 *h, int N, int nnz, int *c0, int *c1);
 /* host arrays, global indexing, only the block is dereferenced; nnz = Ap[N] of the whole matrix */
+int parth_b200_set_matrix_block(parth_b200 *h, int N, int nnz, const int *Ap, const int *Ai, int dim);
+/* device arrays, global indexing, only the block is dereferenced; q0 = Ap[c0], q1 = Ap[c1] (no read-back) */
+int parth_b200_set_matrix_block_dev(parth_b200 *h, int N, int nnz, const int *dAp, const int *dAi, int dim, int q0,
+                                    int q1);
 /* the update of a sharded mesh with a distributed result: as parth_b200_compute_permutation, but this rank's host
  * receives only its block of the expanded permutation, perm[c0 * dim .. c1 * dim) with [c0, c1) from
  * parth_b200_block_range (first / count return that range; a caller that wants the permutation whole on one host
  * gathers the blocks).  The device keeps the whole permutation on every rank. */
 int parth_b200_compute_permutation_block(parth_b200 *h, int *perm_block, int dim, int *first, int *count);
-int parth_b200_set_matrix_block(parth_b200 *h, int N, int nnz, const int *Ap, const int *Ai, int dim);
-/* device arrays, global indexing, only the block is dereferenced; q0 = Ap[c0], q1 = Ap[c1] (no read-back) */
-int parth_b200_set_matrix_block_dev(parth_b200 *h, int N, int nnz, const int *dAp, const int *dAi, int dim, int q0,
-                                    int q1);
 
 #ifdef __cplusplus
 }
