@@ -21,6 +21,7 @@
 //             consecutive leaves meet at an LCA found by binary lifting on the interval test;
 //             column counts are interval sums of the per-vertex deltas.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "scan.cuh"
@@ -232,6 +233,186 @@ etree_node_kernel(const int *__restrict__ ranges, const int *__restrict__ perm, 
     __syncthreads();
   }
   if (in_smem) for (int i = tid; i < e - b; i += E2_THREADS) anc[b + i] = own_get(b + i);
+}
+
+// ---------------------------------------------------------------- batch-parallel node kernel
+// Liu's algorithm visits the columns of a node one after the other (0.5 us per column on one warp: the top separator
+// of a 200^3 grid alone took 19.8 ms, the 256 leaves 16.9 ms).  This kernel takes the columns E2_CHUNK at a time:
+//   phase 1  every lower neighbour that lies before the batch is replaced by the root of its component in the forest
+//            F0 of the earlier columns (all threads, full path compression: links only ever point at true ancestors);
+//   phase 2  the batch is a small etree problem on {F0 roots met, batch columns} with edges (u, j), u < j.  Every edge
+//            climbs from u through the provisional parents smaller than j and proposes j to the vertex it stops at
+//            with an atomicMin; rounds repeat until nothing changes.  Proposals are true ancestors (a climb only
+//            follows true ancestors, and j is adjacent to the sub-tree it started in), values only decrease, and at
+//            the fixed point every edge (u, j) has j above u with parent[x] = the smallest such j: the elimination
+//            tree, which is unique -- the result is bit-identical to the sequential walk (tests/test_gpu_symbolic.py).
+// Ancestor links and provisional parents share the node's shared-memory array (-1 = none = the largest unsigned).
+// A batch that holds a row longer than E2_DEG is walked sequentially by warp 0 (same state, same result).
+__global__ void __launch_bounds__(E2_THREADS)
+etree_node_batch_kernel(const int *__restrict__ ranges, const int *__restrict__ perm, const int *__restrict__ inv,
+                        const int *__restrict__ Mp, const int *__restrict__ Mi, const int *__restrict__ flat,
+                        const int *__restrict__ first, int *anc, int *parent) {
+  extern __shared__ __align__(16) unsigned char e2_raw[];
+  __shared__ int s_nbr[E2_CHUNK][E2_DEG];  // sources of the batch's edges (phase 1: replaced by their F0 roots)
+  __shared__ int s_pos[E2_CHUNK][E2_DEG];  // where the climb of each edge stopped last (it resumes there)
+  __shared__ int s_up[7][E2_CHUNK];        // binary lifting over the batch columns: 2^k-th provisional ancestor (-1: leaves the batch)
+  __shared__ int s_cnt[E2_CHUNK];
+  __shared__ int s_flag[2];  // [0] a round changed something, [1] the batch holds a long row
+  const int b = ranges[2 * blockIdx.x], e = ranges[2 * blockIdx.x + 1];
+  const int tid = threadIdx.x, lane = tid & 31;
+  volatile int *sm = reinterpret_cast<volatile int *>(e2_raw);
+  for (int i = tid; i < e - b; i += E2_THREADS) sm[i] = -1;
+  __syncthreads();
+  for (int j0 = b; j0 < e; j0 += E2_CHUNK) {
+    const int j = j0 + tid;
+    // ---- adjacency of column j, resolved to columns of this node's own slice (as etree_node_kernel::prefetch)
+    int cnt = 0;
+    if (tid == 0) { s_flag[0] = 0; s_flag[1] = 0; }
+    if (j < e) {
+      const int old = __ldg(perm + j);
+      const int s = __ldg(Mp + old), deg = __ldg(Mp + old + 1) - s;
+      if (deg > E2_DEG) cnt = -1;
+      else
+        for (int q0 = 0; q0 < deg; q0 += 8) {
+          int k[8], r[8], f[8];
+#pragma unroll
+          for (int u = 0; u < 8; u++) k[u] = q0 + u < deg ? __ldg(inv + __ldg(Mi + s + q0 + u)) : 0x7fffffff;
+#pragma unroll
+          for (int u = 0; u < 8; u++) r[u] = k[u] < b ? __ldg(flat + k[u]) : -1;
+#pragma unroll
+          for (int u = 0; u < 8; u++) f[u] = r[u] >= 0 ? __ldg(first + r[u]) : -1;
+#pragma unroll
+          for (int u = 0; u < 8; u++) {
+            if (k[u] >= j) continue;
+            if (k[u] >= b) { s_nbr[tid][cnt++] = k[u]; continue; }
+            if (f[u] == j) { parent[r[u]] = j; anc[r[u]] = j; }
+            else if (f[u] >= b && f[u] < j) s_nbr[tid][cnt++] = f[u];
+          }
+        }
+    }
+    s_cnt[tid] = cnt;
+    __syncthreads();
+    if (cnt < 0) s_flag[1] = 1;
+    __syncthreads();
+    if (s_flag[1]) {
+      // sequential walk of this batch (a row longer than E2_DEG): warp 0, lanes over the neighbours
+      if (tid < 32) {
+        const int lim = min(E2_CHUNK, e - j0);
+        for (int t = 0; t < lim; t++) {
+          const int jj = j0 + t, c = s_cnt[t];
+          auto walk = [&](int k) {
+            for (;;) {
+              const int a = sm[k - b];
+              if (a == jj) break;
+              sm[k - b] = jj;
+              if (a == -1) { parent[k] = jj; break; }
+              k = a;
+            }
+          };
+          if (c >= 0) {
+            if (lane < c) walk(s_nbr[t][lane]);
+          } else {
+            const int old = __ldg(perm + jj);
+            for (int p = __ldg(Mp + old) + lane; p < __ldg(Mp + old + 1); p += 32) {
+              const int k = __ldg(inv + __ldg(Mi + p));
+              if (k >= jj) continue;
+              if (k >= b) { walk(k); continue; }
+              const int r = __ldg(flat + k), f = __ldg(first + r);
+              if (f == jj) { parent[r] = jj; anc[r] = jj; }
+              else if (f >= b && f < jj) walk(f);
+            }
+          }
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      continue;
+    }
+    // ---- phase 1: neighbours before the batch -> roots of F0 (path halving)
+    for (int q = 0; q < cnt; q++) {
+      int x = s_nbr[tid][q];
+      if (x >= j0) continue;
+      int r = x;
+      for (int v = sm[r - b]; v != -1; v = sm[r - b]) r = v;
+      while (x != r) {  // second pass: everything on the path points at the root (a true ancestor: safe concurrently)
+        const int v = sm[x - b];
+        sm[x - b] = r;
+        x = v;
+      }
+      s_nbr[tid][q] = r;
+    }
+    for (int q = 0; q < cnt; q++) s_pos[tid][q] = s_nbr[tid][q];
+    __syncthreads();
+    // ---- phase 2: rounds of climb + atomicMin until nothing changes.  Provisional parents grow along a chain, so
+    // "the last ancestor below j" is found by binary lifting over the batch columns (a natural ordering makes the
+    // whole batch one chain: walking it link by link cost 128 dependent shared-memory loads for the last columns)
+    const int jend = j0 + E2_CHUNK;
+    for (;;) {
+      {
+        int v = j < e ? sm[j - b] : -1;
+        s_up[0][tid] = (v != -1 && v < jend) ? v : -1;
+        __syncthreads();
+#pragma unroll
+        for (int k = 1; k < 7; k++) {
+          const int y = s_up[k - 1][tid];
+          s_up[k][tid] = y != -1 ? s_up[k - 1][y - j0] : -1;
+          __syncthreads();
+        }
+      }
+      bool changed = false;
+      for (int q = 0; q < cnt; q++) {
+        // resume where this edge stopped: that vertex stays a true ancestor of the source below j whatever the
+        // parents below it have become since (they only move to closer ancestors)
+        int x = s_pos[tid][q];
+        if (x < j0) {  // a root of F0: one step takes it into the batch (or it stops here)
+          const unsigned v0 = (unsigned)sm[x - b];
+          if (v0 < (unsigned)j) x = (int)v0;
+        }
+        if (x >= j0) {
+#pragma unroll
+          for (int k = 6; k >= 0; k--) {
+            const int y = s_up[k][x - j0];
+            if (y != -1 && y < j) x = y;
+          }
+        }
+        s_pos[tid][q] = x;
+        const unsigned v = (unsigned)sm[x - b];
+        if (v > (unsigned)j) {  // (v < j cannot happen: x is the last ancestor below j)
+          const unsigned was = atomicMin(reinterpret_cast<unsigned *>(const_cast<int *>(sm)) + (x - b), (unsigned)j);
+          changed |= was > (unsigned)j;
+        }
+      }
+      if (changed) s_flag[0] = 1;
+      __syncthreads();
+      const bool again = s_flag[0] != 0;
+      __syncthreads();
+      if (!again) break;
+      if (tid == 0) s_flag[0] = 0;
+      __syncthreads();
+    }
+    // ---- parents decided in this batch: the roots of F0 that were met and the batch columns
+    for (int q = 0; q < cnt; q++) {
+      const int x = s_nbr[tid][q];
+      parent[x] = sm[x - b];  // an edge (x, j) exists, so x has a parent <= j (same value from every writer)
+    }
+    // a batch column can also receive its parent from a climb that only passed through it
+    if (j < e) { const int v = sm[j - b]; if (v != -1) parent[j] = v; }
+    __syncthreads();
+    // the parents are in global memory: the links of the batch columns now become shortcuts (pointer doubling inside
+    // the batch), so that the root searches of later batches cross a batch in one or two steps instead of walking its
+    // chain -- natural orderings make every batch one long chain
+    for (int round = 0; round < 7; round++) {
+      int w = -1;
+      if (j < e) {
+        const int v = sm[j - b];
+        if (v != -1 && v < j0 + E2_CHUNK) w = sm[v - b];
+      }
+      __syncthreads();
+      if (w != -1) sm[j - b] = w;
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < e - b; i += E2_THREADS) anc[b + i] = sm[i];
 }
 
 // after wave w: (i) every column of a wave-w node learns the root of its component ...
@@ -528,6 +709,8 @@ void stage_symbolic(parth_b200 &h, const int *perm_in, int *parent_out, int *col
       const int dyn = max_smem - 36 * 1024;  // static part: two buffers of prefetched adjacency lists
       PB_CUDA(cudaFuncSetAttribute(etree_node_kernel<int, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
       PB_CUDA(cudaFuncSetAttribute(etree_node_kernel<unsigned short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+      const int dyn_batch = max_smem - 40 * 1024;  // static part: the batch's edge sources, climb positions, lifting table
+      PB_CUDA(cudaFuncSetAttribute(etree_node_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_batch));
       int wi = 0;
       for (auto &w : waves) {
         const int nr = (int)w.size() / 2;
@@ -543,7 +726,12 @@ void stage_symbolic(parth_b200 &h, const int *perm_in, int *parent_out, int *col
           int longest = 0;
           for (int r = 0; r < nr; r++) longest = std::max(longest, w[2 * r + 1] - w[2 * r]);
           // 16-bit slots cost ~30 % per column walk: they pay only when the wave has more nodes than the GPU has SMs
-          if (nr > h.num_sms && longest <= 65534 && 2 * longest <= dyn) {
+          static const bool seq_only = std::getenv("PARTH_B200_ETREE_SEQ") != nullptr;
+          if (!seq_only && 4 * longest <= dyn_batch) {
+            const int bytes = ((4 * longest + 1023) / 1024) * 1024;
+            etree_node_batch_kernel<<<nr, E2_THREADS, bytes, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi, flatroot.p, first.p,
+                                                                 anc.p, parent.p);
+          } else if (nr > h.num_sms && longest <= 65534 && 2 * longest <= dyn) {
             const int bytes = ((2 * longest + 1023) / 1024) * 1024;
             etree_node_kernel<unsigned short, true><<<nr, E2_THREADS, bytes, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi,
                                                                                 flatroot.p, first.p, anc.p, parent.p, bytes / 2);
