@@ -726,7 +726,7 @@ void stage_symbolic(parth_b200 &h, const int *perm_in, int *parent_out, int *col
           int longest = 0;
           for (int r = 0; r < nr; r++) longest = std::max(longest, w[2 * r + 1] - w[2 * r]);
           // 16-bit slots cost ~30 % per column walk: they pay only when the wave has more nodes than the GPU has SMs
-          static const bool seq_only = std::getenv("PARTH_B200_ETREE_SEQ") != nullptr;
+          const bool seq_only = std::getenv("PARTH_B200_ETREE_SEQ") != nullptr;
           if (!seq_only && 4 * longest <= dyn_batch) {
             const int bytes = ((4 * longest + 1023) / 1024) * 1024;
             etree_node_batch_kernel<<<nr, E2_THREADS, bytes, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi, flatroot.p, first.p,

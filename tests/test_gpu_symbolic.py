@@ -162,3 +162,33 @@ def test_supernodes_device_pointers(gpu_api, port):
     assert np.array_equal(dmap.cpu().numpy(), want["supermap"]) and np.array_equal(dsp[:ns].cpu().numpy(), want["sparent"])
     # outputs are optional
     assert g.supernodesDev(n, dpar.data_ptr(), dcc.data_ptr()) == (ns, ssize, xsize)
+
+
+@pytest.mark.parametrize("key,hub", [(("geo", 16, 5), 0), (("geo", 16, 5), 45), (("g12",), 20), (("fish",), 60)])
+def test_batch_etree_kernel_equals_sequential_walk_and_oracle(gpu_api, port, key, hub, monkeypatch):
+    """stage (d) etree, valid separator tree: the batch-parallel node kernel (128 columns at a time, climb +
+    atomicMin rounds) against the sequential per-column walk (PARTH_B200_ETREE_SEQ) and the oracle.  `hub` > 0
+    gives one vertex `hub` extra neighbours inside its own tree node, so a row longer than the 32-entry prefetch
+    slot makes its batch fall back to the sequential walk on the same state."""
+    tree, Mp, Mi = sd.tree_of(dict(tree=key))
+    M = len(Mp) - 1
+    if hub:
+        sizes = np.diff(tree.node_ptr)
+        node = int(np.argmax(sizes))
+        d = tree.node_dofs(node)
+        assert len(d) > hub + 1
+        Mp, Mi = synth.add_edges(Mp, Mi, [(int(d[0]), int(x)) for x in d[1:hub + 1]])
+    outs = []
+    for seq in (False, True):
+        if seq:
+            monkeypatch.setenv("PARTH_B200_ETREE_SEQ", "1")
+        g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = tree.levels
+        g.import_tree(tree, Mp, Mi)
+        g.setMesh(M, Mp, Mi)
+        outs.append(g.symbolic(None))
+        assert g.stats()["symbolic_path"] == 2
+        perm = g.mesh_perm()
+    op = port.etree(Mp, Mi, perm)
+    olnz, occ = port.colcount(Mp, Mi, perm, op)
+    for parent, cc, lnz in outs:
+        assert np.array_equal(parent, op) and np.array_equal(cc, occ) and lnz == olnz
