@@ -38,7 +38,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one build_pipe_kernel launch from `ncu --set full` (profiles/), keyed by
 # (grid edge, fused stage b)
-TRAFFIC = {(200, False): 440306944, (200, True): 675790592}
+TRAFFIC = {(200, False): 440306944, (200, True): 671709184}
 
 METRIC = "reuse-update perms/s at 8M DOF 1% change"
 UNIT = "updates/s"
@@ -433,7 +433,7 @@ def run_ours(args, emit=True):
         "roofline": {"bound": "hbm", "kernel": "build_pipe_kernel" + (" (stage a + fused stage b)" if fused else ""),
                      "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/)
-                     "traffic": TRAFFIC.get((args.n, fused)), "traffic_source": "profiles/r05_bench_ncu_summary.md (ncu --set full of "
+                     "traffic": TRAFFIC.get((args.n, fused)), "traffic_source": "profiles/r08_bench_ncu_summary.md (ncu --set full of "
                      "the same kernel and workload; not re-measured by this run)", "algorithmic_bytes": alg,
                      "algorithmic_bytes_stage_a": alg_build, "algorithmic_bytes_snapshot_read": alg_detect // 2 if fused else 0,
                      "algorithmic_bytes_unfused": alg_build + (alg_detect if fused else 0),

@@ -480,7 +480,10 @@ def config5(api, kind, peak, n=512, steps=5):
         "nochange": {"ms_per_update": nochange_ms, "updates_per_s": 1e3 / nochange_ms, "gnnz_per_s": nnzA / nochange_ms / 1e6,
                      "steps": steps, "parity": "size-independent properties: 0 changes, reuse 1, valid permutation = " + str(bool(ok)),
                      "valid": bool(ok)},
-        "dirty_1pct": {"ms_per_update": float(np.mean([d["ms"] for d in dirty])), "updates": dirty,
+        "dirty_1pct": {"ms_per_update": float(np.mean([d["ms"] for d in dirty[1:]])), "first_update_ms": dirty[0]["ms"],
+                       "note": "the first re-ordering update of a handle grows its scratch buffers (memory-pool growth); "
+                               "ms_per_update is the mean of the updates after it",
+                       "updates": dirty,
                        "parity": "size-independent properties: valid permutation after every update; the same path is bit-compared "
                                  "with the oracle at 200^3 (tests/test_gpu_fullsize.py)"},
         "roofline": {"bound": "hbm", "kernel": "build_pipe_kernel" + (" (stage a + fused stage b)" if fused else ""),

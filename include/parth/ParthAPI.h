@@ -463,6 +463,12 @@ public:
     bool ok = std::fread(hdr, sizeof(int), 6, f) == 6 && hdr[0] == 0x54324250 && hdr[1] == 1 && hdr[2] > 0 &&
               hdr[4] > 0 && hdr[5] >= 0;
     const int tm = hdr[2], lv = hdr[3], nodes = hdr[4], nnz = hdr[5];
+    if (ok) {  // the header must describe exactly the bytes that follow (a corrupt file must not size the vectors)
+      const long long want = 4ll * (6 + 7ll * nodes + (nodes + 1ll) + 2ll * tm + (tm + 1ll) + nnz);
+      std::fseek(f, 0, SEEK_END);
+      ok = std::ftell(f) == want && nodes <= 8191;
+      std::fseek(f, 6 * (long)sizeof(int), SEEK_SET);
+    }
     std::vector<int> meta, node_ptr, dofs, labels, gp, gi;
     auto get = [&](std::vector<int> &v, size_t n) { v.resize(n > 0 ? n : 1); ok = ok && std::fread(v.data(), sizeof(int), n, f) == n; };
     if (ok) {
@@ -470,12 +476,15 @@ public:
       get(gp, (size_t)tm + 1); get(gi, (size_t)nnz);
     }
     std::fclose(f);
+    if (ok) ok = node_ptr[(size_t)nodes] <= tm && gp[0] == 0 && gp[(size_t)tm] == nnz;
     if (!ok) return false;
     ND_levels = lv;
     pushOptions();
     check(parth_b200_import_tree(h_, tm, lv, nodes, meta.data(), node_ptr.data(), dofs.data(), labels.data(), gp.data(),
                                  gi.data()));
     M_n_prev = tm;
+    M_n = tm;
+    hmd.HMD_init = true;
     return true;
   }
 
