@@ -1279,18 +1279,27 @@ void stage_integrate(parth_b200 &h) {
 }
 
 
+// the persistent per-DOF scratch of the sparse relocation and its output slices, sized for M DOFs.  Called when a tree
+// is imported, so that the first re-ordering update of a handle does not pay for the memory-pool growth (20 ms at
+// 134 M DOF, profiles/r04_configs.md), and lazily by the relocation itself.
+void relocate_prepare(parth_b200 &h, int M) {
+  cudaStream_t s = h.stream;
+  if (h.rel_M == M || M <= 0) return;
+  h.rel_occ.reserve((size_t)M + 1, s);
+  h.rel_target.reserve((size_t)M + 1, s);
+  h.d_dofs2.reserve((size_t)M, s);
+  h.d_labels2.reserve((size_t)M, s);
+  PB_CUDA(cudaMemsetAsync(h.rel_occ.p, 0, sizeof(int) * (size_t)M, s));
+  fill_kernel<<<nblk(M), 256, 0, s>>>(h.rel_target.p, M, kNoInit);
+  h.stats.kernels_launched++;
+  h.rel_M = M;
+}
+
 // Sparse relocation (kernels: "relocation, sparse formulation" above).  Same result as the dense path below.
 static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> &dirty_fine_out, bool filter_edges) {
   cudaStream_t s = h.stream;
   const int nn = h.num_nodes, M = h.tree_M, ne = h.n_changed;
-  if (h.rel_M != M) {
-    h.rel_occ.reserve((size_t)M + 1, s);
-    h.rel_target.reserve((size_t)M + 1, s);
-    PB_CUDA(cudaMemsetAsync(h.rel_occ.p, 0, sizeof(int) * (size_t)M, s));
-    fill_kernel<<<nblk(M), 256, 0, s>>>(h.rel_target.p, M, kNoInit);
-    h.stats.kernels_launched++;
-    h.rel_M = M;
-  }
+  relocate_prepare(h, M);
   h.w0.reserve((size_t)ne + 2, s);               // keep_edge
   h.w1.reserve((size_t)ne + 2, s);               // its prefix
   h.w2.reserve((size_t)std::max(ne, 1) * 2, s);  // kept edges

@@ -100,6 +100,7 @@ void stage_import_tree(parth_b200 &h, int M_n, int levels, int nodes, const int 
   h.d_mesh_perm.reserve((size_t)M_n, s);
   PB_CUDA(cudaMemsetAsync(h.d_mesh_perm.p, 0, sizeof(int) * (size_t)M_n, s));
   assemble_all(h);
+  relocate_prepare(h, M_n);  // the first re-ordering update must not pay for buffer growth
   h.tree_init = true;
   if (Mp_prev && Mi_prev) {
     const int nnz = Mp_prev[M_n];
