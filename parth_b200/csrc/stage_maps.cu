@@ -623,26 +623,72 @@ inline unsigned nblk(long long n) { return (unsigned)((n + 255) / 256); }
 constexpr int kSparseEdges = 8192;            // changed edges the sparse path takes (2 * kSparseEdges candidates)
 constexpr int kSparseCand = 2 * kSparseEdges;
 
-__global__ void reloc_collect_kernel(const int *__restrict__ edges, int n_edges, const int *__restrict__ target,
-                                     int *__restrict__ occ, int *__restrict__ moved, int *__restrict__ n_moved) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= 2 * n_edges) return;
-  const int d = edges[q];
-  if (target[d] == kNoInit) return;
-  if (atomicExch(occ + d, (int)0x80000000) >= 0) moved[atomicAdd(n_moved, 1)] = d;  // first visitor lists it
-}
-
-// ascending sort of n <= kSparseCand ints by one CTA (bitonic network in shared memory)
-__global__ void __launch_bounds__(1024) reloc_sort_kernel(int *__restrict__ a, const int *__restrict__ n_dev) {
-  extern __shared__ int s[];  // kSparseCand ints
-  const int n = *n_dev;
+// The whole front half of the sparse relocation in ONE launch of ONE CTA (<= 8192 changed edges): occurrence counts,
+// relocation targets, ordered compaction of the edges that stay, collection + ascending sort of the moved DOFs, per-node
+// leaver / joiner counts, redirect of dof2node, reset of the occurrence scratch, and (filter) the kept edges written
+// back over the edge list.  As eleven stream operations of 3-5 us each the same work was launch-bound (~45 us of the
+// headline update); the phases only need CTA barriers.  out: [0] n_moved, [1] unsorted, [2] size mismatch, [3] kept.
+// Dynamic shared memory: kSparseCand ints (the moved list / sort buffer) + kSparseEdges bytes (keep flags).
+__global__ void __launch_bounds__(1024)
+reloc_front_kernel(int *__restrict__ edges, int ne, int *__restrict__ dof2node, const int *__restrict__ meta, int threshold,
+                   int *__restrict__ occ, int *__restrict__ target, int *__restrict__ kept_edges, int *__restrict__ moved,
+                   int *__restrict__ moved_node, int *__restrict__ cnt, int nn, int *__restrict__ out, int filter) {
+  extern __shared__ int s[];
+  unsigned char *keep = reinterpret_cast<unsigned char *>(s + kSparseCand);
+  __shared__ int s_scan[33];
+  __shared__ int s_n;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 2 * nn; i += 1024) cnt[i] = 0;
+  if (tid < 4) out[tid] = 0;
+  if (tid == 0) s_n = 0;
+  for (int q = tid; q < 2 * ne; q += 1024) atomicAdd(occ + edges[q], 1);
+  __syncthreads();
+  for (int e = tid; e < ne; e += 1024) {
+    const int a = edges[2 * e], b = edges[2 * e + 1];
+    const int na = dof2node[a], nb = dof2node[b];
+    const int big = na > nb ? na : nb, small = na > nb ? nb : na;
+    int k = 0;
+    if (small == big) k = 1;
+    else if (!is_sep_d(small, big)) {
+      const int cs = lca_d(meta, na, nb);
+      if (cs < threshold) atomicMin(target + (occ[a] > occ[b] ? a : b), cs);
+      else k = 1;
+    }
+    keep[e] = (unsigned char)k;
+  }
+  __syncthreads();
+  // kept edges, in order (a thread owns 8 consecutive edges of a 8192-edge tile: one tile)
+  {
+    int c = 0;
+    const int e0 = tid * 8;
+#pragma unroll
+    for (int i = 0; i < 8; i++) c += e0 + i < ne ? keep[e0 + i] : 0;
+    int total;
+    int pos = block_excl_scan<1024>(c, s_scan, &total);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      if (e0 + i < ne && keep[e0 + i]) {
+        kept_edges[2 * pos] = edges[2 * (e0 + i)];
+        kept_edges[2 * pos + 1] = edges[2 * (e0 + i) + 1];
+        pos++;
+      }
+    if (tid == 0) out[3] = total;
+  }
+  // moved DOFs: every end point with a target, listed by its first visitor
+  for (int q = tid; q < 2 * ne; q += 1024) {
+    const int d = edges[q];
+    if (target[d] == kNoInit) continue;
+    if (atomicExch(occ + d, (int)0x80000000) >= 0) s[atomicAdd(&s_n, 1)] = d;
+  }
+  __syncthreads();
+  const int n = s_n;
   int P = 1;
   while (P < n) P <<= 1;
-  for (int i = threadIdx.x; i < P; i += 1024) s[i] = i < n ? a[i] : 0x7fffffff;
+  for (int i = n + tid; i < P; i += 1024) s[i] = 0x7fffffff;
   __syncthreads();
   for (int k = 2; k <= P; k <<= 1)
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int i = threadIdx.x; i < P; i += 1024) {
+      for (int i = tid; i < P; i += 1024) {
         const int l = i ^ j;
         if (l > i) {
           const int x = s[i], y = s[l];
@@ -652,21 +698,22 @@ __global__ void __launch_bounds__(1024) reloc_sort_kernel(int *__restrict__ a, c
       }
       __syncthreads();
     }
-  for (int i = threadIdx.x; i < n; i += 1024) a[i] = s[i];
-}
-
-// per moved DOF: its target node, the per-node counts of leavers / joiners, and the redirect of dof2node
-__global__ void reloc_info_kernel(const int *__restrict__ moved, const int *__restrict__ n_dev,
-                                  const int *__restrict__ target, int *__restrict__ dof2node,
-                                  int *__restrict__ moved_node, int *__restrict__ cnt_out, int *__restrict__ cnt_in) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= *n_dev) return;
-  const int d = moved[i];
-  const int t = target[d];
-  atomicAdd(cnt_out + dof2node[d], 1);
-  atomicAdd(cnt_in + t, 1);
-  moved_node[i] = t;
-  dof2node[d] = t;
+  // (before dof2node is redirected: the nodes that lose DOFs are the old ones)
+  for (int i = tid; i < n; i += 1024) {
+    const int d = s[i], t = target[d];
+    atomicAdd(cnt + dof2node[d], 1);
+    atomicAdd(cnt + nn + t, 1);
+    moved[i] = d;
+    moved_node[i] = t;
+    dof2node[d] = t;
+  }
+  for (int q = tid; q < 2 * ne; q += 1024) occ[edges[q]] = 0;
+  if (tid == 0) out[0] = n;
+  __syncthreads();
+  if (filter) {
+    const int kept = out[3];
+    for (int q = tid; q < 2 * kept; q += 1024) edges[q] = kept_edges[q];
+  }
 }
 
 // the slices of the nodes nothing happens to move to their new offsets (8 consecutive entries per thread: one node
@@ -981,11 +1028,7 @@ __global__ void assemble_listed_kernel(const int *__restrict__ list, const int *
     mesh_perm[labels[k] + off] = dofs[k];
 }
 
-// the persistent scratch goes back to its clean state, entry by entry
-__global__ void reloc_reset_occ_kernel(const int *__restrict__ edges, int n_edges, int *__restrict__ occ) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q < 2 * n_edges) occ[edges[q]] = 0;
-}
+// the persistent target scratch goes back to its clean state, entry by entry
 __global__ void reloc_reset_target_kernel(const int *__restrict__ moved, int n_moved, int *__restrict__ target) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q < n_moved) target[moved[q]] = kNoInit;
@@ -1300,51 +1343,35 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
   cudaStream_t s = h.stream;
   const int nn = h.num_nodes, M = h.tree_M, ne = h.n_changed;
   relocate_prepare(h, M);
-  h.w0.reserve((size_t)ne + 2, s);               // keep_edge
-  h.w1.reserve((size_t)ne + 2, s);               // its prefix
   h.w2.reserve((size_t)std::max(ne, 1) * 2, s);  // kept edges
   h.w4.reserve((size_t)nn * 2 + 8, s);           // cnt_out | cnt_in
   h.r_perm.reserve((size_t)kSparseCand, s);      // moved ids, ascending
   h.r_ws.reserve((size_t)kSparseCand, s);        // their target nodes
-  h.scan_ws.reserve(scan_ws_words((size_t)ne + 1), s);
-  int *d_cnt = h.mail.p + 16;  // [0] n_moved, [1] unsorted survivors, [2] size mismatch
-  PB_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int) * 4, s));
-  PB_CUDA(cudaMemsetAsync(h.w4.p, 0, sizeof(int) * (size_t)nn * 2, s));
-  occ_kernel<<<nblk(ne), 256, 0, s>>>(h.d_changed.p, ne, h.rel_occ.p);
-  relocate_targets_kernel<<<nblk(ne), 256, 0, s>>>(h.d_changed.p, ne, h.d_dof2node.p, h.d_meta.p, h.rel_occ.p,
-                                                  threshold_node, h.rel_target.p, h.w0.p);
-  h.stats.kernels_launched += 2 + exclusive_scan<0>(h.w0.p, h.w1.p, ne, h.scan_ws.p, s);
-  compact_edges_kernel<<<nblk(ne), 256, 0, s>>>(h.d_changed.p, ne, h.w0.p, h.w1.p, h.w2.p);
-  reloc_collect_kernel<<<nblk(2 * ne), 256, 0, s>>>(h.d_changed.p, ne, h.rel_target.p, h.rel_occ.p, h.r_perm.p, d_cnt);
+  int *d_cnt = h.mail.p + 16;  // [0] n_moved, [1] unsorted survivors, [2] size mismatch, [3] kept edges
+  const size_t front_smem = sizeof(int) * kSparseCand + kSparseEdges;
   {
-    static bool attr[64] = {};  // 64 KB of dynamic shared memory: opt in once per device
+    static bool attr[64] = {};  // > 48 KB of dynamic shared memory: opt in once per device
     const int dev = h.device;
     if (dev < 0 || dev >= 64 || !attr[dev]) {
-      PB_CUDA(cudaFuncSetAttribute(reloc_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(int) * kSparseCand));
+      PB_CUDA(cudaFuncSetAttribute(reloc_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)front_smem));
       if (dev >= 0 && dev < 64) attr[dev] = true;
     }
   }
-  reloc_sort_kernel<<<1, 1024, sizeof(int) * kSparseCand, s>>>(h.r_perm.p, d_cnt);
-  // (before dof2node is redirected: the nodes that lose DOFs are the old ones)
-  reloc_info_kernel<<<nblk(2 * ne), 256, 0, s>>>(h.r_perm.p, d_cnt, h.rel_target.p, h.d_dof2node.p, h.r_ws.p, h.w4.p,
-                                                h.w4.p + nn);
-  reloc_reset_occ_kernel<<<nblk(2 * ne), 256, 0, s>>>(h.d_changed.p, ne, h.rel_occ.p);
-  h.stats.kernels_launched += 5;
+  reloc_front_kernel<<<1, 1024, front_smem, s>>>(h.d_changed.p, ne, h.d_dof2node.p, h.d_meta.p, threshold_node, h.rel_occ.p,
+                                                 h.rel_target.p, h.w2.p, h.r_perm.p, h.r_ws.p, h.w4.p, nn, d_cnt,
+                                                 filter_edges ? 1 : 0);
+  PB_CUDA(cudaGetLastError());
+  h.stats.kernels_launched++;
   // ONE read-back: kept edges, moved DOFs, leavers / joiners per node
   h.pin.reserve((size_t)2 * nn + 8);
-  PB_CUDA(cudaMemcpyAsync(h.pin.p, h.w1.p + ne, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PB_CUDA(cudaMemcpyAsync(h.pin.p + 1, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, s));
-  PB_CUDA(cudaMemcpyAsync(h.pin.p + 2, h.w4.p, sizeof(int) * (size_t)nn * 2, cudaMemcpyDeviceToHost, s));
+  PB_CUDA(cudaMemcpyAsync(h.pin.p, d_cnt, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
+  PB_CUDA(cudaMemcpyAsync(h.pin.p + 4, h.w4.p, sizeof(int) * (size_t)nn * 2, cudaMemcpyDeviceToHost, s));
   PB_CUDA(cudaStreamSynchronize(s));
-  h.stats.d2h_bytes += (long long)sizeof(int) * (2 * nn + 2);
+  h.stats.d2h_bytes += (long long)sizeof(int) * (2 * nn + 4);
   collect_timers(h);
-  const int kept = h.pin.p[0], n_moved = h.pin.p[1];
-  const std::vector<int> cnt_out(h.pin.p + 2, h.pin.p + 2 + nn), cnt_in(h.pin.p + 2 + nn, h.pin.p + 2 + 2 * nn);
-  if (filter_edges) {
-    if (kept > 0)
-      PB_CUDA(cudaMemcpyAsync(h.d_changed.p, h.w2.p, sizeof(int) * 2 * (size_t)kept, cudaMemcpyDeviceToDevice, s));
-    h.n_changed = kept;
-  }
+  const int kept = h.pin.p[3], n_moved = h.pin.p[0];
+  const std::vector<int> cnt_out(h.pin.p + 4, h.pin.p + 4 + nn), cnt_in(h.pin.p + 4 + nn, h.pin.p + 4 + 2 * nn);
+  if (filter_edges) h.n_changed = kept;
   if (n_moved == 0) return;
   // new layout on the host (<= 8191 nodes)
   std::vector<int> aptr((size_t)nn + 1, 0), nptr((size_t)nn + 1, 0), changed_flag((size_t)nn, 0), changed, touched;
