@@ -179,7 +179,7 @@ rank_joiners_kernel(const int *__restrict__ touched, const int *__restrict__ joi
                     int *__restrict__ joinS) {
   __shared__ int s_scan[33];
   const int node = touched[blockIdx.x];
-  const int base = aptr[node] + segbase[blockIdx.x * gridDim.y + blockIdx.y];
+  const int base = aptr[node] + (segbase ? segbase[blockIdx.x * gridDim.y + blockIdx.y] : 0);
   const int lo = blockIdx.y * seg, hi = min(n_join, lo + seg);
   int running = 0;
   for (int i0 = lo; i0 < hi; i0 += 256) {
@@ -1074,6 +1074,12 @@ void rank_joiners(parth_b200 &h, int n_touched, const int *d_touched, const int 
   cudaStream_t s = h.stream;
   const int n_seg = std::max(1, std::min(128, n_join / 2048));
   const int seg = ((n_join + n_seg - 1) / n_seg + 255) / 256 * 256;
+  if (n_seg == 1) {  // a short joiner list: one CTA per node walks it, no segment bases needed
+    rank_joiners_kernel<<<dim3((unsigned)n_touched, 1), 256, 0, s>>>(d_touched, d_join, d_join_node, n_join, seg, nullptr,
+                                                                     d_aptr, d_out);
+    h.stats.kernels_launched++;
+    return;
+  }
   h.rank_seg.reserve((size_t)n_touched * n_seg + 1, s);
   const dim3 grid((unsigned)n_touched, (unsigned)n_seg);
   rank_joiners_count_kernel<<<grid, 256, 0, s>>>(d_touched, d_join_node, n_join, seg, h.rank_seg.p);
@@ -1457,7 +1463,7 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
     PB_CUDA(cudaGetLastError());
     h.stats.kernels_launched++;
   }
-  upload_tree_meta(h);  // synchronises: the flags below have arrived as well
+  upload_tree_meta(h, /*sync=*/false);  // its sources are staged by the copies; read_ints below synchronises
   int fl[2] = {0, 0};
   read_ints(h, d_cnt + 1, fl, 2);
   if (fl[1]) throw StatusError(PARTH_B200_ERR_INTERNAL, "relocate: regrouped node size mismatch");

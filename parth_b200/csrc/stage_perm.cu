@@ -28,7 +28,7 @@ static void compute_visit(parth_b200 &h, std::vector<int> &visit) {
   }
 }
 
-void upload_tree_meta(parth_b200 &h) {
+void upload_tree_meta(parth_b200 &h, bool sync) {
   cudaStream_t s = h.stream;
   const int nodes = h.num_nodes;
   h.meta_heap = true;
@@ -48,7 +48,7 @@ void upload_tree_meta(parth_b200 &h) {
   PB_CUDA(cudaMemcpyAsync(h.d_meta.p, h.meta.data(), sizeof(int) * (size_t)nodes * 7, cudaMemcpyHostToDevice, s));
   PB_CUDA(cudaMemcpyAsync(h.d_node_ptr.p, h.node_ptr.data(), sizeof(int) * ((size_t)nodes + 1), cudaMemcpyHostToDevice, s));
   PB_CUDA(cudaMemcpyAsync(h.d_visit.p, visit.data(), sizeof(int) * (size_t)nodes, cudaMemcpyHostToDevice, s));
-  PB_CUDA(cudaStreamSynchronize(s));
+  if (sync) PB_CUDA(cudaStreamSynchronize(s));
 }
 
 void assemble_all(parth_b200 &h) {

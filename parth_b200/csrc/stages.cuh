@@ -65,7 +65,7 @@ void block_plan(parth_b200 &h, int M, int nnz);
 void stage_build_block(parth_b200 &h, int N, int nnz, const int *dAp, const int *dAi, int q0, int q1);
 
 // stage_perm.cu
-void upload_tree_meta(parth_b200 &h);
+void upload_tree_meta(parth_b200 &h, bool sync = true);
 void assemble_all(parth_b200 &h);
 void stage_import_tree(parth_b200 &h, int M_n, int levels, int nodes, const int *meta,
                        const int *node_ptr, const int *dofs, const int *labels, const int *Mp_prev,
