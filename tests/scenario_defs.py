@@ -179,6 +179,18 @@ def scenario_list():
                                        opts=opts(nd_levels=4, lagging=False, aggressive=True, relocate_lvl=4), dim=1)
         S["g12metis_add9_nolag"] = dict(tree=("g12",), new=("mesh", P, I, None),
                                         opts=opts(nd_levels=4, lagging=False), dim=1)
+    # ---- added DOFs with rows wider than a warp (placement: the one-thread walk of the pull kernel); own generator,
+    # appended last so that the scenarios above keep their random draws
+    rng2 = np.random.default_rng(77)
+    P, I, m = remesh_box(16, Mp16, Mi16, 5, 12)
+    n_surv = int((m != -1).sum())
+    added_ids = np.arange(n_surv, M16)
+    hub_hi, hub_lo = M16 - 1, n_surv  # waits for every added neighbour / releases every added neighbour
+    e = [(hub_hi, int(x)) for x in rng2.choice(added_ids[:-1], 30, replace=False)]
+    e += [(hub_hi, int(x)) for x in rng2.choice(n_surv, 15, replace=False)]
+    e += [(hub_lo, int(x)) for x in rng2.choice(added_ids[1:-1], 40, replace=False)]
+    P, I = synth.add_edges(P, I, e)
+    S["g16_remesh_5_12_hubs"] = dict(tree=("geo", 16, 5), new=("mesh", P, I, m), opts=opts(nd_levels=5, lagging=False), dim=1)
     return S
 
 
