@@ -1265,12 +1265,17 @@ void stage_integrate(parth_b200 &h) {
         place_pull_count_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.Mp, h.Mi, h.r_g2l.p, h.r_l2g.p, qcount);
         place_pull_offsets_kernel<<<1, 32, 0, s>>>(qcount, qoff, d_cnt);
         place_pull_roots_kernel<<<nblk(n_added), 256, 0, s>>>(h.added.p, n_added, h.r_g2l.p, h.r_l2g.p, fr.p, tails, qoff);
-        place_pass_pull_kernel<<<h.num_sms, kPullThreads, 0, s>>>(fr.p, tails, qoff, h.Mp, h.Mi,
-                                                                 h.meta_heap ? nullptr : h.d_meta.p, h.r_g2l.p, h.r_l2g.p,
-                                                                 pass, d_cnt);
-        h.stats.kernels_launched += 2;
-        PB_CUDA(cudaGetLastError());
-        h.stats.kernels_launched += 2;
+        {
+          // the warps poll each other: a COOPERATIVE launch, so that the runtime refuses the grid instead of letting
+          // resident CTAs spin on tickets of CTAs that cannot be scheduled (a GPU shared with another context)
+          int *a_q = fr.p, *a_t = tails, *a_st = h.r_g2l.p, *a_in = h.r_l2g.p, a_pass = pass;
+          const int *a_off = qoff, *a_mp = h.Mp, *a_mi = h.Mi, *a_meta = h.meta_heap ? nullptr : h.d_meta.p;
+          PlaceCounters *a_cnt = d_cnt;
+          void *args[] = {&a_q, &a_t, &a_off, &a_mp, &a_mi, &a_meta, &a_st, &a_in, &a_pass, &a_cnt};
+          PB_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<const void *>(place_pass_pull_kernel), dim3((unsigned)h.num_sms),
+                                              dim3(kPullThreads), args, 0, s));
+        }
+        h.stats.kernels_launched += 4;
         read_ints(h, reinterpret_cast<const int *>(d_cnt), c, 4);
       } else {
         PB_CUDA(cudaMemsetAsync(fcnt.p, 0, sizeof(int) * ((size_t)max_sweeps + kBatch + 4), s));
