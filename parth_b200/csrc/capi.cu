@@ -14,9 +14,14 @@ using namespace pb;
   if (!h) return PARTH_B200_ERR_ARG; \
   try {                 \
     PB_CUDA(cudaSetDevice(h->device));
-#define PB_API_BEGIN  \
+#define PB_API_BEGIN_STREAM  \
   PB_API_BEGIN_NOSETTLE \
   stage_build_settle(*h);
+// ... and reads the error flags a stream-ordered update left behind (one small read-back when there are any);
+// PB_API_BEGIN_STREAM is for the stream-ordered entry points that must not wait for the previous update
+#define PB_API_BEGIN  \
+  PB_API_BEGIN_STREAM \
+  check_reloc_flags(*h);
 #define PB_API_END                                   \
   }                                                  \
   catch (const pb::CudaError &e) {                   \
@@ -230,7 +235,7 @@ int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out) {
 
 // ------------------------------------------------------------------ matrix / mesh input
 int parth_b200_set_matrix_dev(parth_b200 *h, int N, const int *dAp, const int *dAi, int nnz, int dim) {
-  PB_API_BEGIN
+  PB_API_BEGIN_STREAM
   if (!dAp || !dAi || N <= 0 || dim <= 0 || nnz < 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: bad argument");
   if (N % dim != 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: N is not a multiple of dim (ParthAPI.cpp:371 asserts it)");
   h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
@@ -385,7 +390,14 @@ int parth_b200_compute_permutation_dev(parth_b200 *h, int *dperm, int dim) {
   h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
   // stream-ordered: dperm is valid for work enqueued on the handle's stream after this call (or
   // after parth_b200_synchronize); the stage timers are read at the next synchronisation point
-  rc = stage_compute_permutation(*h, dperm, dim);
+  h->defer_reloc_check = true;  // stream-ordered: the regroup kernels' error flags are read by the next synchronising call
+  try {
+    rc = stage_compute_permutation(*h, dperm, dim);
+  } catch (...) {
+    h->defer_reloc_check = false;
+    throw;
+  }
+  h->defer_reloc_check = false;
   if (rc != PARTH_B200_OK) return rc;
   PB_API_END
 }
@@ -814,7 +826,7 @@ int parth_b200_set_matrix_block(parth_b200 *h, int N, int nnz, const int *Ap, co
 
 int parth_b200_set_matrix_block_dev(parth_b200 *h, int N, int nnz, const int *dAp, const int *dAi, int dim, int q0,
                                     int q1) {
-  PB_API_BEGIN
+  PB_API_BEGIN_STREAM
   if (!dAp || !dAi || N <= 0 || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix_block: bad argument");
   if (!h->comm) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix_block: no communicator (parth_b200_comm_init*)");
   if (dim != 1) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "row-block mode: dim must be 1");

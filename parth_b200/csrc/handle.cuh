@@ -93,6 +93,11 @@ struct parth_b200 {
   pb::DevBuf<int> d_dofs2, d_labels2;  // double buffers for integration / relocation
   // sparse relocation (stage_maps.cu): per-DOF occurrence counts / relocation targets, clean between calls
   pb::DevBuf<int> rel_occ, rel_target, rank_seg;
+  // sticky error flags of the relocation's regroup kernels ([0] unsorted survivors, [1] size mismatch).  The
+  // host-pointer entry points read them before they return; the stream-ordered *_dev entry points leave them to the
+  // next call that synchronises anyway (relocation read-back, synchronize, get_stats, any host-pointer call)
+  pb::DevBuf<int> reloc_sticky;
+  bool defer_reloc_check = false, reloc_check_pending = false;
   int rel_M = 0;
   pb::PinBuf<int> pin_rel;
 

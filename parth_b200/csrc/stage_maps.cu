@@ -1338,6 +1338,10 @@ void stage_integrate(parth_b200 &h) {
 // 134 M DOF, profiles/r04_configs.md), and lazily by the relocation itself.
 void relocate_prepare(parth_b200 &h, int M) {
   cudaStream_t s = h.stream;
+  if (!h.reloc_sticky.p) {
+    h.reloc_sticky.reserve(4, s);
+    PB_CUDA(cudaMemsetAsync(h.reloc_sticky.p, 0, sizeof(int) * 4, s));
+  }
   if (h.rel_M == M || M <= 0) return;
   h.rel_occ.reserve((size_t)M + 1, s);
   h.rel_target.reserve((size_t)M + 1, s);
@@ -1347,6 +1351,20 @@ void relocate_prepare(parth_b200 &h, int M) {
   fill_kernel<<<nblk(M), 256, 0, s>>>(h.rel_target.p, M, kNoInit);
   h.stats.kernels_launched++;
   h.rel_M = M;
+}
+
+// the regroup kernels' sticky error flags: checked now, or left for the next synchronising call (stream-ordered API)
+void check_reloc_flags(parth_b200 &h) {
+  if (!h.reloc_check_pending || !h.reloc_sticky.p) return;
+  h.reloc_check_pending = false;
+  int fl[2] = {0, 0};
+  read_ints(h, h.reloc_sticky.p, fl, 2);
+  if (fl[0] || fl[1]) PB_CUDA(cudaMemsetAsync(h.reloc_sticky.p, 0, sizeof(int) * 2, h.stream));
+  if (fl[1]) throw StatusError(PARTH_B200_ERR_INTERNAL, "relocate: regrouped node size mismatch");
+  if (fl[0])
+    throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
+                      "DOF map: surviving DOFs of a node that receives DOFs are not in ascending order "
+                      "(the reference expects survivors to keep their order, remeshPatch.cpp:160-176)");
 }
 
 // Sparse relocation (kernels: "relocation, sparse formulation" above).  Same result as the dense path below.
@@ -1377,9 +1395,20 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
   h.pin.reserve((size_t)2 * nn + 8);
   PB_CUDA(cudaMemcpyAsync(h.pin.p, d_cnt, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
   PB_CUDA(cudaMemcpyAsync(h.pin.p + 4, h.w4.p, sizeof(int) * (size_t)nn * 2, cudaMemcpyDeviceToHost, s));
+  // the sticky error flags of an earlier stream-ordered update ride along (this update's regroup kernels run later)
+  PB_CUDA(cudaMemcpyAsync(h.pin.p + 4 + 2 * (size_t)nn, h.reloc_sticky.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
   PB_CUDA(cudaStreamSynchronize(s));
-  h.stats.d2h_bytes += (long long)sizeof(int) * (2 * nn + 4);
+  h.stats.d2h_bytes += (long long)sizeof(int) * (2 * nn + 6);
   collect_timers(h);
+  if (h.reloc_check_pending) {
+    h.reloc_check_pending = false;
+    const int f0 = h.pin.p[4 + 2 * (size_t)nn], f1 = h.pin.p[5 + 2 * (size_t)nn];
+    if (f0 || f1) PB_CUDA(cudaMemsetAsync(h.reloc_sticky.p, 0, sizeof(int) * 2, s));
+    if (f1) throw StatusError(PARTH_B200_ERR_INTERNAL, "relocate: regrouped node size mismatch (previous update)");
+    if (f0)
+      throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
+                        "DOF map: surviving DOFs of a node that receives DOFs are not in ascending order (previous update)");
+  }
   const int kept = h.pin.p[3], n_moved = h.pin.p[0];
   const std::vector<int> cnt_out(h.pin.p + 4, h.pin.p + 4 + nn), cnt_in(h.pin.p + 4 + nn, h.pin.p + 4 + 2 * nn);
   if (filter_edges) h.n_changed = kept;
@@ -1446,7 +1475,7 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
       PB_CUDA(cudaFuncSetAttribute(regroup_changed_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
     regroup_changed_cluster_kernel<<<(unsigned)changed.size() * RGC, RG_THREADS, smem_c, s>>>(
         d_changed_list, h.d_node_ptr.p, d_nptr, d_aptr, h.rel_target.p, h.r_sub.p, h.d_dofs.p, h.d_labels.p, h.d_dofs2.p,
-        h.d_labels2.p, d_cnt + 1, wper_cap, hist_cap);
+        h.d_labels2.p, h.reloc_sticky.p, wper_cap, hist_cap);
   } else {
     const size_t smem = sizeof(int) * ((size_t)2 * max_words + max_in + 2);
     if (smem > 200 * 1024) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "relocate: a node is too large for the regroup kernel");
@@ -1454,7 +1483,7 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
       PB_CUDA(cudaFuncSetAttribute(regroup_changed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     regroup_changed_kernel<<<(unsigned)changed.size(), RG_THREADS, smem, s>>>(d_changed_list, h.d_node_ptr.p, d_nptr, d_aptr,
                                                                             h.rel_target.p, h.r_sub.p, h.d_dofs.p, h.d_labels.p,
-                                                                            h.d_dofs2.p, h.d_labels2.p, d_cnt + 1);
+                                                                            h.d_dofs2.p, h.d_labels2.p, h.reloc_sticky.p);
   }
   reloc_reset_target_kernel<<<nblk(n_moved), 256, 0, s>>>(h.r_perm.p, n_moved, h.rel_target.p);
   PB_CUDA(cudaGetLastError());
@@ -1468,14 +1497,9 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
     PB_CUDA(cudaGetLastError());
     h.stats.kernels_launched++;
   }
-  upload_tree_meta(h, /*sync=*/false);  // its sources are staged by the copies; read_ints below synchronises
-  int fl[2] = {0, 0};
-  read_ints(h, d_cnt + 1, fl, 2);
-  if (fl[1]) throw StatusError(PARTH_B200_ERR_INTERNAL, "relocate: regrouped node size mismatch");
-  if (fl[0])
-    throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
-                      "DOF map: surviving DOFs of a node that receives DOFs are not in ascending order "
-                      "(the reference expects survivors to keep their order, remeshPatch.cpp:160-176)");
+  upload_tree_meta(h, /*sync=*/false);  // its sources are staged by the copies
+  h.reloc_check_pending = true;
+  if (!h.defer_reloc_check) check_reloc_flags(h);  // host-pointer API: errors are reported by the call that caused them
   dirty_fine_out.insert(dirty_fine_out.end(), touched.begin(), touched.end());
 }
 

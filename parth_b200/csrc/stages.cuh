@@ -83,6 +83,7 @@ void stage_set_map(parth_b200 &h, const int *map, int len);
 void stage_integrate(parth_b200 &h);
 void stage_relocate(parth_b200 &h, int threshold_node, std::vector<int> &dirty_fine_out, bool filter_edges = true);
 void relocate_prepare(parth_b200 &h, int M);  // pre-sizes the relocation scratch (import_tree)
+void check_reloc_flags(parth_b200 &h);         // deferred error flags of the regroup kernels (throws)
 
 // stage_reorder.cu: (a12-a14) extraction + ordering of dirty fine nodes, coarse-node policy
 void stage_permute_fine(parth_b200 &h, const std::vector<int> &nodes);

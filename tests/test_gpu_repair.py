@@ -160,3 +160,43 @@ def test_sparse_relocation_equals_the_dense_formulation(gpu_api, variant):
             assert np.array_equal(outs[0][2], outs[other][2]) and outs[0][3] == outs[other][3]
             for key in ("labels", "dofs", "mesh_perm", "dof2node", "node_ptr", "meta"):
                 assert np.array_equal(outs[0][1][key], outs[other][1][key]), (step, other, key)
+
+
+def test_regroup_error_flags_immediate_and_deferred(gpu_api):
+    """A node that receives DOFs must hold its survivors in ascending order (the reference's merge relies on it).  The
+    host-pointer update reports the violation itself; the stream-ordered update returns at once and the sticky flag
+    is reported by the next call that synchronises."""
+    import torch
+    tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 16, 5)))
+    M = 16 ** 3
+    # node 0 (top separator) with two of its DOFs swapped: still a valid tree, no longer ascending
+    dofs, labels = tree.dofs.copy(), tree.labels.copy()
+    a, b = int(tree.node_ptr[0]), int(tree.node_ptr[0]) + 5
+    dofs[[a, b]] = dofs[[b, a]]
+    labels[[a, b]] = labels[[b, a]]
+    from oracle.cpu_parth import Tree
+    bad = Tree(tree.M_n, tree.levels, tree.nodes, tree.meta, tree.node_ptr, dofs, labels)
+    # an edge between the two halves below the root: relocation moves an end point into node 0
+    left, right = int(tree.node_dofs(3)[0]), int(tree.node_dofs(5)[0])
+    P, I = synth.add_edges(Mp, Mi, [(left, right)])
+
+    def handle():
+        g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 5; g.lagging = False
+        g.setCoarsePolicy(gpu_api.COARSE_RELOCATE)
+        g.import_tree(bad, Mp, Mi)
+        return g
+
+    g = handle()
+    g.setMesh(M, P, I)
+    with pytest.raises(gpu_api.ParthError) as e:
+        g.computePermutation(1)
+    assert e.value.code == -6  # PARTH_B200_ERR_UNSUPPORTED
+    g = handle()
+    dP, dI = torch.from_numpy(P).cuda(), torch.from_numpy(I).cuda()
+    dperm = torch.empty(M, dtype=torch.int32, device="cuda")
+    g.setMeshDev(M, dP.data_ptr(), dI.data_ptr(), len(I))
+    assert g.computePermutationDev(dperm.data_ptr(), 1) == 0  # stream-ordered: the flag is still on the device
+    with pytest.raises(gpu_api.ParthError) as e:
+        g.synchronize()
+    assert e.value.code == -6
+    g.synchronize()  # reported once
