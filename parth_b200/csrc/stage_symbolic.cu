@@ -237,7 +237,7 @@ etree_node_kernel(const int *__restrict__ ranges, const int *__restrict__ perm, 
 
 // ---------------------------------------------------------------- batch-parallel node kernel
 // Liu's algorithm visits the columns of a node one after the other (0.5 us per column on one warp: the top separator
-// of a 200^3 grid alone took 19.8 ms, the 256 leaves 16.9 ms).  This kernel takes the columns E2_CHUNK at a time:
+// of a 200^3 grid alone took 19.8 ms, the 256 leaves 16.9 ms).  This kernel takes the columns EB_CHUNK at a time:
 //   phase 1  every lower neighbour that lies before the batch is replaced by the root of its component in the forest
 //            F0 of the earlier columns (all threads, full path compression: links only ever point at true ancestors);
 //   phase 2  the batch is a small etree problem on {F0 roots met, batch columns} with edges (u, j), u < j.  Every edge
@@ -247,23 +247,26 @@ etree_node_kernel(const int *__restrict__ ranges, const int *__restrict__ perm, 
 //            the fixed point every edge (u, j) has j above u with parent[x] = the smallest such j: the elimination
 //            tree, which is unique -- the result is bit-identical to the sequential walk (tests/test_gpu_symbolic.py).
 // Ancestor links and provisional parents share the node's shared-memory array (-1 = none = the largest unsigned).
-// A batch that holds a row longer than E2_DEG is walked sequentially by warp 0 (same state, same result).
-__global__ void __launch_bounds__(E2_THREADS)
+// A batch that holds a row longer than EB_DEG is walked sequentially by warp 0 (same state, same result).
+// batch kernel: 256 columns per batch (the per-batch costs -- the dependent global loads of the adjacency, the
+// barriers, the lifting table -- are latency, so a wider batch halves them per column), rows of up to 16 entries
+constexpr int EB_THREADS = 256, EB_CHUNK = 256, EB_DEG = 16, EB_LEVELS = 8;  // 2^EB_LEVELS >= EB_CHUNK
+__global__ void __launch_bounds__(EB_THREADS)
 etree_node_batch_kernel(const int *__restrict__ ranges, const int *__restrict__ perm, const int *__restrict__ inv,
                         const int *__restrict__ Mp, const int *__restrict__ Mi, const int *__restrict__ flat,
                         const int *__restrict__ first, int *anc, int *parent) {
   extern __shared__ __align__(16) unsigned char e2_raw[];
-  __shared__ int s_nbr[E2_CHUNK][E2_DEG];  // sources of the batch's edges (phase 1: replaced by their F0 roots)
-  __shared__ int s_pos[E2_CHUNK][E2_DEG];  // where the climb of each edge stopped last (it resumes there)
-  __shared__ int s_up[7][E2_CHUNK];        // binary lifting over the batch columns: 2^k-th provisional ancestor (-1: leaves the batch)
-  __shared__ int s_cnt[E2_CHUNK];
+  __shared__ int s_nbr[EB_CHUNK][EB_DEG];  // sources of the batch's edges (phase 1: replaced by their F0 roots)
+  __shared__ int s_pos[EB_CHUNK][EB_DEG];  // where the climb of each edge stopped last (it resumes there)
+  __shared__ int s_up[EB_LEVELS][EB_CHUNK];        // binary lifting over the batch columns: 2^k-th provisional ancestor (-1: leaves the batch)
+  __shared__ int s_cnt[EB_CHUNK];
   __shared__ int s_flag[2];  // [0] a round changed something, [1] the batch holds a long row
   const int b = ranges[2 * blockIdx.x], e = ranges[2 * blockIdx.x + 1];
   const int tid = threadIdx.x, lane = tid & 31;
   volatile int *sm = reinterpret_cast<volatile int *>(e2_raw);
-  for (int i = tid; i < e - b; i += E2_THREADS) sm[i] = -1;
+  for (int i = tid; i < e - b; i += EB_THREADS) sm[i] = -1;
   __syncthreads();
-  for (int j0 = b; j0 < e; j0 += E2_CHUNK) {
+  for (int j0 = b; j0 < e; j0 += EB_CHUNK) {
     const int j = j0 + tid;
     // ---- adjacency of column j, resolved to columns of this node's own slice (as etree_node_kernel::prefetch)
     int cnt = 0;
@@ -271,7 +274,7 @@ etree_node_batch_kernel(const int *__restrict__ ranges, const int *__restrict__ 
     if (j < e) {
       const int old = __ldg(perm + j);
       const int s = __ldg(Mp + old), deg = __ldg(Mp + old + 1) - s;
-      if (deg > E2_DEG) cnt = -1;
+      if (deg > EB_DEG) cnt = -1;
       else
         for (int q0 = 0; q0 < deg; q0 += 8) {
           int k[8], r[8], f[8];
@@ -295,9 +298,9 @@ etree_node_batch_kernel(const int *__restrict__ ranges, const int *__restrict__ 
     if (cnt < 0) s_flag[1] = 1;
     __syncthreads();
     if (s_flag[1]) {
-      // sequential walk of this batch (a row longer than E2_DEG): warp 0, lanes over the neighbours
+      // sequential walk of this batch (a row longer than EB_DEG): warp 0, lanes over the neighbours
       if (tid < 32) {
-        const int lim = min(E2_CHUNK, e - j0);
+        const int lim = min(EB_CHUNK, e - j0);
         for (int t = 0; t < lim; t++) {
           const int jj = j0 + t, c = s_cnt[t];
           auto walk = [&](int k) {
@@ -346,14 +349,14 @@ etree_node_batch_kernel(const int *__restrict__ ranges, const int *__restrict__ 
     // ---- phase 2: rounds of climb + atomicMin until nothing changes.  Provisional parents grow along a chain, so
     // "the last ancestor below j" is found by binary lifting over the batch columns (a natural ordering makes the
     // whole batch one chain: walking it link by link cost 128 dependent shared-memory loads for the last columns)
-    const int jend = j0 + E2_CHUNK;
+    const int jend = j0 + EB_CHUNK;
     for (;;) {
       {
         int v = j < e ? sm[j - b] : -1;
         s_up[0][tid] = (v != -1 && v < jend) ? v : -1;
         __syncthreads();
 #pragma unroll
-        for (int k = 1; k < 7; k++) {
+        for (int k = 1; k < EB_LEVELS; k++) {
           const int y = s_up[k - 1][tid];
           s_up[k][tid] = y != -1 ? s_up[k - 1][y - j0] : -1;
           __syncthreads();
@@ -370,7 +373,7 @@ etree_node_batch_kernel(const int *__restrict__ ranges, const int *__restrict__ 
         }
         if (x >= j0) {
 #pragma unroll
-          for (int k = 6; k >= 0; k--) {
+          for (int k = EB_LEVELS - 1; k >= 0; k--) {
             const int y = s_up[k][x - j0];
             if (y != -1 && y < j) x = y;
           }
@@ -401,18 +404,18 @@ etree_node_batch_kernel(const int *__restrict__ ranges, const int *__restrict__ 
     // the parents are in global memory: the links of the batch columns now become shortcuts (pointer doubling inside
     // the batch), so that the root searches of later batches cross a batch in one or two steps instead of walking its
     // chain -- natural orderings make every batch one long chain
-    for (int round = 0; round < 7; round++) {
+    for (int round = 0; round < EB_LEVELS; round++) {
       int w = -1;
       if (j < e) {
         const int v = sm[j - b];
-        if (v != -1 && v < j0 + E2_CHUNK) w = sm[v - b];
+        if (v != -1 && v < j0 + EB_CHUNK) w = sm[v - b];
       }
       __syncthreads();
       if (w != -1) sm[j - b] = w;
       __syncthreads();
     }
   }
-  for (int i = tid; i < e - b; i += E2_THREADS) anc[b + i] = sm[i];
+  for (int i = tid; i < e - b; i += EB_THREADS) anc[b + i] = sm[i];
 }
 
 // after wave w: (i) every column of a wave-w node learns the root of its component ...
@@ -709,7 +712,7 @@ void stage_symbolic(parth_b200 &h, const int *perm_in, int *parent_out, int *col
       const int dyn = max_smem - 36 * 1024;  // static part: two buffers of prefetched adjacency lists
       PB_CUDA(cudaFuncSetAttribute(etree_node_kernel<int, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
       PB_CUDA(cudaFuncSetAttribute(etree_node_kernel<unsigned short, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-      const int dyn_batch = max_smem - 40 * 1024;  // static part: the batch's edge sources, climb positions, lifting table
+      const int dyn_batch = max_smem - 44 * 1024;  // static part: the batch's edge sources, climb positions, lifting table
       PB_CUDA(cudaFuncSetAttribute(etree_node_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_batch));
       int wi = 0;
       for (auto &w : waves) {
@@ -729,7 +732,7 @@ void stage_symbolic(parth_b200 &h, const int *perm_in, int *parent_out, int *col
           const bool seq_only = std::getenv("PARTH_B200_ETREE_SEQ") != nullptr;
           if (!seq_only && 4 * longest <= dyn_batch) {
             const int bytes = ((4 * longest + 1023) / 1024) * 1024;
-            etree_node_batch_kernel<<<nr, E2_THREADS, bytes, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi, flatroot.p, first.p,
+            etree_node_batch_kernel<<<nr, EB_THREADS, bytes, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi, flatroot.p, first.p,
                                                                  anc.p, parent.p);
           } else if (nr > h.num_sms && longest <= 65534 && 2 * longest <= dyn) {
             const int bytes = ((2 * longest + 1023) / 1024) * 1024;
