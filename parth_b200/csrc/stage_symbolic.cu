@@ -477,18 +477,66 @@ __global__ void tour_succ_kernel(const int *__restrict__ parent, int n, const in
   link[2 * (size_t)j] = ((unsigned long long)succ_enter << 32) | 1ull;
   link[2 * (size_t)j + 1] = ((unsigned long long)succ_leave << 32) | 0ull;
 }
-// Wyllie pointer jumping: after ceil(log2(2n)) rounds the low word holds the number of "enter"
-// events from the element (inclusive) to the end of the tour
-__global__ void tour_jump_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
-                                 long long m, int *__restrict__ active) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// ---- sampled list ranking (Helman-JaJa): Wyllie's jumping moves the whole 2n-element list log2(2n) times (25 rounds,
+// 6.3 ms and 25 read-backs at 8 M DOF).  The "enter" and "leave" elements of a pseudo-random 1/32 of the vertices (a
+// multiplicative hash of the vertex id: index-based sampling never meets the odd-numbered "leave" chain of a path-like
+// tree) and the head are splitters; a splitter walks to the next splitter summing the weights of its segment, the
+// splitters are ranked by jumping (a fixed number of rounds, no read-back), and a second walk writes the suffix sums of
+// the segment's elements.  vslot = exclusive scan of the vertex flags; slot of element i = 2 vslot[i / 2] + (i & 1).
+__device__ __forceinline__ bool tour_vertex_sampled(unsigned j) { return ((j * 2654435761u) >> 27) == 0u; }
+__global__ void tour_flag_kernel(int n, int *__restrict__ flag) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) flag[j] = tour_vertex_sampled((unsigned)j);
+}
+__device__ __forceinline__ bool tour_is_splitter(unsigned i, unsigned head) { return tour_vertex_sampled(i >> 1) || i == head; }
+__device__ __forceinline__ unsigned tour_slot(unsigned i, unsigned head, unsigned n_reg, const int *__restrict__ vslot) {
+  return tour_vertex_sampled(i >> 1) ? 2u * (unsigned)__ldg(vslot + (i >> 1)) + (i & 1u) : n_reg;  // head: the extra slot
+}
+// spl[slot] = (next slot << 32) | segment weight
+__global__ void tour_segment_kernel(const unsigned long long *__restrict__ link, long long m, unsigned head, unsigned n_reg,
+                                    const int *__restrict__ vslot, unsigned long long *__restrict__ spl) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == m) {  // the head's extra slot stays an empty tail when the head is a sampled element
+    if (tour_vertex_sampled(head >> 1)) spl[n_reg] = 0xffffffffull << 32;
+    return;
+  }
+  if (i > m || !tour_is_splitter((unsigned)i, head)) return;
+  unsigned long long a = link[i];
+  unsigned acc = (unsigned)a, cur = (unsigned)(a >> 32);
+  while (cur != 0xffffffffu && !tour_is_splitter(cur, head)) {
+    a = link[cur];
+    acc += (unsigned)a;
+    cur = (unsigned)(a >> 32);
+  }
+  const unsigned nxt = cur == 0xffffffffu ? 0xffffffffu : tour_slot(cur, head, n_reg, vslot);
+  spl[tour_slot((unsigned)i, head, n_reg, vslot)] = ((unsigned long long)nxt << 32) | acc;
+}
+// suffix sums of the segment's elements from the ranked splitter (low word of ranked[slot] = weight from the
+// splitter, inclusive, to the end of the tour); out keeps the link format tour_extract_kernel reads
+__global__ void tour_spread_kernel(const unsigned long long *__restrict__ link, long long m, unsigned head, unsigned n_reg,
+                                   const int *__restrict__ vslot, const unsigned long long *__restrict__ ranked,
+                                   unsigned long long *__restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m || !tour_is_splitter((unsigned)i, head)) return;
+  unsigned running = (unsigned)ranked[tour_slot((unsigned)i, head, n_reg, vslot)];
+  unsigned cur = (unsigned)i;
+  do {
+    const unsigned long long a = link[cur];
+    out[cur] = (a & 0xffffffff00000000ull) | running;
+    running -= (unsigned)a;
+    cur = (unsigned)(a >> 32);
+  } while (cur != 0xffffffffu && !tour_is_splitter(cur, head));
+}
+// Wyllie jumping without the activity flag (fixed number of rounds on the short splitter list)
+__global__ void tour_jump_fixed_kernel(const unsigned long long *__restrict__ in, unsigned long long *__restrict__ out,
+                                       unsigned m) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
   const unsigned long long a = in[i];
   const unsigned s = (unsigned)(a >> 32);
   if (s == 0xffffffffu) { out[i] = a; return; }
   const unsigned long long b = in[s];
   out[i] = (b & 0xffffffff00000000ull) | (unsigned long long)((unsigned)a + (unsigned)b);
-  *active = 1;
 }
 __global__ void tour_extract_kernel(const unsigned long long *__restrict__ link, int n, int *__restrict__ tin,
                                     int *__restrict__ size) {
@@ -792,16 +840,34 @@ void stage_symbolic(parth_b200 &h, const int *perm_in, int *parent_out, int *col
     la.reserve((size_t)m, s); lb.reserve((size_t)m, s);
     tour_succ_kernel<<<nblk(n), 256, 0, s>>>(parent.p, n, cptr.p, child.p, slot.p, la.p);
     h.stats.kernels_launched++;
-    unsigned long long *cur = la.p, *nxt = lb.p;
-    for (int round = 0; round < 40; round++) {
-      PB_CUDA(cudaMemsetAsync(flag.p + 2, 0, sizeof(int), s));
-      tour_jump_kernel<<<nblk(m), 256, 0, s>>>(cur, nxt, m, flag.p + 2);
-      h.stats.kernels_launched++;
-      std::swap(cur, nxt);
-      int active = 0;
-      read_ints(h, flag.p + 2, &active, 1);
-      if (!active) break;
+    // the head of the tour: "enter" of the first root (the children of the virtual vertex n)
+    int first_root = 0;
+    {
+      int cp[1];
+      read_ints(h, cptr.p + n, cp, 1);
+      read_ints(h, child.p + cp[0], &first_root, 1);
     }
+    const unsigned head = 2u * (unsigned)first_root;
+    DevBuf<int> vflag, vslot;
+    vflag.reserve((size_t)n + 1, s); vslot.reserve((size_t)n + 2, s);
+    tour_flag_kernel<<<nblk(n), 256, 0, s>>>(n, vflag.p);
+    h.stats.kernels_launched += 1 + exclusive_scan<0>(vflag.p, vslot.p, n, h.scan_ws.p, s);
+    int n_sampled = 0;
+    read_ints(h, vslot.p + n, &n_sampled, 1);
+    const unsigned n_reg = 2u * (unsigned)n_sampled, n_spl = n_reg + 1;
+    DevBuf<unsigned long long> sa, sb;
+    sa.reserve(n_spl, s); sb.reserve(n_spl, s);
+    tour_segment_kernel<<<nblk(m + 1), 256, 0, s>>>(la.p, m, head, n_reg, vslot.p, sa.p);
+    unsigned long long *pc = sa.p, *pn = sb.p;
+    int rounds = 1;
+    while ((1u << rounds) < n_spl) rounds++;
+    for (int r = 0; r < rounds; r++) {
+      tour_jump_fixed_kernel<<<nblk(n_spl), 256, 0, s>>>(pc, pn, n_spl);
+      std::swap(pc, pn);
+    }
+    tour_spread_kernel<<<nblk(m), 256, 0, s>>>(la.p, m, head, n_reg, vslot.p, pc, lb.p);
+    h.stats.kernels_launched += 2 + rounds;
+    unsigned long long *cur = lb.p;
     tour_extract_kernel<<<nblk(n), 256, 0, s>>>(cur, n, tin.p, size.p);
     h.stats.kernels_launched++;
     PB_CUDA(cudaStreamSynchronize(s));
