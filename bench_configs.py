@@ -282,7 +282,7 @@ def config3(api, kind, peak, n=126, frac=0.05):
             e0.record()
             g.setMatrixDev(N3, Ap3.data_ptr(), Ai3.data_ptr(), nnzA, dim)
             sb = g.stats()
-            g.setNewToOldDOFMap(new_to_old)
+            g.setNewToOldDOFMapDev(n2o.data_ptr(), int(n2o.numel()))  # the map is device-resident like the matrix
             rc = g.computePermutationDev(dperm.data_ptr(), dim)
             e1.record()
         torch.cuda.synchronize()

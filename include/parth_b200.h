@@ -96,6 +96,8 @@ int parth_b200_set_mesh(parth_b200 *h, int n, const int *Mp, const int *Mi);
 int parth_b200_set_mesh_dev(parth_b200 *h, int n, const int *dMp, const int *dMi, int nnz);
 /* ParthAPI::setNewToOldDOFMap -> computeOldToNewDOFMap, ParthAPI.cpp:126-189; len 0 clears */
 int parth_b200_set_new_to_old_map(parth_b200 *h, const int *map, int len);
+/* same with the map in device memory (a remesher that runs on the GPU) */
+int parth_b200_set_new_to_old_map_dev(parth_b200 *h, const int *dmap, int len);
 
 /* ParthAPI::old_to_new_map / added_dofs / removed_dofs (ParthAPI.h:79-84) as computeOldToNewDOFMap
  * (ParthAPI.cpp:131-189) left them; two-call protocol: array pointers may be NULL to get the sizes.  All sizes are 0

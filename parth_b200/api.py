@@ -85,6 +85,7 @@ SYMBOLS = {
     "parth_b200_morton_order": (C.c_int, [_vp, _ip, C.c_int]),
     "parth_b200_morton_order_dev": (C.c_int, [_vp, C.POINTER(_vp), _ip]),
     "parth_b200_morton_keys": (C.c_int, [_vp, _vp, C.c_int]),
+    "parth_b200_set_new_to_old_map_dev": (C.c_int, [_vp, _vp, C.c_int]),
     "parth_b200_compute_permutation_block": (C.c_int, [_vp, _ip, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "parth_b200_symbolic": (C.c_int, [_vp, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
     "parth_b200_symbolic_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),
@@ -355,6 +356,9 @@ class ParthAPI:
         else:
             m = _i32(new_to_old)
             self._check(self.lib.parth_b200_set_new_to_old_map(self.h, _p(m), len(m)))
+
+    def setNewToOldDOFMapDev(self, dmap_ptr, length):
+        self._check(self.lib.parth_b200_set_new_to_old_map_dev(self.h, C.c_void_p(dmap_ptr), int(length)))
 
     # ---- mesh / tree access
     def mesh_dims(self):

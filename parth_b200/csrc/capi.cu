@@ -358,6 +358,14 @@ int parth_b200_set_new_to_old_map(parth_b200 *h, const int *map, int len) {
   PB_API_END
 }
 
+int parth_b200_set_new_to_old_map_dev(parth_b200 *h, const int *dmap, int len) {
+  PB_API_BEGIN
+  if (len < 0 || (len > 0 && !dmap)) throw StatusError(PARTH_B200_ERR_ARG, "set_new_to_old_map: bad argument");
+  if (len > 0 && h->block_mode) throw StatusError(PARTH_B200_ERR_UNSUPPORTED, "set_new_to_old_map: DOF maps are not sharded (row-block mode)");
+  stage_set_map(*h, dmap, len, /*on_device=*/true);
+  PB_API_END
+}
+
 int parth_b200_import_tree(parth_b200 *h, int M_n, int levels, int nodes, const int *meta,
                            const int *node_ptr, const int *dofs, const int *labels,
                            const int *Mp_prev, const int *Mi_prev) {

@@ -1169,7 +1169,7 @@ std::vector<int> regroup_finish(parth_b200 &h, int total, const int *key, const 
 }  // namespace
 
 // ------------------------------------------------------------------ (a3)
-void stage_set_map(parth_b200 &h, const int *map, int len) {
+void stage_set_map(parth_b200 &h, const int *map, int len, bool on_device) {
   cudaStream_t s = h.stream;
   h.map_len = 0;
   h.n_added = h.n_removed = 0;
@@ -1179,8 +1179,8 @@ void stage_set_map(parth_b200 &h, const int *map, int len) {
   const int M = h.M_n, Mp = h.M_n_prev;
   h.new_to_old.reserve((size_t)M, s);
   h.old_to_new.reserve((size_t)Mp, s);
-  PB_CUDA(cudaMemcpyAsync(h.new_to_old.p, map, sizeof(int) * (size_t)M, cudaMemcpyHostToDevice, s));
-  h.stats.h2d_bytes += (long long)sizeof(int) * M;
+  PB_CUDA(cudaMemcpyAsync(h.new_to_old.p, map, sizeof(int) * (size_t)M, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s));
+  if (!on_device) h.stats.h2d_bytes += (long long)sizeof(int) * M;
   int *d_bad = h.mail.p + 16;
   PB_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int), s));
   fill_kernel<<<nblk(Mp), 256, 0, s>>>(h.old_to_new.p, Mp, -1);

@@ -79,7 +79,7 @@ void stage_snapshot(parth_b200 &h);
 int stage_compute_permutation(parth_b200 &h, int *dperm, int dim);
 
 // stage_maps.cu: (a3) DOF-map inversion, (a6) integration, (f2) relocation
-void stage_set_map(parth_b200 &h, const int *map, int len);
+void stage_set_map(parth_b200 &h, const int *map, int len, bool on_device = false);
 void stage_integrate(parth_b200 &h);
 void stage_relocate(parth_b200 &h, int threshold_node, std::vector<int> &dirty_fine_out, bool filter_edges = true);
 void relocate_prepare(parth_b200 &h, int M);  // pre-sizes the relocation scratch (import_tree)

@@ -216,3 +216,36 @@ def test_placement_dataflow_kernel_equals_launch_per_sweep(gpu_api, name, monkey
             assert str(res_c[k]) == str(res_s[k]), k
     assert g_s.stats()["integrate_passes"] == g_c.stats()["integrate_passes"]
     assert g_s.stats()["integrate_sweeps"] > 0 or g_s.stats()["integrate_passes"] == 0
+
+
+@pytest.mark.parametrize("name", ["g16_remesh_5_12", "g16_remesh_5_12_hubs", "g16_delete40"])
+def test_device_resident_dof_map_equals_host_map(gpu_api, name):
+    """parth_b200_set_new_to_old_map_dev (mesh, map and permutation stay on the device) against the host-pointer path"""
+    import torch
+    sc = SCEN[name]
+    res, g_host = sd.run_scenario_gpu(gpu_api, sc)
+    tree, Mp, Mi = sd.tree_of(sc)
+    _, P, I, m = sc["new"]
+    o = sc["opts"]
+    g = gpu_api.ParthAPI()
+    g.reorder_type = o["reorder_type"]; g.ND_levels = o["nd_levels"]; g.lagging = o["lagging"]
+    g.activate_aggressive_reuse = o["aggressive"]; g.relocate_lvl = o["relocate_lvl"]; g.lag_lvl = o["lag_lvl"]
+    g.verbose = False
+    g.setCoarsePolicy(gpu_api.COARSE_REPORT)
+    g.import_tree(tree, Mp, Mi)
+    n = len(P) - 1
+    dP, dI = torch.from_numpy(np.ascontiguousarray(P, np.int32)).cuda(), torch.from_numpy(np.ascontiguousarray(I, np.int32)).cuda()
+    dm = torch.from_numpy(np.ascontiguousarray(m, np.int32)).cuda()
+    dperm = torch.empty(n * sc["dim"], dtype=torch.int32, device="cuda")
+    g.setMeshDev(n, dP.data_ptr(), dI.data_ptr(), len(I))
+    g.setNewToOldDOFMapDev(dm.data_ptr(), len(m))
+    st = g.computePermutationDev(dperm.data_ptr(), sc["dim"])
+    g.synchronize()
+    assert st == int(res["status"])
+    a, b = g.export_tree(), g_host.export_tree()
+    for k in ("labels", "dofs", "mesh_perm", "dof2node", "node_ptr", "meta"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.array_equal(g.changed_edges(), g_host.changed_edges()) and g.getReuse() == g_host.getReuse()
+    if st == 0:
+        _, perm_host = None, None
+        assert np.array_equal(dperm.cpu().numpy(), gpu_api.ParthAPI.mapMeshPermToMatrixPerm(g_host, g_host.mesh_perm(), sc["dim"]))
