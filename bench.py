@@ -521,7 +521,7 @@ def run_sharded(args):
     g.acceptSnapshot()  # the tree fixture belongs to the base matrix
 
     need = args.warmup + args.steps + min(args.steps, 8) + (0 if args.no_e2e else 2 + args.steps + max(2, args.steps // 2))
-    D = min(args.steps + args.warmup, 12) if args.variant == "lag" else min(need, 64)
+    D = min(args.steps + args.warmup, 12) if args.variant == "lag" else min(need, 96)  # blocks are 1 / world of a matrix
     mats = [block_of(*stream.matrix(k)) for k in range(D)]  # the same update stream on every rank
     dperm = torch.empty(M, dtype=torch.int32, device=dev)
     hperm = torch.empty(M, dtype=torch.int32).pin_memory()
