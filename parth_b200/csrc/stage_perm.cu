@@ -393,8 +393,13 @@ static void cold_start(parth_b200 &h) {
     for (int x = 0; x < nodes; x++) if (node_ptr[x + 1] > node_ptr[x]) all.push_back(x);
     // (ReorderingType MORTON_CODE with coordinates for every DOF orders them along the Z curve instead)
     h.force_amd = !(h.reorder_type == PARTH_B200_MORTON_CODE && h.morton_n == h.M_n);
-    try { stage_permute_fine(h, all); } catch (...) { h.force_amd = false; throw; }
+    // a cold start orders EVERY node on every rank (the replicated trees must agree before any label exchange):
+    // the per-node sharing of the warm path is switched off for this call
+    const int world = h.world;
+    h.world = 1;
+    try { stage_permute_fine(h, all); } catch (...) { h.force_amd = false; h.world = world; throw; }
     h.force_amd = false;
+    h.world = world;
   }
 }
 
