@@ -159,7 +159,7 @@ def cpu_update_stream(kind, stream, variant, steps, warmup, first=0):
     h = cpu_parth.CpuParth(kind)
     apply_variant(h, variant)
     h.import_tree(stream.tree(), stream.Mp, stream.Mi)
-    times, info = [], {}
+    times, info, first_info = [], {}, None
     for k in range(warmup + steps):
         Ap, Ai = stream.matrix(first + k)
         t0 = time.perf_counter()
@@ -169,7 +169,12 @@ def cpu_update_stream(kind, stream, variant, steps, warmup, first=0):
         if k >= warmup:
             times.append(t1 - t0)
         info = dict(status=int(st), reuse=h.getReuse(), changes=h.getNumChanges())
+        if k == 0:  # METIS-independent results of the first update from the fixture tree (compared with ours)
+            f, c = h.dirty()
+            first_info = dict(changes=h.getNumChanges(), reuse=h.getReuse(), dirty_fine=f.tolist(), dirty_coarse=c.tolist(),
+                              edges=h.changed_edges().copy())
     info["_perm"] = perm
+    info["_first"] = first_info
     return times, info
 
 
@@ -206,6 +211,7 @@ def run_reference(args):
     nnz = int(stream.Ap[-1])
     times, info = cpu_update_stream(kind, stream, args.variant, args.steps, args.warmup)
     info.pop("_perm", None)
+    info.pop("_first", None)
     per = float(np.mean(times))
     value = 1.0 / per
     sample = f"{args.steps} full updates (setMatrix + computePermutation) at {args.n}^3 after {args.warmup} warm-up updates"
@@ -222,7 +228,7 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def nnz_l_block(make_handle, stream, variant, ref_perm, kind):
+def nnz_l_block(make_handle, stream, variant, ref_perm, kind, ref_first=None):
     """the metric's second half ("nnz(L) bit-exact vs ref"): the same two updates the cpu_baseline leg has just run,
     on a fresh handle; nnz(L) of OUR permutation from the device symbolic stage (stage d), the same number from the CPU
     oracle (etree as reference src/utils/etree.cpp:39-115 + column counts), and nnz(L) of the REFERENCE's permutation.
@@ -231,10 +237,18 @@ def nnz_l_block(make_handle, stream, variant, ref_perm, kind):
     from oracle import cpu_parth
     cpu_parth.build("port")
     g = make_handle(variant)
+    parity_first = None
     for k in range(2):
         Ap, Ai = stream.matrix(k)
         g.setMatrix(stream.N, Ap, Ai, 1)
         st, perm = g.computePermutation(1)
+        if k == 0 and ref_first is not None:
+            f, c = g.dirty()
+            parity_first = {"changed_edges_equal": bool(g.getNumChanges() == ref_first["changes"]
+                                                        and np.array_equal(g.changed_edges(), ref_first["edges"])),
+                            "dirty_sets_equal": bool(f.tolist() == ref_first["dirty_fine"] and c.tolist() == ref_first["dirty_coarse"]),
+                            "reuse_equal": bool(g.getReuse() == ref_first["reuse"])}
+            parity_first["parity"] = all(parity_first.values())
     Mp, Mi = g.mesh()
     g.symbolic()  # first call: the stage's scratch buffers are carved out of the memory pool
     parent, cc, lnz = g.symbolic()
@@ -246,7 +260,10 @@ def nnz_l_block(make_handle, stream, variant, ref_perm, kind):
     lnz_o, _ = cpu_parth.colcount(Mp, Mi, perm, par)
     par_r = cpu_parth.etree(Mp, Mi, ref_perm)
     lnz_r, _ = cpu_parth.colcount(Mp, Mi, ref_perm, par_r)
-    return {"nnz_L": int(lnz), "nnz_L_oracle": int(lnz_o), "nnz_L_reference": int(lnz_r),
+    return {"parity_first_update": dict(parity_first or {}, what="first update from the fixture tree, headline variant, full size: "
+                                        f"changed-edge list, dirty sets and reuse ratio against the CPU path ({kind}); what follows "
+                                        "(METIS re-dissection there, relocation here) is compared through nnz(L)"),
+            "nnz_L": int(lnz), "nnz_L_oracle": int(lnz_o), "nnz_L_reference": int(lnz_r),
             "nnz_L_detail": {"what": "nnz(L) = sum of the column counts of P A P^T (lower triangle with diagonal) after 2 updates "
                                      "from the tree fixture; nnz_L: device stage (d) on our permutation (tree-aware path); "
                                      "nnz_L_oracle: CPU oracle on the same permutation; nnz_L_reference: CPU oracle on the "
@@ -460,11 +477,12 @@ def run_ours(args, emit=True):
             cores = os.cpu_count() or 1
             times, cinfo = cpu_update_stream(kind, stream, args.variant, 2, 0)
             ref_perm = cinfo.pop("_perm")
+            ref_first = cinfo.pop("_first")
             line["cpu_baseline"] = {"value": 1.0 / float(np.mean(times)), "unit": UNIT, "cores": cores, "kind": kind,
                                     "sample": f"2 full updates at {args.n}^3 on a freshly injected tree",
                                     "last_update": cinfo}
             if not args.no_nnzl:
-                line.update(nnz_l_block(make_handle, stream, args.variant, ref_perm, kind))
+                line.update(nnz_l_block(make_handle, stream, args.variant, ref_perm, kind, ref_first))
         except Exception as e:  # the checker must never take the product number down
             line.setdefault("cpu_baseline", {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": repr(e)})
             line.setdefault("nnz_L", None)
