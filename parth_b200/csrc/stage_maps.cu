@@ -1235,7 +1235,20 @@ void stage_integrate(parth_b200 &h) {
     h.r_l2g.reserve((size_t)M + 1, s);  // indeg
     // one launch per pass (place_pass_pull_kernel: r_g2l holds the state words); PARTH_B200_PLACE_PER_SWEEP forces
     // the launch-per-sweep path (cross-check in tests/test_gpu_scenarios.py; r_g2l = placed_pass, r_l2g = indeg)
-    const bool pull_path = !std::getenv("PARTH_B200_PLACE_PER_SWEEP") && nn < 65535;
+    // (the pull kernel's warps poll each other: it needs a cooperative launch of one CTA per SM; a context that cannot
+    // give that -- no cooperative launch, SMs taken away by a partition -- takes the launch-per-sweep path)
+    static int pull_ok[64] = {};  // per device: 0 unknown, 1 yes, -1 no
+    {
+      const int dev = h.device;
+      if (dev >= 0 && dev < 64 && pull_ok[dev] == 0) {
+        int coop = 0, per_sm = 0;
+        PB_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+        PB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, place_pass_pull_kernel, kPullThreads, 0));
+        pull_ok[dev] = (coop && per_sm >= 1) ? 1 : -1;
+      }
+    }
+    const bool pull_path = !std::getenv("PARTH_B200_PLACE_PER_SWEEP") && nn < 65535 &&
+                           (h.device < 0 || h.device >= 64 || pull_ok[h.device] == 1);
     if (!pull_path) PB_CUDA(cudaMemsetAsync(h.r_g2l.p, 0, sizeof(int) * (size_t)M, s));
     constexpr int kBatch = 16;          // launch-per-sweep path: sweeps enqueued per read-back
     const int max_sweeps = n_added + kBatch + 2;
