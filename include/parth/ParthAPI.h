@@ -379,6 +379,13 @@ public:
     return lnz;
   }
 
+  /* page-lock an array the caller keeps across updates (Ap, Ai, perm): the host-pointer calls then run at the PCIe
+   * rate; unpin before the array is freed or reallocated.  Returns false when the driver refuses. */
+  template <typename T>
+  static bool pinHost(std::vector<T> &v) { return !v.empty() && parth_b200_pin_host(v.data(), v.size() * sizeof(T)) == PARTH_B200_OK; }
+  template <typename T>
+  static bool unpinHost(std::vector<T> &v) { return !v.empty() && parth_b200_unpin_host(v.data()) == PARTH_B200_OK; }
+
   /* one mesh over the ranks of a communicator (commInit*): the update of computePermutation with a DISTRIBUTED result --
    * this rank receives entries [first, first + perm_block.size()) of the expanded permutation (its row block times dim);
    * returns `first` */

@@ -24,6 +24,7 @@
  */
 #ifndef PARTH_B200_H
 #define PARTH_B200_H
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -231,6 +232,12 @@ typedef struct {
 } parth_b200_stats;
 int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out);
 int parth_b200_synchronize(parth_b200 *h);
+/* Page-locks / releases a host array of the CALLER (cudaHostRegister): the host-pointer entry points then move it at the
+ * PCIe rate (255 MB in 4.8 ms instead of ~20 ms from pageable memory at 200^3).  For callers that keep their Ap / Ai /
+ * perm arrays across updates -- what the reference's users do (LinSysSolver.hpp keeps the matrix arrays alive) -- and
+ * do not link the CUDA runtime themselves.  The array must stay allocated until it is unpinned. */
+int parth_b200_pin_host(void *ptr, size_t bytes);
+int parth_b200_unpin_host(void *ptr);
 /* the stream all work of this handle runs on (cudaStream_t) */
 void *parth_b200_stream(parth_b200 *h);
 

@@ -86,6 +86,8 @@ SYMBOLS = {
     "parth_b200_morton_order_dev": (C.c_int, [_vp, C.POINTER(_vp), _ip]),
     "parth_b200_morton_keys": (C.c_int, [_vp, _vp, C.c_int]),
     "parth_b200_set_new_to_old_map_dev": (C.c_int, [_vp, _vp, C.c_int]),
+    "parth_b200_pin_host": (C.c_int, [_vp, C.c_size_t]),
+    "parth_b200_unpin_host": (C.c_int, [_vp]),
     "parth_b200_compute_permutation_block": (C.c_int, [_vp, _ip, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "parth_b200_symbolic": (C.c_int, [_vp, _ip, _ip, _ip, C.POINTER(C.c_int64)]),
     "parth_b200_symbolic_dev": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(C.c_int64)]),

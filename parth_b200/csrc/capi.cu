@@ -215,6 +215,20 @@ int parth_b200_use_builtin_decomposer(parth_b200 *h, int on) {
 
 void *parth_b200_stream(parth_b200 *h) { return h ? (void *)h->stream : nullptr; }
 
+int parth_b200_pin_host(void *ptr, size_t bytes) {
+  if (!ptr || bytes == 0) return PARTH_B200_ERR_ARG;
+  const cudaError_t e = cudaHostRegister(ptr, bytes, cudaHostRegisterPortable);
+  if (e != cudaSuccess) { cudaGetLastError(); g_create_error = cudaGetErrorString(e); return (int)e; }
+  return PARTH_B200_OK;
+}
+
+int parth_b200_unpin_host(void *ptr) {
+  if (!ptr) return PARTH_B200_ERR_ARG;
+  const cudaError_t e = cudaHostUnregister(ptr);
+  if (e != cudaSuccess) { cudaGetLastError(); g_create_error = cudaGetErrorString(e); return (int)e; }
+  return PARTH_B200_OK;
+}
+
 int parth_b200_synchronize(parth_b200 *h) {
   PB_API_BEGIN
   PB_CUDA(cudaStreamSynchronize(h->stream));

@@ -65,3 +65,16 @@ def test_example_creator_and_tree_fixture(gpu_api, port, tmp_path):
     said2 = {int(m.group(1)): (int(m.group(2)), float(m.group(3)))
              for m in re.finditer(r"test (\d+): changes (\d+) reuse ([0-9.]+)", r2.stdout)}
     assert said2 == said
+
+
+def test_e2e_update_example_runs_pageable_and_pinned(gpu_api):
+    """examples/e2e_update: warm updates through PARTH::ParthAPI with std::vector inputs, pageable and page-locked
+    (parth_b200_pin_host); the permutation it ends with is valid and the update really finds its change"""
+    import json
+    from parth_b200 import build
+    exe = build.build_example("e2e_update")
+    r = subprocess.run([exe, "40", "4"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert out["valid_permutation"] and out["N"] == 64000 and out["ms_per_update_pageable"] > 0
+    assert out["ms_per_update_pinned"] > 0  # pinning the caller's vectors worked
