@@ -284,9 +284,8 @@ int parth_b200_set_matrix(parth_b200 *h, int N, const int *Ap, const int *Ai, in
   }
   h->dAp.reserve((size_t)N + 1, h->stream);
   h->dAi.reserve((size_t)(nnz > 0 ? nnz : 1), h->stream);
-  PB_CUDA(cudaMemcpyAsync(h->dAp.p, Ap, sizeof(int) * ((size_t)N + 1), cudaMemcpyHostToDevice, h->stream));
-  if (nnz > 0)
-    PB_CUDA(cudaMemcpyAsync(h->dAi.p, Ai, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+  h->hostcopy.h2d(h->dAp.p, Ap, sizeof(int) * ((size_t)N + 1), h->stream);
+  if (nnz > 0) h->hostcopy.h2d(h->dAi.p, Ai, sizeof(int) * (size_t)nnz, h->stream);
   h->stats.h2d_bytes = (long long)sizeof(int) * ((long long)N + 1 + nnz);
   h->stats.d2h_bytes = 0;
   h->sim_dim = dim;
@@ -316,9 +315,8 @@ int parth_b200_set_mesh(parth_b200 *h, int n, const int *Mp, const int *Mi) {
   if (Mp[0] != 0 || nnz < 0) throw StatusError(PARTH_B200_ERR_ARG, "set_mesh: Mp[0] != 0 or Mp[n] < 0");
   h->Mp_own.reserve((size_t)n + 1, h->stream);
   h->Mi_own.reserve((size_t)(nnz > 0 ? nnz : 1), h->stream);
-  PB_CUDA(cudaMemcpyAsync(h->Mp_own.p, Mp, sizeof(int) * ((size_t)n + 1), cudaMemcpyHostToDevice, h->stream));
-  if (nnz > 0)
-    PB_CUDA(cudaMemcpyAsync(h->Mi_own.p, Mi, sizeof(int) * (size_t)nnz, cudaMemcpyHostToDevice, h->stream));
+  h->hostcopy.h2d(h->Mp_own.p, Mp, sizeof(int) * ((size_t)n + 1), h->stream);
+  if (nnz > 0) h->hostcopy.h2d(h->Mi_own.p, Mi, sizeof(int) * (size_t)nnz, h->stream);
   PB_CUDA(cudaStreamSynchronize(h->stream));  // the caller may reuse its arrays
   h->stats.h2d_bytes = (long long)sizeof(int) * ((long long)n + 1 + nnz);
   h->Mp = h->Mp_own.p;
@@ -433,7 +431,7 @@ int parth_b200_compute_permutation(parth_b200 *h, int *perm, int dim) {
   h->d_out.reserve(n_out > 0 ? n_out : 1, h->stream);
   rc = stage_compute_permutation(*h, h->d_out.p, dim);
   if (rc == PARTH_B200_OK || rc == PARTH_B200_NEEDS_REDISSECT) {  // REPORT: the tree's current permutation
-    PB_CUDA(cudaMemcpyAsync(perm, h->d_out.p, sizeof(int) * n_out, cudaMemcpyDeviceToHost, h->stream));
+    h->hostcopy.d2h(perm, h->d_out.p, sizeof(int) * n_out, h->stream);
     h->stats.d2h_bytes += (long long)(sizeof(int) * n_out);
   }
   resolve_timers(*h);

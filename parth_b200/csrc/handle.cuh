@@ -12,6 +12,7 @@
 #include "build.cuh"
 #include "comm.cuh"
 #include "common.cuh"
+#include "hostcopy.cuh"
 #include "tree.cuh"
 
 struct parth_b200 {
@@ -154,6 +155,7 @@ struct parth_b200 {
   } pend;
   cudaEvent_t ev_mail = nullptr;
   pb::PinBuf<int> pin_big;                 // pinned staging for big host transfers
+  pb::HostCopier hostcopy;                 // caller arrays <-> device (staged through page-locked chunks when unregistered)
 
   parth_b200_stats stats = {};
 };
