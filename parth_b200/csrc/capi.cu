@@ -62,8 +62,8 @@ static void set_matrix_block_host(parth_b200 &h, int N, int nnz, const int *Ap, 
   const int off = q0 & 3;
   h.dAp.reserve((size_t)(c1 - c0) + 8, s);
   h.dAi.reserve((size_t)(q1 - q0) + 16, s);
-  PB_CUDA(cudaMemcpyAsync(h.dAp.p, Ap + c0, sizeof(int) * ((size_t)(c1 - c0) + 1), cudaMemcpyHostToDevice, s));
-  if (q1 > q0) PB_CUDA(cudaMemcpyAsync(h.dAi.p + off, Ai + q0, sizeof(int) * (size_t)(q1 - q0), cudaMemcpyHostToDevice, s));
+  h.hostcopy.h2d(h.dAp.p, Ap + c0, sizeof(int) * ((size_t)(c1 - c0) + 1), s);
+  if (q1 > q0) h.hostcopy.h2d(h.dAi.p + off, Ai + q0, sizeof(int) * (size_t)(q1 - q0), s);
   h.stats.h2d_bytes = (long long)sizeof(int) * ((long long)(c1 - c0) + 1 + (q1 - q0));
   h.stats.d2h_bytes = 0;
   stage_build_block(h, N, nnz, h.dAp.p - c0, h.dAi.p + off - q0, q0, q1);
@@ -454,7 +454,7 @@ int parth_b200_compute_permutation_block(parth_b200 *h, int *perm_block, int dim
   if (first) *first = (int)b0;
   if (count) *count = (int)nb;
   if ((rc == PARTH_B200_OK || rc == PARTH_B200_NEEDS_REDISSECT) && nb > 0) {
-    PB_CUDA(cudaMemcpyAsync(perm_block, h->d_out.p + b0, sizeof(int) * nb, cudaMemcpyDeviceToHost, h->stream));
+    h->hostcopy.d2h(perm_block, h->d_out.p + b0, sizeof(int) * nb, h->stream);
     h->stats.d2h_bytes += (long long)(sizeof(int) * nb);
   }
   resolve_timers(*h);
