@@ -35,3 +35,11 @@ def test_our_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--n", "24", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode != 0 and "no CUDA device" in (r.stdout + r.stderr)  # no CPU fallback on the product path
+
+
+def test_reference_arm_other_ranks_exit_quietly():
+    """under torchrun (N > 1) rank 0 alone runs the reference arm; the other ranks exit 0 without work or output"""
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--n", "24",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
