@@ -46,14 +46,16 @@ class HostCopier {
       return;
     }
     prepare();
-    size_t k = 0;
-    for (size_t off = 0; off < bytes; off += kChunk, k++) {
-      const int slot = (int)(k % kSlots);
+    // the slot sequence and the per-slot events outlive the call: the DMA of the LAST chunks of one transfer may still
+    // be reading its slots when the next transfer (Ap, then Ai) starts to fill the ring
+    for (size_t off = 0; off < bytes; off += kChunk, next_++) {
+      const int slot = (int)(next_ % kSlots);
       const size_t len = std::min(kChunk, bytes - off);
-      if (k >= kSlots) PB_CUDA(cudaEventSynchronize(ev_[slot]));  // the DMA that read this slot has finished
+      if (busy_[slot]) PB_CUDA(cudaEventSynchronize(ev_[slot]));  // the DMA that read this slot has finished
       parallel_copy(ring_ + (size_t)slot * kChunk, static_cast<const char *>(hsrc) + off, len);
       PB_CUDA(cudaMemcpyAsync(static_cast<char *>(ddst) + off, ring_ + (size_t)slot * kChunk, len, cudaMemcpyHostToDevice, s));
       PB_CUDA(cudaEventRecord(ev_[slot], s));
+      busy_[slot] = true;
     }
   }
 
@@ -65,6 +67,8 @@ class HostCopier {
       return;
     }
     prepare();
+    for (int i = 0; i < kSlots; i++)  // uploads of an earlier call that still read the ring (possibly on another stream)
+      if (busy_[i]) { PB_CUDA(cudaEventSynchronize(ev_[i])); busy_[i] = false; }
     const size_t chunks = (bytes + kChunk - 1) / kChunk;
     size_t issued = 0, drained = 0;
     while (drained < chunks) {
@@ -142,6 +146,8 @@ class HostCopier {
   std::vector<Task> tasks_;
   int pending_ = 0;
   bool stop_ = false;
+  size_t next_ = 0;             // ring position of the next uploaded chunk
+  bool busy_[kSlots] = {};      // slot has an upload recorded on ev_[slot]
 };
 
 }  // namespace pb

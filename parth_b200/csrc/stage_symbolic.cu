@@ -254,7 +254,7 @@ constexpr int EB_THREADS = 256, EB_CHUNK = 256, EB_DEG = 16, EB_LEVELS = 8;  // 
 __global__ void __launch_bounds__(EB_THREADS)
 etree_node_batch_kernel(const int *__restrict__ ranges, const int *__restrict__ perm, const int *__restrict__ inv,
                         const int *__restrict__ Mp, const int *__restrict__ Mi, const int *__restrict__ flat,
-                        const int *__restrict__ first, int *anc, int *parent) {
+                        const int *__restrict__ first, int *anc, int *parent, int links_in_global) {
   extern __shared__ __align__(16) unsigned char e2_raw[];
   __shared__ int s_nbr[EB_CHUNK][EB_DEG];  // sources of the batch's edges (phase 1: replaced by their F0 roots)
   __shared__ int s_pos[EB_CHUNK][EB_DEG];  // where the climb of each edge stopped last (it resumes there)
@@ -263,8 +263,10 @@ etree_node_batch_kernel(const int *__restrict__ ranges, const int *__restrict__ 
   __shared__ int s_flag[2];  // [0] a round changed something, [1] the batch holds a long row
   const int b = ranges[2 * blockIdx.x], e = ranges[2 * blockIdx.x + 1];
   const int tid = threadIdx.x, lane = tid & 31;
-  volatile int *sm = reinterpret_cast<volatile int *>(e2_raw);
-  for (int i = tid; i < e - b; i += EB_THREADS) sm[i] = -1;
+  // the node's links: shared memory, or -- a slice that does not fit (the top separators of a 512^3 mesh) -- the node's
+  // own range of the global anc[] array (initialised to -1 by the host); same algorithm, L2 latency instead of LDS
+  volatile int *sm = links_in_global ? reinterpret_cast<volatile int *>(anc + b) : reinterpret_cast<volatile int *>(e2_raw);
+  if (!links_in_global) for (int i = tid; i < e - b; i += EB_THREADS) sm[i] = -1;
   __syncthreads();
   for (int j0 = b; j0 < e; j0 += EB_CHUNK) {
     const int j = j0 + tid;
@@ -415,7 +417,7 @@ etree_node_batch_kernel(const int *__restrict__ ranges, const int *__restrict__ 
       __syncthreads();
     }
   }
-  for (int i = tid; i < e - b; i += EB_THREADS) anc[b + i] = sm[i];
+  if (!links_in_global) for (int i = tid; i < e - b; i += EB_THREADS) anc[b + i] = sm[i];
 }
 
 // after wave w: (i) every column of a wave-w node learns the root of its component ...
@@ -778,10 +780,16 @@ void stage_symbolic(parth_b200 &h, const int *perm_in, int *parent_out, int *col
           for (int r = 0; r < nr; r++) longest = std::max(longest, w[2 * r + 1] - w[2 * r]);
           // 16-bit slots cost ~30 % per column walk: they pay only when the wave has more nodes than the GPU has SMs
           const bool seq_only = std::getenv("PARTH_B200_ETREE_SEQ") != nullptr;
-          if (!seq_only && 4 * longest <= dyn_batch) {
+          // PARTH_B200_ETREE_SMEM_KB caps the shared-memory budget (tests: the global-links variant on small meshes)
+          const char *cap_kb = std::getenv("PARTH_B200_ETREE_SMEM_KB");
+          const int budget = cap_kb ? std::min(dyn_batch, std::atoi(cap_kb) * 1024) : dyn_batch;
+          if (!seq_only && 4 * longest <= budget) {
             const int bytes = ((4 * longest + 1023) / 1024) * 1024;
             etree_node_batch_kernel<<<nr, EB_THREADS, bytes, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi, flatroot.p, first.p,
-                                                                 anc.p, parent.p);
+                                                                 anc.p, parent.p, 0);
+          } else if (!seq_only) {  // a slice beyond shared memory: the same batches with the links in global memory
+            etree_node_batch_kernel<<<nr, EB_THREADS, 0, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi, flatroot.p, first.p, anc.p,
+                                                             parent.p, 1);
           } else if (nr > h.num_sms && longest <= 65534 && 2 * longest <= dyn) {
             const int bytes = ((2 * longest + 1023) / 1024) * 1024;
             etree_node_kernel<unsigned short, true><<<nr, E2_THREADS, bytes, s>>>(ranges.p + at, perm.p, inv.p, h.Mp, h.Mi,

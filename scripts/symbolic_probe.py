@@ -27,5 +27,10 @@ if check:
     olnz, occ = cpu_parth.colcount(st.Mp, st.Mi, perm, op)
     t2 = time.perf_counter()
     out["cpu_etree_s"] = t1 - t0; out["cpu_colcount_s"] = t2 - t1
+    out["mismatch"] = {"parent": int((op != parent).sum()), "colcount": int((occ != cc).sum()), "lnz": [int(olnz), int(lnz)],
+                       "first_parent": int(np.flatnonzero(op != parent)[0]) if (op != parent).any() else -1,
+                       "first_cc": int(np.flatnonzero(occ != cc)[0]) if (occ != cc).any() else -1}
+    bad = np.flatnonzero(op != parent)[:8]
+    out["mismatch"]["cols"] = [[int(j), int(op[j]), int(parent[j])] for j in bad]
     out["bit_exact"] = bool(np.array_equal(op, parent) and np.array_equal(occ, cc) and int(olnz) == int(lnz))
 print(json.dumps(out))

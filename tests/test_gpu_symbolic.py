@@ -179,8 +179,11 @@ def test_batch_etree_kernel_equals_sequential_walk_and_oracle(gpu_api, port, key
         assert len(d) > hub + 1
         Mp, Mi = synth.add_edges(Mp, Mi, [(int(d[0]), int(x)) for x in d[1:hub + 1]])
     outs = []
-    for seq in (False, True):
-        if seq:
+    for mode in ("batch", "batch_global_links", "sequential"):
+        monkeypatch.delenv("PARTH_B200_ETREE_SMEM_KB", raising=False)
+        if mode == "batch_global_links":  # slices beyond the shared-memory budget keep their links in global memory
+            monkeypatch.setenv("PARTH_B200_ETREE_SMEM_KB", "1")
+        if mode == "sequential":
             monkeypatch.setenv("PARTH_B200_ETREE_SEQ", "1")
         g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = tree.levels
         g.import_tree(tree, Mp, Mi)
