@@ -335,9 +335,13 @@ def run_ours(args, emit=True):
         torch.cuda.synchronize()
 
     def step_resident(g, k):
-        Ap, Ai = dev_mats[k % D]
-        g.setMatrixDev(N, Ap.data_ptr(), Ai.data_ptr(), nnzA, 1)
-        g.computePermutationDev(dperm.data_ptr(), 1)
+        # the update with its ctypes arguments bound once per (handle, matrix): api.preparedUpdateDev
+        prepared = g.__dict__.setdefault("_prepared", {})
+        run = prepared.get(k % D)
+        if run is None:
+            Ap, Ai = dev_mats[k % D]
+            run = prepared[k % D] = g.preparedUpdateDev(N, Ap.data_ptr(), Ai.data_ptr(), nnzA, 1, dperm.data_ptr(), 1)
+        run()
 
     def step_e2e(g, k):
         Ap, Ai = host_mats[k % D]

@@ -7,6 +7,7 @@ device pointers into the C entry points; there is no compute here and no CPU fal
 fails loudly when the CUDA extension is missing, and creating a handle fails without a GPU.
 """
 import ctypes as C
+import weakref
 import os
 
 import numpy as np
@@ -453,6 +454,31 @@ class ParthAPI:
         if rc == NEEDS_REDISSECT and self.report_advances_snapshot:
             self.acceptSnapshot()
         return rc
+
+    def preparedUpdateDev(self, N, dAp_ptr, dAi_ptr, nnz, dim, dperm_ptr, out_dim):
+        """One resident update (setMatrixDev + computePermutationDev on fixed device arrays) as a closure whose ctypes
+        arguments are built once.  The generic methods cost ~25 us of Python per update (option push, argument
+        conversion) -- more than the device idles between two updates -- a hot loop over a fixed set of buffers
+        binds them once instead.  Options are pushed when the closure is made; same status handling as
+        computePermutationDev.  Returns the closure; calling it returns the status of the update."""
+        self._push_options()
+        set_fn, cp_fn = self.lib.parth_b200_set_matrix_dev, self.lib.parth_b200_compute_permutation_dev
+        a_set = (self.h, C.c_int(int(N)), C.c_void_p(dAp_ptr), C.c_void_p(dAi_ptr), C.c_int(int(nnz)), C.c_int(int(dim)))
+        a_cp = (self.h, C.c_void_p(dperm_ptr), C.c_int(int(out_dim)))
+
+        me = weakref.ref(self)  # the closure may be stored on the object itself: no reference cycle
+
+        def run():
+            rc = set_fn(*a_set)
+            if rc:
+                me()._check(rc)
+            rc = cp_fn(*a_cp)
+            if rc:
+                me()._check(rc, allow=(NEEDS_REDISSECT, NEEDS_EXCHANGE))
+                if rc == NEEDS_REDISSECT and me().report_advances_snapshot:
+                    me().acceptSnapshot()
+            return rc
+        return run
 
     def dof_maps(self):
         """(old_to_new_map, added_dofs, removed_dofs) as ParthAPI::computeOldToNewDOFMap leaves them"""

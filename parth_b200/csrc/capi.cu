@@ -101,6 +101,9 @@ int parth_b200_create(parth_b200 **out, int device) {
     PB_CUDA(cudaEventCreate(&h->ev2));
     PB_CUDA(cudaEventCreate(&h->ev3));
     PB_CUDA(cudaEventCreate(&h->ev_mail));
+    PB_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+    PB_CUDA(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    PB_CUDA(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     h->pin.reserve(1 << 16);
     {
       // keep freed work-space in the device's default pool instead of returning it to the driver
@@ -129,11 +132,15 @@ int parth_b200_destroy(parth_b200 *h) {
   if (!h) return PARTH_B200_ERR_ARG;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
+  host_trace().dump();
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev2) cudaEventDestroy(h->ev2);
   if (h->ev3) cudaEventDestroy(h->ev3);
   if (h->ev_mail) cudaEventDestroy(h->ev_mail);
+  if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (auto &e : h->tev) if (e) cudaEventDestroy(e);
   delete h->comm;
   h->comm = nullptr;
@@ -249,6 +256,7 @@ int parth_b200_get_stats(parth_b200 *h, parth_b200_stats *out) {
 
 // ------------------------------------------------------------------ matrix / mesh input
 int parth_b200_set_matrix_dev(parth_b200 *h, int N, const int *dAp, const int *dAi, int nnz, int dim) {
+  PB_MARK("set_matrix_dev: called");
   PB_API_BEGIN_STREAM
   if (!dAp || !dAi || N <= 0 || dim <= 0 || nnz < 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: bad argument");
   if (N % dim != 0) throw StatusError(PARTH_B200_ERR_ARG, "set_matrix: N is not a multiple of dim (ParthAPI.cpp:371 asserts it)");
@@ -267,7 +275,9 @@ int parth_b200_set_matrix_dev(parth_b200 *h, int N, const int *dAp, const int *d
   // steady state: returns with the build, the changed-row proof and stage (b)'s edge kernels in flight;
   // whatever call needs their outcome next waits for the mailbox copy alone (stage_build_settle).
   // Otherwise it ends on its mailbox read-back and nothing is in flight.
+  PB_MARK("set_matrix_dev: entry");
   stage_build(*h, N, dAp, dAi, nnz, dim, /*may_defer=*/true);
+  PB_MARK("set_matrix_dev: build enqueued");
   PB_API_END
 }
 
@@ -405,18 +415,21 @@ int parth_b200_export_tree(parth_b200 *h, int *meta, int *node_ptr, int *dofs, i
 
 int parth_b200_compute_permutation_dev(parth_b200 *h, int *dperm, int dim) {
   int rc = PARTH_B200_OK;
+  PB_MARK("compute_permutation_dev: called");
   PB_API_BEGIN_NOSETTLE
   if (!dperm || dim <= 0) throw StatusError(PARTH_B200_ERR_ARG, "computePermutation: bad argument");
   h->stats.h2d_bytes = h->stats.d2h_bytes = 0;
   // stream-ordered: dperm is valid for work enqueued on the handle's stream after this call (or
   // after parth_b200_synchronize); the stage timers are read at the next synchronisation point
   h->defer_reloc_check = true;  // stream-ordered: the regroup kernels' error flags are read by the next synchronising call
+  PB_MARK("compute_permutation_dev: entry");
   try {
     rc = stage_compute_permutation(*h, dperm, dim);
   } catch (...) {
     h->defer_reloc_check = false;
     throw;
   }
+  PB_MARK("compute_permutation_dev: done");
   h->defer_reloc_check = false;
   if (rc != PARTH_B200_OK) return rc;
   PB_API_END

@@ -13,11 +13,16 @@
 #include "comm.cuh"
 #include "common.cuh"
 #include "hostcopy.cuh"
+#include "hosttrace.cuh"
 #include "tree.cuh"
 
 struct parth_b200 {
   int device = 0, num_sms = pb::kNumSMsB200;
   cudaStream_t stream = nullptr;
+  // side stream of the sparse relocation: the streaming copy of the untouched slices runs beside the joiner ranking and
+  // the regroup kernel of the changed nodes (forked from and joined back into `stream` inside the stage)
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
   // deferred stage timers: events are recorded while the work is enqueued and read once, after the
   // final synchronisation of the API call (no intermediate cudaEventSynchronize on the hot path)

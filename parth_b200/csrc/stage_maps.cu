@@ -627,12 +627,21 @@ constexpr int kSparseCand = 2 * kSparseEdges;
 // relocation targets, ordered compaction of the edges that stay, collection + ascending sort of the moved DOFs, per-node
 // leaver / joiner counts, redirect of dof2node, reset of the occurrence scratch, and (filter) the kept edges written
 // back over the edge list.  As eleven stream operations of 3-5 us each the same work was launch-bound (~45 us of the
-// headline update); the phases only need CTA barriers.  out: [0] n_moved, [1] unsorted, [2] size mismatch, [3] kept.
+// headline update); the phases only need CTA barriers.  out: [0] n_moved, [1] unsorted, [2] size mismatch, [3] kept,
+// [4..5] a copy of sticky_in (the regroup kernels' error flags).
 // Dynamic shared memory: kSparseCand ints (the moved list / sort buffer) + kSparseEdges bytes (keep flags).
+__global__ void apply_layout_kernel(const int *__restrict__ nptr, const int *__restrict__ off, int nn,
+                                    int *__restrict__ node_ptr, int *__restrict__ meta) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  if (x <= nn) node_ptr[x] = nptr[x];
+  if (x < nn) meta[(size_t)x * 7 + 4] = off[x];
+}
+
 __global__ void __launch_bounds__(1024)
 reloc_front_kernel(int *__restrict__ edges, int ne, int *__restrict__ dof2node, const int *__restrict__ meta, int threshold,
                    int *__restrict__ occ, int *__restrict__ target, int *__restrict__ kept_edges, int *__restrict__ moved,
-                   int *__restrict__ moved_node, int *__restrict__ cnt, int nn, int *__restrict__ out, int filter) {
+                   int *__restrict__ moved_node, int *__restrict__ cnt, int nn, int *__restrict__ out, int filter,
+                   const int *__restrict__ sticky_in) {
   extern __shared__ int s[];
   unsigned char *keep = reinterpret_cast<unsigned char *>(s + kSparseCand);
   __shared__ int s_scan[33];
@@ -640,6 +649,7 @@ reloc_front_kernel(int *__restrict__ edges, int ne, int *__restrict__ dof2node, 
   const int tid = threadIdx.x;
   for (int i = tid; i < 2 * nn; i += 1024) cnt[i] = 0;
   if (tid < 4) out[tid] = 0;
+  else if (tid < 6) out[tid] = sticky_in[tid - 4];  // error flags of earlier stream-ordered updates ride along
   if (tid == 0) s_n = 0;
   for (int q = tid; q < 2 * ne; q += 1024) atomicAdd(occ + edges[q], 1);
   __syncthreads();
@@ -1389,7 +1399,9 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
   h.w4.reserve((size_t)nn * 2 + 8, s);           // cnt_out | cnt_in
   h.r_perm.reserve((size_t)kSparseCand, s);      // moved ids, ascending
   h.r_ws.reserve((size_t)kSparseCand, s);        // their target nodes
-  int *d_cnt = h.mail.p + 16;  // [0] n_moved, [1] unsorted survivors, [2] size mismatch, [3] kept edges
+  // behind the per-node counts, so that ONE copy fetches everything:
+  // [0] n_moved, [1] unsorted survivors, [2] size mismatch, [3] kept edges, [4..5] sticky flags of earlier updates
+  int *d_cnt = h.w4.p + 2 * (size_t)nn;
   const size_t front_smem = sizeof(int) * kSparseCand + kSparseEdges;
   {
     static bool attr[64] = {};  // > 48 KB of dynamic shared memory: opt in once per device
@@ -1399,34 +1411,34 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
       if (dev >= 0 && dev < 64) attr[dev] = true;
     }
   }
+  PB_MARK("reloc: entry");
   reloc_front_kernel<<<1, 1024, front_smem, s>>>(h.d_changed.p, ne, h.d_dof2node.p, h.d_meta.p, threshold_node, h.rel_occ.p,
                                                  h.rel_target.p, h.w2.p, h.r_perm.p, h.r_ws.p, h.w4.p, nn, d_cnt,
-                                                 filter_edges ? 1 : 0);
+                                                 filter_edges ? 1 : 0, h.reloc_sticky.p);
   PB_CUDA(cudaGetLastError());
   h.stats.kernels_launched++;
   // ONE read-back: kept edges, moved DOFs, leavers / joiners per node
   h.pin.reserve((size_t)2 * nn + 8);
-  PB_CUDA(cudaMemcpyAsync(h.pin.p, d_cnt, sizeof(int) * 4, cudaMemcpyDeviceToHost, s));
-  PB_CUDA(cudaMemcpyAsync(h.pin.p + 4, h.w4.p, sizeof(int) * (size_t)nn * 2, cudaMemcpyDeviceToHost, s));
-  // the sticky error flags of an earlier stream-ordered update ride along (this update's regroup kernels run later)
-  PB_CUDA(cudaMemcpyAsync(h.pin.p + 4 + 2 * (size_t)nn, h.reloc_sticky.p, sizeof(int) * 2, cudaMemcpyDeviceToHost, s));
+  // (the sticky error flags of an earlier stream-ordered update ride along: this update's regroup kernels run later)
+  PB_CUDA(cudaMemcpyAsync(h.pin.p, h.w4.p, sizeof(int) * ((size_t)nn * 2 + 6), cudaMemcpyDeviceToHost, s));
+  PB_MARK("reloc: front + read-back enqueued");
   PB_CUDA(cudaStreamSynchronize(s));
+  PB_MARK("reloc: read-back arrived");
   h.stats.d2h_bytes += (long long)sizeof(int) * (2 * nn + 6);
-  collect_timers(h);
   if (h.reloc_check_pending) {
     h.reloc_check_pending = false;
-    const int f0 = h.pin.p[4 + 2 * (size_t)nn], f1 = h.pin.p[5 + 2 * (size_t)nn];
+    const int f0 = h.pin.p[2 * (size_t)nn + 4], f1 = h.pin.p[2 * (size_t)nn + 5];
     if (f0 || f1) PB_CUDA(cudaMemsetAsync(h.reloc_sticky.p, 0, sizeof(int) * 2, s));
     if (f1) throw StatusError(PARTH_B200_ERR_INTERNAL, "relocate: regrouped node size mismatch (previous update)");
     if (f0)
       throw StatusError(PARTH_B200_ERR_UNSUPPORTED,
                         "DOF map: surviving DOFs of a node that receives DOFs are not in ascending order (previous update)");
   }
-  const int kept = h.pin.p[3], n_moved = h.pin.p[0];
-  const std::vector<int> cnt_out(h.pin.p + 4, h.pin.p + 4 + nn), cnt_in(h.pin.p + 4 + nn, h.pin.p + 4 + 2 * nn);
+  const int kept = h.pin.p[2 * (size_t)nn + 3], n_moved = h.pin.p[2 * (size_t)nn];
+  const std::vector<int> cnt_out(h.pin.p, h.pin.p + nn), cnt_in(h.pin.p + nn, h.pin.p + 2 * nn);
   if (filter_edges) h.n_changed = kept;
-  if (n_moved == 0) return;
-  // new layout on the host (<= 8191 nodes)
+  if (n_moved == 0) { collect_timers(h); return; }
+  // new layout on the host (<= 8191 nodes); the device idles until the kernels below are enqueued
   std::vector<int> aptr((size_t)nn + 1, 0), nptr((size_t)nn + 1, 0), changed_flag((size_t)nn, 0), changed, touched;
   int max_words = 0, max_in = 0;
   for (int x = 0; x < nn; x++) {
@@ -1455,8 +1467,9 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
       asm_list.push_back(x);
       asm_off.push_back(h.meta[(size_t)x * 7 + 4]);
     }
-  // one upload: aptr | nptr | changed flags | changed list | touched list | assemble list | its offsets  (pinned: no wait)
-  const size_t up = (size_t)3 * nn + 2 + changed.size() + touched.size() + 2 * asm_list.size();
+  // one upload: aptr | nptr | changed flags | changed list | touched list | assemble list | its offsets | the offsets of
+  // all nodes (pinned: no wait)
+  const size_t up = (size_t)3 * nn + 2 + changed.size() + touched.size() + 2 * asm_list.size() + nn;
   h.pin_rel.reserve(up + 8);
   h.w5.reserve(up + 8, s);
   {
@@ -1467,18 +1480,31 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
     std::copy(changed.begin(), changed.end(), q); q += changed.size();
     std::copy(touched.begin(), touched.end(), q); q += touched.size();
     std::copy(asm_list.begin(), asm_list.end(), q); q += asm_list.size();
-    std::copy(asm_off.begin(), asm_off.end(), q);
+    std::copy(asm_off.begin(), asm_off.end(), q); q += asm_off.size();
+    for (int x = 0; x < nn; x++) q[x] = h.meta[(size_t)x * 7 + 4];
   }
+  PB_MARK("reloc: layout planned");
   PB_CUDA(cudaMemcpyAsync(h.w5.p, h.pin_rel.p, sizeof(int) * up, cudaMemcpyHostToDevice, s));
   const int *d_aptr = h.w5.p, *d_nptr = h.w5.p + (nn + 1), *d_flag = h.w5.p + 2 * (nn + 1);
   const int *d_changed_list = d_flag + nn, *d_touched = d_changed_list + changed.size();
   const int *d_asm = d_touched + touched.size(), *d_asm_off = d_asm + asm_list.size();
+  const int *d_off_all = d_asm_off + asm_list.size();
   h.r_sub.reserve((size_t)std::max(n_moved, 1), s);  // joiners grouped by node
-  rank_joiners(h, (int)touched.size(), d_touched, h.r_perm.p, h.r_ws.p, n_moved, d_aptr, h.r_sub.p);
   h.d_dofs2.reserve((size_t)std::max(new_total, 1), s);
   h.d_labels2.reserve((size_t)std::max(new_total, 1), s);
-  regroup_copy_kernel<<<nblk((new_total + RC_RUN - 1) / RC_RUN), 256, 0, s>>>(h.d_node_ptr.p, d_nptr, d_flag, nn, new_total,
-                                                                            h.d_dofs.p, h.d_labels.p, h.d_dofs2.p, h.d_labels2.p);
+  // fork: the streaming copy of the untouched slices (the longest kernel of the stage, it only needs the upload) runs
+  // on the side stream while this one ranks the joiners and regroups the changed nodes (a few CTAs, latency-bound);
+  // the two write disjoint slices of the new arrays.  PARTH_B200_RELOC_ONE_STREAM keeps everything on one stream.
+  static const bool one_stream = std::getenv("PARTH_B200_RELOC_ONE_STREAM") != nullptr;
+  cudaStream_t sc = one_stream ? s : h.stream2;
+  if (!one_stream) {
+    PB_CUDA(cudaEventRecord(h.ev_fork, s));
+    PB_CUDA(cudaStreamWaitEvent(sc, h.ev_fork, 0));
+  }
+  regroup_copy_kernel<<<nblk((new_total + RC_RUN - 1) / RC_RUN), 256, 0, sc>>>(h.d_node_ptr.p, d_nptr, d_flag, nn, new_total,
+                                                                             h.d_dofs.p, h.d_labels.p, h.d_dofs2.p, h.d_labels2.p);
+  if (!one_stream) PB_CUDA(cudaEventRecord(h.ev_join, sc));
+  rank_joiners(h, (int)touched.size(), d_touched, h.r_perm.p, h.r_ws.p, n_moved, d_aptr, h.r_sub.p);
   // one cluster of RGC CTAs per changed node; shared memory: its slice of the label bitmap + word prefix, and (rank 0)
   // the joiner histogram.  PARTH_B200_REGROUP_ONE_CTA keeps the one-CTA-per-node kernel (cross-check in tests)
   const int wper_cap = ((max_words + RGC - 1) / RGC + 3) & ~3, hist_cap = max_in + 2;
@@ -1500,6 +1526,7 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
   }
   reloc_reset_target_kernel<<<nblk(n_moved), 256, 0, s>>>(h.r_perm.p, n_moved, h.rel_target.p);
   PB_CUDA(cudaGetLastError());
+  if (!one_stream) PB_CUDA(cudaStreamWaitEvent(s, h.ev_join, 0));  // join: everything below reads the copied slices
   h.stats.kernels_launched += 3;
   h.d_dofs.swap(h.d_dofs2);
   h.d_labels.swap(h.d_labels2);
@@ -1510,7 +1537,15 @@ static void relocate_sparse(parth_b200 &h, int threshold_node, std::vector<int> 
     PB_CUDA(cudaGetLastError());
     h.stats.kernels_launched++;
   }
-  upload_tree_meta(h, /*sync=*/false);  // its sources are staged by the copies
+  PB_MARK("reloc: kernels enqueued");
+  // the device mirrors of node_ptr and of the offsets (only these two change: ids, links, levels and the visit order
+  // stay) are refreshed from the upload above -- upload_tree_meta's three pageable copies cost ~20 us of host time
+  // right where the host has to get ahead of the device again
+  apply_layout_kernel<<<nblk(nn + 1), 256, 0, s>>>(d_nptr, d_off_all, nn, h.d_node_ptr.p, h.d_meta.p);
+  PB_CUDA(cudaGetLastError());
+  h.stats.kernels_launched++;
+  PB_MARK("reloc: tree meta uploaded");
+  collect_timers(h);  // (the stage timers that completed with the read-back; off the critical path here)
   h.reloc_check_pending = true;
   if (!h.defer_reloc_check) check_reloc_flags(h);  // host-pointer API: errors are reported by the call that caused them
   dirty_fine_out.insert(dirty_fine_out.end(), touched.begin(), touched.end());

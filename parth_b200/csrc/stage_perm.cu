@@ -445,7 +445,9 @@ int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
       spec_end = tm.stop();
       spec_expanded = true;
     }
+    PB_MARK("cp: speculative expansion enqueued");
     stage_build_settle(h);
+    PB_MARK("cp: build settled (mailbox read)");
   }
   for (double &t : h.timer_ms) t = 0;
   h.xchg_pending = false;
@@ -472,6 +474,7 @@ int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
   } else {
     if (h.map_len > 0) stage_integrate(h);
     stage_detect(h);
+    PB_MARK("cp: detect done");
     // compute_permutation bracket: opens at the end of the speculative expansion when there is one
     StageTimer tc(h, &h.timer_ms[3], false, nullptr, spec_end);
     const long long launched0 = h.stats.kernels_launched;
@@ -480,6 +483,7 @@ int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
       h.reuse = 1;
     } else {
       rc = global_perm(h);
+      PB_MARK("cp: global_perm done");
     }
     if (rc == PARTH_B200_OK && h.xchg_pending) {
       // sharded mode: the other ranks' nodes are still missing; the caller gathers them, then
@@ -505,8 +509,10 @@ int stage_compute_permutation(parth_b200 &h, int *dperm, int dim) {
       return rc;
     }
     if (h.stats.kernels_launched == launched0) tc.cancel(); else tc.stop();
+    PB_MARK("cp: expanded");
   }
   stage_snapshot(h);
+  PB_MARK("cp: snapshot done");
   return rc;
 }
 

@@ -249,3 +249,42 @@ def test_device_resident_dof_map_equals_host_map(gpu_api, name):
     if st == 0:
         _, perm_host = None, None
         assert np.array_equal(dperm.cpu().numpy(), gpu_api.ParthAPI.mapMeshPermToMatrixPerm(g_host, g_host.mesh_perm(), sc["dim"]))
+
+
+def test_prepared_update_closure_equals_generic_calls(gpu_api):
+    """api.preparedUpdateDev (setMatrixDev + computePermutationDev with the ctypes arguments bound once: what the
+    resident bench loop calls) against the generic methods on the same update stream, relocation policy included"""
+    import torch
+    from parth_b200 import synth
+    tree, Mp, Mi = sd.tree_of(dict(tree=("geo", 16, 5)))
+    n = len(Mp) - 1
+    rng = np.random.default_rng(77)
+    mats, cur = [], (Mp, Mi)
+    for step in range(4):
+        e = [(int(a), int(b)) for a, b in rng.integers(0, n, size=(12, 2)) if a != b]
+        cur = synth.add_edges(cur[0], cur[1], e)
+        N, Ap, Ai = synth.graph_to_matrix(*cur)
+        mats.append((torch.from_numpy(np.ascontiguousarray(Ap, np.int32)).cuda(),
+                     torch.from_numpy(np.ascontiguousarray(Ai, np.int32)).cuda()))
+    outs = []
+    for prepared in (False, True):
+        g = gpu_api.ParthAPI(); g.verbose = False; g.ND_levels = 5; g.reorder_type = 1; g.lagging = False
+        g.setCoarsePolicy(gpu_api.COARSE_RELOCATE)
+        g.import_tree(tree, Mp, Mi)
+        dperm = torch.empty(n, dtype=torch.int32, device="cuda")
+        seq = []
+        for dAp, dAi in mats:
+            if prepared:
+                run = g.preparedUpdateDev(n, dAp.data_ptr(), dAi.data_ptr(), int(dAi.numel()), 1, dperm.data_ptr(), 1)
+                st = run()
+            else:
+                g.setMatrixDev(n, dAp.data_ptr(), dAi.data_ptr(), int(dAi.numel()), 1)
+                st = g.computePermutationDev(dperm.data_ptr(), 1)
+            g.synchronize()
+            seq.append((st, dperm.cpu().numpy().copy(), g.changed_edges().copy(), g.getReuse(), [x.tolist() for x in g.dirty()]))
+        outs.append((seq, g.export_tree()))
+    for a, b in zip(outs[0][0], outs[1][0]):
+        assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and a[3] == b[3] and a[4] == b[4]
+        assert sorted(a[1].tolist()) == list(range(n))
+    for k in ("labels", "dofs", "mesh_perm", "dof2node", "node_ptr", "meta"):
+        assert np.array_equal(outs[0][1][k], outs[1][1][k]), k
